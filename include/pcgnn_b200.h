@@ -1,0 +1,142 @@
+/*
+ * pcgnn_b200 — C ABI of the B200-native pick-and-choose message-passing path.
+ *
+ * One shared library (libpcgnn_b200.so, built from pc-gnn_b200/csrc/ for sm_100a). Every entry
+ * point takes plain device pointers and sizes, is asynchronous on the given stream, never
+ * allocates or frees, and returns 0 on success or a non-zero cudaError_t-compatible code
+ * (pcg_last_error() then holds the message; thread-local). The caller owns every buffer.
+ *
+ * The reference (h22hyeon/PC-GNN) is pure Python; each function below names the reference
+ * lines whose work it replaces (paths relative to /root/reference/).
+ *
+ * Conventions
+ *   work item   w = r * B + i        (relation r of target i; relation-major)
+ *   graph       stacked CSR: row r*N+v of `indptr` (int64 [R*N+1]) / `indices` (int32, ids
+ *               ascending inside a row) is the neighbour list of node v under relation r
+ *   feat        fp32 [N, ldf], ldf % 4 == 0, 16-byte aligned, columns >= F are zero
+ *   slot        PCG_SLOT consecutive selected ids of ONE item; items own whole slots
+ */
+#ifndef PCGNN_B200_H
+#define PCGNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCG_SLOT 64          /* selected ids per aggregation slot */
+#define PCG_MAX_REL 8        /* relations per graph (reference ships 1, 3 and 5) */
+#define PCG_NORM_MEAN 0      /* sum / n        (src/layers.py:612-614, src/graphsage.py:86-88) */
+#define PCG_NORM_RSQRT 1     /* sum / sqrt(n)  (src/graphsage.py:224-226) */
+
+/* status words written by the kernels (int32 device array of PCG_STATUS_WORDS) */
+#define PCG_STATUS_WORDS 8
+#define PCG_ST_SLOTS 0       /* slots handed out (aggregation consumes [0, this)) */
+#define PCG_ST_OVERFLOW 3    /* != 0: `cap_slots` was too small, results are incomplete */
+
+typedef void* pcg_stream_t;  /* a cudaStream_t */
+
+#define PCG_API __attribute__((visibility("default")))
+
+PCG_API const char* pcg_last_error(void);
+PCG_API int pcg_version(void);
+/* SM count of the current device (grid sizing), or a negative error. */
+PCG_API int pcg_device_sms(void);
+
+/*
+ * Label-aware score table, column 0 only: score[v] = dot(feat[v, :F], w) + b[0] for all N nodes (w, b device pointers),
+ * then pool_score[p] = score[pool[p]] for the train-positive pool.
+ * Replaces src/layers.py:231-237 (label_clf over the batch's unique nodes and over train_pos);
+ * only column 0 is ever compared (src/layers.py:649-650, 685, 714-715).
+ */
+PCG_API int pcg_score_table(const float* feat, int64_t n_nodes, int F, int64_t ldf, const float* w, const float* b,
+                    float* score, const int32_t* pool, int P, float* pool_score, pcg_stream_t stream);
+
+/* Bytes of scratch pcg_choose needs for B targets x R relations on a graph whose largest row has
+ * max_degree entries. */
+PCG_API size_t pcg_choose_workspace_bytes(int B, int R, int64_t max_degree);
+
+/*
+ * Choose step for a batch: per item keep the ceil(d*thresh[r]) neighbours nearest in label score
+ * (ties by position == id) when d > that + 1, else all; for positive targets in train mode add the
+ * int(ceil(d*thresh)*rho) nearest train positives (ties by pool position) that are not already kept.
+ * Replaces src/layers.py:216-227 (neighbour lookup), :246-262 (per-relation prep),
+ * :633-697 choose_step_neighs, :700-738 choose_step_test and the set-union of :594/:694.
+ *
+ *   score        [N] table, or NULL with entry_score/center_score given (explicit scores, the
+ *                IntraAgg.forward calling convention of src/layers.py:562)
+ *   entry_score  per CSR entry (same indexing as `indices`) or NULL
+ *   center_score [B] or NULL (then score[targets[i]])
+ *   labels       int64 [B] (== 1 means positive) or NULL; ignored unless train != 0
+ *   thresh_host  HOST array of R doubles (src/layers.py:193 hard-codes 0.5)
+ *   k_override   int32 [R*B] explicit num_sample per item (src/layers.py:260-262) or NULL
+ *   pool         int32 [P] train-positive ids, pool_score [P] their scores
+ * Outputs
+ *   sel_idx      int32 [cap_slots * PCG_SLOT]; item w's ids are sel_idx[it_base[w] .. + it_m[w])
+ *   sel_dist     optional fp32 [cap_slots * PCG_SLOT] (NULL to skip): the distances the reference returns as
+ *                samp_scores (src/layers.py:666-672, 691): at it_base[w] + [0,k) the kept neighbours' |Δ| in row
+ *                order, at it_base[w] + k + [0,o) the o nearest pool members' |Δ| in pool order (duplicates of
+ *                kept ids included, as in the reference's list)
+ *   slot_item    int32 [cap_slots]  owning item of each handed-out slot, or -1
+ *   it_slot0/it_m int32 [R*B], it_base int64 [R*B], it_done int32 [R*B] (zeroed; aggregation tickets)
+ *   status       int32 [PCG_STATUS_WORDS] (zeroed here)
+ */
+PCG_API int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t n_nodes, int R, const float* score,
+               const float* entry_score, const float* center_score, const int32_t* targets,
+               const int64_t* labels, int B, const double* thresh_host, const int32_t* k_override, double rho,
+               const int32_t* pool, const float* pool_score, int P, int train, int64_t max_degree,
+               int32_t* sel_idx, float* sel_dist, int64_t cap_slots, int32_t* slot_item, int32_t* it_slot0,
+               int32_t* it_m, int64_t* it_base, int32_t* it_done, void* workspace, size_t workspace_bytes, int32_t* status,
+               pcg_stream_t stream);
+
+/*
+ * Select-all variant for the GraphSAGE / GCN baselines: the item list IS the CSR row (no copy);
+ * with add_self the target itself is added when its row lacks it.
+ * Replaces src/graphsage.py:69-80 (MeanAggregator neighbour handling) and :206-212 (GCNAggregator).
+ * it_extra[w] = node id to add on top of the row, or -1. Items index `indices` directly.
+ */
+PCG_API int pcg_select_all(const int64_t* indptr, const int32_t* indices, int64_t n_nodes, int R, const int32_t* targets,
+                   int B, int add_self, int64_t cap_slots, int32_t* slot_item, int32_t* it_slot0, int32_t* it_m,
+                   int64_t* it_base, int32_t* it_extra, int32_t* it_done, int32_t* status, pcg_stream_t stream);
+
+/*
+ * Segmented aggregation: agg[w, :] = norm(sum of feat rows of item w's id list).
+ * Replaces the dense-mask matmul of src/layers.py:593-624 and src/graphsage.py:80-95, 212-231.
+ *   idx       the id array the items index (sel_idx from pcg_choose, or CSR indices from select_all)
+ *   partial   fp32 [cap_slots, ldf] scratch, it_done int32 [n_items] tickets zeroed by choose/select
+ *   agg       fp32 [n_items, ldf]
+ */
+PCG_API int pcg_aggregate(const float* feat, int64_t ldf, const int32_t* idx, const int32_t* slot_item,
+                  const int32_t* it_slot0, const int32_t* it_m, const int64_t* it_base, const int32_t* it_extra,
+                  int n_items, int64_t cap_slots, const int32_t* status, int norm, float* partial,
+                  int32_t* it_done, float* agg, pcg_stream_t stream);
+
+/*
+ * Backward of pcg_aggregate w.r.t. the feature table (only needed when `features` is trainable; the
+ * reference freezes it, src/model_handler.py:85-86): feat_grad[j, :] += d_agg[w, :] * norm(n_w) for
+ * every j in item w's list (vector red.global.add, one row per lane group).
+ */
+PCG_API int pcg_aggregate_bwd(const float* d_agg, int64_t ldf, const int32_t* idx, const int32_t* slot_item,
+                      const int32_t* it_slot0, const int32_t* it_m, const int64_t* it_base, const int32_t* it_extra,
+                      int n_items, int64_t cap_slots, const int32_t* status, int norm, float* feat_grad,
+                      pcg_stream_t stream);
+
+/*
+ * Label-balanced pick step, replay form: out[t] = idx_train[bisect_right(cum, u[t]*total, 0, n-1)],
+ * total = cum[n-1]. Bit-compatible with random.choices(idx_train, weights, k) of
+ * src/utils.py:274-278 when `u` are the doubles random.random() would have produced and `cum` is
+ * the sequential fp64 prefix sum of the weights. idx_train may be NULL (positions are returned).
+ */
+PCG_API int pcg_pick_step(const double* cum, int64_t n, const double* u, int64_t k, const int32_t* idx_train,
+                  int32_t* out, pcg_stream_t stream);
+/* Same draw with device-generated uniforms (Philox4x32-10 counter RNG, 53-bit doubles): matches the
+ * reference in distribution only. */
+PCG_API int pcg_pick_step_philox(const double* cum, int64_t n, uint64_t seed, uint64_t offset, int64_t k,
+                         const int32_t* idx_train, int32_t* out, pcg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCGNN_B200_H */

@@ -197,7 +197,7 @@ class PortPCGNN:
             p.grad = None
         loss = self.loss(nodes, labels, True)
         loss.backward()
-        return float(loss)
+        return float(loss.detach())
 
 
 class _PortHomo:

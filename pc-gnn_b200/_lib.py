@@ -1,0 +1,81 @@
+"""ctypes binding of libpcgnn_b200.so (the C ABI declared in include/pcgnn_b200.h).
+
+There is no CPU fallback: if the library has not been built, or a kernel call fails, this raises.
+Build it with ``python -c "import __graft_entry__ as g; g.build()"`` (or ``make -C pc-gnn_b200/csrc``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libpcgnn_b200.so")
+
+SLOT = 64            # PCG_SLOT
+MAX_REL = 8          # PCG_MAX_REL
+STATUS_WORDS = 8     # PCG_STATUS_WORDS
+ST_SLOTS, ST_OVERFLOW = 0, 3
+NORM_MEAN, NORM_RSQRT = 0, 1
+
+_p = C.c_void_p
+_i = C.c_int
+_l = C.c_int64
+_z = C.c_size_t
+_d = C.c_double
+_u64 = C.c_uint64
+
+# name -> (restype, argtypes); mirrors include/pcgnn_b200.h one to one
+SIGNATURES = {
+    "pcg_last_error": (C.c_char_p, []),
+    "pcg_version": (_i, []),
+    "pcg_device_sms": (_i, []),
+    "pcg_score_table": (_i, [_p, _l, _i, _l, _p, _p, _p, _p, _i, _p, _p]),
+    "pcg_choose_workspace_bytes": (_z, [_i, _i, _l]),
+    "pcg_choose": (_i, [_p, _p, _l, _i, _p, _p, _p, _p, _p, _i, C.POINTER(_d), _p, _d, _p, _p, _i, _i, _l,
+                        _p, _p, _l, _p, _p, _p, _p, _p, _p, _z, _p, _p]),
+    "pcg_select_all": (_i, [_p, _p, _l, _i, _p, _i, _i, _l, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "pcg_aggregate": (_i, [_p, _l, _p, _p, _p, _p, _p, _p, _i, _l, _p, _i, _p, _p, _p, _p]),
+    "pcg_aggregate_bwd": (_i, [_p, _l, _p, _p, _p, _p, _p, _p, _i, _l, _p, _i, _p, _p]),
+    "pcg_pick_step": (_i, [_p, _l, _p, _l, _p, _p, _p]),
+    "pcg_pick_step_philox": (_i, [_p, _l, _u64, _u64, _l, _p, _p, _p]),
+}
+
+_lib = None
+
+
+class PcgError(RuntimeError):
+    pass
+
+
+def lib():
+    """The loaded library (dlopen on first use). Raises if it was never built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise PcgError(
+                f"{SO_PATH} is missing: the CUDA extension has not been built "
+                "(run `python -c \"import __graft_entry__ as g; g.build()\"`). There is no CPU fallback.")
+        L = C.CDLL(SO_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib().pcg_last_error().decode("utf-8", "replace")
+        raise PcgError(f"{what or 'pcgnn_b200'} failed (code {rc}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream

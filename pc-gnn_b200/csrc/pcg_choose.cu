@@ -1,0 +1,473 @@
+// Choose step on the GPU: label-aware top-k neighbour filtering + minority oversampling.
+//
+// Replaces the per-target Python loop of /root/reference/src/layers.py:633-738 (one torch.sort and
+// two .tolist() host syncs per target per relation) by an exact k-smallest selection on the key
+// (|s_v - s_u| as fp32 bits, position in the id-sorted row):
+//   1. radix-select (4 x 8-bit passes over the distance bits, shared-memory histogram) finds the
+//      k-th smallest distance T and how many elements equal to T are still needed,
+//   2. an ORDERED compaction writes every element with d < T plus the first `need` elements with
+//      d == T (row order == id order, which is the reference's stable-sort tie rule),
+//   3. for positive targets the same selection runs over the train-positive pool, and pool ids that
+//      are already kept (binary search in the row + a kept-bitmask) are dropped: the union of
+//      src/layers.py:690-694.
+// Rows up to PCG_SMALL_MAX entries are handled one per warp, longer rows one per CTA; both kernels
+// are persistent and pull items from queues filled by a classification kernel.
+#include "pcg_common.cuh"
+
+#define PCG_SMALL_MAX 512      // entries a warp keeps in its shared-memory slice
+#define PCG_WARPS_PER_CTA 8    // warp kernel: 8 items in flight per CTA
+#define PCG_LARGE_NT 512       // CTA kernel threads
+#define PCG_LARGE_CAP_MAX 32768
+
+struct ChooseP {
+    const int64_t* indptr;
+    const int32_t* indices;
+    const float* score;
+    const float* entry_score;
+    const float* center_score;
+    const int32_t* targets;
+    const int64_t* labels;
+    const int32_t* k_override;
+    const int32_t* pool;
+    const float* pool_score;
+    int64_t n_nodes;
+    int R, B, P, train;
+    double thresh[PCG_MAX_REL];
+    double rho;
+    int32_t* sel_idx;
+    float* sel_dist;
+    int64_t cap_slots;
+    int32_t* slot_item;
+    int32_t* it_slot0;
+    int32_t* it_m;
+    int64_t* it_base;
+    int32_t* it_done;
+    int32_t* status;
+    int32_t* small_q;
+    int32_t* large_q;
+    uint32_t* bits_slab;        // [grid_large, slab_words]
+    int64_t slab_words;
+    int large_cap;              // entries of the CTA kernel's shared distance buffer
+};
+
+template <int NT>
+__device__ __forceinline__ void grp_sync() {
+    if (NT == 32) __syncwarp(); else __syncthreads();
+}
+
+// Exclusive prefix counts of two flags over the NT threads of the group (tile order == thread
+// order), plus the totals. xw: >= 2*(NT/32) ints of group-private shared memory.
+template <int NT>
+__device__ __forceinline__ void grp_excl2(bool fa, bool fb, int tid, int* xw, int& ea, int& eb, int& ta, int& tb) {
+    const unsigned lt = lanemask_lt();
+    unsigned ma = __ballot_sync(PCG_FULL, fa), mb = __ballot_sync(PCG_FULL, fb);
+    ea = __popc(ma & lt);
+    eb = __popc(mb & lt);
+    if (NT == 32) {
+        ta = __popc(ma);
+        tb = __popc(mb);
+    } else {
+        constexpr int NW = NT / 32;
+        const int wid = tid >> 5;
+        if ((tid & 31) == 0) xw[wid] = __popc(ma) | (__popc(mb) << 16);
+        __syncthreads();
+        int sa = 0, sb = 0;
+        ta = tb = 0;
+#pragma unroll
+        for (int q = 0; q < NW; ++q) {
+            int pk = xw[q];
+            int ca = pk & 0xffff, cb = pk >> 16;
+            if (q < wid) { sa += ca; sb += cb; }
+            ta += ca; tb += cb;
+        }
+        ea += sa;
+        eb += sb;
+        __syncthreads();
+    }
+}
+
+// k-th smallest (kth is 1-based) of get(0..n-1) as (T, need): T = that value, need = how many of
+// the elements equal to T belong to the kth smallest (in position order).
+template <int NT, class Get>
+__device__ __forceinline__ void radix_select(Get get, int n, int kth, uint32_t* hist, int* xw, int tid, uint32_t& T,
+                                             int& need) {
+    uint32_t prefix = 0, mask = 0;
+    int remaining = kth;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        for (int b = tid; b < 256; b += NT) hist[b] = 0;
+        grp_sync<NT>();
+        for (int j = tid; j < n; j += NT) {
+            uint32_t key = get(j);
+            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xffu], 1u);
+        }
+        grp_sync<NT>();
+        if (tid < 32) {
+            uint32_t c[8];
+            int s = 0;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) { c[b] = hist[tid * 8 + b]; s += (int)c[b]; }
+            int incl = s;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                int t = __shfl_up_sync(PCG_FULL, incl, off);
+                if (tid >= off) incl += t;
+            }
+            int excl = incl - s;
+            if (excl < remaining && remaining <= incl) {
+                int run = excl;
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    if (run + (int)c[b] >= remaining) { xw[30] = tid * 8 + b; xw[31] = remaining - run; break; }
+                    run += (int)c[b];
+                }
+            }
+        }
+        grp_sync<NT>();
+        uint32_t digit = (uint32_t)xw[30];
+        remaining = xw[31];
+        prefix |= digit << shift;
+        mask |= 0xffu << shift;
+    }
+    T = prefix;
+    need = remaining;
+}
+
+// One item (target i, relation r) handled by a group of NT threads.
+//   sd/sd_cap   group-private shared distance cache (uint32), bits_s/bits_cap_words kept-bitmask
+//   bits_g      global bitmask slab for rows that exceed the shared one (may be null if never needed)
+//   xw          group-private int[32] scratch
+template <int NT>
+__device__ void choose_item(const ChooseP& p, int w, int tid, uint32_t* sd, int sd_cap, uint32_t* hist,
+                            uint32_t* bits_s, int bits_cap_words, uint32_t* bits_g, int* xw) {
+    const int r = w / p.B, i = w - r * p.B;
+    const int32_t v = p.targets[i];
+    const int64_t row = (int64_t)r * p.n_nodes + v;
+    const int64_t beg = p.indptr[row];
+    const int d = (int)(p.indptr[row + 1] - beg);
+    const float sv = p.center_score ? p.center_score[i] : p.score[v];
+    const bool positive = p.train && p.labels && p.labels[i] == 1;
+    int k, o;
+    item_counts(d, p.thresh[r], p.rho, positive, p.P, p.k_override ? p.k_override[w] : 0, p.k_override != nullptr, k, o);
+    const int nslots = (k + o + PCG_SLOT - 1) / PCG_SLOT;
+    if (tid == 0) xw[29] = atomicAdd(&p.status[ST_SLOTS], nslots);
+    grp_sync<NT>();
+    const int slot0 = xw[29];
+    if ((int64_t)slot0 + nslots > p.cap_slots) {   // caller's buffer too small: flag, emit nothing
+        if (tid == 0) {
+            atomicExch(&p.status[ST_OVERFLOW], 1);
+            p.it_slot0[w] = 0; p.it_m[w] = 0; p.it_base[w] = 0; p.it_done[w] = 0;
+        }
+        for (int c = tid; c < nslots; c += NT)
+            if ((int64_t)slot0 + c < p.cap_slots) p.slot_item[slot0 + c] = -1;
+        grp_sync<NT>();
+        return;
+    }
+    const int64_t off = (int64_t)slot0 * PCG_SLOT;
+    const int32_t* __restrict__ nbr = p.indices + beg;
+    const float* __restrict__ escore = p.entry_score ? p.entry_score + beg : nullptr;
+    const float* __restrict__ score = p.score;
+    const bool cached = d <= sd_cap;
+    if (cached) {
+        for (int j = tid; j < d; j += NT) sd[j] = dist_bits(sv, escore ? escore[j] : __ldg(score + nbr[j]));
+        grp_sync<NT>();
+    }
+    auto get = [&](int j) -> uint32_t {
+        return cached ? sd[j] : dist_bits(sv, escore ? escore[j] : __ldg(score + nbr[j]));
+    };
+    uint32_t T = 0xffffffffu;
+    int need = 0x7fffffff;
+    if (k < d) {
+        if (k > 0) radix_select<NT>(get, d, k, hist, xw, tid, T, need);
+        else { T = 0; need = 0; }
+    }
+    uint32_t* bits = (d <= bits_cap_words * 32) ? bits_s : bits_g;
+    const int wid = tid >> 5, lane = tid & 31;
+    // ---- ordered compaction of the kept neighbours (row order) ----
+    int run_less = 0, run_tie = 0;
+    for (int base = 0; base < d; base += NT) {
+        const int j = base + tid;
+        const bool valid = j < d;
+        const uint32_t key = valid ? get(j) : 0xffffffffu;
+        const bool less = valid && key < T;
+        const bool tie = valid && key == T;
+        int el, et, tl, tt;
+        grp_excl2<NT>(less, tie, tid, xw, el, et, tl, tt);
+        const int tie_before = run_tie + et;
+        const bool sel = less || (tie && tie_before < need);
+        if (sel) {
+            const int64_t at = off + run_less + el + min(tie_before, need);
+            p.sel_idx[at] = nbr[j];
+            if (p.sel_dist) p.sel_dist[at] = __uint_as_float(key);
+        }
+        const unsigned sm = __ballot_sync(PCG_FULL, sel);
+        if (lane == 0 && o > 0) bits[(base >> 5) + wid] = sm;
+        run_less += tl;
+        run_tie += tt;
+    }
+    // ---- minority oversampling: nearest train positives not already kept ----
+    int n_emit = 0;
+    if (o > 0) {
+        const float* __restrict__ ps = p.pool_score;
+        auto getp = [&](int q) -> uint32_t { return dist_bits(sv, __ldg(ps + q)); };
+        uint32_t Tp = 0xffffffffu;
+        int needp = 0x7fffffff;
+        if (o < p.P) radix_select<NT>(getp, p.P, o, hist, xw, tid, Tp, needp);
+        grp_sync<NT>();   // kept-bitmask visible to the whole group
+        int run_tp = 0, run_lp = 0;
+        for (int base = 0; base < p.P; base += NT) {
+            const int q = base + tid;
+            const bool valid = q < p.P;
+            const uint32_t key = valid ? getp(q) : 0xffffffffu;
+            const bool less = valid && key < Tp;
+            const bool tie = valid && key == Tp;
+            int e0, et, t0, tt;
+            grp_excl2<NT>(less, tie, tid, xw, e0, et, t0, tt);
+            const bool selp = less || (tie && run_tp + et < needp);
+            if (selp && p.sel_dist) p.sel_dist[off + k + run_lp + e0 + min(run_tp + et, needp)] = __uint_as_float(key);
+            bool emit = false;
+            int32_t id = 0;
+            if (selp) {
+                id = p.pool[q];
+                int lo = 0, hi = d;            // lower_bound of id in the id-sorted row
+                while (lo < hi) {
+                    int mid = (lo + hi) >> 1;
+                    if (nbr[mid] < id) lo = mid + 1; else hi = mid;
+                }
+                bool dup = false;
+                if (lo < d && nbr[lo] == id) dup = (k == d) || ((bits[lo >> 5] >> (lo & 31)) & 1u);
+                emit = !dup;
+            }
+            int ee, e1, te, t1;
+            grp_excl2<NT>(emit, false, tid, xw, ee, e1, te, t1);
+            if (emit) p.sel_idx[off + k + n_emit + ee] = id;
+            n_emit += te;
+            run_tp += tt;
+            run_lp += t0;
+        }
+    }
+    const int m = k + n_emit;
+    if (tid == 0) {
+        p.it_slot0[w] = slot0;
+        p.it_m[w] = m;
+        p.it_base[w] = off;
+        p.it_done[w] = 0;
+    }
+    for (int c = tid; c < nslots; c += NT) p.slot_item[slot0 + c] = (c * PCG_SLOT < m) ? w : -1;
+    grp_sync<NT>();
+}
+
+// Classify items by row length into the warp queue and the CTA queue.
+__global__ void k_choose_classify(ChooseP p) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    const int W = p.R * p.B;
+    bool small = false, large = false;
+    if (w < W) {
+        const int r = w / p.B, i = w - r * p.B;
+        const int64_t row = (int64_t)r * p.n_nodes + p.targets[i];
+        const int64_t d = p.indptr[row + 1] - p.indptr[row];
+        small = d <= PCG_SMALL_MAX;
+        large = !small;
+    }
+    const unsigned lt = lanemask_lt();
+    const int lane = threadIdx.x & 31;
+    unsigned ms = __ballot_sync(PCG_FULL, small), ml = __ballot_sync(PCG_FULL, large);
+    int bs = 0, bl = 0;
+    if (lane == 0) {
+        if (ms) bs = atomicAdd(&p.status[ST_NSMALL], __popc(ms));
+        if (ml) bl = atomicAdd(&p.status[ST_NLARGE], __popc(ml));
+    }
+    bs = __shfl_sync(PCG_FULL, bs, 0);
+    bl = __shfl_sync(PCG_FULL, bl, 0);
+    if (small) p.small_q[bs + __popc(ms & lt)] = w;
+    if (large) p.large_q[bl + __popc(ml & lt)] = w;
+}
+
+struct WarpSmem {
+    uint32_t sd[PCG_SMALL_MAX];
+    uint32_t hist[256];
+    uint32_t bits[PCG_SMALL_MAX / 32];
+    int xw[32];
+};
+
+__global__ void __launch_bounds__(PCG_WARPS_PER_CTA * 32) k_choose_warp(ChooseP p) {
+    __shared__ WarpSmem sm[PCG_WARPS_PER_CTA];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpSmem& s = sm[wid];
+    const int n = p.status[ST_NSMALL];
+    for (;;) {
+        int q = 0;
+        if (lane == 0) q = atomicAdd(&p.status[ST_SMALL_CTR], 1);
+        q = __shfl_sync(PCG_FULL, q, 0);
+        if (q >= n) break;
+        choose_item<32>(p, p.small_q[q], lane, s.sd, PCG_SMALL_MAX, s.hist, s.bits, PCG_SMALL_MAX / 32, nullptr, s.xw);
+    }
+}
+
+__global__ void __launch_bounds__(PCG_LARGE_NT) k_choose_cta(ChooseP p) {
+    extern __shared__ uint32_t dyn[];
+    __shared__ uint32_t hist[256];
+    __shared__ int xw[32];
+    __shared__ int s_q;
+    uint32_t* sd = dyn;                              // [large_cap]
+    uint32_t* bits = dyn + p.large_cap;              // [large_cap / 32]
+    const int n = p.status[ST_NLARGE];
+    for (;;) {
+        if (threadIdx.x == 0) s_q = atomicAdd(&p.status[ST_LARGE_CTR], 1);
+        __syncthreads();
+        const int q = s_q;
+        __syncthreads();
+        if (q >= n) break;
+        choose_item<PCG_LARGE_NT>(p, p.large_q[q], threadIdx.x, sd, p.large_cap, hist, bits, p.large_cap / 32,
+                                  p.bits_slab + (int64_t)blockIdx.x * p.slab_words, xw);
+    }
+}
+
+// Select-all (GraphSAGE / GCN): the item list is the CSR row itself. One warp per item.
+__global__ void k_select_all(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, int64_t n_nodes,
+                             int R, const int32_t* __restrict__ targets, int B, int add_self, int64_t cap_slots,
+                             int32_t* slot_item, int32_t* it_slot0, int32_t* it_m, int64_t* it_base, int32_t* it_extra,
+                             int32_t* it_done, int32_t* status) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= R * B) return;
+    const int r = w / B, i = w - r * B;
+    const int32_t v = targets[i];
+    const int64_t row = (int64_t)r * n_nodes + v;
+    const int64_t beg = indptr[row];
+    const int d = (int)(indptr[row + 1] - beg);
+    int extra = -1;
+    if (add_self) {   // graphsage.py:210: union with {self}
+        int lo = 0, hi = d;
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (indices[beg + mid] < v) lo = mid + 1; else hi = mid;
+        }
+        if (!(lo < d && indices[beg + lo] == v)) extra = v;
+    }
+    int nslots = (d + PCG_SLOT - 1) / PCG_SLOT;
+    if (nslots == 0 && extra >= 0) nslots = 1;
+    int slot0 = 0;
+    if (lane == 0) slot0 = atomicAdd(&status[ST_SLOTS], nslots);
+    slot0 = __shfl_sync(PCG_FULL, slot0, 0);
+    const bool ovf = (int64_t)slot0 + nslots > cap_slots;
+    if (lane == 0) {
+        if (ovf) atomicExch(&status[ST_OVERFLOW], 1);
+        it_slot0[w] = ovf ? 0 : slot0;
+        it_m[w] = ovf ? 0 : d;
+        it_base[w] = beg;
+        it_extra[w] = ovf ? -1 : extra;
+        it_done[w] = 0;
+    }
+    for (int c = lane; c < nslots; c += 32)
+        if ((int64_t)slot0 + c < cap_slots) slot_item[slot0 + c] = ovf ? -1 : w;
+}
+
+// ------------------------------------------------------------------------------------------- C ABI
+struct WsLayout {
+    size_t small_q, large_q, bits_slab, total;
+    int64_t slab_words;
+    int grid_large;
+};
+
+static WsLayout ws_layout(int B, int R, int64_t max_degree, int sms) {
+    WsLayout L;
+    size_t W = (size_t)B * R;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    L.grid_large = sms * 2;
+    L.slab_words = max_degree > PCG_LARGE_CAP_MAX ? (max_degree + 31) / 32 : 0;
+    size_t o = 0;
+    L.small_q = o; o = al(o + W * 4);
+    L.large_q = o; o = al(o + W * 4);
+    L.bits_slab = o; o = al(o + (size_t)L.grid_large * L.slab_words * 4);
+    L.total = o;
+    return L;
+}
+
+static int g_sms = 0;
+static int device_sms() {
+    if (g_sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_sms <= 0) g_sms = 148;
+    }
+    return g_sms;
+}
+
+extern "C" int pcg_device_sms(void) { return device_sms(); }
+
+extern "C" size_t pcg_choose_workspace_bytes(int B, int R, int64_t max_degree) {
+    return ws_layout(B, R, max_degree, 148 * 2).total;   // sized for the largest grid we ever launch
+}
+
+extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t n_nodes, int R, const float* score,
+                          const float* entry_score, const float* center_score, const int32_t* targets,
+                          const int64_t* labels, int B, const double* thresh_host, const int32_t* k_override,
+                          double rho, const int32_t* pool, const float* pool_score, int P, int train,
+                          int64_t max_degree, int32_t* sel_idx, float* sel_dist, int64_t cap_slots,
+                          int32_t* slot_item, int32_t* it_slot0, int32_t* it_m, int64_t* it_base, int32_t* it_done, void* workspace,
+                          size_t workspace_bytes, int32_t* status, pcg_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PCG_REQUIRE(R >= 1 && R <= PCG_MAX_REL, "pcg_choose: R=%d outside [1,%d]", R, PCG_MAX_REL);
+    PCG_REQUIRE(B >= 0, "pcg_choose: negative batch");
+    PCG_REQUIRE(score || (entry_score && center_score), "pcg_choose: need a score table or explicit scores");
+    PCG_REQUIRE(!(train && P > 0) || (pool && pool_score), "pcg_choose: pool/pool_score missing");
+    PCG_REQUIRE(indptr && indices && targets && sel_idx && slot_item && it_slot0 && it_m && it_base && it_done && status,
+                "pcg_choose: null pointer");
+    const int sms = device_sms();
+    WsLayout L = ws_layout(B, R, max_degree, sms);
+    PCG_REQUIRE(workspace && workspace_bytes >= L.total, "pcg_choose: workspace too small (%zu < %zu)", workspace_bytes,
+                L.total);
+    cudaError_t e = cudaMemsetAsync(status, 0, PCG_STATUS_WORDS * sizeof(int32_t), stream);
+    if (e != cudaSuccess) { pcg_set_error("pcg_choose: memset: %s", cudaGetErrorString(e)); return (int)e; }
+    if (B == 0) return 0;
+    ChooseP p;
+    p.indptr = indptr; p.indices = indices; p.score = score; p.entry_score = entry_score;
+    p.center_score = center_score; p.targets = targets; p.labels = labels; p.k_override = k_override;
+    p.pool = pool; p.pool_score = pool_score; p.n_nodes = n_nodes; p.R = R; p.B = B;
+    p.P = (train && pool) ? P : 0; p.train = train;
+    for (int r = 0; r < PCG_MAX_REL; ++r) p.thresh[r] = r < R ? thresh_host[r] : 0.5;
+    p.rho = rho; p.sel_idx = sel_idx; p.sel_dist = sel_dist; p.cap_slots = cap_slots; p.slot_item = slot_item;
+    p.it_slot0 = it_slot0; p.it_m = it_m; p.it_base = it_base; p.status = status;
+    char* ws = (char*)workspace;
+    p.small_q = (int32_t*)(ws + L.small_q);
+    p.large_q = (int32_t*)(ws + L.large_q);
+    p.it_done = it_done;
+    p.bits_slab = (uint32_t*)(ws + L.bits_slab);
+    p.slab_words = L.slab_words;
+    int64_t cap = max_degree < PCG_SMALL_MAX + 1 ? PCG_SMALL_MAX + 1 : max_degree;
+    if (cap > PCG_LARGE_CAP_MAX) cap = PCG_LARGE_CAP_MAX;
+    p.large_cap = (int)((cap + 31) / 32 * 32);
+    const int W = R * B;
+    k_choose_classify<<<(W + 255) / 256, 256, 0, stream>>>(p);
+    int gw = (W + PCG_WARPS_PER_CTA - 1) / PCG_WARPS_PER_CTA;
+    if (gw > sms * 8) gw = sms * 8;
+    k_choose_warp<<<gw, PCG_WARPS_PER_CTA * 32, 0, stream>>>(p);
+    if (max_degree > PCG_SMALL_MAX) {
+        size_t dyn = (size_t)p.large_cap * 4 + (size_t)p.large_cap / 32 * 4;
+        static size_t configured = 0;
+        if (dyn > 48 * 1024 && dyn > configured) {
+            e = cudaFuncSetAttribute(k_choose_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+            if (e != cudaSuccess) { pcg_set_error("pcg_choose: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+            configured = dyn;
+        }
+        int gl = W < L.grid_large ? W : L.grid_large;
+        k_choose_cta<<<gl, PCG_LARGE_NT, dyn, stream>>>(p);
+    }
+    return pcg_check_launch("pcg_choose");
+}
+
+extern "C" int pcg_select_all(const int64_t* indptr, const int32_t* indices, int64_t n_nodes, int R,
+                              const int32_t* targets, int B, int add_self, int64_t cap_slots, int32_t* slot_item,
+                              int32_t* it_slot0, int32_t* it_m, int64_t* it_base, int32_t* it_extra, int32_t* it_done,
+                              int32_t* status, pcg_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PCG_REQUIRE(R >= 1 && B >= 0, "pcg_select_all: bad sizes");
+    PCG_REQUIRE(indptr && indices && targets && slot_item && it_slot0 && it_m && it_base && it_extra && it_done && status,
+                "pcg_select_all: null pointer");
+    cudaError_t e = cudaMemsetAsync(status, 0, PCG_STATUS_WORDS * sizeof(int32_t), stream);
+    if (e != cudaSuccess) { pcg_set_error("pcg_select_all: memset: %s", cudaGetErrorString(e)); return (int)e; }
+    if (B == 0) return 0;
+    const int W = R * B;
+    k_select_all<<<(W * 32 + 255) / 256, 256, 0, stream>>>(indptr, indices, n_nodes, R, targets, B, add_self, cap_slots,
+                                                           slot_item, it_slot0, it_m, it_base, it_extra, it_done, status);
+    return pcg_check_launch("pcg_select_all");
+}

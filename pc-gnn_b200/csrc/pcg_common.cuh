@@ -1,0 +1,61 @@
+// Shared helpers for the pcgnn_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "pcgnn_b200.h"
+
+#define PCG_FULL 0xffffffffu
+
+// status / counter words (device int32 array, PCG_STATUS_WORDS long)
+#define ST_SLOTS PCG_ST_SLOTS
+#define ST_NSMALL 1
+#define ST_NLARGE 2
+#define ST_OVERFLOW PCG_ST_OVERFLOW
+#define ST_SMALL_CTR 4
+#define ST_LARGE_CTR 5
+
+void pcg_set_error(const char* fmt, ...);
+int pcg_check_launch(const char* what);
+
+#define PCG_REQUIRE(cond, ...)            \
+    do {                                  \
+        if (!(cond)) {                    \
+            pcg_set_error(__VA_ARGS__);   \
+            return (int)cudaErrorInvalidValue; \
+        }                                 \
+    } while (0)
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// |a - b| in fp32 as ordered bits: non-negative floats compare like unsigned ints, so the 32-bit
+// pattern is the radix key (reference: torch.abs(center - neigh), src/layers.py:657).
+__device__ __forceinline__ uint32_t dist_bits(float a, float b) {
+    return __float_as_uint(fabsf(__fsub_rn(a, b)));
+}
+
+// Per-item sizes, in the reference's own double arithmetic:
+//   c = math.ceil(d * threshold)   (src/layers.py:260)
+//   keep c if d > c + 1 else all   (src/layers.py:662-672)
+//   o = int(c * rho) for positive targets in train mode, at most P (src/layers.py:681, 690)
+__device__ __forceinline__ void item_counts(int64_t d, double thr, double rho, bool positive, int P, int c_override,
+                                            bool has_override, int& k, int& o) {
+    int64_t c = has_override ? (int64_t)c_override : (int64_t)ceil((double)d * thr);
+    k = (int)((d > c + 1) ? c : d);
+    if (k < 0) k = 0;
+    int64_t oo = positive ? (int64_t)((double)c * rho) : 0;
+    if (oo > P) oo = P;
+    if (oo < 0) oo = 0;
+    o = (int)oo;
+}
+
+__device__ __forceinline__ float4 ld_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ld_f4_cg(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void f4_add(float4& a, const float4& b) {
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+}

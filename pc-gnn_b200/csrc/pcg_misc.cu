@@ -1,0 +1,150 @@
+// Error plumbing, the label-score table and the label-balanced pick step.
+#include <stdarg.h>
+
+#include "pcg_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void pcg_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int pcg_check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        pcg_set_error("%s: %s", what, cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+
+extern "C" const char* pcg_last_error(void) { return g_err; }
+extern "C" int pcg_version(void) { return 100; }
+
+// ------------------------------------------------------------------------------- score table
+// score[v] = <feat[v, :], w> + b. Eight lanes per row, float4 loads, fixed reduction tree (so the
+// table is bit-reproducible run to run). The weight vector is zero-padded to ldf in shared memory.
+// Reference: label_clf = nn.Linear(F, 2) (src/layers.py:200) applied at :236-237; only output
+// column 0 feeds the choose step.
+__global__ void __launch_bounds__(256) k_score_table(const float* __restrict__ feat, int64_t n, int F, int64_t ldf,
+                                                     const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ score) {
+    extern __shared__ float sw[];
+    for (int c = threadIdx.x; c < ldf; c += blockDim.x) sw[c] = c < F ? w[c] : 0.f;
+    const float bias = b ? b[0] : 0.f;
+    __syncthreads();
+    const int l = threadIdx.x & 7;
+    const int V = (int)(ldf >> 2);
+    const int64_t rows_per_block = blockDim.x >> 3;
+    // vb is warp-uniform (4 rows per warp), so every lane runs the same trip count for the shuffles
+    for (int64_t vb = (int64_t)blockIdx.x * rows_per_block + ((threadIdx.x >> 5) << 2); vb < n;
+         vb += (int64_t)gridDim.x * rows_per_block) {
+        const int64_t v = vb + ((threadIdx.x & 31) >> 3);
+        float acc = 0.f;
+        if (v < n) {
+            const float* rowp = feat + v * ldf;
+            for (int c = l; c < V; c += 8) {
+                float4 x = ld_f4(rowp + 4 * c);
+                const float4 ww = *reinterpret_cast<const float4*>(sw + 4 * c);
+                acc = fmaf(x.x, ww.x, acc); acc = fmaf(x.y, ww.y, acc);
+                acc = fmaf(x.z, ww.z, acc); acc = fmaf(x.w, ww.w, acc);
+            }
+        }
+        acc += __shfl_xor_sync(PCG_FULL, acc, 4);
+        acc += __shfl_xor_sync(PCG_FULL, acc, 2);
+        acc += __shfl_xor_sync(PCG_FULL, acc, 1);
+        if (l == 0 && v < n) score[v] = acc + bias;
+    }
+}
+
+__global__ void k_gather_pool(const float* __restrict__ score, const int32_t* __restrict__ pool, int P,
+                              float* __restrict__ pool_score) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < P) pool_score[p] = score[pool[p]];
+}
+
+extern "C" int pcg_score_table(const float* feat, int64_t n_nodes, int F, int64_t ldf, const float* w, const float* b,
+                               float* score, const int32_t* pool, int P, float* pool_score, pcg_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PCG_REQUIRE(feat && w && score, "pcg_score_table: null pointer");
+    PCG_REQUIRE(ldf % 4 == 0 && F <= ldf && F > 0, "pcg_score_table: need F <= ldf, ldf %% 4 == 0 (F=%d ldf=%lld)", F,
+                (long long)ldf);
+    PCG_REQUIRE(ldf * 4 <= 48 * 1024, "pcg_score_table: rows wider than 12288 floats unsupported");
+    PCG_REQUIRE(((uintptr_t)feat & 15) == 0, "pcg_score_table: feat must be 16-byte aligned");
+    if (n_nodes > 0) {
+        int64_t blocks = (n_nodes + 31) / 32;
+        const int sms = pcg_device_sms();
+        if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;
+        k_score_table<<<(int)blocks, 256, (size_t)ldf * 4, stream>>>(feat, n_nodes, F, ldf, w, b, score);
+    }
+    if (P > 0 && pool && pool_score) k_gather_pool<<<(P + 255) / 256, 256, 0, stream>>>(score, pool, P, pool_score);
+    return pcg_check_launch("pcg_score_table");
+}
+
+// ------------------------------------------------------------------------------- pick step
+// index = bisect_right(cum, x, 0, n-1): first position in [0, n-1) with x < cum[pos], else n-1
+// (CPython random.choices: bisect(cum_weights, random() * total, 0, hi) with hi = n - 1).
+__device__ __forceinline__ int64_t bisect_right_hi(const double* __restrict__ cum, int64_t n, double x) {
+    int64_t lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (x < cum[mid]) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+__global__ void k_pick_replay(const double* __restrict__ cum, int64_t n, const double* __restrict__ u, int64_t k,
+                              const int32_t* __restrict__ idx_train, int32_t* __restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= k) return;
+    const double total = cum[n - 1] + 0.0;
+    const int64_t pos = bisect_right_hi(cum, n, __dmul_rn(u[t], total));
+    out[t] = idx_train ? idx_train[pos] : (int32_t)pos;
+}
+
+// Philox4x32-10 (Salmon et al., SC'11): counter = (offset + t, 0), key = seed.
+__device__ __forceinline__ void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0,
+                                             uint32_t k1) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+}
+
+__global__ void k_pick_philox(const double* __restrict__ cum, int64_t n, uint64_t seed, uint64_t offset, int64_t k,
+                              const int32_t* __restrict__ idx_train, int32_t* __restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= k) return;
+    const uint64_t ctr = offset + (uint64_t)t;
+    uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0, c3 = 0;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        philox_round(c0, c1, c2, c3, k0, k1);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    // 53-bit double in [0,1), built the way CPython's random() builds it from two 32-bit words
+    const double u = ((double)(c0 >> 5) * 67108864.0 + (double)(c1 >> 6)) * (1.0 / 9007199254740992.0);
+    const double total = cum[n - 1] + 0.0;
+    const int64_t pos = bisect_right_hi(cum, n, __dmul_rn(u, total));
+    out[t] = idx_train ? idx_train[pos] : (int32_t)pos;
+}
+
+extern "C" int pcg_pick_step(const double* cum, int64_t n, const double* u, int64_t k, const int32_t* idx_train,
+                             int32_t* out, pcg_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PCG_REQUIRE(cum && u && out && n > 0, "pcg_pick_step: null pointer or empty population");
+    if (k > 0) k_pick_replay<<<(int)((k + 255) / 256), 256, 0, stream>>>(cum, n, u, k, idx_train, out);
+    return pcg_check_launch("pcg_pick_step");
+}
+
+extern "C" int pcg_pick_step_philox(const double* cum, int64_t n, uint64_t seed, uint64_t offset, int64_t k,
+                                    const int32_t* idx_train, int32_t* out, pcg_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PCG_REQUIRE(cum && out && n > 0, "pcg_pick_step_philox: null pointer or empty population");
+    if (k > 0) k_pick_philox<<<(int)((k + 255) / 256), 256, 0, stream>>>(cum, n, seed, offset, k, idx_train, out);
+    return pcg_check_launch("pcg_pick_step_philox");
+}

@@ -1,0 +1,260 @@
+"""Device-side runtime of the pick-and-choose path: owns the HBM-resident graph, the padded feature
+table, the score table and the per-step scratch, and issues the C-ABI calls (``_lib``).
+
+One engine per (graph, device). Everything is asynchronous on torch's current CUDA stream; the only
+host<->device traffic per step is the upload of the target ids (and labels if they arrive on the
+host), which the reference's ``forward(nodes: list, labels)`` signature makes unavoidable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from .graph import RelGraph
+
+__all__ = ["Engine", "Selection", "padded_ld"]
+
+
+def padded_ld(feat_dim: int) -> int:
+    """Row stride (floats) of the device feature table: one 128-byte line for F <= 32, else the next
+    multiple of 4 (16-byte vector loads)."""
+    return 32 if feat_dim <= 32 else (feat_dim + 3) // 4 * 4
+
+
+class Selection:
+    """Result of a choose / select-all call: per item w = r*B + i an id list inside ``idx``."""
+
+    __slots__ = ("B", "R", "idx", "slot_item", "it_slot0", "it_m", "it_base", "it_extra", "it_done",
+                 "status", "cap_slots", "norm", "_blob")
+
+    def lists(self):
+        """Host copy: list over items of sorted id arrays (tests / compat API only: syncs)."""
+        m = self.it_m.cpu().numpy()
+        base = self.it_base.cpu().numpy()
+        idx = self.idx.cpu().numpy()
+        extra = self.it_extra.cpu().numpy() if self.it_extra is not None else None
+        out = []
+        for w in range(self.B * self.R):
+            ids = idx[base[w]:base[w] + m[w]]
+            if extra is not None and extra[w] >= 0:
+                ids = np.append(ids, extra[w])
+            out.append(np.sort(ids))
+        return out
+
+    def overflowed(self) -> bool:
+        return bool(self.status[_lib.ST_OVERFLOW].item())
+
+
+class Engine:
+    def __init__(self, graph: RelGraph | None, device=None):
+        if not torch.cuda.is_available():
+            raise _lib.PcgError("pcgnn_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = _lib.lib()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.graph = graph
+        if graph is not None:
+            self.N, self.R = graph.n_nodes, graph.n_rel
+            if self.R > _lib.MAX_REL:
+                raise ValueError(f"at most {_lib.MAX_REL} relations are supported")
+            self.indptr, self.indices = graph.device(self.device)
+            deg = np.diff(graph.indptr)
+            self.max_degree = int(deg.max()) if deg.size else 0
+        else:   # explicit-list use only (IntraAgg.forward / choose_step_* compat calls)
+            self.N = self.R = self.max_degree = 0
+            self.indptr = self.indices = None
+        self.strict_rows = True     # feature table must have exactly one row per graph node
+        self._feat_key = None
+        self.feat = None            # [N, ldf] fp32, zero padded
+        self.F = self.ldf = 0
+        self.score = None           # [N]
+        self.pool = None            # int32 [P]
+        self.pool_score = None
+        self.P = 0
+        self._pin = None
+        self._ws = None
+
+    # ------------------------------------------------------------------ resident tables
+    def set_features(self, weight: torch.Tensor):
+        """Padded device copy of the [N,F] feature table (re-made only when the source changes)."""
+        key = (weight.data_ptr(), weight._version, tuple(weight.shape), weight.device)
+        if key == self._feat_key:
+            return self.feat
+        w = weight.detach()
+        if self.graph is not None and self.strict_rows and w.shape[0] != self.N:
+            raise ValueError(f"feature table has {w.shape[0]} rows, graph has {self.N} nodes")
+        F_ = w.shape[1]
+        ld = padded_ld(F_)
+        if ld == F_ and w.is_contiguous() and w.dtype == torch.float32 and w.device == self.device \
+                and w.data_ptr() % 16 == 0:
+            feat = w
+        else:
+            feat = torch.zeros((w.shape[0], ld), dtype=torch.float32, device=self.device)
+            feat[:, :F_] = w.to(self.device, torch.float32)
+        self.feat, self.F, self.ldf = feat, F_, ld
+        self._feat_key = key
+        if self.score is None and self.graph is not None:
+            self.score = torch.empty(self.N, dtype=torch.float32, device=self.device)
+        return feat
+
+    def set_pool(self, train_pos):
+        """Train-positive pool (order preserved: ties are broken by pool position, src/layers.py:687-690)."""
+        arr = np.asarray(list(train_pos), dtype=np.int32)
+        self.pool = torch.from_numpy(arr).to(self.device)
+        self.P = int(arr.shape[0])
+        self.pool_score = torch.empty(max(self.P, 1), dtype=torch.float32, device=self.device)
+
+    def score_table(self, clf_weight: torch.Tensor, clf_bias: torch.Tensor):
+        """score[v] = <feat[v], clf_weight[0]> + clf_bias[0] for all nodes, and the pool's scores."""
+        w = clf_weight.detach()
+        b = clf_bias.detach()
+        if not w.is_contiguous():
+            w = w.contiguous()
+        rc = self.lib.pcg_score_table(self.feat.data_ptr(), self.N, self.F, self.ldf, w.data_ptr(), b.data_ptr(),
+                                      self.score.data_ptr(), _lib.ptr(self.pool), self.P,
+                                      _lib.ptr(self.pool_score), _lib.stream_ptr())
+        _lib.check(rc, "pcg_score_table")
+        return self.score, self.pool_score
+
+    # ------------------------------------------------------------------ per-step inputs
+    def upload_targets(self, nodes):
+        """int32 device tensor of the batch's node ids (+ the host copy, for capacity sizing)."""
+        if isinstance(nodes, torch.Tensor):
+            if nodes.is_cuda:
+                return nodes.to(torch.int32), None
+            host = nodes.numpy().astype(np.int32, copy=False)
+        else:
+            host = np.asarray(nodes, dtype=np.int32)
+        B = host.shape[0]
+        if self._pin is None or self._pin.shape[0] < B:
+            self._pin = torch.empty(max(B, 1024), dtype=torch.int32, pin_memory=True)
+        self._pin[:B].numpy()[:] = host
+        return self._pin[:B].to(self.device, non_blocking=True), host
+
+    def slots_bound(self, host_targets, thresh, rho, train, *, k_override=None) -> int:
+        """Upper bound of the slots a batch needs, from the host copy of the CSR offsets (every
+        target counted as positive when training, since labels may live on the device)."""
+        t = host_targets.astype(np.int64)
+        total = 0
+        for r in range(self.R):
+            rows = r * self.N + t
+            d = self.graph.indptr[rows + 1] - self.graph.indptr[rows]
+            if k_override is not None:
+                c = np.asarray(k_override[r * len(t):(r + 1) * len(t)], dtype=np.int64)
+            else:
+                c = np.ceil(d * float(thresh[r])).astype(np.int64)
+            k = np.where(d > c + 1, c, d)
+            o = np.minimum((c * float(rho)).astype(np.int64), self.P) if train else 0
+            total += int(((k + o + _lib.SLOT - 1) // _lib.SLOT).sum())
+        return max(total, 1)
+
+    def slots_bound_all(self, B: int) -> int:
+        """Select-all bound without host ids: every item as long as the longest row."""
+        return B * self.R * max(1, (self.max_degree + _lib.SLOT - 1) // _lib.SLOT)
+
+    # ------------------------------------------------------------------ kernels
+    def _new_selection(self, B, R, cap_slots, with_sel_idx, with_extra):
+        W = B * R
+        dev = self.device
+        # one allocation, carved into typed views (int64 part first for alignment)
+        n64 = W
+        n32 = (cap_slots * _lib.SLOT if with_sel_idx else 0) + cap_slots + 3 * W + (W if with_extra else 0) \
+            + _lib.STATUS_WORDS
+        blob = torch.empty(n64 * 2 + n32, dtype=torch.int32, device=dev)
+        s = Selection()
+        s._blob = blob
+        s.B, s.R, s.cap_slots = B, R, cap_slots
+        s.it_base = blob[:n64 * 2].view(torch.int64)
+        o = n64 * 2
+
+        def take(n):
+            nonlocal o
+            v = blob[o:o + n]
+            o += n
+            return v
+
+        s.idx = take(cap_slots * _lib.SLOT) if with_sel_idx else self.indices
+        s.slot_item = take(cap_slots)
+        s.it_slot0 = take(W)
+        s.it_m = take(W)
+        s.it_done = take(W)
+        s.it_extra = take(W) if with_extra else None
+        s.status = take(_lib.STATUS_WORDS)
+        s.norm = _lib.NORM_MEAN
+        return s
+
+    def choose(self, targets, labels, train: bool, thresh, rho: float, cap_slots: int, *,
+               entry_score=None, center_score=None, k_override=None, pool=None, pool_score=None,
+               indptr=None, indices=None, n_nodes=None, n_rel=None, max_degree=None,
+               want_dist: bool = False):
+        """Top-k filter + oversample for every (relation, target) item (``pcg_choose``).
+
+        Default: the engine's resident graph, score table and pool. The keyword overrides carry the
+        explicit-list calling convention of IntraAgg.forward / choose_step_* (src/layers.py:562, 633).
+        Returns the Selection (and the distance buffer when want_dist)."""
+        B = int(targets.shape[0])
+        R = self.R if n_rel is None else n_rel
+        s = self._new_selection(B, R, cap_slots, True, False)
+        maxdeg = self.max_degree if max_degree is None else max_degree
+        ws_bytes = self.lib.pcg_choose_workspace_bytes(B, R, maxdeg)
+        if self._ws is None or self._ws.numel() < ws_bytes:
+            self._ws = torch.empty(int(ws_bytes), dtype=torch.uint8, device=self.device)
+        th = (C.c_double * R)(*[float(x) for x in thresh])
+        use_table = entry_score is None
+        pool = self.pool if pool is None else pool
+        pool_score = self.pool_score if pool_score is None else pool_score
+        P = 0 if pool is None else int(pool.shape[0])
+        dist = torch.empty(cap_slots * _lib.SLOT, dtype=torch.float32, device=self.device) if want_dist else None
+        rc = self.lib.pcg_choose(
+            (self.indptr if indptr is None else indptr).data_ptr(),
+            (self.indices if indices is None else indices).data_ptr(),
+            self.N if n_nodes is None else n_nodes, R,
+            self.score.data_ptr() if use_table else None, _lib.ptr(entry_score), _lib.ptr(center_score),
+            targets.data_ptr(), _lib.ptr(labels) if train else None, B, th, _lib.ptr(k_override), float(rho),
+            _lib.ptr(pool), _lib.ptr(pool_score), P, int(bool(train)), maxdeg, s.idx.data_ptr(), _lib.ptr(dist),
+            cap_slots, s.slot_item.data_ptr(), s.it_slot0.data_ptr(), s.it_m.data_ptr(), s.it_base.data_ptr(),
+            s.it_done.data_ptr(), self._ws.data_ptr(), int(ws_bytes), s.status.data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "pcg_choose")
+        return (s, dist) if want_dist else s
+
+    def select_all(self, targets, add_self: bool, cap_slots: int, norm: int) -> Selection:
+        """GraphSAGE / GCN selection: whole rows (∪ self), no copy (``pcg_select_all``)."""
+        B = int(targets.shape[0])
+        s = self._new_selection(B, self.R, cap_slots, False, True)
+        s.norm = norm
+        rc = self.lib.pcg_select_all(self.indptr.data_ptr(), self.indices.data_ptr(), self.N, self.R,
+                                     targets.data_ptr(), B, int(bool(add_self)), cap_slots, s.slot_item.data_ptr(),
+                                     s.it_slot0.data_ptr(), s.it_m.data_ptr(), s.it_base.data_ptr(),
+                                     s.it_extra.data_ptr(), s.it_done.data_ptr(), s.status.data_ptr(),
+                                     _lib.stream_ptr())
+        _lib.check(rc, "pcg_select_all")
+        return s
+
+    def aggregate(self, sel: Selection, feat=None) -> torch.Tensor:
+        """agg [R*B, ldf] = normalised sum of the selected rows (``pcg_aggregate``)."""
+        feat = self.feat if feat is None else feat
+        ldf = feat.shape[1]
+        W = sel.B * sel.R
+        agg = torch.empty((W, ldf), dtype=torch.float32, device=self.device)
+        partial = torch.empty((sel.cap_slots, ldf), dtype=torch.float32, device=self.device)
+        rc = self.lib.pcg_aggregate(feat.data_ptr(), ldf, sel.idx.data_ptr(), sel.slot_item.data_ptr(),
+                                    sel.it_slot0.data_ptr(), sel.it_m.data_ptr(), sel.it_base.data_ptr(),
+                                    _lib.ptr(sel.it_extra), W, sel.cap_slots, sel.status.data_ptr(), sel.norm,
+                                    partial.data_ptr(), sel.it_done.data_ptr(), agg.data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "pcg_aggregate")
+        return agg
+
+    def aggregate_bwd(self, sel: Selection, d_agg: torch.Tensor, feat_grad: torch.Tensor):
+        """feat_grad[j] += d_agg[w] * norm for every selected j (``pcg_aggregate_bwd``)."""
+        ldf = feat_grad.shape[1]
+        W = sel.B * sel.R
+        d_agg = d_agg.contiguous()
+        rc = self.lib.pcg_aggregate_bwd(d_agg.data_ptr(), ldf, sel.idx.data_ptr(), sel.slot_item.data_ptr(),
+                                        sel.it_slot0.data_ptr(), sel.it_m.data_ptr(), sel.it_base.data_ptr(),
+                                        _lib.ptr(sel.it_extra), W, sel.cap_slots, sel.status.data_ptr(), sel.norm,
+                                        feat_grad.data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "pcg_aggregate_bwd")
+        return feat_grad

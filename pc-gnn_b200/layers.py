@@ -1,0 +1,332 @@
+"""PC-GNN layers on the B200-native kernels — same public surface as /root/reference/src/layers.py.
+
+  InterAgg1 / InterAgg3 / InterAgg5 (features, feature_dim, embed_dim, train_pos, adj_lists, intraggs,
+                                     inter='GNN', cuda=True)       reference: layers.py:417, :161, :16
+      .forward(nodes, labels, train_flag=True) -> (combined [E,B], center_scores [B,2])  (:207-291)
+  IntraAgg(features, feat_dim, embed_dim, train_pos, rho, cuda=False)                    (:539-560)
+      .forward(nodes, batch_labels, to_neighs_list, batch_scores, neigh_scores, pos_scores,
+               sample_list, train_flag) -> (to_feats [B,E], samp_scores)                 (:562-630)
+  choose_step_neighs(...), choose_step_test(...)                                         (:633-738)
+
+Parameter names, shapes and state_dict keys are the reference's, so its ``model.py`` /
+``model_handler.py`` (and checkpoints) work unchanged. What differs is where the work happens: the
+neighbour lookup, label-aware filter, oversampling, set union and mean aggregation are CUDA kernels
+over an HBM-resident CSR (``engine.Engine``); nothing is computed on the host and there is no CPU
+path (constructing on a machine without the built extension / a GPU raises at first use).
+
+Tie rule (the reference's is implementation-defined): equal distances are ordered by
+neighbour id, pool ties by position in ``train_pos``.
+"""
+from __future__ import annotations
+
+import math
+from itertools import chain
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.nn import init
+
+from . import _lib
+from .engine import Engine, padded_ld
+from .graph import RelGraph
+
+__all__ = ["InterAgg1", "InterAgg3", "InterAgg5", "InterAgg", "IntraAgg", "choose_step_neighs",
+           "choose_step_test"]
+
+
+# ------------------------------------------------------------------------------------------------
+class _AggregateFn(torch.autograd.Function):
+    """agg = engine.aggregate(selection); differentiable w.r.t. the feature table only when that
+    table is trainable (the reference freezes it, model_handler.py:85-86)."""
+
+    @staticmethod
+    def forward(ctx, table, engine, sel, feat_dim):
+        feat = engine.set_features(table)
+        ctx.engine, ctx.sel, ctx.feat_dim, ctx.shape = engine, sel, feat_dim, tuple(feat.shape)
+        return engine.aggregate(sel, feat)
+
+    @staticmethod
+    def backward(ctx, d_agg):
+        g = torch.zeros(ctx.shape, dtype=torch.float32, device=d_agg.device)
+        ctx.engine.aggregate_bwd(ctx.sel, d_agg, g)
+        return g[:, :ctx.feat_dim], None, None, None
+
+
+def _feature_table(features, n_nodes, device, ids=None):
+    """The [N,F] table behind the reference's `features` callable (an nn.Embedding in
+    model_handler.py:85; any id->rows callable is accepted)."""
+    if isinstance(features, nn.Embedding):
+        return features.weight
+    w = getattr(features, "weight", None)
+    if isinstance(w, torch.Tensor) and w.dim() == 2 and (n_nodes is None or w.shape[0] >= n_nodes):
+        return w
+    if n_nodes is None:   # explicit-list call: the largest id mentioned bounds the table
+        lists, nodes, pool = ids
+        n_nodes = 1 + max(max((int(x) for x in chain.from_iterable(lists)), default=0),
+                          max((int(v) for v in nodes), default=0), max((int(p) for p in pool), default=0))
+    return features(torch.arange(n_nodes, device=device))
+
+
+def _as_device_labels(labels, device):
+    if labels is None:
+        return None
+    if not isinstance(labels, torch.Tensor):
+        labels = torch.as_tensor(np.asarray(labels))
+    return labels.to(device=device, dtype=torch.int64).reshape(-1).contiguous()
+
+
+class IntraAgg(nn.Module):
+    """Intra-relation aggregator (reference: layers.py:539-630). Holds W_r [2F,E]."""
+
+    def __init__(self, features, feat_dim, embed_dim, train_pos, rho, cuda=False):
+        super().__init__()
+        self.features = features
+        self.cuda = cuda
+        self.feat_dim = feat_dim
+        self.embed_dim = embed_dim
+        self.train_pos = train_pos
+        self.rho = rho
+        self.weight = nn.Parameter(torch.FloatTensor(2 * self.feat_dim, self.embed_dim))
+        init.xavier_uniform_(self.weight)
+        self._engine = None
+
+    def transform(self, self_feats, agg_feats):
+        """relu(cat(self, agg) @ W_r)  (layers.py:625-629)."""
+        return F.relu(torch.cat((self_feats, agg_feats), dim=1).mm(self.weight))
+
+    def forward(self, nodes, batch_labels, to_neighs_list, batch_scores, neigh_scores, pos_scores, sample_list,
+                train_flag):
+        """Reference calling convention with explicit neighbour lists and scores (layers.py:562)."""
+        dev = self.weight.device
+        if self._engine is None or self._engine.device != dev:
+            self._engine = Engine(None, dev)
+        eng = self._engine
+        sel, dist, meta = _choose_explicit(eng, batch_scores, batch_labels if train_flag else None, neigh_scores,
+                                           to_neighs_list, pos_scores if train_flag else None,
+                                           self.train_pos if train_flag else None, sample_list, self.rho, train_flag)
+        table = _feature_table(self.features, None, dev, ids=(to_neighs_list, nodes, self.train_pos))
+        agg = _AggregateFn.apply(table, eng, sel, self.feat_dim)
+        idx = torch.as_tensor(np.asarray([int(v) for v in nodes]), device=dev, dtype=torch.long)
+        to_feats = self.transform(self.features(idx), agg[:, :self.feat_dim])
+        lab = _as_device_labels(batch_labels, dev) if train_flag else None
+        return to_feats, _LazyScores(sel, dist, meta, lab, train_flag)
+
+
+class _LazyScores:
+    """`samp_scores` (layers.py:695, 736): list over targets of the distances of the chosen
+    neighbours. InterAgg discards it (layers.py:268-270), so it is materialised only on access."""
+
+    def __init__(self, sel, dist, meta, labels, train):
+        self._args = (sel, dist, meta, labels, train)
+        self._val = None
+
+    def _get(self):
+        if self._val is None:
+            sel, dist, meta, labels, train = self._args
+            lab = labels.cpu().numpy() if labels is not None else None
+            self._val = _sets_and_scores(sel, dist, meta, lab, train)[1]
+            self._args = None
+        return self._val
+
+    def __iter__(self):
+        return iter(self._get())
+
+    def __len__(self):
+        return len(self._get())
+
+    def __getitem__(self, i):
+        return self._get()[i]
+
+
+def _explicit_csr(neighs_list, neigh_scores, device):
+    """Batch-local CSR (row i = neighbour ids of target i, ascending) + per-entry score column 0."""
+    lens = np.fromiter((len(x) for x in neighs_list), dtype=np.int64, count=len(neighs_list))
+    indptr = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=indptr[1:])
+    ids = np.fromiter((int(x) for x in chain.from_iterable(neighs_list)), dtype=np.int64, count=int(indptr[-1]))
+    rows = np.repeat(np.arange(len(lens), dtype=np.int64), lens)
+    order = np.lexsort((ids, rows))
+    flat = torch.cat([torch.as_tensor(s).reshape(-1, 2)[:, 0] for s in neigh_scores]).detach()
+    entry_score = flat.to(device=device, dtype=torch.float32)[torch.from_numpy(order).to(device)].contiguous()
+    return (torch.from_numpy(indptr).to(device), torch.from_numpy(ids[order].astype(np.int32)).to(device),
+            entry_score, lens)
+
+
+def _choose_explicit(eng, center_scores, center_labels, neigh_scores, neighs_list, minor_scores, minor_list,
+                     sample_list, sample_rate, train):
+    dev = eng.device
+    B = len(neighs_list)
+    indptr, indices, entry_score, lens = _explicit_csr(neighs_list, neigh_scores, dev)
+    center = torch.as_tensor(center_scores).detach().to(dev, torch.float32).reshape(-1, 2)[:, 0].contiguous()
+    k_list = np.asarray([int(k) for k in sample_list], dtype=np.int64)
+    k_over = torch.from_numpy(k_list.astype(np.int32)).to(dev)
+    pool = pool_score = None
+    P = 0
+    if train and minor_list is not None and len(minor_list):
+        pool = torch.as_tensor(np.asarray([int(p) for p in minor_list], dtype=np.int32)).to(dev)
+        pool_score = torch.as_tensor(minor_scores).detach().to(dev, torch.float32).reshape(-1, 2)[:, 0].contiguous()
+        P = int(pool.shape[0])
+    kk = np.where(lens > k_list + 1, k_list, lens)
+    oo = np.minimum((k_list * float(sample_rate)).astype(np.int64), P) if train else np.zeros_like(kk)
+    cap = int(((kk + oo + _lib.SLOT - 1) // _lib.SLOT).sum()) + 1
+    targets = torch.arange(B, dtype=torch.int32, device=dev)
+    labels = _as_device_labels(center_labels, dev) if train else None
+    sel, dist = eng.choose(targets, labels, train, [0.5], float(sample_rate), cap, entry_score=entry_score,
+                           center_score=center, k_override=k_over, pool=pool, pool_score=pool_score,
+                           indptr=indptr, indices=indices, n_nodes=B, n_rel=1,
+                           max_degree=int(lens.max()) if B else 0, want_dist=True)
+    return sel, dist, (lens, k_list, oo)
+
+
+def _sets_and_scores(sel, dist, meta, labels_host, train):
+    lens, k_list, oo = meta
+    base = sel.it_base.cpu().numpy()
+    m = sel.it_m.cpu().numpy()
+    idx = sel.idx.cpu().numpy()
+    dist = dist.cpu().numpy()
+    sets, scores = [], []
+    for i in range(sel.B):
+        d, c = int(lens[i]), int(k_list[i])
+        k = c if d > c + 1 else d
+        sets.append(set(idx[base[i]:base[i] + m[i]].tolist()))
+        seg = dist[base[i]:base[i] + k]
+        row = np.sort(seg, kind="stable").tolist() if d > c + 1 else seg.tolist()
+        if train and labels_host is not None and labels_host[i] == 1:
+            o = int(oo[i])
+            row = row + np.sort(dist[base[i] + k:base[i] + k + o], kind="stable").tolist()
+        scores.append(row)
+    return sets, scores
+
+
+def choose_step_neighs(center_scores, center_labels, neigh_scores, neighs_list, minor_scores, minor_list, sample_list,
+                       sample_rate):
+    """Train-mode choose step with the reference's signature and return value (layers.py:633-697):
+    (list of sets of kept ids, list of distance lists). The selection runs on the GPU; the host only
+    formats the kernel's output into Python sets and ordered distance lists."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    eng = Engine(None, dev)
+    sel, dist, meta = _choose_explicit(eng, center_scores, center_labels, neigh_scores, neighs_list, minor_scores,
+                                       minor_list, sample_list, sample_rate, True)
+    lab = _as_device_labels(center_labels, dev).cpu().numpy()
+    return _sets_and_scores(sel, dist, meta, lab, True)
+
+
+def choose_step_test(center_scores, neigh_scores, neighs_list, sample_list):
+    """Eval-mode choose step (layers.py:700-738)."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    eng = Engine(None, dev)
+    sel, dist, meta = _choose_explicit(eng, center_scores, None, neigh_scores, neighs_list, None, None, sample_list,
+                                       0.0, False)
+    return _sets_and_scores(sel, dist, meta, None, False)
+
+
+# ------------------------------------------------------------------------------------------------
+class InterAgg(nn.Module):
+    """Inter-relation aggregator for any number of relations R (reference: three hand-unrolled
+    copies InterAgg1 / InterAgg3 / InterAgg5, layers.py:417-535, :161-291, :16-158).
+
+    adj_lists: the reference's ``list[dict[int -> set[int]]]`` (converted to a CSR once, here), or a
+    ready ``graph.RelGraph`` (needed when a dict-of-sets is infeasible)."""
+
+    n_relations = None
+
+    def __init__(self, features, feature_dim, embed_dim, train_pos, adj_lists, intraggs, inter='GNN', cuda=True):
+        super().__init__()
+        R = len(intraggs)
+        if self.n_relations is not None and R != self.n_relations:
+            raise ValueError(f"{type(self).__name__} takes {self.n_relations} intra-aggregators, got {R}")
+        self.features = features
+        self.dropout = 0.6
+        self.adj_lists = adj_lists
+        for r, ia in enumerate(intraggs):
+            setattr(self, f"intra_agg{r + 1}", ia)
+            ia.cuda = cuda
+        self.embed_dim = embed_dim
+        self.feat_dim = feature_dim
+        self.cuda = cuda
+        self.train_pos = train_pos
+        self.thresholds = [0.5] * R                      # layers.py:193 (hard-coded filter ratio)
+        self.weight = nn.Parameter(torch.FloatTensor(self.embed_dim * R + self.feat_dim, self.embed_dim))
+        init.xavier_uniform_(self.weight)
+        self.label_clf = nn.Linear(self.feat_dim, 2)     # layers.py:200
+        self.weights_log = []
+        self.thresholds_log = [self.thresholds]
+        self.relation_score_log = []
+        self._R = R
+        self._graph = adj_lists if isinstance(adj_lists, RelGraph) else None
+        self._engine = None
+        self.cap_slots_hint = None      # set to a fixed capacity to avoid sizing from host ids
+        self.score_override = None      # tests: inject an [N] score table (identical score bits)
+        self.last_selection = None
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def intra_aggs(self):
+        return [getattr(self, f"intra_agg{r + 1}") for r in range(self._R)]
+
+    def engine(self) -> Engine:
+        dev = self.weight.device
+        if self._engine is None or self._engine.device != dev:
+            if self._graph is None:
+                self._graph = RelGraph.from_adj_lists(self.adj_lists)
+            if self._graph.n_rel != self._R:
+                raise ValueError(f"{self._R} intra-aggregators but {self._graph.n_rel} relations")
+            self._engine = Engine(self._graph, dev)
+            self._engine.set_pool(self.train_pos)
+        return self._engine
+
+    # -- forward ----------------------------------------------------------------------------
+    def forward(self, nodes, labels, train_flag=True):
+        eng = self.engine()
+        dev = eng.device
+        table = _feature_table(self.features, eng.N, dev)
+        eng.set_features(table)
+        targets, host = eng.upload_targets(nodes)
+        rho = self.intra_agg1.rho
+        lab = _as_device_labels(labels, dev) if train_flag else None
+
+        # label-aware scores for every node (column 0 only) + the pool's: layers.py:231-237
+        if self.score_override is not None:
+            eng.score.copy_(self.score_override)
+            if eng.P:
+                eng.pool_score[:eng.P] = eng.score[eng.pool.long()]
+        else:
+            eng.score_table(self.label_clf.weight, self.label_clf.bias)
+        idx = targets.long()
+        self_feats = self.features(idx)
+        center_scores = self.label_clf(self_feats)                   # [B,2], carries grad (layers.py:243)
+
+        # choose (filter + oversample + union) and aggregate: layers.py:246-270, 589-624
+        if self.cap_slots_hint is not None:
+            cap = int(self.cap_slots_hint)
+        elif host is not None:
+            cap = eng.slots_bound(host, self.thresholds, rho, train_flag)
+        else:
+            cap = eng.slots_bound(targets.cpu().numpy(), self.thresholds, rho, train_flag)
+        sel = eng.choose(targets, lab, train_flag, self.thresholds, rho, cap)
+        self.last_selection = sel
+        if table.requires_grad:
+            agg = _AggregateFn.apply(table, eng, sel, self.feat_dim)
+        else:
+            agg = eng.aggregate(sel)
+        B = targets.shape[0]
+        agg = agg.view(self._R, B, -1)[:, :, :self.feat_dim]
+
+        # relation transforms + inter-relation combine: layers.py:625-629, 273-289
+        r_feats = [ia.transform(self_feats, agg[r]) for r, ia in enumerate(self.intra_aggs())]
+        cat_feats = torch.cat([self_feats] + r_feats, dim=1)
+        combined = F.relu(cat_feats.mm(self.weight).t())
+        return combined, center_scores
+
+
+class InterAgg1(InterAgg):
+    n_relations = 1
+
+
+class InterAgg3(InterAgg):
+    n_relations = 3
+
+
+class InterAgg5(InterAgg):
+    n_relations = 5

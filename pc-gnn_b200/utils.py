@@ -1,0 +1,110 @@
+"""Sampler and small data helpers — same names and meaning as /root/reference/src/utils.py.
+
+  pick_step(idx_train, y_train, adj_list, size)      label-balanced sampler      (utils.py:274-278)
+  pos_neg_split(nodes, labels)                       ids split by label          (utils.py:256-271)
+  normalize(mx)                                      row-normalise features      (utils.py:213-223)
+  sparse_to_adjlist_for_train(sp_matrix)             scipy matrix -> graph       (utils.py:244-254)
+  set_seeds(seed)                                                                (utils.py:462-470)
+
+``pick_step`` keeps the reference's random stream: it consumes exactly ``size`` doubles from
+Python's global ``random`` (what ``random.choices`` does) and returns the same list the reference
+returns for the same seed; the weighted search itself runs on the GPU (``pcg_pick_step``).
+"""
+from __future__ import annotations
+
+import random
+
+import numpy as np
+import torch
+
+from . import _lib
+from .graph import RelGraph
+
+__all__ = ["pick_step", "pick_step_device", "pos_neg_split", "normalize", "sparse_to_adjlist_for_train",
+           "set_seeds", "pick_weights"]
+
+
+def _degrees(adj_list, idx_train):
+    if isinstance(adj_list, RelGraph):
+        ip = adj_list.indptr
+        t = np.asarray(idx_train, dtype=np.int64)
+        return (ip[t + 1] - ip[t]).astype(np.int64)
+    return np.fromiter((len(adj_list[node]) for node in idx_train), dtype=np.int64, count=len(idx_train))
+
+
+def pick_weights(idx_train, y_train, adj_list):
+    """Sampling weight deg(v) / LF(label(v)) in float64, exactly as utils.py:275-277: the label
+    frequency is sum(y) for positives and len(y) (not the negative count) for negatives."""
+    y = np.asarray(y_train)
+    lf_train = (y.sum() - len(y)) * y + len(y)
+    return np.array(_degrees(adj_list, idx_train)) / lf_train
+
+
+def pick_step_device(idx_train, y_train, adj_list, size, *, uniforms=None, seed=None, offset=0, device=None):
+    """Device-resident pick step: int32 CUDA tensor of `size` sampled node ids.
+
+    uniforms: the doubles to replay (bit-compatible with random.choices); if None a Philox4x32-10
+    counter stream keyed by `seed` is drawn on the device (same distribution, different stream)."""
+    device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+    L = _lib.lib()
+    w = pick_weights(idx_train, y_train, adj_list)
+    cum = torch.from_numpy(np.cumsum(w.astype(np.float64))).to(device)    # sequential fp64 == itertools.accumulate
+    ids = torch.from_numpy(np.asarray(idx_train, dtype=np.int32)).to(device)
+    out = torch.empty(size, dtype=torch.int32, device=device)
+    if uniforms is not None:
+        u = torch.from_numpy(np.asarray(uniforms, dtype=np.float64)).to(device)
+        rc = L.pcg_pick_step(cum.data_ptr(), cum.shape[0], u.data_ptr(), size, ids.data_ptr(), out.data_ptr(),
+                             _lib.stream_ptr())
+    else:
+        if seed is None:
+            seed = random.getrandbits(63)
+        rc = L.pcg_pick_step_philox(cum.data_ptr(), cum.shape[0], int(seed), int(offset), size, ids.data_ptr(),
+                                    out.data_ptr(), _lib.stream_ptr())
+    _lib.check(rc, "pcg_pick_step")
+    return out
+
+
+def pick_step(idx_train, y_train, adj_list, size):
+    """Drop-in for the reference's pick_step: same arguments, same returned list, same consumption of
+    the global `random` stream (one random() per draw, as in CPython's random.choices)."""
+    u = [random.random() for _ in range(size)]
+    out = pick_step_device(idx_train, y_train, adj_list, size, uniforms=u)
+    picked = out.cpu().tolist()
+    if len(idx_train) and not isinstance(idx_train[0], int):
+        lut = {int(v): v for v in idx_train}     # hand back the caller's own objects (e.g. numpy ints)
+        picked = [lut[p] for p in picked]
+    return picked
+
+
+def pos_neg_split(nodes, labels):
+    """(positive ids, negative ids) in `nodes` order (utils.py:256-271, without its O(n^2) remove)."""
+    pos, neg = [], []
+    for node, label in zip(nodes, labels):
+        (pos if label == 1 else neg).append(node)
+    return pos, neg
+
+
+def normalize(mx):
+    """Row-normalise: x / (rowsum + 0.01) (utils.py:213-223). Accepts scipy sparse or dense arrays."""
+    import scipy.sparse as sp
+
+    rowsum = np.array(mx.sum(1)) + 0.01
+    r_inv = np.power(rowsum, -1).flatten()
+    r_inv[np.isinf(r_inv)] = 0.
+    return sp.diags(r_inv).dot(mx)
+
+
+def sparse_to_adjlist_for_train(sp_matrix):
+    """Self loops + symmetrisation like utils.py:244-254, but straight to a CSR ``RelGraph`` (one
+    relation) instead of a dict of sets."""
+    return RelGraph.from_scipy([sp_matrix])
+
+
+def set_seeds(seed):
+
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed(seed)
+        torch.cuda.manual_seed_all(seed)

@@ -1,0 +1,193 @@
+"""GPU: the CUDA choose + aggregate kernels (through the C ABI) against the oracle and the golden
+vectors. Integer results (kept-id sets) must be bit-exact; aggregated rows within 1e-5 relative."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, graph_of, load_golden, rel_err, split_sets
+from oracle import c_oracle
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def run_choose(graph, feat, score, nodes, labels, pool, train, rho=0.5, thresh=None):
+    from pcgnn_b200.engine import Engine
+
+    eng = Engine(graph, "cuda")
+    eng.set_features(torch.from_numpy(np.ascontiguousarray(feat)).cuda())
+    eng.set_pool(pool)
+    eng.score.copy_(torch.from_numpy(np.ascontiguousarray(score)).cuda())
+    if eng.P:
+        eng.pool_score[:eng.P] = eng.score[eng.pool.long()]
+    thresh = thresh or [0.5] * graph.n_rel
+    targets, host = eng.upload_targets(list(nodes))
+    cap = eng.slots_bound(host, thresh, rho, train)
+    lab = torch.from_numpy(np.asarray(labels, dtype=np.int64)).cuda()
+    sel = eng.choose(targets, lab, train, thresh, rho, cap)
+    agg = eng.aggregate(sel)
+    torch.cuda.synchronize()
+    assert not sel.overflowed()
+    return eng, sel, agg
+
+
+def check_against_oracle(graph, feat, score, nodes, labels, pool, train, rho=0.5, thresh=None):
+    eng, sel, agg = run_choose(graph, feat, score, nodes, labels, pool, train, rho, thresh)
+    sp, si = c_oracle.choose(graph, score, nodes, np.asarray(labels) == 1, rho=rho, pool=pool, train=train,
+                             thresh=thresh)
+    got = sel.lists()
+    W = graph.n_rel * len(nodes)
+    for w in range(W):
+        want = si[sp[w]:sp[w + 1]]
+        assert np.array_equal(got[w], want), f"item {w}: {got[w][:8]}.. vs {want[:8]}.."
+    want_agg = c_oracle.aggregate(feat, sp, si)
+    got_agg = agg.cpu().numpy()[:, :feat.shape[1]]
+    assert rel_err(got_agg, want_agg) <= TOL
+    if agg.shape[1] > feat.shape[1]:
+        assert float(agg[:, feat.shape[1]:].abs().max()) == 0.0      # padding stays zero
+    return sel
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_choose_matches_golden(name, mode):
+    g = load_golden(name)
+    graph = graph_of(g)
+    nodes = g["nodes"]
+    labels = g["labels"][nodes]
+    eng, sel, agg = run_choose(graph, g["feat"], g["score_table"][:, 0], nodes, labels, g["train_pos"],
+                               mode == "train", rho=float(g["rho"]))
+    want = split_sets(g[f"{mode}_sel_ptr"], g[f"{mode}_sel_idx"], graph.n_rel, len(nodes))
+    got = sel.lists()
+    B = len(nodes)
+    for r in range(graph.n_rel):
+        for i in range(B):
+            assert got[r * B + i].tolist() == want[r][i], (r, i)
+
+
+@pytest.mark.parametrize("spec,B,dup", [("tiny", 200, 0.3), ("tiny_amz", 256, 0.0), ("tiny", 7, 0.9)])
+@pytest.mark.parametrize("train", [True, False])
+def test_choose_matches_oracle_small(spec, B, dup, train):
+    from pcgnn_b200.synth import make_graph
+
+    d = make_graph(spec, seed=17, dup_feature_frac=dup)
+    rng = np.random.default_rng(B)
+    score = (d.feat @ rng.normal(size=d.feat.shape[1]).astype(np.float32)).astype(np.float32)
+    nodes = rng.choice(d.idx_train, B)
+    check_against_oracle(d.graph, d.feat, score, nodes, d.labels[nodes], sorted(d.train_pos), train)
+
+
+def test_quantised_scores_many_ties():
+    """Scores on a coarse grid: most distances tie, so the (distance, id) rule decides nearly
+    everything, for the neighbours and for the pool."""
+    from pcgnn_b200.synth import make_graph
+
+    d = make_graph("tiny", seed=23)
+    rng = np.random.default_rng(1)
+    score = (rng.integers(0, 4, d.feat.shape[0]) * 0.25).astype(np.float32)
+    nodes = rng.choice(d.idx_train, 128)
+    check_against_oracle(d.graph, d.feat, score, nodes, d.labels[nodes], sorted(d.train_pos), True)
+    score[:] = 0.5                                                   # every distance is exactly 0
+    check_against_oracle(d.graph, d.feat, score, nodes, d.labels[nodes], sorted(d.train_pos), True)
+
+
+def test_unsorted_pool_ties_by_position():
+    from pcgnn_b200.synth import make_graph
+
+    d = make_graph("tiny", seed=29)
+    rng = np.random.default_rng(2)
+    score = (rng.integers(0, 3, d.feat.shape[0]) * 0.5).astype(np.float32)
+    pool = list(d.train_pos)                                         # idx_train order, not sorted
+    assert pool != sorted(pool)
+    nodes = rng.choice(d.idx_train, 64)
+    check_against_oracle(d.graph, d.feat, score, nodes, d.labels[nodes], pool, True)
+
+
+@pytest.mark.parametrize("rho,thresh", [(0.8, None), (0.2, [0.3, 0.5, 0.9]), (1.7, [1.0, 0.1, 0.5])])
+def test_other_ratios(rho, thresh):
+    from pcgnn_b200.synth import make_graph
+
+    d = make_graph("tiny", seed=37, dup_feature_frac=0.2)
+    rng = np.random.default_rng(3)
+    score = rng.normal(size=d.feat.shape[0]).astype(np.float32)
+    nodes = rng.choice(d.idx_train, 96)
+    check_against_oracle(d.graph, d.feat, score, nodes, d.labels[nodes], sorted(d.train_pos), True, rho, thresh)
+
+
+def test_hub_rows_take_the_cta_path_and_multi_slot_aggregation():
+    """A graph with rows longer than the warp tier (512) and than one aggregation slot (64)."""
+    from pcgnn_b200.graph import RelGraph, csr_from_edges
+
+    rng = np.random.default_rng(5)
+    n = 6000
+    rels = []
+    for r in range(3):
+        hubs = np.arange(10) + 10 * r
+        src = np.concatenate([np.repeat(hubs, 1500 + 400 * r), rng.integers(0, n, 4000)])
+        dst = np.concatenate([rng.integers(0, n, len(src) - 4000), rng.integers(0, n, 4000)])
+        rels.append(csr_from_edges(n, src, dst))
+    graph = RelGraph(n, [a for a, _ in rels], [b for _, b in rels])
+    assert np.diff(graph.indptr).max() > 1024
+    feat = rng.random((n, 100), dtype=np.float32)                    # F=100: 25 float4 per row
+    score = np.round(rng.normal(size=n), 2).astype(np.float32)       # coarse => ties inside hubs
+    labels = (rng.random(n) < 0.3).astype(np.int64)
+    pool = np.nonzero(labels)[0][::2]
+    nodes = np.concatenate([np.arange(30), rng.integers(0, n, 70)])
+    check_against_oracle(graph, feat, score, nodes, labels[nodes], pool, True)
+    check_against_oracle(graph, feat, score, nodes, labels[nodes], pool, False)
+
+
+def test_capacity_overflow_is_flagged_not_silent():
+    from pcgnn_b200.engine import Engine
+    from pcgnn_b200.synth import make_graph
+
+    d = make_graph("tiny", seed=3)
+    eng = Engine(d.graph, "cuda")
+    eng.set_features(torch.from_numpy(d.feat).cuda())
+    eng.set_pool(sorted(d.train_pos))
+    eng.score.zero_()
+    eng.pool_score.zero_()
+    targets, host = eng.upload_targets(d.idx_train[:64])
+    lab = torch.from_numpy(d.labels[d.idx_train[:64]]).cuda()
+    sel = eng.choose(targets, lab, True, [0.5] * 3, 0.5, 3)          # far too few slots
+    eng.aggregate(sel)
+    torch.cuda.synchronize()
+    assert sel.overflowed()
+
+
+def test_empty_batch():
+    from pcgnn_b200.engine import Engine
+    from pcgnn_b200.synth import make_graph
+
+    d = make_graph("tiny", seed=3)
+    eng = Engine(d.graph, "cuda")
+    eng.set_features(torch.from_numpy(d.feat).cuda())
+    eng.set_pool(sorted(d.train_pos))
+    targets = torch.zeros(0, dtype=torch.int32, device="cuda")
+    sel = eng.choose(targets, None, False, [0.5] * 3, 0.5, 1)
+    agg = eng.aggregate(sel)
+    assert agg.shape[0] == 0
+
+
+def test_full_size_yelp_shape_bit_exact():
+    """BASELINE config C2 shape (N=45,954, F=32, ~4.0M edges, B=1024): every kept-id set equals the
+    C oracle's; sizes follow the reference's rules (property checks, no Python port needed)."""
+    from pcgnn_b200.synth import make_graph
+    from pcgnn_b200.utils import pick_weights
+
+    d = make_graph("yelp", seed=72)
+    rng = np.random.default_rng(72)
+    score = (d.feat @ rng.normal(size=32).astype(np.float32) * 0.3).astype(np.float32)
+    w = pick_weights(d.idx_train, d.y_train, d.homo)
+    nodes = rng.choice(d.idx_train, 1024, p=w / w.sum())             # degree-biased like pick_step
+    labels = d.labels[nodes]
+    pool = sorted(d.train_pos)
+    sel = check_against_oracle(d.graph, d.feat, score, nodes, labels, pool, True)
+    m = sel.it_m.cpu().numpy()
+    for r in range(3):
+        deg = d.graph.degrees(r)[nodes]
+        c = np.ceil(deg * 0.5).astype(np.int64)
+        k = np.where(deg > c + 1, c, deg)
+        o = np.where(labels == 1, np.minimum((c * 0.5).astype(np.int64), len(pool)), 0)
+        mm = m[r * 1024:(r + 1) * 1024]
+        assert np.all(mm >= k) and np.all(mm <= k + o)
