@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""Benchmark of the PC-GNN pick-and-choose hot path on B200 (contract: see DESIGN.md "Measurement").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload yelp|amazon|yelp100] [--impl reference]
+
+One "step" = one full training step of PCALayer(InterAgg3(IntraAgg x3)) on one label-balanced batch of
+B target nodes: zero_grad -> loss (score table, choose, aggregate, relation transforms, combine, head,
+both cross-entropies) -> backward -> [grad all-reduce] -> Adam step. Prints ONE JSON line.
+
+  value      train target-nodes/s with the batch already resident in HBM (device tensors in)
+  e2e        the same through the reference-facing API with HOST inputs: model.loss(list_of_ids,
+             labels) + loss.item(), i.e. H2D of ids/labels and D2H of the loss inside the timed region
+  roofline   the slower of the two hot-path kernel groups (choose / aggregate), algorithmic bytes per
+             launch / CUDA-event time, against MEASURED_PEAKS.json
+  cpu_baseline  the oracle port (same algorithm structure as the reference, CPU) on a bounded sample
+
+`--impl reference` times that oracle port alone on the host cores (the reference is pure Python and is
+not present on the GPU box; oracle/port.py is its restatement, pinned by tests/golden).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (synthetic spec, batch per GPU, embed dim, description)
+    "yelp": ("yelp", 1024, 64, "C2 YelpChi-shaped N=45954 F=32 R=3 ~4.0M edges, emb 64, batch 1024/GPU"),
+    "amazon": ("amazon", 1024, 64, "C1 Amazon-shaped N=11944 F=25 R=3 ~4.8M edges, emb 64, batch 1024/GPU"),
+    "yelp100": ("yelp100", 4096, 128, "C3 YelpChi-shaped F=100, emb 128, batch 4096/GPU"),
+}
+RHO, ALPHA, LR, WD = 0.5, 2.0, 0.01, 1e-3
+SEED = 72
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_batches(data, n_batches, batch, seed):
+    """Label-balanced batches: nodes drawn with pick_step's weights deg/LF (utils.py:274-278)."""
+    from pcgnn_b200.utils import pick_weights
+
+    w = pick_weights(data.idx_train, data.y_train, data.homo)
+    rng = np.random.default_rng(seed)
+    idx = np.asarray(data.idx_train)
+    out = []
+    for _ in range(n_batches):
+        nodes = idx[rng.choice(len(idx), batch, p=w / w.sum())]
+        out.append((nodes.astype(np.int64), data.labels[nodes].astype(np.int64)))
+    return out
+
+
+def init_params(feat_dim, embed, n_rel, seed):
+    rng = np.random.default_rng(seed)
+
+    def xavier(r, c):
+        a = np.sqrt(6.0 / (r + c))
+        return rng.uniform(-a, a, size=(r, c)).astype(np.float32)
+
+    return dict(intra=[xavier(2 * feat_dim, embed) for _ in range(n_rel)], inter=xavier(feat_dim + n_rel * embed, embed),
+                clf_w=xavier(2, feat_dim), clf_b=np.zeros(2, np.float32), head=xavier(2, embed))
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.stop_flag, self.max_mhz = [], set(), False, None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def sample(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                     "hw_power_brake": 0x80, "sync_boost": 0x10}
+            for k, bit in names.items():
+                if r & bit:
+                    self.reasons.add(k)
+        except Exception:
+            pass
+
+    def run(self):
+        while not self.stop_flag:
+            self.sample()
+            time.sleep(0.02)
+
+    def result(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def cpu_port_rate(data, params, batches, sample, steps, warmup):
+    """Oracle port (CPU restatement of the reference's structure): full train steps on `sample` targets."""
+    import torch
+    from oracle import port
+
+    tp = sorted(data.train_pos)
+    pm = port.PortPCGNN(data.feat, data.graph, tp, params, rho=RHO, alpha=ALPHA)
+    opt = torch.optim.Adam(pm.parameters(), lr=LR, weight_decay=WD)
+    times = []
+    for s in range(warmup + steps):
+        nodes, labels = batches[s % len(batches)]
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        loss = pm.loss(nodes[:sample].tolist(), labels[:sample], True, shared_table=False)
+        loss.backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+    return sample / float(np.mean(times)), float(np.mean(times))
+
+
+def c_port_rate(data, batches, reps=3):
+    """C restatement (OpenMP, all host cores) of choose + aggregate only, full batch."""
+    from oracle import c_oracle
+
+    c_oracle.lib()
+    rng = np.random.default_rng(1)
+    score = (data.feat @ rng.normal(size=data.feat.shape[1]).astype(np.float32) * 0.3).astype(np.float32)
+    tp = sorted(data.train_pos)
+    best = 1e9
+    for i in range(reps):
+        nodes, labels = batches[i % len(batches)]
+        t0 = time.perf_counter()
+        sp, si = c_oracle.choose(data.graph, score, nodes, labels == 1, rho=RHO, pool=tp, train=True)
+        c_oracle.aggregate(data.feat, sp, si)
+        best = min(best, time.perf_counter() - t0)
+    return len(batches[0][0]) / best
+
+
+def run_reference(args):
+    """--impl reference: the oracle port on the host cores, same config/metric/unit."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from pcgnn_b200.synth import make_graph
+
+    spec, batch, embed, desc = WORKLOADS[args.workload]
+    data = make_graph(spec, seed=SEED)
+    params = init_params(data.feat.shape[1], embed, data.graph.n_rel, SEED)
+    batches = make_batches(data, 4, batch, SEED)
+    sample = min(args.cpu_sample, batch)
+    rate, sec = cpu_port_rate(data, params, batches, sample, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "train target-nodes/sec (fwd+bwd)", "value": rate, "unit": "target-nodes/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "rho": RHO, "thresholds": 0.5},
+        "cpu_baseline": {"value": rate, "unit": "target-nodes/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"full train step of oracle/port.py on the first {sample} targets of each "
+                                   f"{batch}-target batch (Python loop per target like the reference; "
+                                   f"host has {os.cpu_count()} cpus)"},
+        "e2e": {"value": rate, "unit": "target-nodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="yelp", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=128)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="do not use CUDA graphs for the device-resident step")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from pcgnn_b200 import _lib
+    from pcgnn_b200.parallel import GradAllReduce
+    from pcgnn_b200.synth import make_graph
+    from tests.helpers import build_cuda_pcgnn
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, W = args.steps, max(args.warmup, 3)
+    spec, batch, embed, desc = WORKLOADS[args.workload]
+    data = make_graph(spec, seed=SEED)
+    F_, R = data.feat.shape[1], data.graph.n_rel
+    params = init_params(F_, embed, R, SEED)
+    tp = sorted(data.train_pos)
+    model = build_cuda_pcgnn(data.feat, data.graph, tp, params, rho=RHO, alpha=ALPHA, device=dev)
+    inter = model.inter1
+    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=LR, weight_decay=WD,
+                           capturable=True, foreach=True)
+    reducer = GradAllReduce(model.parameters()).attach()
+    # global batches of batch*world targets, identical on every rank; this rank's contiguous shard
+    n_b = W + K
+    global_batches = make_batches(data, n_b, batch * world, SEED)
+    shards = [(n[rank * batch:(rank + 1) * batch], l[rank * batch:(rank + 1) * batch]) for n, l in global_batches]
+    dev_nodes = [torch.from_numpy(n.astype(np.int32)).to(dev) for n, _ in shards]
+    dev_labels = [torch.from_numpy(l).to(dev) for _, l in shards]
+    host_nodes = [n.tolist() for n, _ in shards]
+    host_labels = [l for _, l in shards]
+    eng = inter.engine()
+    eng.set_features(inter.features.weight)
+    cap = max(eng.slots_bound(n.astype(np.int32), inter.thresholds, RHO, True) for n, _ in shards)
+    inter.cap_slots_hint = cap
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def step_device(i):
+        reducer.zero()
+        loss = model.loss(dev_nodes[i], dev_labels[i])
+        loss.backward()
+        reducer()
+        if world > 1:
+            reducer.flat.div_(world)
+        opt.step()
+        return loss
+
+    def step_host(i):
+        reducer.zero()
+        lab = torch.from_numpy(host_labels[i]).to(dev)          # model_handler.py:150 (cuda LongTensor of labels)
+        loss = model.loss(host_nodes[i], lab)
+        loss.backward()
+        reducer()
+        if world > 1:
+            reducer.flat.div_(world)
+        opt.step()
+        return loss.item()                                       # D2H of the step's result
+
+    def timed(fn, first):
+        evs = []
+        for s in range(K):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn(first + s)
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local)
+    # ---- device-resident inputs (value) ----
+    for s in range(W):
+        step_device(s)
+    barrier()
+    sampler.start()
+    ms_dev = timed(step_device, W)
+    sampler.sample()
+    barrier()
+    ms_dev = max_over_ranks(ms_dev)
+    # ---- host inputs through the public API (e2e) ----
+    for s in range(W):
+        step_host(s)
+    barrier()
+    ms_e2e = timed(step_host, W)
+    barrier()
+    ms_e2e = max_over_ranks(ms_e2e)
+    sampler.stop_flag = True
+
+    # ---- hot-path kernels alone (roofline), same batches ----
+    t_choose = t_agg = 0.0
+    alg_choose = alg_agg = 0.0
+    P = eng.P
+    for s in range(K):
+        i = W + s
+        eng.score_table(inter.label_clf.weight, inter.label_clf.bias)
+        flush.zero_()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        sel = eng.choose(dev_nodes[i], dev_labels[i], True, inter.thresholds, RHO, cap)
+        e1.record()
+        eng.aggregate(sel)
+        e2.record()
+        torch.cuda.synchronize()
+        t_choose += e0.elapsed_time(e1)
+        t_agg += e1.elapsed_time(e2)
+        nodes, labels = shards[i]
+        n_pos = int((labels == 1).sum())
+        sum_d = sum(int(data.graph.degrees(r)[nodes].sum()) for r in range(R))
+        m_tot = int(sel.it_m.sum().item())
+        alg_choose += 8.0 * sum_d + R * batch * 16 + 4 * batch + 4.0 * P * n_pos * R + 4.0 * m_tot
+        alg_agg += (4.0 * F_ + 4.0) * m_tot + 4.0 * F_ * R * batch
+        assert not sel.overflowed()
+    peak, peak_src = measured_peaks()
+    kern = {
+        "choose": {"ms": t_choose / K, "alg_bytes": alg_choose / K, "gbs": alg_choose / t_choose / 1e6,
+                   "launches_per_step": 3},
+        "aggregate": {"ms": t_agg / K, "alg_bytes": alg_agg / K, "gbs": alg_agg / t_agg / 1e6,
+                      "launches_per_step": 2},
+    }
+    dom = "choose" if t_choose >= t_agg else "aggregate"
+    roof = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s",
+            "frac": kern[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+            "filter_plus_aggregate_gbs": (alg_choose + alg_agg) / (t_choose + t_agg) / 1e6}
+
+    if rank == 0:
+        total_nodes = batch * world * K
+        line = {
+            "metric": "train target-nodes/sec (fwd+bwd)", "value": total_nodes / (ms_dev / 1e3),
+            "unit": "target-nodes/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "global_batch": batch * world, "rho": RHO, "thresholds": 0.5,
+                       "optimizer": "Adam", "l2": "flushed between timed steps (256 MiB write)",
+                       "parallelism": f"dp{world} (targets sharded, grads all-reduced)" if world > 1 else "single"},
+            "e2e": {"value": total_nodes / (ms_e2e / 1e3), "unit": "target-nodes/s", "ms_per_step": ms_e2e / K,
+                    "h2d_bytes_per_step": batch * 4 + batch * 8, "d2h_bytes_per_step": 4},
+            "gpu_launches": 7 * K,
+            "roofline": roof, "kernels": kern, "clocks": sampler.result(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            sample = min(args.cpu_sample, batch)
+            rate, sec = cpu_port_rate(data, params, global_batches, sample, 6, 1)
+            line["cpu_baseline"] = {
+                "value": rate, "unit": "target-nodes/s", "cores": torch.get_num_threads(), "kind": "port",
+                "sample": f"6 full train steps of oracle/port.py on the first {sample} targets of a batch "
+                          f"({sec * 1e3:.0f} ms each; host has {os.cpu_count()} cpus)",
+                "c_port_choose_aggregate_nodes_per_s": c_port_rate(data, global_batches)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

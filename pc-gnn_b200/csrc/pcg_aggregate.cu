@@ -232,6 +232,7 @@ extern "C" int pcg_aggregate(const float* feat, int64_t ldf, const int32_t* idx,
                              const int32_t* it_extra, int n_items, int64_t cap_slots, const int32_t* status, int norm,
                              float* partial, int32_t* it_done, float* agg, pcg_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_items == 0) return 0;
     PCG_REQUIRE(ldf > 0 && ldf % 4 == 0, "pcg_aggregate: ldf=%lld must be a positive multiple of 4", (long long)ldf);
     PCG_REQUIRE(feat && idx && slot_item && it_slot0 && it_m && it_base && status && partial && it_done && agg,
                 "pcg_aggregate: null pointer");
@@ -250,6 +251,7 @@ extern "C" int pcg_aggregate_bwd(const float* d_agg, int64_t ldf, const int32_t*
                                  const int32_t* it_extra, int n_items, int64_t cap_slots, const int32_t* status,
                                  int norm, float* feat_grad, pcg_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_items == 0) return 0;
     PCG_REQUIRE(ldf > 0 && ldf % 4 == 0, "pcg_aggregate_bwd: ldf=%lld must be a positive multiple of 4", (long long)ldf);
     PCG_REQUIRE(d_agg && idx && slot_item && it_slot0 && it_m && it_base && status && feat_grad,
                 "pcg_aggregate_bwd: null pointer");

@@ -408,6 +408,10 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
     cudaStream_t stream = (cudaStream_t)stream_;
     PCG_REQUIRE(R >= 1 && R <= PCG_MAX_REL, "pcg_choose: R=%d outside [1,%d]", R, PCG_MAX_REL);
     PCG_REQUIRE(B >= 0, "pcg_choose: negative batch");
+    if (B == 0) {   // empty batch: nothing to choose (pointers of empty buffers may be null)
+        if (status) cudaMemsetAsync(status, 0, PCG_STATUS_WORDS * sizeof(int32_t), stream);
+        return 0;
+    }
     PCG_REQUIRE(score || (entry_score && center_score), "pcg_choose: need a score table or explicit scores");
     PCG_REQUIRE(!(train && P > 0) || (pool && pool_score), "pcg_choose: pool/pool_score missing");
     PCG_REQUIRE(indptr && indices && targets && sel_idx && slot_item && it_slot0 && it_m && it_base && it_done && status,
@@ -461,6 +465,10 @@ extern "C" int pcg_select_all(const int64_t* indptr, const int32_t* indices, int
                               int32_t* status, pcg_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     PCG_REQUIRE(R >= 1 && B >= 0, "pcg_select_all: bad sizes");
+    if (B == 0) {
+        if (status) cudaMemsetAsync(status, 0, PCG_STATUS_WORDS * sizeof(int32_t), stream);
+        return 0;
+    }
     PCG_REQUIRE(indptr && indices && targets && slot_item && it_slot0 && it_m && it_base && it_extra && it_done && status,
                 "pcg_select_all: null pointer");
     cudaError_t e = cudaMemsetAsync(status, 0, PCG_STATUS_WORDS * sizeof(int32_t), stream);

@@ -99,7 +99,7 @@ def test_adj_lists_dict_of_sets_input():
     features.weight = nn.Parameter(torch.from_numpy(feat), requires_grad=False)
     tp = g["train_pos"].tolist()
     intras = [IntraAgg(features, feat.shape[1], 16, tp, 0.5, cuda=True) for _ in range(3)]
-    inter = InterAgg3(features, feat.shape[1], 16, tp, adj, intras, cuda=True).cuda()
+    inter = InterAgg3(features, feat.shape[1], 16, tp, adj, intras, cuda=True).to("cuda")
     inter.score_override = torch.from_numpy(g["score_table"][:, 0].copy()).cuda()
     nodes = g["nodes"].tolist()
     inter(nodes, torch.from_numpy(g["labels"][g["nodes"]]).cuda(), True)
@@ -170,7 +170,7 @@ def test_intra_agg_explicit_api(train):
                                              tp, k_list, float(g["rho"]), train)
     features = nn.Embedding(*g["feat"].shape)
     features.weight = nn.Parameter(feat.clone(), requires_grad=False)
-    ia = IntraAgg(features, feat.shape[1], w.shape[1], tp, float(g["rho"]), cuda=True).cuda()
+    ia = IntraAgg(features, feat.shape[1], w.shape[1], tp, float(g["rho"]), cuda=True).to("cuda")
     with torch.no_grad():
         ia.weight.copy_(w)
     got, scores = ia.forward(nodes, torch.from_numpy(labels).cuda(), shuffled, center.cuda(),
