@@ -240,7 +240,7 @@ def main():
     inter.cap_slots_hint = cap
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
-    def step_device(i):
+    def step_device_eager(i):
         reducer.zero()
         loss = model.loss(dev_nodes[i], dev_labels[i])
         loss.backward()
@@ -250,7 +250,7 @@ def main():
         opt.step()
         return loss
 
-    def step_host(i):
+    def step_host_eager(i):
         reducer.zero()
         lab = torch.from_numpy(host_labels[i]).to(dev)          # model_handler.py:150 (cuda LongTensor of labels)
         loss = model.loss(host_nodes[i], lab)
@@ -260,6 +260,20 @@ def main():
             reducer.flat.div_(world)
         opt.step()
         return loss.item()                                       # D2H of the step's result
+
+    use_graph = not args.no_graph
+    if use_graph:
+        from pcgnn_b200.runtime import GraphedTrainStep
+
+        gstep = GraphedTrainStep(model, opt, batch, cap, reducer=reducer, world=world, warmup_batch=shards[0])
+
+        def step_device(i):
+            return gstep.run_device(dev_nodes[i], dev_labels[i])
+
+        def step_host(i):
+            return gstep.run(host_nodes[i], host_labels[i]).item()     # H2D ids+labels, replay, D2H loss
+    else:
+        step_device, step_host = step_device_eager, step_host_eager
 
     def timed(fn, first):
         evs = []
@@ -303,6 +317,14 @@ def main():
     ms_e2e = timed(step_host, W)
     barrier()
     ms_e2e = max_over_ranks(ms_e2e)
+    ms_api = None
+    if use_graph:      # the reference-facing eager call model.loss(list, labels) for comparison
+        for s in range(W):
+            step_host_eager(s)
+        barrier()
+        ms_api = max_over_ranks(timed(step_host_eager, W))
+        barrier()
+        assert not gstep.overflowed()
     sampler.stop_flag = True
 
     # ---- hot-path kernels alone (roofline), same batches ----
@@ -336,6 +358,7 @@ def main():
         "aggregate": {"ms": t_agg / K, "alg_bytes": alg_agg / K, "gbs": alg_agg / t_agg / 1e6,
                       "launches_per_step": 2},
     }
+    kern["score_table_and_pool_sort"] = {"launches_per_step": 3}
     dom = "choose" if t_choose >= t_agg else "aggregate"
     roof = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s",
             "frac": kern[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
@@ -352,9 +375,14 @@ def main():
                        "parallelism": f"dp{world} (targets sharded, grads all-reduced)" if world > 1 else "single"},
             "e2e": {"value": total_nodes / (ms_e2e / 1e3), "unit": "target-nodes/s", "ms_per_step": ms_e2e / K,
                     "h2d_bytes_per_step": batch * 4 + batch * 8, "d2h_bytes_per_step": 4},
-            "gpu_launches": 7 * K,
+            "gpu_launches": 8 * K,
+            "mode": "cuda-graph replay (runtime.GraphedTrainStep)" if use_graph else "eager",
             "roofline": roof, "kernels": kern, "clocks": sampler.result(),
         }
+        if ms_api is not None:
+            line["e2e_reference_api_eager"] = {"value": total_nodes / (ms_api / 1e3), "unit": "target-nodes/s",
+                                               "ms_per_step": ms_api / K,
+                                               "call": "model.loss(list_of_ids, cuda_labels); backward; Adam.step; loss.item()"}
         if world == 1 and not args.no_cpu_baseline:
             sample = min(args.cpu_sample, batch)
             rate, sec = cpu_port_rate(data, params, global_batches, sample, 6, 1)

@@ -46,13 +46,25 @@ PCG_API int pcg_version(void);
 PCG_API int pcg_device_sms(void);
 
 /*
- * Label-aware score table, column 0 only: score[v] = dot(feat[v, :F], w) + b[0] for all N nodes (w, b device pointers),
- * then pool_score[p] = score[pool[p]] for the train-positive pool.
+ * Label-aware score table, column 0 only: score[v] = dot(feat[v, :F], w) + b[0] for all N nodes (w, b
+ * device pointers), then the train-positive pool sorted by that score (see pcg_sort_pool).
  * Replaces src/layers.py:231-237 (label_clf over the batch's unique nodes and over train_pos);
  * only column 0 is ever compared (src/layers.py:649-650, 685, 714-715).
+ *   workspace  pcg_sort_pool_workspace_bytes(P) bytes
  */
 PCG_API int pcg_score_table(const float* feat, int64_t n_nodes, int F, int64_t ldf, const float* w, const float* b,
-                    float* score, const int32_t* pool, int P, float* pool_score, pcg_stream_t stream);
+                    float* score, const int32_t* pool, int P, float* ps_score, int32_t* ps_pos, int32_t* ps_id,
+                    void* workspace, size_t workspace_bytes, pcg_stream_t stream);
+
+/*
+ * Pool sorted by score: ps_score ascending with ties in pool-position order, ps_pos[i] = position in
+ * `pool` of sorted entry i, ps_id[i] = pool[ps_pos[i]]. One sort per step replaces the reference's
+ * torch.sort over all P pool distances for EVERY positive target (src/layers.py:683-690): with the pool
+ * sorted, a target's nearest positives are a window around lower_bound(score[target]).
+ */
+PCG_API size_t pcg_sort_pool_workspace_bytes(int P);
+PCG_API int pcg_sort_pool(const float* pool_score, const int32_t* pool, int P, float* ps_score, int32_t* ps_pos,
+                  int32_t* ps_id, void* workspace, size_t workspace_bytes, pcg_stream_t stream);
 
 /* Bytes of scratch pcg_choose needs for B targets x R relations on a graph whose largest row has
  * max_degree entries. */
@@ -72,13 +84,13 @@ PCG_API size_t pcg_choose_workspace_bytes(int B, int R, int64_t max_degree);
  *   labels       int64 [B] (== 1 means positive) or NULL; ignored unless train != 0
  *   thresh_host  HOST array of R doubles (src/layers.py:193 hard-codes 0.5)
  *   k_override   int32 [R*B] explicit num_sample per item (src/layers.py:260-262) or NULL
- *   pool         int32 [P] train-positive ids, pool_score [P] their scores
+ *   ps_score/ps_pos/ps_id  the score-sorted pool from pcg_score_table / pcg_sort_pool (P entries)
  * Outputs
  *   sel_idx      int32 [cap_slots * PCG_SLOT]; item w's ids are sel_idx[it_base[w] .. + it_m[w])
  *   sel_dist     optional fp32 [cap_slots * PCG_SLOT] (NULL to skip): the distances the reference returns as
  *                samp_scores (src/layers.py:666-672, 691): at it_base[w] + [0,k) the kept neighbours' |Δ| in row
- *                order, at it_base[w] + k + [0,o) the o nearest pool members' |Δ| in pool order (duplicates of
- *                kept ids included, as in the reference's list)
+ *                order, at it_base[w] + k + [0,o) the o nearest pool members' |Δ| (duplicates of kept ids
+ *                included, as in the reference's list; unordered)
  *   slot_item    int32 [cap_slots]  owning item of each handed-out slot, or -1
  *   it_slot0/it_m int32 [R*B], it_base int64 [R*B], it_done int32 [R*B] (zeroed; aggregation tickets)
  *   status       int32 [PCG_STATUS_WORDS] (zeroed here)
@@ -86,7 +98,7 @@ PCG_API size_t pcg_choose_workspace_bytes(int B, int R, int64_t max_degree);
 PCG_API int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t n_nodes, int R, const float* score,
                const float* entry_score, const float* center_score, const int32_t* targets,
                const int64_t* labels, int B, const double* thresh_host, const int32_t* k_override, double rho,
-               const int32_t* pool, const float* pool_score, int P, int train, int64_t max_degree,
+               const float* ps_score, const int32_t* ps_pos, const int32_t* ps_id, int P, int train, int64_t max_degree,
                int32_t* sel_idx, float* sel_dist, int64_t cap_slots, int32_t* slot_item, int32_t* it_slot0,
                int32_t* it_m, int64_t* it_base, int32_t* it_done, void* workspace, size_t workspace_bytes, int32_t* status,
                pcg_stream_t stream);

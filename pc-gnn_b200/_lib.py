@@ -29,9 +29,11 @@ SIGNATURES = {
     "pcg_last_error": (C.c_char_p, []),
     "pcg_version": (_i, []),
     "pcg_device_sms": (_i, []),
-    "pcg_score_table": (_i, [_p, _l, _i, _l, _p, _p, _p, _p, _i, _p, _p]),
+    "pcg_score_table": (_i, [_p, _l, _i, _l, _p, _p, _p, _p, _i, _p, _p, _p, _p, _z, _p]),
+    "pcg_sort_pool_workspace_bytes": (_z, [_i]),
+    "pcg_sort_pool": (_i, [_p, _p, _i, _p, _p, _p, _p, _z, _p]),
     "pcg_choose_workspace_bytes": (_z, [_i, _i, _l]),
-    "pcg_choose": (_i, [_p, _p, _l, _i, _p, _p, _p, _p, _p, _i, C.POINTER(_d), _p, _d, _p, _p, _i, _i, _l,
+    "pcg_choose": (_i, [_p, _p, _l, _i, _p, _p, _p, _p, _p, _i, C.POINTER(_d), _p, _d, _p, _p, _p, _i, _i, _l,
                         _p, _p, _l, _p, _p, _p, _p, _p, _p, _z, _p, _p]),
     "pcg_select_all": (_i, [_p, _p, _l, _i, _p, _i, _i, _l, _p, _p, _p, _p, _p, _p, _p, _p]),
     "pcg_aggregate": (_i, [_p, _l, _p, _p, _p, _p, _p, _p, _i, _l, _p, _i, _p, _p, _p, _p]),

@@ -38,20 +38,21 @@ __global__ void __launch_bounds__(256) k_aggregate(const float* __restrict__ fea
                                                    int32_t* it_done, float* __restrict__ agg) {
     constexpr int G = 32 / LPR;          // rows per warp-wide load
     constexpr int UN = (LPR == 32) ? 8 : 4;
-    const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     int64_t n_slots = status[ST_SLOTS];
     if (n_slots > cap_slots) n_slots = cap_slots;
-    if (s >= n_slots) return;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int V = (int)(ldf >> 2);       // float4 per row
+    const int g = lane / LPR, l = lane % LPR;
+    // grid-stride over the handed-out slots: the launch size does not depend on the capacity
+    for (int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_slots; s += n_warps) {
     const int w = slot_item[s];
-    if (w < 0) return;
+    if (w < 0) continue;
     const int slot0 = it_slot0[w];
     const int m = it_m[w];
     const int c = (int)(s - slot0);
     const int len = min(PCG_SLOT, m - c * PCG_SLOT);
     const int32_t* __restrict__ ids = idx + it_base[w] + (int64_t)c * PCG_SLOT;
-    const int V = (int)(ldf >> 2);       // float4 per row
-    const int g = lane / LPR, l = lane % LPR;
 
     // ids of this slot: two per lane, broadcast by shuffle
     int32_t id_lo = lane < len ? __ldg(ids + lane) : 0;
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(256) k_aggregate(const float* __restrict__ fea
                 }
             }
         }
-        return;
+        continue;
     }
     // multi-slot item: publish the partial, last arriver reduces in slot order
     if (g == 0) {
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(256) k_aggregate(const float* __restrict__ fea
     int ticket = 0;
     if (lane == 0) ticket = atomicAdd(&it_done[w], 1);
     ticket = __shfl_sync(PCG_FULL, ticket, 0);
-    if (ticket != nch - 1) return;
+    if (ticket != nch - 1) continue;
     __threadfence();
     const float sc = norm_scale(m + (extra >= 0 ? 1 : 0), norm);
     for (int col = lane; col < V; col += 32) {
@@ -122,6 +123,7 @@ __global__ void __launch_bounds__(256) k_aggregate(const float* __restrict__ fea
         if (extra >= 0) f4_add(a, ld_f4(feat + (int64_t)extra * ldf + 4 * col));
         a.x *= sc; a.y *= sc; a.z *= sc; a.w *= sc;
         *reinterpret_cast<float4*>(agg + (int64_t)w * ldf + 4 * col) = a;
+    }
     }
 }
 
@@ -146,13 +148,13 @@ __global__ void __launch_bounds__(256) k_aggregate_bwd(const float* __restrict__
                                                        const int32_t* __restrict__ status, int norm,
                                                        float* feat_grad) {
     constexpr int G = 32 / LPR;
-    const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     int64_t n_slots = status[ST_SLOTS];
     if (n_slots > cap_slots) n_slots = cap_slots;
-    if (s >= n_slots) return;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_slots; s += n_warps) {
     const int w = slot_item[s];
-    if (w < 0) return;
+    if (w < 0) continue;
     const int slot0 = it_slot0[w];
     const int m = it_m[w];
     const int c = (int)(s - slot0);
@@ -189,6 +191,7 @@ __global__ void __launch_bounds__(256) k_aggregate_bwd(const float* __restrict__
             }
         }
     }
+    }
 }
 
 template <int LPR, int NV>
@@ -196,8 +199,9 @@ static void launch_agg(bool bwd, const float* a0, int64_t ldf, const int32_t* id
                        const int32_t* it_slot0, const int32_t* it_m, const int64_t* it_base, const int32_t* it_extra,
                        int64_t cap_slots, const int32_t* status, int norm, float* partial, int32_t* it_done, float* out,
                        cudaStream_t stream) {
-    const int64_t warps = cap_slots;
-    const int blocks = (int)((warps * 32 + 255) / 256);
+    int64_t blocks64 = (cap_slots * 32 + 255) / 256;
+    const int64_t max_blocks = (int64_t)pcg_device_sms() * 8;      // 8 resident CTAs of 8 warps per SM
+    const int blocks = (int)(blocks64 < max_blocks ? blocks64 : max_blocks);
     if (!bwd)
         k_aggregate<LPR, NV><<<blocks, 256, 0, stream>>>(a0, ldf, idx, slot_item, it_slot0, it_m, it_base, it_extra,
                                                          cap_slots, status, norm, partial, it_done, out);

@@ -28,8 +28,9 @@ struct ChooseP {
     const int32_t* targets;
     const int64_t* labels;
     const int32_t* k_override;
-    const int32_t* pool;
-    const float* pool_score;
+    const float* ps_score;      // pool scores ascending (ties by pool position)
+    const int32_t* ps_pos;      // pool position of each sorted entry
+    const int32_t* ps_id;       // node id of each sorted entry
     int64_t n_nodes;
     int R, B, P, train;
     double thresh[PCG_MAX_REL];
@@ -96,9 +97,24 @@ __device__ __forceinline__ void radix_select(Get get, int n, int kth, uint32_t* 
     for (int shift = 24; shift >= 0; shift -= 8) {
         for (int b = tid; b < 256; b += NT) hist[b] = 0;
         grp_sync<NT>();
-        for (int j = tid; j < n; j += NT) {
-            uint32_t key = get(j);
-            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xffu], 1u);
+        // Distance bits share their top digits, so a plain per-lane atomicAdd serialises up to 32-way
+        // on one bin. Peel the (up to 3) most common digits of each warp with ballots first.
+        const int n_up = (n + 31) & ~31;
+        for (int j = tid; j < n_up; j += NT) {
+            const bool valid = j < n;
+            const uint32_t key = valid ? get(j) : 0u;
+            const bool active = valid && (key & mask) == prefix;
+            const uint32_t digit = (key >> shift) & 0xffu;
+            unsigned rem = __ballot_sync(PCG_FULL, active);
+#pragma unroll 1
+            for (int it = 0; it < 3 && rem; ++it) {
+                const int ldr = __ffs(rem) - 1;
+                const uint32_t d0 = __shfl_sync(PCG_FULL, digit, ldr);
+                const unsigned same = __ballot_sync(PCG_FULL, active && digit == d0);
+                if ((tid & 31) == ldr) atomicAdd(&hist[d0], (uint32_t)__popc(same));
+                rem &= ~same;
+            }
+            if ((rem >> (tid & 31)) & 1u) atomicAdd(&hist[digit], 1u);
         }
         grp_sync<NT>();
         if (tid < 32) {
@@ -205,44 +221,83 @@ __device__ void choose_item(const ChooseP& p, int w, int tid, uint32_t* sd, int 
         run_tie += tt;
     }
     // ---- minority oversampling: nearest train positives not already kept ----
+    // The pool is sorted by score once per step (pcg_sort_pool). Around the split point c =
+    // lower_bound(sv) the distances grow monotonically to the left (A) and to the right (B), so the
+    // o-th smallest distance T is a "k-th of two sorted sequences" search, everything below T is two
+    // contiguous runs, and only the run of elements equal to T needs the position tie rule.
     int n_emit = 0;
     if (o > 0) {
-        const float* __restrict__ ps = p.pool_score;
-        auto getp = [&](int q) -> uint32_t { return dist_bits(sv, __ldg(ps + q)); };
-        uint32_t Tp = 0xffffffffu;
-        int needp = 0x7fffffff;
-        if (o < p.P) radix_select<NT>(getp, p.P, o, hist, xw, tid, Tp, needp);
+        const float* __restrict__ S = p.ps_score;
+        const int32_t* __restrict__ SP = p.ps_pos;
+        const int32_t* __restrict__ SI = p.ps_id;
+        const int P = p.P;
+        int c;
+        {
+            int lo = 0, hi = P;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(S + mid) < sv) lo = mid + 1; else hi = mid; }
+            c = lo;
+        }
+        const int nA = c, nB = P - c;
+        auto A = [&](int i) -> uint32_t { return dist_bits(sv, __ldg(S + (c - 1 - i))); };
+        auto Bq = [&](int j) -> uint32_t { return dist_bits(sv, __ldg(S + (c + j))); };
+        int lo = max(0, o - nB), hi = min(o, nA);
+        while (lo < hi) {   // how many of the o nearest come from the left side
+            const int mid = (lo + hi) >> 1;
+            if (Bq(o - mid - 1) > A(mid)) lo = mid + 1; else hi = mid;
+        }
+        const int ia = lo, ib = o - lo;
+        uint32_t Tp = 0;
+        if (ia > 0) Tp = A(ia - 1);
+        if (ib > 0) Tp = max(Tp, Bq(ib - 1));
+        auto bound = [&](auto seq, int n, uint32_t t, bool upper) {   // first idx with seq >= t (or > t)
+            int l = 0, h = n;
+            while (l < h) {
+                const int mid = (l + h) >> 1;
+                const uint32_t x = seq(mid);
+                if (upper ? (x <= t) : (x < t)) l = mid + 1; else h = mid;
+            }
+            return l;
+        };
+        const int a_less = bound(A, nA, Tp, false), a_le = bound(A, nA, Tp, true);
+        const int b_less = bound(Bq, nB, Tp, false), b_le = bound(Bq, nB, Tp, true);
+        const int cnt_less = a_less + b_less;
+        const int tie_a = a_le - a_less, ties = tie_a + (b_le - b_less);
+        const int needp = o - cnt_less;            // 1 <= needp <= ties
+        auto tie_index = [&](int t) -> int { return t < tie_a ? c - 1 - (a_less + t) : c + b_less + (t - tie_a); };
+        uint32_t Tpos = 0xffffffffu;
+        if (needp < ties) {   // more equal-distance candidates than needed: smallest pool positions win
+            auto getpos = [&](int t) -> uint32_t { return (uint32_t)__ldg(SP + tie_index(t)); };
+            int unused;
+            radix_select<NT>(getpos, ties, needp, hist, xw, tid, Tpos, unused);
+        }
         grp_sync<NT>();   // kept-bitmask visible to the whole group
-        int run_tp = 0, run_lp = 0;
-        for (int base = 0; base < p.P; base += NT) {
-            const int q = base + tid;
-            const bool valid = q < p.P;
-            const uint32_t key = valid ? getp(q) : 0xffffffffu;
-            const bool less = valid && key < Tp;
-            const bool tie = valid && key == Tp;
-            int e0, et, t0, tt;
-            grp_excl2<NT>(less, tie, tid, xw, e0, et, t0, tt);
-            const bool selp = less || (tie && run_tp + et < needp);
-            if (selp && p.sel_dist) p.sel_dist[off + k + run_lp + e0 + min(run_tp + et, needp)] = __uint_as_float(key);
+        const int total = cnt_less + ties;
+        int run_sel = 0;
+        for (int base = 0; base < total; base += NT) {
+            const int e = base + tid;
+            const bool valid = e < total;
+            int idx = 0;
+            if (valid) idx = e < a_less ? c - 1 - e : (e < cnt_less ? c + (e - a_less) : tie_index(e - cnt_less));
+            const bool selp = valid && (e < cnt_less || (uint32_t)__ldg(SP + idx) <= Tpos);
             bool emit = false;
             int32_t id = 0;
             if (selp) {
-                id = p.pool[q];
-                int lo = 0, hi = d;            // lower_bound of id in the id-sorted row
-                while (lo < hi) {
-                    int mid = (lo + hi) >> 1;
-                    if (nbr[mid] < id) lo = mid + 1; else hi = mid;
+                id = __ldg(SI + idx);
+                int l = 0, h = d;            // lower_bound of id in the id-sorted row
+                while (l < h) {
+                    const int mid = (l + h) >> 1;
+                    if (nbr[mid] < id) l = mid + 1; else h = mid;
                 }
                 bool dup = false;
-                if (lo < d && nbr[lo] == id) dup = (k == d) || ((bits[lo >> 5] >> (lo & 31)) & 1u);
+                if (l < d && nbr[l] == id) dup = (k == d) || ((bits[l >> 5] >> (l & 31)) & 1u);
                 emit = !dup;
             }
-            int ee, e1, te, t1;
-            grp_excl2<NT>(emit, false, tid, xw, ee, e1, te, t1);
+            int es, ee, ts, te;
+            grp_excl2<NT>(selp, emit, tid, xw, es, ee, ts, te);
+            if (selp && p.sel_dist) p.sel_dist[off + k + run_sel + es] = __uint_as_float(dist_bits(sv, __ldg(S + idx)));
             if (emit) p.sel_idx[off + k + n_emit + ee] = id;
+            run_sel += ts;
             n_emit += te;
-            run_tp += tt;
-            run_lp += t0;
         }
     }
     const int m = k + n_emit;
@@ -401,7 +456,7 @@ extern "C" size_t pcg_choose_workspace_bytes(int B, int R, int64_t max_degree) {
 extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t n_nodes, int R, const float* score,
                           const float* entry_score, const float* center_score, const int32_t* targets,
                           const int64_t* labels, int B, const double* thresh_host, const int32_t* k_override,
-                          double rho, const int32_t* pool, const float* pool_score, int P, int train,
+                          double rho, const float* ps_score, const int32_t* ps_pos, const int32_t* ps_id, int P, int train,
                           int64_t max_degree, int32_t* sel_idx, float* sel_dist, int64_t cap_slots,
                           int32_t* slot_item, int32_t* it_slot0, int32_t* it_m, int64_t* it_base, int32_t* it_done, void* workspace,
                           size_t workspace_bytes, int32_t* status, pcg_stream_t stream_) {
@@ -413,7 +468,7 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
         return 0;
     }
     PCG_REQUIRE(score || (entry_score && center_score), "pcg_choose: need a score table or explicit scores");
-    PCG_REQUIRE(!(train && P > 0) || (pool && pool_score), "pcg_choose: pool/pool_score missing");
+    PCG_REQUIRE(!(train && P > 0) || (ps_score && ps_pos && ps_id), "pcg_choose: sorted pool arrays missing");
     PCG_REQUIRE(indptr && indices && targets && sel_idx && slot_item && it_slot0 && it_m && it_base && it_done && status,
                 "pcg_choose: null pointer");
     const int sms = device_sms();
@@ -426,8 +481,8 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
     ChooseP p;
     p.indptr = indptr; p.indices = indices; p.score = score; p.entry_score = entry_score;
     p.center_score = center_score; p.targets = targets; p.labels = labels; p.k_override = k_override;
-    p.pool = pool; p.pool_score = pool_score; p.n_nodes = n_nodes; p.R = R; p.B = B;
-    p.P = (train && pool) ? P : 0; p.train = train;
+    p.ps_score = ps_score; p.ps_pos = ps_pos; p.ps_id = ps_id; p.n_nodes = n_nodes; p.R = R; p.B = B;
+    p.P = (train && ps_score) ? P : 0; p.train = train;
     for (int r = 0; r < PCG_MAX_REL; ++r) p.thresh[r] = r < R ? thresh_host[r] : 0.5;
     p.rho = rho; p.sel_idx = sel_idx; p.sel_dist = sel_dist; p.cap_slots = cap_slots; p.slot_item = slot_item;
     p.it_slot0 = it_slot0; p.it_m = it_m; p.it_base = it_base; p.status = status;

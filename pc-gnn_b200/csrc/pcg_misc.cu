@@ -1,6 +1,8 @@
 // Error plumbing, the label-score table and the label-balanced pick step.
 #include <stdarg.h>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "pcg_common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -65,8 +67,123 @@ __global__ void k_gather_pool(const float* __restrict__ score, const int32_t* __
     if (p < P) pool_score[p] = score[pool[p]];
 }
 
+// ------------------------------------------------------------------------------- pool sort
+// The train-positive pool sorted by score (ties by pool position), once per step; the choose kernels
+// then find every target's o nearest positives by binary search instead of scanning the pool
+// (reference: one torch.sort over all P pool distances per positive target, src/layers.py:685-690).
+__device__ __forceinline__ uint32_t orderable(float f) {   // float order -> unsigned order
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// P <= 8192: one CTA, bitonic sort of (orderable(score) << 32 | position) in shared memory.
+__global__ void __launch_bounds__(1024) k_sort_pool_small(const float* __restrict__ pool_score,
+                                                          const int32_t* __restrict__ pool, int P, int n2,
+                                                          float* __restrict__ ps_score, int32_t* __restrict__ ps_pos,
+                                                          int32_t* __restrict__ ps_id) {
+    extern __shared__ unsigned long long keys[];
+    for (int i = threadIdx.x; i < n2; i += blockDim.x)
+        keys[i] = i < P ? (((unsigned long long)orderable(pool_score[i]) << 32) | (unsigned)i) : ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= n2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long a = keys[i], b = keys[ixj];
+                    if ((a > b) == ((i & k) == 0)) { keys[i] = b; keys[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const int pos = (int)(keys[i] & 0xffffffffull);
+        ps_score[i] = pool_score[pos];
+        ps_pos[i] = pos;
+        ps_id[i] = pool[pos];
+    }
+}
+
+__global__ void k_sort_prepare(const float* __restrict__ pool_score, int P, uint32_t* __restrict__ keys,
+                               int32_t* __restrict__ vals) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P) { keys[i] = orderable(pool_score[i]); vals[i] = i; }
+}
+
+__global__ void k_sort_finish(const float* __restrict__ pool_score, const int32_t* __restrict__ pool,
+                              const int32_t* __restrict__ order, int P, float* __restrict__ ps_score,
+                              int32_t* __restrict__ ps_pos, int32_t* __restrict__ ps_id) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P) { const int pos = order[i]; ps_score[i] = pool_score[pos]; ps_pos[i] = pos; ps_id[i] = pool[pos]; }
+}
+
+#define PCG_SORT_SMALL_MAX 8192
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static size_t cub_sort_temp_bytes(int P) {
+    size_t temp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, temp, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                    (const int32_t*)nullptr, (int32_t*)nullptr, P);
+    return temp;
+}
+
+extern "C" size_t pcg_sort_pool_workspace_bytes(int P) {
+    // [gathered pool scores][keys in/out][vals in/out][cub temp]; the last three only for big pools
+    size_t o = align256((size_t)(P > 0 ? P : 1) * 4);
+    if (P > PCG_SORT_SMALL_MAX) o += 4 * align256((size_t)P * 4) + align256(cub_sort_temp_bytes(P));
+    return o;
+}
+
+static int sort_pool_impl(const float* pool_score, const int32_t* pool, int P, float* ps_score, int32_t* ps_pos,
+                          int32_t* ps_id, char* ws, size_t ws_bytes, cudaStream_t stream) {
+    if (P <= 0) return 0;
+    if (P <= PCG_SORT_SMALL_MAX) {
+        int n2 = 32;
+        while (n2 < P) n2 <<= 1;
+        const size_t smem = (size_t)n2 * 8;
+        static bool configured = false;
+        if (!configured) {
+            cudaError_t e = cudaFuncSetAttribute(k_sort_pool_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 PCG_SORT_SMALL_MAX * 8);
+            if (e != cudaSuccess) { pcg_set_error("pcg_sort_pool: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+            configured = true;
+        }
+        k_sort_pool_small<<<1, 1024, smem, stream>>>(pool_score, pool, P, n2, ps_score, ps_pos, ps_id);
+        return 0;
+    }
+    const size_t a = align256((size_t)P * 4);
+    size_t temp = cub_sort_temp_bytes(P);
+    PCG_REQUIRE(ws && ws_bytes >= 4 * a + align256(temp), "pcg_sort_pool: workspace too small");
+    uint32_t* k_in = (uint32_t*)ws;
+    uint32_t* k_out = (uint32_t*)(ws + a);
+    int32_t* v_in = (int32_t*)(ws + 2 * a);
+    int32_t* v_out = (int32_t*)(ws + 3 * a);
+    void* d_temp = ws + 4 * a;
+    k_sort_prepare<<<(P + 255) / 256, 256, 0, stream>>>(pool_score, P, k_in, v_in);
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(d_temp, temp, k_in, k_out, v_in, v_out, P, 0, 32, stream);
+    if (e != cudaSuccess) { pcg_set_error("pcg_sort_pool: cub: %s", cudaGetErrorString(e)); return (int)e; }
+    k_sort_finish<<<(P + 255) / 256, 256, 0, stream>>>(pool_score, pool, v_out, P, ps_score, ps_pos, ps_id);
+    return 0;
+}
+
+extern "C" int pcg_sort_pool(const float* pool_score, const int32_t* pool, int P, float* ps_score, int32_t* ps_pos,
+                             int32_t* ps_id, void* workspace, size_t workspace_bytes, pcg_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (P <= 0) return 0;
+    PCG_REQUIRE(pool_score && pool && ps_score && ps_pos && ps_id, "pcg_sort_pool: null pointer");
+    size_t skip = align256((size_t)P * 4);   // the gathered-score slot of the shared layout is unused here
+    char* ws = workspace ? (char*)workspace + skip : nullptr;
+    int rc = sort_pool_impl(pool_score, pool, P, ps_score, ps_pos, ps_id, ws,
+                            workspace_bytes > skip ? workspace_bytes - skip : 0, stream);
+    if (rc) return rc;
+    return pcg_check_launch("pcg_sort_pool");
+}
+
 extern "C" int pcg_score_table(const float* feat, int64_t n_nodes, int F, int64_t ldf, const float* w, const float* b,
-                               float* score, const int32_t* pool, int P, float* pool_score, pcg_stream_t stream_) {
+                               float* score, const int32_t* pool, int P, float* ps_score, int32_t* ps_pos,
+                               int32_t* ps_id, void* workspace, size_t workspace_bytes, pcg_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     PCG_REQUIRE(feat && w && score, "pcg_score_table: null pointer");
     PCG_REQUIRE(ldf % 4 == 0 && F <= ldf && F > 0, "pcg_score_table: need F <= ldf, ldf %% 4 == 0 (F=%d ldf=%lld)", F,
@@ -79,7 +196,16 @@ extern "C" int pcg_score_table(const float* feat, int64_t n_nodes, int F, int64_
         if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;
         k_score_table<<<(int)blocks, 256, (size_t)ldf * 4, stream>>>(feat, n_nodes, F, ldf, w, b, score);
     }
-    if (P > 0 && pool && pool_score) k_gather_pool<<<(P + 255) / 256, 256, 0, stream>>>(score, pool, P, pool_score);
+    if (P > 0 && pool) {
+        PCG_REQUIRE(ps_score && ps_pos && ps_id, "pcg_score_table: sorted pool outputs missing");
+        const size_t skip = align256((size_t)P * 4);
+        PCG_REQUIRE(workspace && workspace_bytes >= skip, "pcg_score_table: workspace too small");
+        float* gathered = (float*)workspace;
+        k_gather_pool<<<(P + 255) / 256, 256, 0, stream>>>(score, pool, P, gathered);
+        int rc = sort_pool_impl(gathered, pool, P, ps_score, ps_pos, ps_id, (char*)workspace + skip,
+                                workspace_bytes - skip, stream);
+        if (rc) return rc;
+    }
     return pcg_check_launch("pcg_score_table");
 }
 

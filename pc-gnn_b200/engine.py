@@ -72,7 +72,7 @@ class Engine:
         self.F = self.ldf = 0
         self.score = None           # [N]
         self.pool = None            # int32 [P]
-        self.pool_score = None
+        self.sorted_pool = None     # (ps_score, ps_pos, ps_id, workspace)
         self.P = 0
         self._pin = None
         self._ws = None
@@ -105,19 +105,45 @@ class Engine:
         arr = np.asarray(list(train_pos), dtype=np.int32)
         self.pool = torch.from_numpy(arr).to(self.device)
         self.P = int(arr.shape[0])
-        self.pool_score = torch.empty(max(self.P, 1), dtype=torch.float32, device=self.device)
+        self.sorted_pool = self._alloc_sorted_pool(self.P)
+
+    def _alloc_sorted_pool(self, P):
+        n = max(P, 1)
+        dev = self.device
+        ws = torch.empty(int(self.lib.pcg_sort_pool_workspace_bytes(P)), dtype=torch.uint8, device=dev)
+        return (torch.empty(n, dtype=torch.float32, device=dev), torch.empty(n, dtype=torch.int32, device=dev),
+                torch.empty(n, dtype=torch.int32, device=dev), ws)
+
+    def sort_pool(self, pool, pool_score):
+        """Score-sorted view of an explicit pool (``pcg_sort_pool``): (ps_score, ps_pos, ps_id)."""
+        P = int(pool.shape[0])
+        ps, pp, pi, ws = self._alloc_sorted_pool(P)
+        rc = self.lib.pcg_sort_pool(pool_score.data_ptr(), pool.data_ptr(), P, ps.data_ptr(), pp.data_ptr(),
+                                    pi.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr())
+        _lib.check(rc, "pcg_sort_pool")
+        return ps, pp, pi
 
     def score_table(self, clf_weight: torch.Tensor, clf_bias: torch.Tensor):
-        """score[v] = <feat[v], clf_weight[0]> + clf_bias[0] for all nodes, and the pool's scores."""
+        """score[v] = <feat[v], clf_weight[0]> + clf_bias[0] for all nodes, then the pool sorted by it."""
         w = clf_weight.detach()
         b = clf_bias.detach()
         if not w.is_contiguous():
             w = w.contiguous()
+        ps, pp, pi, ws = self.sorted_pool if self.pool is not None else (None, None, None, None)
         rc = self.lib.pcg_score_table(self.feat.data_ptr(), self.N, self.F, self.ldf, w.data_ptr(), b.data_ptr(),
-                                      self.score.data_ptr(), _lib.ptr(self.pool), self.P,
-                                      _lib.ptr(self.pool_score), _lib.stream_ptr())
+                                      self.score.data_ptr(), _lib.ptr(self.pool), self.P, _lib.ptr(ps), _lib.ptr(pp),
+                                      _lib.ptr(pi), _lib.ptr(ws), 0 if ws is None else ws.numel(), _lib.stream_ptr())
         _lib.check(rc, "pcg_score_table")
-        return self.score, self.pool_score
+        return self.score
+
+    def resort_pool(self):
+        """Re-sort the resident pool after ``self.score`` was written by someone else (tests inject a table)."""
+        if self.P:
+            ps, pp, pi, ws = self.sorted_pool
+            gathered = self.score[self.pool.long()].contiguous()
+            rc = self.lib.pcg_sort_pool(gathered.data_ptr(), self.pool.data_ptr(), self.P, ps.data_ptr(), pp.data_ptr(),
+                                        pi.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr())
+            _lib.check(rc, "pcg_sort_pool")
 
     # ------------------------------------------------------------------ per-step inputs
     def upload_targets(self, nodes):
@@ -187,7 +213,7 @@ class Engine:
         return s
 
     def choose(self, targets, labels, train: bool, thresh, rho: float, cap_slots: int, *,
-               entry_score=None, center_score=None, k_override=None, pool=None, pool_score=None,
+               entry_score=None, center_score=None, k_override=None, sorted_pool=None,
                indptr=None, indices=None, n_nodes=None, n_rel=None, max_degree=None,
                want_dist: bool = False):
         """Top-k filter + oversample for every (relation, target) item (``pcg_choose``).
@@ -204,9 +230,10 @@ class Engine:
             self._ws = torch.empty(int(ws_bytes), dtype=torch.uint8, device=self.device)
         th = (C.c_double * R)(*[float(x) for x in thresh])
         use_table = entry_score is None
-        pool = self.pool if pool is None else pool
-        pool_score = self.pool_score if pool_score is None else pool_score
-        P = 0 if pool is None else int(pool.shape[0])
+        if sorted_pool is None and self.sorted_pool is not None and use_table:
+            sorted_pool = self.sorted_pool[:3]
+        ps, pp, pi = sorted_pool if sorted_pool is not None else (None, None, None)
+        P = (self.P if use_table else int(ps.shape[0])) if ps is not None else 0
         dist = torch.empty(cap_slots * _lib.SLOT, dtype=torch.float32, device=self.device) if want_dist else None
         rc = self.lib.pcg_choose(
             (self.indptr if indptr is None else indptr).data_ptr(),
@@ -214,7 +241,7 @@ class Engine:
             self.N if n_nodes is None else n_nodes, R,
             self.score.data_ptr() if use_table else None, _lib.ptr(entry_score), _lib.ptr(center_score),
             targets.data_ptr(), _lib.ptr(labels) if train else None, B, th, _lib.ptr(k_override), float(rho),
-            _lib.ptr(pool), _lib.ptr(pool_score), P, int(bool(train)), maxdeg, s.idx.data_ptr(), _lib.ptr(dist),
+            _lib.ptr(ps), _lib.ptr(pp), _lib.ptr(pi), P, int(bool(train)), maxdeg, s.idx.data_ptr(), _lib.ptr(dist),
             cap_slots, s.slot_item.data_ptr(), s.it_slot0.data_ptr(), s.it_m.data_ptr(), s.it_base.data_ptr(),
             s.it_done.data_ptr(), self._ws.data_ptr(), int(ws_bytes), s.status.data_ptr(), _lib.stream_ptr())
         _lib.check(rc, "pcg_choose")

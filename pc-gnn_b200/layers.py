@@ -162,19 +162,20 @@ def _choose_explicit(eng, center_scores, center_labels, neigh_scores, neighs_lis
     center = torch.as_tensor(center_scores).detach().to(dev, torch.float32).reshape(-1, 2)[:, 0].contiguous()
     k_list = np.asarray([int(k) for k in sample_list], dtype=np.int64)
     k_over = torch.from_numpy(k_list.astype(np.int32)).to(dev)
-    pool = pool_score = None
+    sorted_pool = None
     P = 0
     if train and minor_list is not None and len(minor_list):
         pool = torch.as_tensor(np.asarray([int(p) for p in minor_list], dtype=np.int32)).to(dev)
         pool_score = torch.as_tensor(minor_scores).detach().to(dev, torch.float32).reshape(-1, 2)[:, 0].contiguous()
         P = int(pool.shape[0])
+        sorted_pool = eng.sort_pool(pool, pool_score)
     kk = np.where(lens > k_list + 1, k_list, lens)
     oo = np.minimum((k_list * float(sample_rate)).astype(np.int64), P) if train else np.zeros_like(kk)
     cap = int(((kk + oo + _lib.SLOT - 1) // _lib.SLOT).sum()) + 1
     targets = torch.arange(B, dtype=torch.int32, device=dev)
     labels = _as_device_labels(center_labels, dev) if train else None
     sel, dist = eng.choose(targets, labels, train, [0.5], float(sample_rate), cap, entry_score=entry_score,
-                           center_score=center, k_override=k_over, pool=pool, pool_score=pool_score,
+                           center_score=center, k_override=k_over, sorted_pool=sorted_pool,
                            indptr=indptr, indices=indices, n_nodes=B, n_rel=1,
                            max_degree=int(lens.max()) if B else 0, want_dist=True)
     return sel, dist, (lens, k_list, oo)
@@ -289,8 +290,7 @@ class InterAgg(nn.Module):
         # label-aware scores for every node (column 0 only) + the pool's: layers.py:231-237
         if self.score_override is not None:
             eng.score.copy_(self.score_override)
-            if eng.P:
-                eng.pool_score[:eng.P] = eng.score[eng.pool.long()]
+            eng.resort_pool()
         else:
             eng.score_table(self.label_clf.weight, self.label_clf.bias)
         idx = targets.long()

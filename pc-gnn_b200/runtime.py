@@ -1,0 +1,104 @@
+"""CUDA-graph training step: the whole step (score table, pool sort, choose, aggregate, relation
+transforms, combine, head, both losses, backward, Adam) captured once and replayed per batch.
+
+The reference's trainer (/root/reference/src/model_handler.py:128-156) rebuilds Python lists and
+launches ~70 small library kernels per batch; once the hot path is a handful of kernels the step is
+launch-bound, so the launches are recorded into a graph and only the batch's ids/labels are copied
+into static device buffers before each replay. Per-batch sizes that depend on the data (how many
+neighbours survive the filter) stay on the device: the kernels write counts into a status block and
+work inside a fixed-capacity slot buffer sized from the epoch's batches (``plan``).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+__all__ = ["GraphedTrainStep"]
+
+
+class GraphedTrainStep:
+    """model: pcgnn_b200.model.PCALayer (or any module with .loss(nodes, labels) whose hot path is an
+    InterAgg at ``model.inter1``); optimizer must be capturable (e.g. Adam(capturable=True))."""
+
+    def __init__(self, model, optimizer, batch_size: int, cap_slots: int, reducer=None, world: int = 1,
+                 warmup_batch=None):
+        self.model, self.opt, self.B = model, optimizer, int(batch_size)
+        self.reducer, self.world = reducer, world
+        inter = model.inter1
+        dev = inter.weight.device
+        self.dev = dev
+        inter.cap_slots_hint = int(cap_slots)
+        self.cap_slots = int(cap_slots)
+        self.nodes = torch.zeros(self.B, dtype=torch.int32, device=dev)
+        self.labels = torch.zeros(self.B, dtype=torch.int64, device=dev)
+        self.pin_nodes = torch.zeros(self.B, dtype=torch.int32, pin_memory=True)
+        self.pin_labels = torch.zeros(self.B, dtype=torch.int64, pin_memory=True)
+        self.loss = None
+        if warmup_batch is not None:
+            self.nodes.copy_(torch.as_tensor(np.asarray(warmup_batch[0], dtype=np.int32)))
+            self.labels.copy_(torch.as_tensor(np.asarray(warmup_batch[1], dtype=np.int64)))
+        self._capture()
+
+    # -- one eager step on the static buffers (also what gets captured) -------------------------
+    def _fwd_bwd(self):
+        if self.reducer is not None:
+            self.reducer.zero()
+        else:
+            self.opt.zero_grad(set_to_none=False)
+        loss = self.model.loss(self.nodes, self.labels)
+        loss.backward()
+        return loss.detach()
+
+    def _capture(self):
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):       # warm-up on a side stream (allocator, lazy inits, cuBLAS handles)
+            for _ in range(3):
+                if self.reducer is None:
+                    for p in self.model.parameters():
+                        if p.requires_grad and p.grad is None:
+                            p.grad = torch.zeros_like(p)
+                self._fwd_bwd()
+                # no optimizer step during warm-up: parameters stay as the caller initialised them
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        self.g_fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_fb):
+            self.loss = self._fwd_bwd()
+        self.g_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_opt):
+            self.opt.step()
+
+    def _replay(self):
+        self.g_fb.replay()
+        if self.world > 1 and self.reducer is not None:
+            self.reducer()                       # one NCCL all-reduce of the flat gradient
+            self.reducer.flat.div_(self.world)
+        self.g_opt.replay()
+        return self.loss
+
+    # -- public --------------------------------------------------------------------------------
+    def run_device(self, nodes_dev: torch.Tensor, labels_dev: torch.Tensor):
+        """Batch already in HBM (int32 ids, int64 labels). Returns the (device) loss tensor."""
+        self.nodes.copy_(nodes_dev, non_blocking=True)
+        self.labels.copy_(labels_dev, non_blocking=True)
+        return self._replay()
+
+    def run(self, nodes, labels):
+        """Batch on the host (list / numpy of ids, numpy labels): pinned staging + H2D + replay."""
+        self.pin_nodes.numpy()[:] = np.asarray(nodes, dtype=np.int32)
+        self.pin_labels.numpy()[:] = np.asarray(labels, dtype=np.int64)
+        self.nodes.copy_(self.pin_nodes, non_blocking=True)
+        self.labels.copy_(self.pin_labels, non_blocking=True)
+        return self._replay()
+
+    def overflowed(self) -> bool:
+        """True if some replay needed more slots than the captured capacity (results then incomplete:
+        re-plan with a larger capacity). Syncs."""
+        sel = self.model.inter1.last_selection
+        return bool(sel is not None and sel.overflowed())
+
+    @staticmethod
+    def plan(engine, batches, thresholds, rho) -> int:
+        """Slot capacity covering every batch of an epoch plan (host arithmetic on CSR offsets)."""
+        return max(engine.slots_bound(np.asarray(n, dtype=np.int32), thresholds, rho, True) for n in batches)

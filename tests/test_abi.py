@@ -38,7 +38,7 @@ def test_binding_table_matches_header():
     assert sorted(_lib.SIGNATURES) == declared()
     src = open(HEADER).read()
     for name, (_, args) in _lib.SIGNATURES.items():
-        m = re.search(r"\b" + name + r"\s*\(([^;]*?)\)\s*;", src, re.S)
+        m = re.search(r"PCG_API\s+[\w\s\*]+?\b" + name + r"\s*\(([^;]*?)\)\s*;", src, re.S)
         assert m, name
         params = m.group(1).strip()
         n = 0 if params in ("void", "") else len(params.split(","))

@@ -18,8 +18,7 @@ def run_choose(graph, feat, score, nodes, labels, pool, train, rho=0.5, thresh=N
     eng.set_features(torch.from_numpy(np.ascontiguousarray(feat)).cuda())
     eng.set_pool(pool)
     eng.score.copy_(torch.from_numpy(np.ascontiguousarray(score)).cuda())
-    if eng.P:
-        eng.pool_score[:eng.P] = eng.score[eng.pool.long()]
+    eng.resort_pool()
     thresh = thresh or [0.5] * graph.n_rel
     targets, host = eng.upload_targets(list(nodes))
     cap = eng.slots_bound(host, thresh, rho, train)
@@ -146,7 +145,7 @@ def test_capacity_overflow_is_flagged_not_silent():
     eng.set_features(torch.from_numpy(d.feat).cuda())
     eng.set_pool(sorted(d.train_pos))
     eng.score.zero_()
-    eng.pool_score.zero_()
+    eng.resort_pool()
     targets, host = eng.upload_targets(d.idx_train[:64])
     lab = torch.from_numpy(d.labels[d.idx_train[:64]]).cuda()
     sel = eng.choose(targets, lab, True, [0.5] * 3, 0.5, 3)          # far too few slots
