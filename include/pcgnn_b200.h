@@ -66,6 +66,9 @@ PCG_API size_t pcg_sort_pool_workspace_bytes(int P);
 PCG_API int pcg_sort_pool(const float* pool_score, const int32_t* pool, int P, float* ps_score, int32_t* ps_pos,
                   int32_t* ps_id, void* workspace, size_t workspace_bytes, pcg_stream_t stream);
 
+/* pool_pos_of[v] = position of node v in `pool`, -1 for every other node (once per pool; pool ids distinct). */
+PCG_API int pcg_pool_positions(const int32_t* pool, int P, int64_t n_nodes, int32_t* pool_pos_of, pcg_stream_t stream);
+
 /* Bytes of scratch pcg_choose needs for B targets x R relations on a graph whose largest row has
  * max_degree entries. */
 PCG_API size_t pcg_choose_workspace_bytes(int B, int R, int64_t max_degree);
@@ -85,6 +88,8 @@ PCG_API size_t pcg_choose_workspace_bytes(int B, int R, int64_t max_degree);
  *   thresh_host  HOST array of R doubles (src/layers.py:193 hard-codes 0.5)
  *   k_override   int32 [R*B] explicit num_sample per item (src/layers.py:260-262) or NULL
  *   ps_score/ps_pos/ps_id  the score-sorted pool from pcg_score_table / pcg_sort_pool (P entries)
+ *   pool_pos_of  int32 [N] from pcg_pool_positions (node id -> pool position, -1 otherwise), or NULL: the
+ *                kernels then test "already kept" by binary search in the row instead of a bitmap
  * Outputs
  *   sel_idx      int32 [cap_slots * PCG_SLOT]; item w's ids are sel_idx[it_base[w] .. + it_m[w])
  *   sel_dist     optional fp32 [cap_slots * PCG_SLOT] (NULL to skip): the distances the reference returns as
@@ -98,7 +103,8 @@ PCG_API size_t pcg_choose_workspace_bytes(int B, int R, int64_t max_degree);
 PCG_API int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t n_nodes, int R, const float* score,
                const float* entry_score, const float* center_score, const int32_t* targets,
                const int64_t* labels, int B, const double* thresh_host, const int32_t* k_override, double rho,
-               const float* ps_score, const int32_t* ps_pos, const int32_t* ps_id, int P, int train, int64_t max_degree,
+               const float* ps_score, const int32_t* ps_pos, const int32_t* ps_id, const int32_t* pool_pos_of, int P,
+               int train, int64_t max_degree,
                int32_t* sel_idx, float* sel_dist, int64_t cap_slots, int32_t* slot_item, int32_t* it_slot0,
                int32_t* it_m, int64_t* it_base, int32_t* it_done, void* workspace, size_t workspace_bytes, int32_t* status,
                pcg_stream_t stream);

@@ -3,21 +3,29 @@
 // Replaces the per-target Python loop of /root/reference/src/layers.py:633-738 (one torch.sort and
 // two .tolist() host syncs per target per relation) by an exact k-smallest selection on the key
 // (|s_v - s_u| as fp32 bits, position in the id-sorted row):
-//   1. radix-select (4 x 8-bit passes over the distance bits, shared-memory histogram) finds the
-//      k-th smallest distance T and how many elements equal to T are still needed,
+//   1. the row's distances go to shared memory; rows of <= 128 entries get their exact ranks by
+//      counting (no atomics, no passes), longer rows by a radix-select (8-bit passes over the
+//      distance bits, skipping the digits all keys share) that yields the k-th smallest distance T
+//      and how many elements equal to T are still needed,
 //   2. an ORDERED compaction writes every element with d < T plus the first `need` elements with
 //      d == T (row order == id order, which is the reference's stable-sort tie rule),
-//   3. for positive targets the same selection runs over the train-positive pool, and pool ids that
-//      are already kept (binary search in the row + a kept-bitmask) are dropped: the union of
-//      src/layers.py:690-694.
+//   3. for positive targets the o nearest train positives come from the score-sorted pool
+//      (pcg_sort_pool): around lower_bound(s_v) the distances grow monotonically to both sides, so
+//      the o-th smallest distance is a k-th-of-two-sorted-sequences search done with warp-wide
+//      32-ary probes; pool members that are already kept (a per-item bitmap over pool positions,
+//      filled during the compaction) are dropped: the set union of src/layers.py:690-694.
 // Rows up to PCG_SMALL_MAX entries are handled one per warp, longer rows one per CTA; both kernels
-// are persistent and pull items from queues filled by a classification kernel.
+// are persistent, pull items from queues filled by a classification kernel and run concurrently on
+// two streams.
 #include "pcg_common.cuh"
 
 #define PCG_SMALL_MAX 512      // entries a warp keeps in its shared-memory slice
+#define PCG_RANK_MAX 128       // rows up to this length are ranked by counting
 #define PCG_WARPS_PER_CTA 8    // warp kernel: 8 items in flight per CTA
 #define PCG_LARGE_NT 512       // CTA kernel threads
 #define PCG_LARGE_CAP_MAX 32768
+#define PCG_KB_WORDS_WARP 256  // kept-pool bitmap words per warp  (pools up to 8192 positives)
+#define PCG_KB_WORDS_CTA 2048  // ... per CTA                      (pools up to 65536 positives)
 
 struct ChooseP {
     const int64_t* indptr;
@@ -31,6 +39,7 @@ struct ChooseP {
     const float* ps_score;      // pool scores ascending (ties by pool position)
     const int32_t* ps_pos;      // pool position of each sorted entry
     const int32_t* ps_id;       // node id of each sorted entry
+    const int32_t* pool_pos_of; // [N] node id -> pool position or -1 (NULL: binary-search fallback)
     int64_t n_nodes;
     int R, B, P, train;
     double thresh[PCG_MAX_REL];
@@ -57,7 +66,7 @@ __device__ __forceinline__ void grp_sync() {
 }
 
 // Exclusive prefix counts of two flags over the NT threads of the group (tile order == thread
-// order), plus the totals. xw: >= 2*(NT/32) ints of group-private shared memory.
+// order), plus the totals. xw: >= NT/32 ints of group-private shared memory.
 template <int NT>
 __device__ __forceinline__ void grp_excl2(bool fa, bool fb, int tid, int* xw, int& ea, int& eb, int& ta, int& tb) {
     const unsigned lt = lanemask_lt();
@@ -69,22 +78,48 @@ __device__ __forceinline__ void grp_excl2(bool fa, bool fb, int tid, int* xw, in
         tb = __popc(mb);
     } else {
         constexpr int NW = NT / 32;
-        const int wid = tid >> 5;
-        if ((tid & 31) == 0) xw[wid] = __popc(ma) | (__popc(mb) << 16);
+        const int wid = tid >> 5, lane = tid & 31;
+        if (lane == 0) xw[wid] = __popc(ma) | (__popc(mb) << 16);
         __syncthreads();
-        int sa = 0, sb = 0;
-        ta = tb = 0;
+        // every warp scans the NW packed counts with shuffles (NW <= 32)
+        int pk = lane < NW ? xw[lane] : 0;
+        int incl = pk;
 #pragma unroll
-        for (int q = 0; q < NW; ++q) {
-            int pk = xw[q];
-            int ca = pk & 0xffff, cb = pk >> 16;
-            if (q < wid) { sa += ca; sb += cb; }
-            ta += ca; tb += cb;
+        for (int off = 1; off < NW; off <<= 1) {
+            int t = __shfl_up_sync(PCG_FULL, incl, off);
+            if (lane >= off) incl += t;
         }
-        ea += sa;
-        eb += sb;
+        const int tot = __shfl_sync(PCG_FULL, incl, NW - 1);
+        const int mine = __shfl_sync(PCG_FULL, incl - pk, wid);
+        ea += mine & 0xffff;
+        eb += mine >> 16;
+        ta = tot & 0xffff;
+        tb = tot >> 16;
         __syncthreads();
     }
+}
+
+// Group-wide min and max of get(0..n-1). xw[24..27] used as scratch for NT > 32.
+template <int NT, class Get>
+__device__ __forceinline__ void grp_minmax(Get get, int n, int tid, int* xw, uint32_t& kmin, uint32_t& kmax) {
+    uint32_t lo = 0xffffffffu, hi = 0u;
+    for (int j = tid; j < n; j += NT) { const uint32_t x = get(j); lo = min(lo, x); hi = max(hi, x); }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        lo = min(lo, __shfl_xor_sync(PCG_FULL, lo, off));
+        hi = max(hi, __shfl_xor_sync(PCG_FULL, hi, off));
+    }
+    if (NT > 32) {
+        if (tid == 0) { xw[24] = (int)0xffffffffu; xw[25] = 0; }
+        __syncthreads();
+        if ((tid & 31) == 0) { atomicMin((uint32_t*)&xw[24], lo); atomicMax((uint32_t*)&xw[25], hi); }
+        __syncthreads();
+        lo = (uint32_t)xw[24];
+        hi = (uint32_t)xw[25];
+        __syncthreads();
+    }
+    kmin = lo;
+    kmax = hi;
 }
 
 // k-th smallest (kth is 1-based) of get(0..n-1) as (T, need): T = that value, need = how many of
@@ -92,13 +127,19 @@ __device__ __forceinline__ void grp_excl2(bool fa, bool fb, int tid, int* xw, in
 template <int NT, class Get>
 __device__ __forceinline__ void radix_select(Get get, int n, int kth, uint32_t* hist, int* xw, int tid, uint32_t& T,
                                              int& need) {
-    uint32_t prefix = 0, mask = 0;
+    // digits shared by every key need no pass: start at the first 8-bit digit where min and max differ
+    uint32_t kmin, kmax;
+    grp_minmax<NT>(get, n, tid, xw, kmin, kmax);
+    if (kmin == kmax) { T = kmin; need = kth; return; }
+    const int top = (31 - __clz(kmin ^ kmax)) >> 3;          // index of the highest differing byte
+    uint32_t mask = top == 3 ? 0u : (0xffffffffu << ((top + 1) * 8));
+    uint32_t prefix = kmin & mask;
     int remaining = kth;
-    for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int shift = top * 8; shift >= 0; shift -= 8) {
         for (int b = tid; b < 256; b += NT) hist[b] = 0;
         grp_sync<NT>();
-        // Distance bits share their top digits, so a plain per-lane atomicAdd serialises up to 32-way
-        // on one bin. Peel the (up to 3) most common digits of each warp with ballots first.
+        // Distance bits share their leading digits, so a plain per-lane atomicAdd serialises up to
+        // 32-way on one bin. Peel the (up to 3) most common digits of each warp with ballots first.
         const int n_up = (n + 31) & ~31;
         for (int j = tid; j < n_up; j += NT) {
             const bool valid = j < n;
@@ -148,13 +189,35 @@ __device__ __forceinline__ void radix_select(Get get, int n, int kth, uint32_t* 
     need = remaining;
 }
 
+// First index in [lo, hi) where pred turns false (pred is true on a prefix), found with warp-wide
+// 32-ary probes: ceil(log32(range)) rounds of one predicate evaluation per lane. Every warp of the
+// group runs it redundantly (same addresses -> broadcast loads), so no block barrier is needed.
+template <class Pred>
+__device__ __forceinline__ int warp_partition_point(int lo, int hi, Pred pred) {
+    const int lane = threadIdx.x & 31;
+    while (hi > lo) {
+        const int span = hi - lo;
+        const int step = (span + 31) >> 5;
+        const int idx = lo + lane * step;
+        const bool t = idx < hi ? pred(idx) : false;
+        const int cnt = __popc(__ballot_sync(PCG_FULL, t));
+        if (cnt == 0) return lo;
+        const int nlo = lo + (cnt - 1) * step + 1;
+        hi = min(hi, lo + cnt * step);
+        lo = nlo;
+    }
+    return lo;
+}
+
 // One item (target i, relation r) handled by a group of NT threads.
-//   sd/sd_cap   group-private shared distance cache (uint32), bits_s/bits_cap_words kept-bitmask
-//   bits_g      global bitmask slab for rows that exceed the shared one (may be null if never needed)
+//   sd/sd_cap   group-private shared distance cache (uint32)
+//   kbits       group-private bitmap over pool positions (kb_words words): kept neighbours that are
+//               pool members; bits_s / bits_g: kept-position bitmask for the fallback membership test
 //   xw          group-private int[32] scratch
 template <int NT>
 __device__ void choose_item(const ChooseP& p, int w, int tid, uint32_t* sd, int sd_cap, uint32_t* hist,
-                            uint32_t* bits_s, int bits_cap_words, uint32_t* bits_g, int* xw) {
+                            uint32_t* kbits, int kb_words, uint32_t* bits_s, int bits_cap_words, uint32_t* bits_g,
+                            int* xw) {
     const int r = w / p.B, i = w - r * p.B;
     const int32_t v = p.targets[i];
     const int64_t row = (int64_t)r * p.n_nodes + v;
@@ -165,7 +228,11 @@ __device__ void choose_item(const ChooseP& p, int w, int tid, uint32_t* sd, int 
     int k, o;
     item_counts(d, p.thresh[r], p.rho, positive, p.P, p.k_override ? p.k_override[w] : 0, p.k_override != nullptr, k, o);
     const int nslots = (k + o + PCG_SLOT - 1) / PCG_SLOT;
+    const int wid = tid >> 5, lane = tid & 31;
+    const bool use_kb = o > 0 && p.pool_pos_of != nullptr && p.P <= kb_words * 32;
     if (tid == 0) xw[29] = atomicAdd(&p.status[ST_SLOTS], nslots);
+    if (use_kb)
+        for (int q = tid; q < (p.P + 31) >> 5; q += NT) kbits[q] = 0u;
     grp_sync<NT>();
     const int slot0 = xw[29];
     if ((int64_t)slot0 + nslots > p.cap_slots) {   // caller's buffer too small: flag, emit nothing
@@ -182,6 +249,7 @@ __device__ void choose_item(const ChooseP& p, int w, int tid, uint32_t* sd, int 
     const int32_t* __restrict__ nbr = p.indices + beg;
     const float* __restrict__ escore = p.entry_score ? p.entry_score + beg : nullptr;
     const float* __restrict__ score = p.score;
+    const int32_t* __restrict__ ppo = p.pool_pos_of;
     const bool cached = d <= sd_cap;
     if (cached) {
         for (int j = tid; j < d; j += NT) sd[j] = dist_bits(sv, escore ? escore[j] : __ldg(score + nbr[j]));
@@ -190,76 +258,132 @@ __device__ void choose_item(const ChooseP& p, int w, int tid, uint32_t* sd, int 
     auto get = [&](int j) -> uint32_t {
         return cached ? sd[j] : dist_bits(sv, escore ? escore[j] : __ldg(score + nbr[j]));
     };
-    uint32_t T = 0xffffffffu;
-    int need = 0x7fffffff;
-    if (k < d) {
-        if (k > 0) radix_select<NT>(get, d, k, hist, xw, tid, T, need);
-        else { T = 0; need = 0; }
-    }
     uint32_t* bits = (d <= bits_cap_words * 32) ? bits_s : bits_g;
-    const int wid = tid >> 5, lane = tid & 31;
-    // ---- ordered compaction of the kept neighbours (row order) ----
-    int run_less = 0, run_tie = 0;
-    for (int base = 0; base < d; base += NT) {
-        const int j = base + tid;
-        const bool valid = j < d;
-        const uint32_t key = valid ? get(j) : 0xffffffffu;
-        const bool less = valid && key < T;
-        const bool tie = valid && key == T;
-        int el, et, tl, tt;
-        grp_excl2<NT>(less, tie, tid, xw, el, et, tl, tt);
-        const int tie_before = run_tie + et;
-        const bool sel = less || (tie && tie_before < need);
-        if (sel) {
-            const int64_t at = off + run_less + el + min(tie_before, need);
-            p.sel_idx[at] = nbr[j];
-            if (p.sel_dist) p.sel_dist[at] = __uint_as_float(key);
+    const bool want_bits = o > 0 && !use_kb;
+    // what to do with a kept neighbour at row position j
+    auto keep = [&](int j, int64_t at, uint32_t key) {
+        const int32_t id = nbr[j];
+        p.sel_idx[at] = id;
+        if (p.sel_dist) p.sel_dist[at] = __uint_as_float(key);
+        if (use_kb) {
+            const int pp = __ldg(ppo + id);
+            if (pp >= 0) atomicOr(&kbits[pp >> 5], 1u << (pp & 31));
         }
-        const unsigned sm = __ballot_sync(PCG_FULL, sel);
-        if (lane == 0 && o > 0) bits[(base >> 5) + wid] = sm;
-        run_less += tl;
-        run_tie += tt;
+    };
+
+    if (NT == 32 && k < d && d <= PCG_RANK_MAX) {
+        // ---- short row: exact rank of every element by counting (keys (distance, position) are unique) ----
+        constexpr int EPL = PCG_RANK_MAX / 32;
+        uint32_t mykey[EPL];
+        int rank[EPL];
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) { const int j = lane + 32 * e; mykey[e] = j < d ? sd[j] : 0xffffffffu; rank[e] = 0; }
+        for (int q = 0; q < d; ++q) {
+            const uint32_t x = sd[q];
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) rank[e] += (x < mykey[e]) || (x == mykey[e] && q < lane + 32 * e);
+        }
+        int n_out = 0;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+            const int j = lane + 32 * e;
+            if (32 * e < d) {                        // warp-uniform
+                const bool sel = j < d && rank[e] < k;
+                const unsigned sm = __ballot_sync(PCG_FULL, sel);
+                if (sel) keep(j, off + n_out + __popc(sm & lanemask_lt()), mykey[e]);
+                if (want_bits && lane == 0) bits[e] = sm;
+                n_out += __popc(sm);
+            }
+        }
+    } else {
+        uint32_t T = 0xffffffffu;
+        int need = 0x7fffffff;
+        if (k < d) {
+            if (k > 0) radix_select<NT>(get, d, k, hist, xw, tid, T, need);
+            else { T = 0; need = 0; }
+        }
+        if (NT == 32) {
+            // ---- ordered compaction, one warp: tiles of 32 row positions ----
+            int run_less = 0, run_tie = 0;
+            for (int base = 0; base < d; base += 32) {
+                const int j = base + lane;
+                const bool valid = j < d;
+                const uint32_t key = valid ? get(j) : 0xffffffffu;
+                const bool less = valid && key < T;
+                const bool tie = valid && key == T;
+                const unsigned lt = lanemask_lt();
+                const unsigned ml = __ballot_sync(PCG_FULL, less), mt = __ballot_sync(PCG_FULL, tie);
+                const int tie_before = run_tie + __popc(mt & lt);
+                const bool sel = less || (tie && tie_before < need);
+                if (sel) keep(j, off + run_less + __popc(ml & lt) + min(tie_before, need), key);
+                if (want_bits) {
+                    const unsigned sm = __ballot_sync(PCG_FULL, sel);
+                    if (lane == 0) bits[base >> 5] = sm;
+                }
+                run_less += __popc(ml);
+                run_tie += __popc(mt);
+            }
+        } else {
+            // ---- ordered compaction, one CTA: every warp owns a contiguous chunk of the row; count,
+            // one scan of the per-warp counts, then each warp writes its chunk with ballots only ----
+            constexpr int NW = NT / 32;
+            const int chunk = (((d + NW - 1) / NW) + 31) & ~31;       // multiple of 32 positions per warp
+            const int cb = wid * chunk, ce = min(d, cb + chunk);
+            int cl = 0, ct = 0;
+            for (int base = cb; base < ce; base += 32) {
+                const int j = base + lane;
+                const uint32_t key = j < ce ? get(j) : 0xffffffffu;
+                cl += __popc(__ballot_sync(PCG_FULL, j < ce && key < T));
+                ct += __popc(__ballot_sync(PCG_FULL, j < ce && key == T));
+            }
+            if (lane == 0) { xw[wid] = cl; hist[wid] = (uint32_t)ct; }   // hist is free here
+            __syncthreads();
+            int run_less = 0, run_tie = 0;
+            for (int q = 0; q < wid; ++q) { run_less += xw[q]; run_tie += (int)hist[q]; }
+            __syncthreads();
+            for (int base = cb; base < ce; base += 32) {
+                const int j = base + lane;
+                const bool valid = j < ce;
+                const uint32_t key = valid ? get(j) : 0xffffffffu;
+                const bool less = valid && key < T;
+                const bool tie = valid && key == T;
+                const unsigned lt = lanemask_lt();
+                const unsigned ml = __ballot_sync(PCG_FULL, less), mt = __ballot_sync(PCG_FULL, tie);
+                const int tie_before = run_tie + __popc(mt & lt);
+                const bool sel = less || (tie && tie_before < need);
+                if (sel) keep(j, off + run_less + __popc(ml & lt) + min(tie_before, need), key);
+                if (want_bits) {
+                    const unsigned sm = __ballot_sync(PCG_FULL, sel);
+                    if (lane == 0) bits[base >> 5] = sm;
+                }
+                run_less += __popc(ml);
+                run_tie += __popc(mt);
+            }
+        }
     }
+
     // ---- minority oversampling: nearest train positives not already kept ----
-    // The pool is sorted by score once per step (pcg_sort_pool). Around the split point c =
-    // lower_bound(sv) the distances grow monotonically to the left (A) and to the right (B), so the
-    // o-th smallest distance T is a "k-th of two sorted sequences" search, everything below T is two
-    // contiguous runs, and only the run of elements equal to T needs the position tie rule.
     int n_emit = 0;
     if (o > 0) {
         const float* __restrict__ S = p.ps_score;
         const int32_t* __restrict__ SP = p.ps_pos;
         const int32_t* __restrict__ SI = p.ps_id;
         const int P = p.P;
-        int c;
-        {
-            int lo = 0, hi = P;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(S + mid) < sv) lo = mid + 1; else hi = mid; }
-            c = lo;
-        }
+        // split point: first sorted entry with score >= sv; A walks left from it, B right
+        const int c = warp_partition_point(0, P, [&](int q) { return __ldg(S + q) < sv; });
         const int nA = c, nB = P - c;
-        auto A = [&](int i) -> uint32_t { return dist_bits(sv, __ldg(S + (c - 1 - i))); };
-        auto Bq = [&](int j) -> uint32_t { return dist_bits(sv, __ldg(S + (c + j))); };
-        int lo = max(0, o - nB), hi = min(o, nA);
-        while (lo < hi) {   // how many of the o nearest come from the left side
-            const int mid = (lo + hi) >> 1;
-            if (Bq(o - mid - 1) > A(mid)) lo = mid + 1; else hi = mid;
-        }
-        const int ia = lo, ib = o - lo;
+        auto A = [&](int q) -> uint32_t { return dist_bits(sv, __ldg(S + (c - 1 - q))); };
+        auto Bq = [&](int q) -> uint32_t { return dist_bits(sv, __ldg(S + (c + q))); };
+        // how many of the o nearest come from the left side (k-th of two sorted sequences)
+        const int ia = warp_partition_point(max(0, o - nB), min(o, nA), [&](int m) { return Bq(o - m - 1) > A(m); });
+        const int ib = o - ia;
         uint32_t Tp = 0;
         if (ia > 0) Tp = A(ia - 1);
         if (ib > 0) Tp = max(Tp, Bq(ib - 1));
-        auto bound = [&](auto seq, int n, uint32_t t, bool upper) {   // first idx with seq >= t (or > t)
-            int l = 0, h = n;
-            while (l < h) {
-                const int mid = (l + h) >> 1;
-                const uint32_t x = seq(mid);
-                if (upper ? (x <= t) : (x < t)) l = mid + 1; else h = mid;
-            }
-            return l;
-        };
-        const int a_less = bound(A, nA, Tp, false), a_le = bound(A, nA, Tp, true);
-        const int b_less = bound(Bq, nB, Tp, false), b_le = bound(Bq, nB, Tp, true);
+        const int a_less = warp_partition_point(0, nA, [&](int q) { return A(q) < Tp; });
+        const int a_le = warp_partition_point(a_less, nA, [&](int q) { return A(q) <= Tp; });
+        const int b_less = warp_partition_point(0, nB, [&](int q) { return Bq(q) < Tp; });
+        const int b_le = warp_partition_point(b_less, nB, [&](int q) { return Bq(q) <= Tp; });
         const int cnt_less = a_less + b_less;
         const int tie_a = a_le - a_less, ties = tie_a + (b_le - b_less);
         const int needp = o - cnt_less;            // 1 <= needp <= ties
@@ -270,26 +394,33 @@ __device__ void choose_item(const ChooseP& p, int w, int tid, uint32_t* sd, int 
             int unused;
             radix_select<NT>(getpos, ties, needp, hist, xw, tid, Tpos, unused);
         }
-        grp_sync<NT>();   // kept-bitmask visible to the whole group
+        grp_sync<NT>();   // kept bitmaps complete and visible to the whole group
         const int total = cnt_less + ties;
         int run_sel = 0;
         for (int base = 0; base < total; base += NT) {
             const int e = base + tid;
             const bool valid = e < total;
-            int idx = 0;
-            if (valid) idx = e < a_less ? c - 1 - e : (e < cnt_less ? c + (e - a_less) : tie_index(e - cnt_less));
-            const bool selp = valid && (e < cnt_less || (uint32_t)__ldg(SP + idx) <= Tpos);
+            int idx = 0, pos = 0;
+            if (valid) {
+                idx = e < a_less ? c - 1 - e : (e < cnt_less ? c + (e - a_less) : tie_index(e - cnt_less));
+                pos = __ldg(SP + idx);
+            }
+            const bool selp = valid && (e < cnt_less || (uint32_t)pos <= Tpos);
             bool emit = false;
             int32_t id = 0;
             if (selp) {
                 id = __ldg(SI + idx);
-                int l = 0, h = d;            // lower_bound of id in the id-sorted row
-                while (l < h) {
-                    const int mid = (l + h) >> 1;
-                    if (nbr[mid] < id) l = mid + 1; else h = mid;
+                bool dup;
+                if (use_kb) {
+                    dup = (kbits[pos >> 5] >> (pos & 31)) & 1u;
+                } else {
+                    int l = 0, h = d;            // lower_bound of id in the id-sorted row
+                    while (l < h) {
+                        const int mid = (l + h) >> 1;
+                        if (nbr[mid] < id) l = mid + 1; else h = mid;
+                    }
+                    dup = l < d && nbr[l] == id && ((k == d) || ((bits[l >> 5] >> (l & 31)) & 1u));
                 }
-                bool dup = false;
-                if (l < d && nbr[l] == id) dup = (k == d) || ((bits[l >> 5] >> (l & 31)) & 1u);
                 emit = !dup;
             }
             int es, ee, ts, te;
@@ -340,6 +471,7 @@ __global__ void k_choose_classify(ChooseP p) {
 struct WarpSmem {
     uint32_t sd[PCG_SMALL_MAX];
     uint32_t hist[256];
+    uint32_t kbits[PCG_KB_WORDS_WARP];
     uint32_t bits[PCG_SMALL_MAX / 32];
     int xw[32];
 };
@@ -354,13 +486,15 @@ __global__ void __launch_bounds__(PCG_WARPS_PER_CTA * 32) k_choose_warp(ChooseP 
         if (lane == 0) q = atomicAdd(&p.status[ST_SMALL_CTR], 1);
         q = __shfl_sync(PCG_FULL, q, 0);
         if (q >= n) break;
-        choose_item<32>(p, p.small_q[q], lane, s.sd, PCG_SMALL_MAX, s.hist, s.bits, PCG_SMALL_MAX / 32, nullptr, s.xw);
+        choose_item<32>(p, p.small_q[q], lane, s.sd, PCG_SMALL_MAX, s.hist, s.kbits, PCG_KB_WORDS_WARP, s.bits,
+                        PCG_SMALL_MAX / 32, nullptr, s.xw);
     }
 }
 
 __global__ void __launch_bounds__(PCG_LARGE_NT) k_choose_cta(ChooseP p) {
     extern __shared__ uint32_t dyn[];
     __shared__ uint32_t hist[256];
+    __shared__ uint32_t kbits[PCG_KB_WORDS_CTA];
     __shared__ int xw[32];
     __shared__ int s_q;
     uint32_t* sd = dyn;                              // [large_cap]
@@ -372,8 +506,8 @@ __global__ void __launch_bounds__(PCG_LARGE_NT) k_choose_cta(ChooseP p) {
         const int q = s_q;
         __syncthreads();
         if (q >= n) break;
-        choose_item<PCG_LARGE_NT>(p, p.large_q[q], threadIdx.x, sd, p.large_cap, hist, bits, p.large_cap / 32,
-                                  p.bits_slab + (int64_t)blockIdx.x * p.slab_words, xw);
+        choose_item<PCG_LARGE_NT>(p, p.large_q[q], threadIdx.x, sd, p.large_cap, hist, kbits, PCG_KB_WORDS_CTA, bits,
+                                  p.large_cap / 32, p.bits_slab + (int64_t)blockIdx.x * p.slab_words, xw);
     }
 }
 
@@ -416,6 +550,16 @@ __global__ void k_select_all(const int64_t* __restrict__ indptr, const int32_t* 
         if ((int64_t)slot0 + c < cap_slots) slot_item[slot0 + c] = ovf ? -1 : w;
 }
 
+// pool_pos_of[v] = position of node v in the pool, -1 for everyone else (built once per pool).
+__global__ void k_fill_i32(int32_t* a, int64_t n, int32_t val) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = val;
+}
+__global__ void k_pool_positions(const int32_t* __restrict__ pool, int P, int32_t* __restrict__ pool_pos_of) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P) pool_pos_of[pool[i]] = i;
+}
+
 // ------------------------------------------------------------------------------------------- C ABI
 struct WsLayout {
     size_t small_q, large_q, bits_slab, total;
@@ -453,10 +597,24 @@ extern "C" size_t pcg_choose_workspace_bytes(int B, int R, int64_t max_degree) {
     return ws_layout(B, R, max_degree, 148 * 2).total;   // sized for the largest grid we ever launch
 }
 
+extern "C" int pcg_pool_positions(const int32_t* pool, int P, int64_t n_nodes, int32_t* pool_pos_of,
+                                  pcg_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PCG_REQUIRE(pool_pos_of && (P == 0 || pool), "pcg_pool_positions: null pointer");
+    if (n_nodes > 0) k_fill_i32<<<(int)((n_nodes + 255) / 256), 256, 0, stream>>>(pool_pos_of, n_nodes, -1);
+    if (P > 0) k_pool_positions<<<(P + 255) / 256, 256, 0, stream>>>(pool, P, pool_pos_of);
+    return pcg_check_launch("pcg_pool_positions");
+}
+
+// second stream + events so the warp tier and the CTA tier run side by side (fork/join; capturable)
+static cudaStream_t g_side = nullptr;
+static cudaEvent_t g_fork = nullptr, g_join = nullptr;
+
 extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t n_nodes, int R, const float* score,
                           const float* entry_score, const float* center_score, const int32_t* targets,
                           const int64_t* labels, int B, const double* thresh_host, const int32_t* k_override,
-                          double rho, const float* ps_score, const int32_t* ps_pos, const int32_t* ps_id, int P, int train,
+                          double rho, const float* ps_score, const int32_t* ps_pos, const int32_t* ps_id,
+                          const int32_t* pool_pos_of, int P, int train,
                           int64_t max_degree, int32_t* sel_idx, float* sel_dist, int64_t cap_slots,
                           int32_t* slot_item, int32_t* it_slot0, int32_t* it_m, int64_t* it_base, int32_t* it_done, void* workspace,
                           size_t workspace_bytes, int32_t* status, pcg_stream_t stream_) {
@@ -477,19 +635,18 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
                 L.total);
     cudaError_t e = cudaMemsetAsync(status, 0, PCG_STATUS_WORDS * sizeof(int32_t), stream);
     if (e != cudaSuccess) { pcg_set_error("pcg_choose: memset: %s", cudaGetErrorString(e)); return (int)e; }
-    if (B == 0) return 0;
     ChooseP p;
     p.indptr = indptr; p.indices = indices; p.score = score; p.entry_score = entry_score;
     p.center_score = center_score; p.targets = targets; p.labels = labels; p.k_override = k_override;
-    p.ps_score = ps_score; p.ps_pos = ps_pos; p.ps_id = ps_id; p.n_nodes = n_nodes; p.R = R; p.B = B;
+    p.ps_score = ps_score; p.ps_pos = ps_pos; p.ps_id = ps_id; p.pool_pos_of = pool_pos_of;
+    p.n_nodes = n_nodes; p.R = R; p.B = B;
     p.P = (train && ps_score) ? P : 0; p.train = train;
     for (int r = 0; r < PCG_MAX_REL; ++r) p.thresh[r] = r < R ? thresh_host[r] : 0.5;
     p.rho = rho; p.sel_idx = sel_idx; p.sel_dist = sel_dist; p.cap_slots = cap_slots; p.slot_item = slot_item;
-    p.it_slot0 = it_slot0; p.it_m = it_m; p.it_base = it_base; p.status = status;
+    p.it_slot0 = it_slot0; p.it_m = it_m; p.it_base = it_base; p.it_done = it_done; p.status = status;
     char* ws = (char*)workspace;
     p.small_q = (int32_t*)(ws + L.small_q);
     p.large_q = (int32_t*)(ws + L.large_q);
-    p.it_done = it_done;
     p.bits_slab = (uint32_t*)(ws + L.bits_slab);
     p.slab_words = L.slab_words;
     int64_t cap = max_degree < PCG_SMALL_MAX + 1 ? PCG_SMALL_MAX + 1 : max_degree;
@@ -497,19 +654,37 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
     p.large_cap = (int)((cap + 31) / 32 * 32);
     const int W = R * B;
     k_choose_classify<<<(W + 255) / 256, 256, 0, stream>>>(p);
-    int gw = (W + PCG_WARPS_PER_CTA - 1) / PCG_WARPS_PER_CTA;
-    if (gw > sms * 8) gw = sms * 8;
-    k_choose_warp<<<gw, PCG_WARPS_PER_CTA * 32, 0, stream>>>(p);
-    if (max_degree > PCG_SMALL_MAX) {
+    const bool have_large = max_degree > PCG_SMALL_MAX;
+    cudaStream_t s_large = stream;
+    if (have_large) {
+        if (!g_side) {
+            if ((e = cudaStreamCreateWithFlags(&g_side, cudaStreamNonBlocking)) != cudaSuccess ||
+                (e = cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming)) != cudaSuccess ||
+                (e = cudaEventCreateWithFlags(&g_join, cudaEventDisableTiming)) != cudaSuccess) {
+                pcg_set_error("pcg_choose: side stream: %s", cudaGetErrorString(e));
+                return (int)e;
+            }
+        }
         size_t dyn = (size_t)p.large_cap * 4 + (size_t)p.large_cap / 32 * 4;
         static size_t configured = 0;
-        if (dyn > 48 * 1024 && dyn > configured) {
+        if (dyn > 32 * 1024 && dyn > configured) {
             e = cudaFuncSetAttribute(k_choose_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
             if (e != cudaSuccess) { pcg_set_error("pcg_choose: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
             configured = dyn;
         }
+        // fork: the CTA tier (long rows first: they are the critical path) on the side stream
+        cudaEventRecord(g_fork, stream);
+        cudaStreamWaitEvent(g_side, g_fork, 0);
+        s_large = g_side;
         int gl = W < L.grid_large ? W : L.grid_large;
-        k_choose_cta<<<gl, PCG_LARGE_NT, dyn, stream>>>(p);
+        k_choose_cta<<<gl, PCG_LARGE_NT, dyn, s_large>>>(p);
+    }
+    int gw = (W + PCG_WARPS_PER_CTA - 1) / PCG_WARPS_PER_CTA;
+    if (gw > sms * 6) gw = sms * 6;
+    k_choose_warp<<<gw, PCG_WARPS_PER_CTA * 32, 0, stream>>>(p);
+    if (have_large) {   // join
+        cudaEventRecord(g_join, s_large);
+        cudaStreamWaitEvent(stream, g_join, 0);
     }
     return pcg_check_launch("pcg_choose");
 }
@@ -528,7 +703,6 @@ extern "C" int pcg_select_all(const int64_t* indptr, const int32_t* indices, int
                 "pcg_select_all: null pointer");
     cudaError_t e = cudaMemsetAsync(status, 0, PCG_STATUS_WORDS * sizeof(int32_t), stream);
     if (e != cudaSuccess) { pcg_set_error("pcg_select_all: memset: %s", cudaGetErrorString(e)); return (int)e; }
-    if (B == 0) return 0;
     const int W = R * B;
     k_select_all<<<(W * 32 + 255) / 256, 256, 0, stream>>>(indptr, indices, n_nodes, R, targets, B, add_self, cap_slots,
                                                            slot_item, it_slot0, it_m, it_base, it_extra, it_done, status);

@@ -76,32 +76,30 @@ __device__ __forceinline__ uint32_t orderable(float f) {   // float order -> uns
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
-// P <= 8192: one CTA, bitonic sort of (orderable(score) << 32 | position) in shared memory.
-__global__ void __launch_bounds__(1024) k_sort_pool_small(const float* __restrict__ pool_score,
-                                                          const int32_t* __restrict__ pool, int P, int n2,
-                                                          float* __restrict__ ps_score, int32_t* __restrict__ ps_pos,
-                                                          int32_t* __restrict__ ps_id) {
+// P <= 8192: rank sort. Every CTA stages all P keys (orderable(score) << 32 | position, unique) in
+// shared memory and ranks 32 of them by counting smaller keys, 8 lanes per element; the rank is the
+// element's place in the sorted order. O(P^2) compares spread over P/32 CTAs: a few microseconds and
+// no serial merge chain (a single-CTA bitonic sort of the same pool took ~48 us on B200).
+__global__ void __launch_bounds__(256) k_sort_pool_rank(const float* __restrict__ pool_score,
+                                                        const int32_t* __restrict__ pool, int P,
+                                                        float* __restrict__ ps_score, int32_t* __restrict__ ps_pos,
+                                                        int32_t* __restrict__ ps_id) {
     extern __shared__ unsigned long long keys[];
-    for (int i = threadIdx.x; i < n2; i += blockDim.x)
-        keys[i] = i < P ? (((unsigned long long)orderable(pool_score[i]) << 32) | (unsigned)i) : ~0ull;
+    for (int i = threadIdx.x; i < P; i += blockDim.x)
+        keys[i] = ((unsigned long long)orderable(pool_score[i]) << 32) | (unsigned)i;
     __syncthreads();
-    for (int k = 2; k <= n2; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < n2; i += blockDim.x) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const unsigned long long a = keys[i], b = keys[ixj];
-                    if ((a > b) == ((i & k) == 0)) { keys[i] = b; keys[ixj] = a; }
-                }
-            }
-            __syncthreads();
-        }
-    }
-    for (int i = threadIdx.x; i < P; i += blockDim.x) {
-        const int pos = (int)(keys[i] & 0xffffffffull);
-        ps_score[i] = pool_score[pos];
-        ps_pos[i] = pos;
-        ps_id[i] = pool[pos];
+    const int e = threadIdx.x >> 3, part = threadIdx.x & 7;
+    const int i = blockIdx.x * 32 + e;
+    const unsigned long long mine = i < P ? keys[i] : ~0ull;
+    int cnt = 0;
+    for (int j = part; j < P; j += 8) cnt += keys[j] < mine;
+    cnt += __shfl_xor_sync(PCG_FULL, cnt, 1);
+    cnt += __shfl_xor_sync(PCG_FULL, cnt, 2);
+    cnt += __shfl_xor_sync(PCG_FULL, cnt, 4);
+    if (part == 0 && i < P) {
+        ps_score[cnt] = pool_score[i];
+        ps_pos[cnt] = i;
+        ps_id[cnt] = pool[i];
     }
 }
 
@@ -140,17 +138,15 @@ static int sort_pool_impl(const float* pool_score, const int32_t* pool, int P, f
                           int32_t* ps_id, char* ws, size_t ws_bytes, cudaStream_t stream) {
     if (P <= 0) return 0;
     if (P <= PCG_SORT_SMALL_MAX) {
-        int n2 = 32;
-        while (n2 < P) n2 <<= 1;
-        const size_t smem = (size_t)n2 * 8;
+        const size_t smem = (size_t)P * 8;
         static bool configured = false;
         if (!configured) {
-            cudaError_t e = cudaFuncSetAttribute(k_sort_pool_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            cudaError_t e = cudaFuncSetAttribute(k_sort_pool_rank, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  PCG_SORT_SMALL_MAX * 8);
             if (e != cudaSuccess) { pcg_set_error("pcg_sort_pool: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
             configured = true;
         }
-        k_sort_pool_small<<<1, 1024, smem, stream>>>(pool_score, pool, P, n2, ps_score, ps_pos, ps_id);
+        k_sort_pool_rank<<<(P + 31) / 32, 256, smem, stream>>>(pool_score, pool, P, ps_score, ps_pos, ps_id);
         return 0;
     }
     const size_t a = align256((size_t)P * 4);
