@@ -68,6 +68,9 @@ PCG_API int pcg_sort_pool(const float* pool_score, const int32_t* pool, int P, f
 
 /* pool_pos_of[v] = position of node v in `pool`, -1 for every other node (once per pool; pool ids distinct). */
 PCG_API int pcg_pool_positions(const int32_t* pool, int P, int64_t n_nodes, int32_t* pool_pos_of, pcg_stream_t stream);
+/* entry_pool_pos[e] = pool_pos_of[indices[e]] for every CSR entry (once per pool; same size as `indices`). */
+PCG_API int pcg_entry_pool_positions(const int32_t* indices, int64_t nnz, const int32_t* pool_pos_of,
+                             int32_t* entry_pool_pos, pcg_stream_t stream);
 
 /* Bytes of scratch pcg_choose needs for B targets x R relations on a graph whose largest row has
  * max_degree entries. */
@@ -88,13 +91,14 @@ PCG_API size_t pcg_choose_workspace_bytes(int B, int R, int64_t max_degree);
  *   thresh_host  HOST array of R doubles (src/layers.py:193 hard-codes 0.5)
  *   k_override   int32 [R*B] explicit num_sample per item (src/layers.py:260-262) or NULL
  *   ps_score/ps_pos/ps_id  the score-sorted pool from pcg_score_table / pcg_sort_pool (P entries)
- *   pool_pos_of  int32 [N] from pcg_pool_positions (node id -> pool position, -1 otherwise), or NULL: the
- *                kernels then test "already kept" by binary search in the row instead of a bitmap
+ *   entry_pool_pos  int32 [nnz] from pcg_entry_pool_positions (pool position of every CSR entry's node, -1 if
+ *                it is not in the pool), or NULL: "already kept" is then tested by binary search in the row
+ *                instead of a per-item bitmap over pool positions
  * Outputs
  *   sel_idx      int32 [cap_slots * PCG_SLOT]; item w's ids are sel_idx[it_base[w] .. + it_m[w])
  *   sel_dist     optional fp32 [cap_slots * PCG_SLOT] (NULL to skip): the distances the reference returns as
- *                samp_scores (src/layers.py:666-672, 691): at it_base[w] + [0,k) the kept neighbours' |Δ| in row
- *                order, at it_base[w] + k + [0,o) the o nearest pool members' |Δ| (duplicates of kept ids
+ *                samp_scores (src/layers.py:666-672, 691): at it_base[w] + [0,k) the kept neighbours' |Δ|
+ *                (aligned with sel_idx), at it_base[w] + k + [0,o) the o nearest pool members' |Δ| (duplicates of kept ids
  *                included, as in the reference's list; unordered)
  *   slot_item    int32 [cap_slots]  owning item of each handed-out slot, or -1
  *   it_slot0/it_m int32 [R*B], it_base int64 [R*B], it_done int32 [R*B] (zeroed; aggregation tickets)
@@ -103,7 +107,7 @@ PCG_API size_t pcg_choose_workspace_bytes(int B, int R, int64_t max_degree);
 PCG_API int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t n_nodes, int R, const float* score,
                const float* entry_score, const float* center_score, const int32_t* targets,
                const int64_t* labels, int B, const double* thresh_host, const int32_t* k_override, double rho,
-               const float* ps_score, const int32_t* ps_pos, const int32_t* ps_id, const int32_t* pool_pos_of, int P,
+               const float* ps_score, const int32_t* ps_pos, const int32_t* ps_id, const int32_t* entry_pool_pos, int P,
                int train, int64_t max_degree,
                int32_t* sel_idx, float* sel_dist, int64_t cap_slots, int32_t* slot_item, int32_t* it_slot0,
                int32_t* it_m, int64_t* it_base, int32_t* it_done, void* workspace, size_t workspace_bytes, int32_t* status,

@@ -21,7 +21,7 @@
 
 #define PCG_SMALL_MAX 512      // entries a warp keeps in its shared-memory slice
 #define PCG_RANK_MAX 128       // rows up to this length are ranked by counting
-#define PCG_WARPS_PER_CTA 8    // warp kernel: 8 items in flight per CTA
+#define PCG_WARPS_PER_CTA 4    // warp kernel: 4 items in flight per CTA (8.4 KB of shared memory each)
 #define PCG_LARGE_NT 512       // CTA kernel threads
 #define PCG_LARGE_CAP_MAX 32768
 #define PCG_KB_WORDS_WARP 256  // kept-pool bitmap words per warp  (pools up to 8192 positives)
@@ -39,7 +39,7 @@ struct ChooseP {
     const float* ps_score;      // pool scores ascending (ties by pool position)
     const int32_t* ps_pos;      // pool position of each sorted entry
     const int32_t* ps_id;       // node id of each sorted entry
-    const int32_t* pool_pos_of; // [N] node id -> pool position or -1 (NULL: binary-search fallback)
+    const int32_t* entry_pool_pos; // [nnz] pool position of every CSR entry's node, or -1 (NULL: binary-search fallback)
     int64_t n_nodes;
     int R, B, P, train;
     double thresh[PCG_MAX_REL];
@@ -59,6 +59,16 @@ struct ChooseP {
     int64_t slab_words;
     int large_cap;              // entries of the CTA kernel's shared distance buffer
 };
+
+#ifdef PCG_TRACE
+// Debug build only (make EXTRA=-DPCG_TRACE): per-item phase timestamps, 12 int64 per item.
+__device__ long long* g_trace = nullptr;
+#define TRACE(slot) do { if (g_trace && tid == 0) g_trace[(int64_t)w * 12 + (slot)] = clock64(); } while (0)
+#define TRACE_VAL(slot, val) do { if (g_trace && tid == 0) g_trace[(int64_t)w * 12 + (slot)] = (val); } while (0)
+#else
+#define TRACE(slot) do {} while (0)
+#define TRACE_VAL(slot, val) do {} while (0)
+#endif
 
 template <int NT>
 __device__ __forceinline__ void grp_sync() {
@@ -124,38 +134,46 @@ __device__ __forceinline__ void grp_minmax(Get get, int n, int tid, int* xw, uin
 
 // k-th smallest (kth is 1-based) of get(0..n-1) as (T, need): T = that value, need = how many of
 // the elements equal to T belong to the kth smallest (in position order).
+// Digits are cut from the highest bit in which min and max differ (bits every key shares need no
+// pass, and the first digit then spans exponent AND mantissa bits, which spreads the histogram).
 template <int NT, class Get>
 __device__ __forceinline__ void radix_select(Get get, int n, int kth, uint32_t* hist, int* xw, int tid, uint32_t& T,
                                              int& need) {
-    // digits shared by every key need no pass: start at the first 8-bit digit where min and max differ
     uint32_t kmin, kmax;
     grp_minmax<NT>(get, n, tid, xw, kmin, kmax);
     if (kmin == kmax) { T = kmin; need = kth; return; }
-    const int top = (31 - __clz(kmin ^ kmax)) >> 3;          // index of the highest differing byte
-    uint32_t mask = top == 3 ? 0u : (0xffffffffu << ((top + 1) * 8));
+    int hb = 31 - __clz(kmin ^ kmax);
+    uint32_t mask = hb == 31 ? 0u : ~((2u << hb) - 1u);
     uint32_t prefix = kmin & mask;
     int remaining = kth;
-    for (int shift = top * 8; shift >= 0; shift -= 8) {
+    bool first = true;
+    while (hb >= 0) {
+        const int shift = max(hb - 7, 0);
+        const uint32_t dmask = (1u << (hb - shift + 1)) - 1u;
         for (int b = tid; b < 256; b += NT) hist[b] = 0;
         grp_sync<NT>();
-        // Distance bits share their leading digits, so a plain per-lane atomicAdd serialises up to
-        // 32-way on one bin. Peel the (up to 3) most common digits of each warp with ballots first.
         const int n_up = (n + 31) & ~31;
         for (int j = tid; j < n_up; j += NT) {
             const bool valid = j < n;
             const uint32_t key = valid ? get(j) : 0u;
             const bool active = valid && (key & mask) == prefix;
-            const uint32_t digit = (key >> shift) & 0xffu;
-            unsigned rem = __ballot_sync(PCG_FULL, active);
+            const uint32_t digit = (key >> shift) & dmask;
+            if (first) {
+                // the leading digit is the skewed one: peel the two most common values of each warp
+                // with ballots so that one lane adds the whole count instead of 32 colliding atomics
+                unsigned rem = __ballot_sync(PCG_FULL, active);
 #pragma unroll 1
-            for (int it = 0; it < 3 && rem; ++it) {
-                const int ldr = __ffs(rem) - 1;
-                const uint32_t d0 = __shfl_sync(PCG_FULL, digit, ldr);
-                const unsigned same = __ballot_sync(PCG_FULL, active && digit == d0);
-                if ((tid & 31) == ldr) atomicAdd(&hist[d0], (uint32_t)__popc(same));
-                rem &= ~same;
+                for (int it = 0; it < 2 && rem; ++it) {
+                    const int ldr = __ffs(rem) - 1;
+                    const uint32_t d0 = __shfl_sync(PCG_FULL, digit, ldr);
+                    const unsigned same = __ballot_sync(PCG_FULL, active && digit == d0);
+                    if ((tid & 31) == ldr) atomicAdd(&hist[d0], (uint32_t)__popc(same));
+                    rem &= ~same;
+                }
+                if ((rem >> (tid & 31)) & 1u) atomicAdd(&hist[digit], 1u);
+            } else if (active) {
+                atomicAdd(&hist[digit], 1u);
             }
-            if ((rem >> (tid & 31)) & 1u) atomicAdd(&hist[digit], 1u);
         }
         grp_sync<NT>();
         if (tid < 32) {
@@ -180,10 +198,12 @@ __device__ __forceinline__ void radix_select(Get get, int n, int kth, uint32_t* 
             }
         }
         grp_sync<NT>();
-        uint32_t digit = (uint32_t)xw[30];
+        const uint32_t digit = (uint32_t)xw[30];
         remaining = xw[31];
         prefix |= digit << shift;
-        mask |= 0xffu << shift;
+        mask |= dmask << shift;
+        hb = shift - 1;
+        first = false;
     }
     T = prefix;
     need = remaining;
@@ -209,70 +229,188 @@ __device__ __forceinline__ int warp_partition_point(int lo, int hi, Pred pred) {
     return lo;
 }
 
-// One item (target i, relation r) handled by a group of NT threads.
-//   sd/sd_cap   group-private shared distance cache (uint32)
-//   kbits       group-private bitmap over pool positions (kb_words words): kept neighbours that are
-//               pool members; bits_s / bits_g: kept-position bitmask for the fallback membership test
-//   xw          group-private int[32] scratch
-template <int NT>
-__device__ void choose_item(const ChooseP& p, int w, int tid, uint32_t* sd, int sd_cap, uint32_t* hist,
-                            uint32_t* kbits, int kb_words, uint32_t* bits_s, int bits_cap_words, uint32_t* bits_g,
-                            int* xw) {
-    const int r = w / p.B, i = w - r * p.B;
-    const int32_t v = p.targets[i];
-    const int64_t row = (int64_t)r * p.n_nodes + v;
-    const int64_t beg = p.indptr[row];
-    const int d = (int)(p.indptr[row + 1] - beg);
-    const float sv = p.center_score ? p.center_score[i] : p.score[v];
-    const bool positive = p.train && p.labels && p.labels[i] == 1;
-    int k, o;
-    item_counts(d, p.thresh[r], p.rho, positive, p.P, p.k_override ? p.k_override[w] : 0, p.k_override != nullptr, k, o);
-    const int nslots = (k + o + PCG_SLOT - 1) / PCG_SLOT;
-    const int wid = tid >> 5, lane = tid & 31;
-    const bool use_kb = o > 0 && p.pool_pos_of != nullptr && p.P <= kb_words * 32;
-    if (tid == 0) xw[29] = atomicAdd(&p.status[ST_SLOTS], nslots);
-    if (use_kb)
-        for (int q = tid; q < (p.P + 31) >> 5; q += NT) kbits[q] = 0u;
-    grp_sync<NT>();
-    const int slot0 = xw[29];
-    if ((int64_t)slot0 + nslots > p.cap_slots) {   // caller's buffer too small: flag, emit nothing
-        if (tid == 0) {
-            atomicExch(&p.status[ST_OVERFLOW], 1);
-            p.it_slot0[w] = 0; p.it_m[w] = 0; p.it_base[w] = 0; p.it_done[w] = 0;
-        }
-        for (int c = tid; c < nslots; c += NT)
-            if ((int64_t)slot0 + c < p.cap_slots) p.slot_item[slot0 + c] = -1;
-        grp_sync<NT>();
-        return;
-    }
-    const int64_t off = (int64_t)slot0 * PCG_SLOT;
-    const int32_t* __restrict__ nbr = p.indices + beg;
-    const float* __restrict__ escore = p.entry_score ? p.entry_score + beg : nullptr;
-    const float* __restrict__ score = p.score;
-    const int32_t* __restrict__ ppo = p.pool_pos_of;
-    const bool cached = d <= sd_cap;
-    if (cached) {
-        for (int j = tid; j < d; j += NT) sd[j] = dist_bits(sv, escore ? escore[j] : __ldg(score + nbr[j]));
-        grp_sync<NT>();
-    }
-    auto get = [&](int j) -> uint32_t {
-        return cached ? sd[j] : dist_bits(sv, escore ? escore[j] : __ldg(score + nbr[j]));
-    };
-    uint32_t* bits = (d <= bits_cap_words * 32) ? bits_s : bits_g;
-    const bool want_bits = o > 0 && !use_kb;
-    // what to do with a kept neighbour at row position j
-    auto keep = [&](int j, int64_t at, uint32_t key) {
-        const int32_t id = nbr[j];
-        p.sel_idx[at] = id;
-        if (p.sel_dist) p.sel_dist[at] = __uint_as_float(key);
-        if (use_kb) {
-            const int pp = __ldg(ppo + id);
-            if (pp >= 0) atomicOr(&kbits[pp >> 5], 1u << (pp & 31));
-        }
-    };
+// Per-item header shared by both tiers.
+struct Item {
+    int w, r, i, d, k, o, nslots, slot0;
+    int32_t v;
+    int64_t beg, off;
+    float sv;
+    bool use_kb, want_bits;
+};
 
-    if (NT == 32 && k < d && d <= PCG_RANK_MAX) {
-        // ---- short row: exact rank of every element by counting (keys (distance, position) are unique) ----
+__device__ __forceinline__ void item_header(const ChooseP& p, int w, int kb_words, Item& it) {
+    it.w = w;
+    it.r = w / p.B;
+    it.i = w - it.r * p.B;
+    it.v = p.targets[it.i];
+    const int64_t row = (int64_t)it.r * p.n_nodes + it.v;
+    it.beg = p.indptr[row];
+    it.d = (int)(p.indptr[row + 1] - it.beg);
+    it.sv = p.center_score ? p.center_score[it.i] : p.score[it.v];
+    const bool positive = p.train && p.labels && p.labels[it.i] == 1;
+    item_counts(it.d, p.thresh[it.r], p.rho, positive, p.P, p.k_override ? p.k_override[w] : 0, p.k_override != nullptr,
+                it.k, it.o);
+    it.nslots = (it.k + it.o + PCG_SLOT - 1) / PCG_SLOT;
+    it.use_kb = it.o > 0 && p.entry_pool_pos != nullptr && p.P <= kb_words * 32;
+    it.want_bits = it.o > 0 && !it.use_kb;
+}
+
+// Slot buffer too small: flag, emit nothing for this item (group-uniform decision).
+template <int NT>
+__device__ __forceinline__ bool item_overflow(const ChooseP& p, const Item& it, int tid) {
+    if ((int64_t)it.slot0 + it.nslots <= p.cap_slots) return false;
+    if (tid == 0) {
+        atomicExch(&p.status[ST_OVERFLOW], 1);
+        p.it_slot0[it.w] = 0; p.it_m[it.w] = 0; p.it_base[it.w] = 0; p.it_done[it.w] = 0;
+    }
+    for (int c = tid; c < it.nslots; c += NT)
+        if ((int64_t)it.slot0 + c < p.cap_slots) p.slot_item[it.slot0 + c] = -1;
+    return true;
+}
+
+// Minority oversampling for one positive item: the o nearest train positives (score-sorted pool)
+// that are not already kept, appended behind the k kept neighbours. Returns how many were added.
+//   kbits   bitmap over pool positions of kept neighbours (use_kb), else bits = kept row positions
+template <int NT>
+__device__ __forceinline__ int oversample(const ChooseP& p, const Item& it, int tid, const int32_t* __restrict__ nbr,
+                                          const uint32_t* kbits, const uint32_t* bits, uint32_t* hist, int* xw) {
+    const float* __restrict__ S = p.ps_score;
+    const int32_t* __restrict__ SP = p.ps_pos;
+    const int32_t* __restrict__ SI = p.ps_id;
+    const int P = p.P, o = it.o, k = it.k, d = it.d;
+    const float sv = it.sv;
+    const int w = it.w;
+    // split point: first sorted entry with score >= sv; A walks left from it, B right. The distances
+    // grow monotonically along both, so the o-th smallest is a k-th-of-two-sorted-sequences search.
+    const int c = warp_partition_point(0, P, [&](int q) { return __ldg(S + q) < sv; });
+    const int nA = c, nB = P - c;
+    auto A = [&](int q) -> uint32_t { return dist_bits(sv, __ldg(S + (c - 1 - q))); };
+    auto Bq = [&](int q) -> uint32_t { return dist_bits(sv, __ldg(S + (c + q))); };
+    const int ia = warp_partition_point(max(0, o - nB), min(o, nA), [&](int m) { return Bq(o - m - 1) > A(m); });
+    const int ib = o - ia;
+    uint32_t Tp = 0;
+    if (ia > 0) Tp = A(ia - 1);
+    if (ib > 0) Tp = max(Tp, Bq(ib - 1));
+    const int a_less = warp_partition_point(0, nA, [&](int q) { return A(q) < Tp; });
+    const int a_le = warp_partition_point(a_less, nA, [&](int q) { return A(q) <= Tp; });
+    const int b_less = warp_partition_point(0, nB, [&](int q) { return Bq(q) < Tp; });
+    const int b_le = warp_partition_point(b_less, nB, [&](int q) { return Bq(q) <= Tp; });
+    const int cnt_less = a_less + b_less;
+    const int tie_a = a_le - a_less, ties = tie_a + (b_le - b_less);
+    const int needp = o - cnt_less;            // 1 <= needp <= ties
+    auto tie_index = [&](int t) -> int { return t < tie_a ? c - 1 - (a_less + t) : c + b_less + (t - tie_a); };
+    uint32_t Tpos = 0xffffffffu;
+    if (needp < ties) {   // more equal-distance candidates than needed: smallest pool positions win
+        auto getpos = [&](int t) -> uint32_t { return (uint32_t)__ldg(SP + tie_index(t)); };
+        int unused;
+        radix_select<NT>(getpos, ties, needp, hist, xw, tid, Tpos, unused);
+    }
+    TRACE(5);
+    const int total = cnt_less + ties;
+    int run_sel = 0, n_emit = 0;
+    for (int base = 0; base < total; base += NT) {
+        const int e = base + tid;
+        const bool valid = e < total;
+        int idx = 0, pos = 0;
+        if (valid) {
+            idx = e < a_less ? c - 1 - e : (e < cnt_less ? c + (e - a_less) : tie_index(e - cnt_less));
+            pos = __ldg(SP + idx);
+        }
+        const bool selp = valid && (e < cnt_less || (uint32_t)pos <= Tpos);
+        bool emit = false;
+        int32_t id = 0;
+        if (selp) {
+            id = __ldg(SI + idx);
+            bool dup;
+            if (it.use_kb) {
+                dup = (kbits[pos >> 5] >> (pos & 31)) & 1u;
+            } else {
+                int l = 0, h = d;            // lower_bound of id in the id-sorted row
+                while (l < h) {
+                    const int mid = (l + h) >> 1;
+                    if (nbr[mid] < id) l = mid + 1; else h = mid;
+                }
+                dup = l < d && nbr[l] == id && ((k == d) || ((bits[l >> 5] >> (l & 31)) & 1u));
+            }
+            emit = !dup;
+        }
+        int es, ee, ts, te;
+        grp_excl2<NT>(selp, emit, tid, xw, es, ee, ts, te);
+        if (selp && p.sel_dist) p.sel_dist[it.off + k + run_sel + es] = __uint_as_float(dist_bits(sv, __ldg(S + idx)));
+        if (emit) p.sel_idx[it.off + k + n_emit + ee] = id;
+        run_sel += ts;
+        n_emit += te;
+    }
+    return n_emit;
+}
+
+template <int NT>
+__device__ __forceinline__ void item_finish(const ChooseP& p, const Item& it, int tid, int m) {
+    if (tid == 0) {
+        p.it_slot0[it.w] = it.slot0;
+        p.it_m[it.w] = m;
+        p.it_base[it.w] = it.off;
+        p.it_done[it.w] = 0;
+    }
+    for (int c = tid; c < it.nslots; c += NT) p.slot_item[it.slot0 + c] = (c * PCG_SLOT < m) ? it.w : -1;
+}
+
+// --------------------------------------------------------------------------------- warp tier
+struct WarpSmem {
+    unsigned long long keys[PCG_SMALL_MAX];   // sort path: (distance << 32 | row position); else uint32 distances
+    int32_t ids[PCG_SMALL_MAX];               // the row's neighbour ids
+    uint32_t hist[256];                       // rank path: kept row positions; pool phase: radix histogram
+    uint32_t kbits[PCG_KB_WORDS_WARP];
+    uint32_t bits[PCG_SMALL_MAX / 32];
+    int xw[32];
+};
+
+// One item handled by one warp (d <= PCG_SMALL_MAX). The kept list comes out ordered by (distance,
+// position) for sorted rows and in row order otherwise: any fixed order serves (it is a set).
+__device__ void choose_item_warp(const ChooseP& p, int w, WarpSmem& s) {
+    const int lane = threadIdx.x & 31;
+    const int tid = lane;
+    Item it;
+    item_header(p, w, PCG_KB_WORDS_WARP, it);
+    TRACE(0); TRACE_VAL(8, it.d); TRACE_VAL(9, it.k); TRACE_VAL(10, it.o);
+    int slot0 = 0;
+    if (lane == 0) slot0 = atomicAdd(&p.status[ST_SLOTS], it.nslots);
+    it.slot0 = __shfl_sync(PCG_FULL, slot0, 0);
+    it.off = (int64_t)it.slot0 * PCG_SLOT;
+    if (item_overflow<32>(p, it, lane)) { __syncwarp(); return; }
+    TRACE(1);
+    const int d = it.d, k = it.k;
+    const int32_t* __restrict__ nbr = p.indices + it.beg;
+    const float* __restrict__ escore = p.entry_score ? p.entry_score + it.beg : nullptr;
+    uint32_t* sd = reinterpret_cast<uint32_t*>(s.keys);
+    if (it.use_kb)
+        for (int q = lane; q < (p.P + 31) >> 5; q += 32) s.kbits[q] = 0u;
+    if (it.want_bits)
+        for (int q = lane; q < (d + 31) >> 5; q += 32) s.bits[q] = 0u;
+    for (int j = lane; j < d; j += 32) s.ids[j] = __ldg(nbr + j);
+    __syncwarp();
+    const bool all = k >= d;
+    const bool by_rank = !all && d <= PCG_RANK_MAX;
+    const bool by_sort = !all && !by_rank;
+    const bool need_dist = !all || p.sel_dist != nullptr;
+    int n2 = 0;
+    if (need_dist) {
+        if (by_sort) {
+            n2 = 256;
+            while (n2 < d) n2 <<= 1;
+            for (int j = lane; j < n2; j += 32) {
+                unsigned long long key = ~0ull;
+                if (j < d) key = ((unsigned long long)dist_bits(it.sv, escore ? escore[j] : __ldg(p.score + s.ids[j])) << 32) | (unsigned)j;
+                s.keys[j] = key;
+            }
+        } else {
+            for (int j = lane; j < d; j += 32) sd[j] = dist_bits(it.sv, escore ? escore[j] : __ldg(p.score + s.ids[j]));
+        }
+        __syncwarp();
+    }
+    TRACE(2);
+    if (by_rank) {
+        // exact rank of every element by counting (keys (distance, position) are unique)
         constexpr int EPL = PCG_RANK_MAX / 32;
         uint32_t mykey[EPL];
         int rank[EPL];
@@ -290,156 +428,151 @@ __device__ void choose_item(const ChooseP& p, int w, int tid, uint32_t* sd, int 
             if (32 * e < d) {                        // warp-uniform
                 const bool sel = j < d && rank[e] < k;
                 const unsigned sm = __ballot_sync(PCG_FULL, sel);
-                if (sel) keep(j, off + n_out + __popc(sm & lanemask_lt()), mykey[e]);
-                if (want_bits && lane == 0) bits[e] = sm;
+                if (sel) s.hist[n_out + __popc(sm & lanemask_lt())] = (uint32_t)j;
                 n_out += __popc(sm);
             }
         }
-    } else {
-        uint32_t T = 0xffffffffu;
-        int need = 0x7fffffff;
-        if (k < d) {
-            if (k > 0) radix_select<NT>(get, d, k, hist, xw, tid, T, need);
-            else { T = 0; need = 0; }
-        }
-        if (NT == 32) {
-            // ---- ordered compaction, one warp: tiles of 32 row positions ----
-            int run_less = 0, run_tie = 0;
-            for (int base = 0; base < d; base += 32) {
-                const int j = base + lane;
-                const bool valid = j < d;
-                const uint32_t key = valid ? get(j) : 0xffffffffu;
-                const bool less = valid && key < T;
-                const bool tie = valid && key == T;
-                const unsigned lt = lanemask_lt();
-                const unsigned ml = __ballot_sync(PCG_FULL, less), mt = __ballot_sync(PCG_FULL, tie);
-                const int tie_before = run_tie + __popc(mt & lt);
-                const bool sel = less || (tie && tie_before < need);
-                if (sel) keep(j, off + run_less + __popc(ml & lt) + min(tie_before, need), key);
-                if (want_bits) {
-                    const unsigned sm = __ballot_sync(PCG_FULL, sel);
-                    if (lane == 0) bits[base >> 5] = sm;
+        __syncwarp();
+    } else if (by_sort) {
+        // bitonic sort of the n2 (distance, position) keys in shared memory
+        for (int k2 = 2; k2 <= n2; k2 <<= 1) {
+            for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+                for (int t = lane; t < (n2 >> 1); t += 32) {
+                    const int lo = ((t & ~(j2 - 1)) << 1) | (t & (j2 - 1));
+                    const int hi = lo + j2;
+                    const unsigned long long a = s.keys[lo], b = s.keys[hi];
+                    if ((a > b) == ((lo & k2) == 0)) { s.keys[lo] = b; s.keys[hi] = a; }
                 }
-                run_less += __popc(ml);
-                run_tie += __popc(mt);
-            }
-        } else {
-            // ---- ordered compaction, one CTA: every warp owns a contiguous chunk of the row; count,
-            // one scan of the per-warp counts, then each warp writes its chunk with ballots only ----
-            constexpr int NW = NT / 32;
-            const int chunk = (((d + NW - 1) / NW) + 31) & ~31;       // multiple of 32 positions per warp
-            const int cb = wid * chunk, ce = min(d, cb + chunk);
-            int cl = 0, ct = 0;
-            for (int base = cb; base < ce; base += 32) {
-                const int j = base + lane;
-                const uint32_t key = j < ce ? get(j) : 0xffffffffu;
-                cl += __popc(__ballot_sync(PCG_FULL, j < ce && key < T));
-                ct += __popc(__ballot_sync(PCG_FULL, j < ce && key == T));
-            }
-            if (lane == 0) { xw[wid] = cl; hist[wid] = (uint32_t)ct; }   // hist is free here
-            __syncthreads();
-            int run_less = 0, run_tie = 0;
-            for (int q = 0; q < wid; ++q) { run_less += xw[q]; run_tie += (int)hist[q]; }
-            __syncthreads();
-            for (int base = cb; base < ce; base += 32) {
-                const int j = base + lane;
-                const bool valid = j < ce;
-                const uint32_t key = valid ? get(j) : 0xffffffffu;
-                const bool less = valid && key < T;
-                const bool tie = valid && key == T;
-                const unsigned lt = lanemask_lt();
-                const unsigned ml = __ballot_sync(PCG_FULL, less), mt = __ballot_sync(PCG_FULL, tie);
-                const int tie_before = run_tie + __popc(mt & lt);
-                const bool sel = less || (tie && tie_before < need);
-                if (sel) keep(j, off + run_less + __popc(ml & lt) + min(tie_before, need), key);
-                if (want_bits) {
-                    const unsigned sm = __ballot_sync(PCG_FULL, sel);
-                    if (lane == 0) bits[base >> 5] = sm;
-                }
-                run_less += __popc(ml);
-                run_tie += __popc(mt);
+                __syncwarp();
             }
         }
     }
+    TRACE(3);
+    // ---- emit the kept neighbours ----
+    const int32_t* __restrict__ epp = it.use_kb ? p.entry_pool_pos + it.beg : nullptr;
+    for (int t = lane; t < k; t += 32) {
+        int j;
+        uint32_t key = 0;
+        if (by_sort) { const unsigned long long kk = s.keys[t]; j = (int)(uint32_t)kk; key = (uint32_t)(kk >> 32); }
+        else { j = all ? t : (int)s.hist[t]; if (need_dist) key = sd[j]; }
+        p.sel_idx[it.off + t] = s.ids[j];
+        if (p.sel_dist) p.sel_dist[it.off + t] = __uint_as_float(key);
+        if (epp) {
+            const int pp = __ldg(epp + j);
+            if (pp >= 0) atomicOr(&s.kbits[pp >> 5], 1u << (pp & 31));
+        }
+        if (it.want_bits) atomicOr(&s.bits[j >> 5], 1u << (j & 31));
+    }
+    __syncwarp();
+    TRACE(4);
+    int m = k;
+    if (it.o > 0) m += oversample<32>(p, it, lane, nbr, s.kbits, s.bits, s.hist, s.xw);
+    TRACE(6);
+    item_finish<32>(p, it, lane, m);
+    __syncwarp();
+    TRACE(7);
+}
 
-    // ---- minority oversampling: nearest train positives not already kept ----
-    int n_emit = 0;
-    if (o > 0) {
-        const float* __restrict__ S = p.ps_score;
-        const int32_t* __restrict__ SP = p.ps_pos;
-        const int32_t* __restrict__ SI = p.ps_id;
-        const int P = p.P;
-        // split point: first sorted entry with score >= sv; A walks left from it, B right
-        const int c = warp_partition_point(0, P, [&](int q) { return __ldg(S + q) < sv; });
-        const int nA = c, nB = P - c;
-        auto A = [&](int q) -> uint32_t { return dist_bits(sv, __ldg(S + (c - 1 - q))); };
-        auto Bq = [&](int q) -> uint32_t { return dist_bits(sv, __ldg(S + (c + q))); };
-        // how many of the o nearest come from the left side (k-th of two sorted sequences)
-        const int ia = warp_partition_point(max(0, o - nB), min(o, nA), [&](int m) { return Bq(o - m - 1) > A(m); });
-        const int ib = o - ia;
-        uint32_t Tp = 0;
-        if (ia > 0) Tp = A(ia - 1);
-        if (ib > 0) Tp = max(Tp, Bq(ib - 1));
-        const int a_less = warp_partition_point(0, nA, [&](int q) { return A(q) < Tp; });
-        const int a_le = warp_partition_point(a_less, nA, [&](int q) { return A(q) <= Tp; });
-        const int b_less = warp_partition_point(0, nB, [&](int q) { return Bq(q) < Tp; });
-        const int b_le = warp_partition_point(b_less, nB, [&](int q) { return Bq(q) <= Tp; });
-        const int cnt_less = a_less + b_less;
-        const int tie_a = a_le - a_less, ties = tie_a + (b_le - b_less);
-        const int needp = o - cnt_less;            // 1 <= needp <= ties
-        auto tie_index = [&](int t) -> int { return t < tie_a ? c - 1 - (a_less + t) : c + b_less + (t - tie_a); };
-        uint32_t Tpos = 0xffffffffu;
-        if (needp < ties) {   // more equal-distance candidates than needed: smallest pool positions win
-            auto getpos = [&](int t) -> uint32_t { return (uint32_t)__ldg(SP + tie_index(t)); };
-            int unused;
-            radix_select<NT>(getpos, ties, needp, hist, xw, tid, Tpos, unused);
-        }
-        grp_sync<NT>();   // kept bitmaps complete and visible to the whole group
-        const int total = cnt_less + ties;
-        int run_sel = 0;
-        for (int base = 0; base < total; base += NT) {
-            const int e = base + tid;
-            const bool valid = e < total;
-            int idx = 0, pos = 0;
-            if (valid) {
-                idx = e < a_less ? c - 1 - e : (e < cnt_less ? c + (e - a_less) : tie_index(e - cnt_less));
-                pos = __ldg(SP + idx);
-            }
-            const bool selp = valid && (e < cnt_less || (uint32_t)pos <= Tpos);
-            bool emit = false;
-            int32_t id = 0;
-            if (selp) {
-                id = __ldg(SI + idx);
-                bool dup;
-                if (use_kb) {
-                    dup = (kbits[pos >> 5] >> (pos & 31)) & 1u;
-                } else {
-                    int l = 0, h = d;            // lower_bound of id in the id-sorted row
-                    while (l < h) {
-                        const int mid = (l + h) >> 1;
-                        if (nbr[mid] < id) l = mid + 1; else h = mid;
-                    }
-                    dup = l < d && nbr[l] == id && ((k == d) || ((bits[l >> 5] >> (l & 31)) & 1u));
-                }
-                emit = !dup;
-            }
-            int es, ee, ts, te;
-            grp_excl2<NT>(selp, emit, tid, xw, es, ee, ts, te);
-            if (selp && p.sel_dist) p.sel_dist[off + k + run_sel + es] = __uint_as_float(dist_bits(sv, __ldg(S + idx)));
-            if (emit) p.sel_idx[off + k + n_emit + ee] = id;
-            run_sel += ts;
-            n_emit += te;
-        }
+// --------------------------------------------------------------------------------- CTA tier
+// One item handled by one CTA (long rows). Kept list in row order.
+__device__ void choose_item_cta(const ChooseP& p, int w, uint32_t* sd, int sd_cap, uint32_t* hist, uint32_t* kbits,
+                                uint32_t* bits_s, int bits_cap_words, uint32_t* bits_g, int* xw) {
+    constexpr int NT = PCG_LARGE_NT, NW = NT / 32;
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    Item it;
+    item_header(p, w, PCG_KB_WORDS_CTA, it);
+    TRACE(0); TRACE_VAL(8, it.d); TRACE_VAL(9, it.k); TRACE_VAL(10, it.o);
+    if (tid == 0) xw[29] = atomicAdd(&p.status[ST_SLOTS], it.nslots);
+    if (it.use_kb)
+        for (int q = tid; q < (p.P + 31) >> 5; q += NT) kbits[q] = 0u;
+    __syncthreads();
+    it.slot0 = xw[29];
+    it.off = (int64_t)it.slot0 * PCG_SLOT;
+    if (item_overflow<NT>(p, it, tid)) { __syncthreads(); return; }
+    TRACE(1);
+    const int d = it.d, k = it.k;
+    const float sv = it.sv;
+    const int32_t* __restrict__ nbr = p.indices + it.beg;
+    const float* __restrict__ escore = p.entry_score ? p.entry_score + it.beg : nullptr;
+    const float* __restrict__ score = p.score;
+    const bool cached = d <= sd_cap;
+    if (cached) {
+#pragma unroll 4
+        for (int j = tid; j < d; j += NT) sd[j] = dist_bits(sv, escore ? escore[j] : __ldg(score + __ldg(nbr + j)));
+        __syncthreads();
     }
-    const int m = k + n_emit;
-    if (tid == 0) {
-        p.it_slot0[w] = slot0;
-        p.it_m[w] = m;
-        p.it_base[w] = off;
-        p.it_done[w] = 0;
+    auto get = [&](int j) -> uint32_t {
+        return cached ? sd[j] : dist_bits(sv, escore ? escore[j] : __ldg(score + __ldg(nbr + j)));
+    };
+    TRACE(2);
+    uint32_t T = 0xffffffffu;
+    int need = 0x7fffffff;
+    if (k < d) {
+        if (k > 0) radix_select<NT>(get, d, k, hist, xw, tid, T, need);
+        else { T = 0; need = 0; }
     }
-    for (int c = tid; c < nslots; c += NT) p.slot_item[slot0 + c] = (c * PCG_SLOT < m) ? w : -1;
-    grp_sync<NT>();
+    TRACE(3);
+    uint32_t* bits = (d <= bits_cap_words * 32) ? bits_s : bits_g;
+    // ---- ordered compaction: every warp owns a contiguous chunk of the row; count, one scan of the
+    // per-warp counts, then each warp writes its chunk using ballots only ----
+    const int chunk = (((d + NW - 1) / NW) + 31) & ~31;       // multiple of 32 positions per warp
+    const int cb = min(d, wid * chunk), ce = min(d, cb + chunk);
+    int cl = 0, ct = 0;
+    if (k < d) {
+        for (int base = cb; base < ce; base += 32) {
+            const int j = base + lane;
+            const uint32_t key = j < ce ? get(j) : 0xffffffffu;
+            cl += __popc(__ballot_sync(PCG_FULL, j < ce && key < T));
+            ct += __popc(__ballot_sync(PCG_FULL, j < ce && key == T));
+        }
+    } else {
+        cl = ce - cb;
+    }
+    if (lane == 0) { xw[wid] = cl; hist[wid] = (uint32_t)ct; }   // hist is free here
+    __syncthreads();
+    int run_less = 0, run_tie = 0;
+    for (int q = 0; q < wid; ++q) { run_less += xw[q]; run_tie += (int)hist[q]; }
+    __syncthreads();
+    const int32_t* __restrict__ epp = it.use_kb ? p.entry_pool_pos + it.beg : nullptr;
+    int32_t id_n = cb + lane < ce ? __ldg(nbr + cb + lane) : 0;
+    int pp_n = (epp && cb + lane < ce) ? __ldg(epp + cb + lane) : -1;
+    for (int base = cb; base < ce; base += 32) {
+        const int j = base + lane;
+        const bool valid = j < ce;
+        const int32_t id = id_n;
+        const int pp = pp_n;
+        if (j + 32 < ce) {                                   // prefetch the next tile
+            id_n = __ldg(nbr + j + 32);
+            pp_n = epp ? __ldg(epp + j + 32) : -1;
+        }
+        const uint32_t key = (valid && (k < d || p.sel_dist)) ? get(j) : 0u;
+        const bool less = valid && (k >= d || key < T);
+        const bool tie = valid && k < d && key == T;
+        const unsigned lt = lanemask_lt();
+        const unsigned ml = __ballot_sync(PCG_FULL, less), mt = __ballot_sync(PCG_FULL, tie);
+        const int tie_before = run_tie + __popc(mt & lt);
+        const bool sel = less || (tie && tie_before < need);
+        if (sel) {
+            const int64_t at = it.off + run_less + __popc(ml & lt) + min(tie_before, need);
+            p.sel_idx[at] = id;
+            if (p.sel_dist) p.sel_dist[at] = __uint_as_float(key);
+            if (pp >= 0) atomicOr(&kbits[pp >> 5], 1u << (pp & 31));
+        }
+        if (it.want_bits) {
+            const unsigned sm = __ballot_sync(PCG_FULL, sel);
+            if (lane == 0) bits[base >> 5] = sm;
+        }
+        run_less += __popc(ml);
+        run_tie += __popc(mt);
+    }
+    __syncthreads();   // kept bitmaps complete and visible to the whole CTA
+    TRACE(4);
+    int m = k;
+    if (it.o > 0) m += oversample<NT>(p, it, tid, nbr, kbits, bits, hist, xw);
+    TRACE(6);
+    item_finish<NT>(p, it, tid, m);
+    __syncthreads();
+    TRACE(7);
 }
 
 // Classify items by row length into the warp queue and the CTA queue.
@@ -468,14 +601,6 @@ __global__ void k_choose_classify(ChooseP p) {
     if (large) p.large_q[bl + __popc(ml & lt)] = w;
 }
 
-struct WarpSmem {
-    uint32_t sd[PCG_SMALL_MAX];
-    uint32_t hist[256];
-    uint32_t kbits[PCG_KB_WORDS_WARP];
-    uint32_t bits[PCG_SMALL_MAX / 32];
-    int xw[32];
-};
-
 __global__ void __launch_bounds__(PCG_WARPS_PER_CTA * 32) k_choose_warp(ChooseP p) {
     __shared__ WarpSmem sm[PCG_WARPS_PER_CTA];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -486,8 +611,7 @@ __global__ void __launch_bounds__(PCG_WARPS_PER_CTA * 32) k_choose_warp(ChooseP 
         if (lane == 0) q = atomicAdd(&p.status[ST_SMALL_CTR], 1);
         q = __shfl_sync(PCG_FULL, q, 0);
         if (q >= n) break;
-        choose_item<32>(p, p.small_q[q], lane, s.sd, PCG_SMALL_MAX, s.hist, s.kbits, PCG_KB_WORDS_WARP, s.bits,
-                        PCG_SMALL_MAX / 32, nullptr, s.xw);
+        choose_item_warp(p, p.small_q[q], s);
     }
 }
 
@@ -506,8 +630,8 @@ __global__ void __launch_bounds__(PCG_LARGE_NT) k_choose_cta(ChooseP p) {
         const int q = s_q;
         __syncthreads();
         if (q >= n) break;
-        choose_item<PCG_LARGE_NT>(p, p.large_q[q], threadIdx.x, sd, p.large_cap, hist, kbits, PCG_KB_WORDS_CTA, bits,
-                                  p.large_cap / 32, p.bits_slab + (int64_t)blockIdx.x * p.slab_words, xw);
+        choose_item_cta(p, p.large_q[q], sd, p.large_cap, hist, kbits, bits, p.large_cap / 32,
+                        p.bits_slab + (int64_t)blockIdx.x * p.slab_words, xw);
     }
 }
 
@@ -560,6 +684,12 @@ __global__ void k_pool_positions(const int32_t* __restrict__ pool, int P, int32_
     if (i < P) pool_pos_of[pool[i]] = i;
 }
 
+__global__ void k_entry_pool_pos(const int32_t* __restrict__ indices, int64_t nnz,
+                                 const int32_t* __restrict__ pool_pos_of, int32_t* __restrict__ out) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < nnz) out[e] = pool_pos_of[indices[e]];
+}
+
 // ------------------------------------------------------------------------------------------- C ABI
 struct WsLayout {
     size_t small_q, large_q, bits_slab, total;
@@ -593,6 +723,12 @@ static int device_sms() {
 
 extern "C" int pcg_device_sms(void) { return device_sms(); }
 
+#ifdef PCG_TRACE
+extern "C" __attribute__((visibility("default"))) int pcg_debug_set_trace(long long* buf) {
+    return (int)cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf));
+}
+#endif
+
 extern "C" size_t pcg_choose_workspace_bytes(int B, int R, int64_t max_degree) {
     return ws_layout(B, R, max_degree, 148 * 2).total;   // sized for the largest grid we ever launch
 }
@@ -606,6 +742,15 @@ extern "C" int pcg_pool_positions(const int32_t* pool, int P, int64_t n_nodes, i
     return pcg_check_launch("pcg_pool_positions");
 }
 
+extern "C" int pcg_entry_pool_positions(const int32_t* indices, int64_t nnz, const int32_t* pool_pos_of,
+                                        int32_t* entry_pool_pos, pcg_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PCG_REQUIRE(nnz == 0 || (indices && pool_pos_of && entry_pool_pos), "pcg_entry_pool_positions: null pointer");
+    if (nnz > 0)
+        k_entry_pool_pos<<<(unsigned)((nnz + 255) / 256), 256, 0, stream>>>(indices, nnz, pool_pos_of, entry_pool_pos);
+    return pcg_check_launch("pcg_entry_pool_positions");
+}
+
 // second stream + events so the warp tier and the CTA tier run side by side (fork/join; capturable)
 static cudaStream_t g_side = nullptr;
 static cudaEvent_t g_fork = nullptr, g_join = nullptr;
@@ -614,7 +759,7 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
                           const float* entry_score, const float* center_score, const int32_t* targets,
                           const int64_t* labels, int B, const double* thresh_host, const int32_t* k_override,
                           double rho, const float* ps_score, const int32_t* ps_pos, const int32_t* ps_id,
-                          const int32_t* pool_pos_of, int P, int train,
+                          const int32_t* entry_pool_pos, int P, int train,
                           int64_t max_degree, int32_t* sel_idx, float* sel_dist, int64_t cap_slots,
                           int32_t* slot_item, int32_t* it_slot0, int32_t* it_m, int64_t* it_base, int32_t* it_done, void* workspace,
                           size_t workspace_bytes, int32_t* status, pcg_stream_t stream_) {
@@ -638,7 +783,7 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
     ChooseP p;
     p.indptr = indptr; p.indices = indices; p.score = score; p.entry_score = entry_score;
     p.center_score = center_score; p.targets = targets; p.labels = labels; p.k_override = k_override;
-    p.ps_score = ps_score; p.ps_pos = ps_pos; p.ps_id = ps_id; p.pool_pos_of = pool_pos_of;
+    p.ps_score = ps_score; p.ps_pos = ps_pos; p.ps_id = ps_id; p.entry_pool_pos = entry_pool_pos;
     p.n_nodes = n_nodes; p.R = R; p.B = B;
     p.P = (train && ps_score) ? P : 0; p.train = train;
     for (int r = 0; r < PCG_MAX_REL; ++r) p.thresh[r] = r < R ? thresh_host[r] : 0.5;

@@ -74,6 +74,7 @@ class Engine:
         self.pool = None            # int32 [P]
         self.sorted_pool = None     # (ps_score, ps_pos, ps_id, workspace)
         self.pool_pos_of = None     # int32 [N]: node id -> pool position or -1
+        self.entry_pool_pos = None  # int32 [nnz]: the same per CSR entry (coalesced reads in the kernels)
         self.P = 0
         self._pin = None
         self._ws = None
@@ -113,6 +114,11 @@ class Engine:
             rc = self.lib.pcg_pool_positions(self.pool.data_ptr(), self.P, self.N, self.pool_pos_of.data_ptr(),
                                              _lib.stream_ptr())
             _lib.check(rc, "pcg_pool_positions")
+            self.entry_pool_pos = torch.empty(max(self.indices.shape[0], 1), dtype=torch.int32, device=self.device)
+            rc = self.lib.pcg_entry_pool_positions(self.indices.data_ptr(), self.indices.shape[0],
+                                                   self.pool_pos_of.data_ptr(), self.entry_pool_pos.data_ptr(),
+                                                   _lib.stream_ptr())
+            _lib.check(rc, "pcg_entry_pool_positions")
 
     def _alloc_sorted_pool(self, P):
         n = max(P, 1)
@@ -248,7 +254,7 @@ class Engine:
             self.N if n_nodes is None else n_nodes, R,
             self.score.data_ptr() if use_table else None, _lib.ptr(entry_score), _lib.ptr(center_score),
             targets.data_ptr(), _lib.ptr(labels) if train else None, B, th, _lib.ptr(k_override), float(rho),
-            _lib.ptr(ps), _lib.ptr(pp), _lib.ptr(pi), _lib.ptr(self.pool_pos_of) if use_table else None, P,
+            _lib.ptr(ps), _lib.ptr(pp), _lib.ptr(pi), _lib.ptr(self.entry_pool_pos) if use_table else None, P,
             int(bool(train)), maxdeg, s.idx.data_ptr(), _lib.ptr(dist),
             cap_slots, s.slot_item.data_ptr(), s.it_slot0.data_ptr(), s.it_m.data_ptr(), s.it_base.data_ptr(),
             s.it_done.data_ptr(), self._ws.data_ptr(), int(ws_bytes), s.status.data_ptr(), _lib.stream_ptr())
