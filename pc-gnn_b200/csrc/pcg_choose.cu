@@ -3,10 +3,11 @@
 // Replaces the per-target Python loop of /root/reference/src/layers.py:633-738 (one torch.sort and
 // two .tolist() host syncs per target per relation) by an exact k-smallest selection on the key
 // (|s_v - s_u| as fp32 bits, position in the id-sorted row):
-//   1. the row's distances go to shared memory; rows of <= 128 entries get their exact ranks by
-//      counting (no atomics, no passes), longer rows by a radix-select (8-bit passes over the
-//      distance bits, skipping the digits all keys share) that yields the k-th smallest distance T
-//      and how many elements equal to T are still needed,
+//   1. the k-th smallest distance T (and how many elements equal to T are still needed) is found by a
+//      bit-serial selection: two key bits per step, decided from counts obtained by warp reductions
+//      (no atomics, no histogram); bits all keys share are skipped. Rows of <= 512 entries live in the
+//      REGISTERS of one warp; longer rows in the shared memory of one CTA, which switches to a short
+//      candidate list once few keys still match the prefix,
 //   2. an ORDERED compaction writes every element with d < T plus the first `need` elements with
 //      d == T (row order == id order, which is the reference's stable-sort tie rule),
 //   3. for positive targets the o nearest train positives come from the score-sorted pool
@@ -20,12 +21,13 @@
 #include "pcg_common.cuh"
 
 #define PCG_SMALL_MAX 512      // entries a warp keeps in its shared-memory slice
-#define PCG_RANK_MAX 128       // rows up to this length are ranked by counting
-#define PCG_WARPS_PER_CTA 4    // warp kernel: 4 items in flight per CTA (8.4 KB of shared memory each)
+#define PCG_WARPS_PER_CTA 8    // warp kernel: 8 items in flight per CTA
 #define PCG_LARGE_NT 512       // CTA kernel threads
+#define PCG_HUGE_MIN 4096      // rows longer than this are scheduled first
 #define PCG_LARGE_CAP_MAX 32768
 #define PCG_KB_WORDS_WARP 256  // kept-pool bitmap words per warp  (pools up to 8192 positives)
 #define PCG_KB_WORDS_CTA 2048  // ... per CTA                      (pools up to 65536 positives)
+#define PCG_CAND_CAP 2048      // CTA-tier selection: candidate keys kept in shared memory once they fit
 
 struct ChooseP {
     const int64_t* indptr;
@@ -209,6 +211,130 @@ __device__ __forceinline__ void radix_select(Get get, int n, int kth, uint32_t* 
     need = remaining;
 }
 
+// ---- bit-serial selection (two bits per step, counts by warp reduction; no atomics, no histogram) ----
+// Decide the next digit of the k-th smallest key from the counts of the three lowest digit values.
+__device__ __forceinline__ uint32_t pick_digit(int c0, int c1, int c2, int& remaining) {
+    if (remaining <= c0) return 0u;
+    remaining -= c0;
+    if (remaining <= c1) return 1u;
+    remaining -= c1;
+    if (remaining <= c2) return 2u;
+    remaining -= c2;
+    return 3u;
+}
+
+// One warp, NE keys per lane in REGISTERS (row position of key[e] is e*32 + lane; vmask marks the valid e).
+// Returns (T, need) like radix_select. ~ (bits that differ)/2 steps of NE*8 ALU ops + 3 warp reductions.
+template <int NE>
+__device__ __forceinline__ void warp_bitselect(const uint32_t (&key)[NE], uint32_t vmask, int kth, uint32_t& T,
+                                               int& need) {
+    uint32_t lo = 0xffffffffu, hi = 0u;
+#pragma unroll
+    for (int e = 0; e < NE; ++e)
+        if ((vmask >> e) & 1u) { lo = min(lo, key[e]); hi = max(hi, key[e]); }
+    lo = __reduce_min_sync(PCG_FULL, lo);
+    hi = __reduce_max_sync(PCG_FULL, hi);
+    if (lo == hi) { T = lo; need = kth; return; }
+    int hb = 31 - __clz(lo ^ hi);
+    uint32_t mask = hb == 31 ? 0u : ~((2u << hb) - 1u);
+    uint32_t prefix = lo & mask;
+    int remaining = kth;
+    while (hb >= 0) {
+        const int shift = max(hb - 1, 0);
+        const uint32_t dmask = hb >= 1 ? 3u : 1u;
+        int c0 = 0, c1 = 0, c2 = 0;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            const bool active = ((vmask >> e) & 1u) && ((key[e] ^ prefix) & mask) == 0u;
+            const uint32_t dg = (key[e] >> shift) & dmask;
+            c0 += active && dg == 0u;
+            c1 += active && dg == 1u;
+            c2 += active && dg == 2u;
+        }
+        c0 = __reduce_add_sync(PCG_FULL, c0);
+        c1 = __reduce_add_sync(PCG_FULL, c1);
+        c2 = __reduce_add_sync(PCG_FULL, c2);
+        const uint32_t dg = pick_digit(c0, c1, c2, remaining);
+        prefix |= dg << shift;
+        mask |= dmask << shift;
+        hb = shift - 1;
+    }
+    T = prefix;
+    need = remaining;
+}
+
+// One CTA, keys behind get(0..n-1) (shared memory). Same two-bit steps; as soon as the keys still matching
+// the prefix fit into `cand` they are copied there and the remaining steps only look at that list.
+//   wsum: >= 3 * NT/32 ints of scratch, xw[24..28] scratch
+template <int NT, class Get>
+__device__ __forceinline__ void cta_bitselect(Get get, int n, int kth, uint32_t* cand, int cand_cap, int* wsum, int* xw,
+                                              int tid, uint32_t& T, int& need) {
+    constexpr int NW = NT / 32;
+    const int wid = tid >> 5, lane = tid & 31;
+    uint32_t kmin, kmax;
+    grp_minmax<NT>(get, n, tid, xw, kmin, kmax);
+    if (kmin == kmax) { T = kmin; need = kth; return; }
+    int hb = 31 - __clz(kmin ^ kmax);
+    uint32_t mask = hb == 31 ? 0u : ~((2u << hb) - 1u);
+    uint32_t prefix = kmin & mask;
+    int remaining = kth;
+    bool listed = false;
+    int n_act = n;                 // keys matching the prefix
+    while (hb >= 0) {
+        const int shift = max(hb - 1, 0);
+        const uint32_t dmask = hb >= 1 ? 3u : 1u;
+        int c0 = 0, c1 = 0, c2 = 0;
+        const int lim = listed ? n_act : n;
+        for (int j = tid; j < lim; j += NT) {
+            const uint32_t key = listed ? cand[j] : get(j);
+            const bool active = ((key ^ prefix) & mask) == 0u;
+            const uint32_t dg = (key >> shift) & dmask;
+            c0 += active && dg == 0u;
+            c1 += active && dg == 1u;
+            c2 += active && dg == 2u;
+        }
+        c0 = __reduce_add_sync(PCG_FULL, c0);
+        c1 = __reduce_add_sync(PCG_FULL, c1);
+        c2 = __reduce_add_sync(PCG_FULL, c2);
+        if (lane == 0) { wsum[wid * 3] = c0; wsum[wid * 3 + 1] = c1; wsum[wid * 3 + 2] = c2; }
+        __syncthreads();
+        c0 = lane < NW ? wsum[lane * 3] : 0;
+        c1 = lane < NW ? wsum[lane * 3 + 1] : 0;
+        c2 = lane < NW ? wsum[lane * 3 + 2] : 0;
+        c0 = __reduce_add_sync(PCG_FULL, c0);
+        c1 = __reduce_add_sync(PCG_FULL, c1);
+        c2 = __reduce_add_sync(PCG_FULL, c2);
+        const int before = remaining;
+        const uint32_t dg = pick_digit(c0, c1, c2, remaining);
+        const int cnt_dg = dg == 0u ? c0 : (dg == 1u ? c1 : (dg == 2u ? c2 : n_act - c0 - c1 - c2));
+        (void)before;
+        prefix |= dg << shift;
+        mask |= dmask << shift;
+        hb = shift - 1;
+        n_act = cnt_dg;
+        __syncthreads();                       // wsum may be rewritten next step
+        if (!listed && hb >= 0 && n_act <= cand_cap) {
+            // copy the surviving keys into the candidate list (order is irrelevant for counting)
+            if (tid == 0) xw[26] = 0;
+            __syncthreads();
+            const int n_up = (n + 31) & ~31;
+            for (int j = tid; j < n_up; j += NT) {
+                const uint32_t key = j < n ? get(j) : 0u;
+                const bool active = j < n && ((key ^ prefix) & mask) == 0u;
+                const unsigned m = __ballot_sync(PCG_FULL, active);
+                int base = 0;
+                if (lane == 0 && m) base = atomicAdd(&xw[26], __popc(m));
+                base = __shfl_sync(PCG_FULL, base, 0);
+                if (active) cand[base + __popc(m & lanemask_lt())] = key;
+            }
+            __syncthreads();
+            listed = true;
+        }
+    }
+    T = prefix;
+    need = remaining;
+}
+
 // First index in [lo, hi) where pred turns false (pred is true on a prefix), found with warp-wide
 // 32-ary probes: ceil(log32(range)) rounds of one predicate evaluation per lane. Every warp of the
 // group runs it redundantly (same addresses -> broadcast loads), so no block barrier is needed.
@@ -357,16 +483,81 @@ __device__ __forceinline__ void item_finish(const ChooseP& p, const Item& it, in
 
 // --------------------------------------------------------------------------------- warp tier
 struct WarpSmem {
-    unsigned long long keys[PCG_SMALL_MAX];   // sort path: (distance << 32 | row position); else uint32 distances
-    int32_t ids[PCG_SMALL_MAX];               // the row's neighbour ids
-    uint32_t hist[256];                       // rank path: kept row positions; pool phase: radix histogram
-    uint32_t kbits[PCG_KB_WORDS_WARP];
-    uint32_t bits[PCG_SMALL_MAX / 32];
+    uint32_t hist[256];                       // pool phase: radix histogram (equal-distance pool ties)
+    uint32_t kbits[PCG_KB_WORDS_WARP];        // kept neighbours that are pool members, by pool position
+    uint32_t bits[PCG_SMALL_MAX / 32];        // kept row positions (fallback membership test)
     int xw[32];
 };
 
-// One item handled by one warp (d <= PCG_SMALL_MAX). The kept list comes out ordered by (distance,
-// position) for sorted rows and in row order otherwise: any fixed order serves (it is a set).
+// One item handled by one warp with the whole row in registers: NE ids/keys per lane, row position of
+// slot e is e*32 + lane. Two memory round trips (ids, then scores), selection and compaction without
+// shared memory, kept list written in row order.
+template <int NE>
+__device__ __forceinline__ int warp_row(const ChooseP& p, const Item& it, WarpSmem& s, const int32_t* __restrict__ nbr) {
+    const int lane = threadIdx.x & 31;
+    const int tid = lane, w = it.w;
+    const int d = it.d, k = it.k;
+    const float* __restrict__ escore = p.entry_score ? p.entry_score + it.beg : nullptr;
+    const int32_t* __restrict__ epp = it.use_kb ? p.entry_pool_pos + it.beg : nullptr;
+    const bool all = k >= d;
+    const bool need_dist = !all || p.sel_dist != nullptr;
+    int32_t id[NE];
+    int pp[NE];
+    uint32_t key[NE];
+    uint32_t vmask = 0;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        const int j = e * 32 + lane;
+        const bool valid = j < d;
+        vmask |= (uint32_t)valid << e;
+        id[e] = valid ? __ldg(nbr + j) : 0;
+        pp[e] = (valid && epp) ? __ldg(epp + j) : -1;
+    }
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        const int j = e * 32 + lane;
+        uint32_t x = 0u;
+        if (((vmask >> e) & 1u) && need_dist) x = dist_bits(it.sv, escore ? escore[j] : __ldg(p.score + id[e]));
+        key[e] = x;
+    }
+    TRACE(2);
+    uint32_t T = 0xffffffffu;
+    int need = 0x7fffffff;
+    if (!all) {
+        if (k > 0) warp_bitselect<NE>(key, vmask, k, T, need);
+        else { T = 0; need = 0; }
+    }
+    TRACE(3);
+    int run_less = 0, run_tie = 0;
+    const unsigned lt = lanemask_lt();
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        if (e * 32 < d) {                               // warp-uniform
+            const bool valid = (vmask >> e) & 1u;
+            const bool less = valid && (all || key[e] < T);
+            const bool tie = valid && !all && key[e] == T;
+            const unsigned ml = __ballot_sync(PCG_FULL, less), mt = __ballot_sync(PCG_FULL, tie);
+            const int tie_before = run_tie + __popc(mt & lt);
+            const bool sel = less || (tie && tie_before < need);
+            if (sel) {
+                const int64_t at = it.off + run_less + __popc(ml & lt) + min(tie_before, need);
+                p.sel_idx[at] = id[e];
+                if (p.sel_dist) p.sel_dist[at] = __uint_as_float(key[e]);
+                if (pp[e] >= 0) atomicOr(&s.kbits[pp[e] >> 5], 1u << (pp[e] & 31));
+            }
+            if (it.want_bits) {
+                const unsigned sm = __ballot_sync(PCG_FULL, sel);
+                if (lane == 0) s.bits[e] = sm;
+            }
+            run_less += __popc(ml);
+            run_tie += __popc(mt);
+        }
+    }
+    __syncwarp();
+    TRACE(4);
+    return 0;
+}
+
 __device__ void choose_item_warp(const ChooseP& p, int w, WarpSmem& s) {
     const int lane = threadIdx.x & 31;
     const int tid = lane;
@@ -379,93 +570,18 @@ __device__ void choose_item_warp(const ChooseP& p, int w, WarpSmem& s) {
     it.off = (int64_t)it.slot0 * PCG_SLOT;
     if (item_overflow<32>(p, it, lane)) { __syncwarp(); return; }
     TRACE(1);
-    const int d = it.d, k = it.k;
     const int32_t* __restrict__ nbr = p.indices + it.beg;
-    const float* __restrict__ escore = p.entry_score ? p.entry_score + it.beg : nullptr;
-    uint32_t* sd = reinterpret_cast<uint32_t*>(s.keys);
-    if (it.use_kb)
+    if (it.use_kb) {
         for (int q = lane; q < (p.P + 31) >> 5; q += 32) s.kbits[q] = 0u;
-    if (it.want_bits)
-        for (int q = lane; q < (d + 31) >> 5; q += 32) s.bits[q] = 0u;
-    for (int j = lane; j < d; j += 32) s.ids[j] = __ldg(nbr + j);
-    __syncwarp();
-    const bool all = k >= d;
-    const bool by_rank = !all && d <= PCG_RANK_MAX;
-    const bool by_sort = !all && !by_rank;
-    const bool need_dist = !all || p.sel_dist != nullptr;
-    int n2 = 0;
-    if (need_dist) {
-        if (by_sort) {
-            n2 = 256;
-            while (n2 < d) n2 <<= 1;
-            for (int j = lane; j < n2; j += 32) {
-                unsigned long long key = ~0ull;
-                if (j < d) key = ((unsigned long long)dist_bits(it.sv, escore ? escore[j] : __ldg(p.score + s.ids[j])) << 32) | (unsigned)j;
-                s.keys[j] = key;
-            }
-        } else {
-            for (int j = lane; j < d; j += 32) sd[j] = dist_bits(it.sv, escore ? escore[j] : __ldg(p.score + s.ids[j]));
-        }
         __syncwarp();
     }
-    TRACE(2);
-    if (by_rank) {
-        // exact rank of every element by counting (keys (distance, position) are unique)
-        constexpr int EPL = PCG_RANK_MAX / 32;
-        uint32_t mykey[EPL];
-        int rank[EPL];
-#pragma unroll
-        for (int e = 0; e < EPL; ++e) { const int j = lane + 32 * e; mykey[e] = j < d ? sd[j] : 0xffffffffu; rank[e] = 0; }
-        for (int q = 0; q < d; ++q) {
-            const uint32_t x = sd[q];
-#pragma unroll
-            for (int e = 0; e < EPL; ++e) rank[e] += (x < mykey[e]) || (x == mykey[e] && q < lane + 32 * e);
-        }
-        int n_out = 0;
-#pragma unroll
-        for (int e = 0; e < EPL; ++e) {
-            const int j = lane + 32 * e;
-            if (32 * e < d) {                        // warp-uniform
-                const bool sel = j < d && rank[e] < k;
-                const unsigned sm = __ballot_sync(PCG_FULL, sel);
-                if (sel) s.hist[n_out + __popc(sm & lanemask_lt())] = (uint32_t)j;
-                n_out += __popc(sm);
-            }
-        }
-        __syncwarp();
-    } else if (by_sort) {
-        // bitonic sort of the n2 (distance, position) keys in shared memory
-        for (int k2 = 2; k2 <= n2; k2 <<= 1) {
-            for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
-                for (int t = lane; t < (n2 >> 1); t += 32) {
-                    const int lo = ((t & ~(j2 - 1)) << 1) | (t & (j2 - 1));
-                    const int hi = lo + j2;
-                    const unsigned long long a = s.keys[lo], b = s.keys[hi];
-                    if ((a > b) == ((lo & k2) == 0)) { s.keys[lo] = b; s.keys[hi] = a; }
-                }
-                __syncwarp();
-            }
-        }
-    }
-    TRACE(3);
-    // ---- emit the kept neighbours ----
-    const int32_t* __restrict__ epp = it.use_kb ? p.entry_pool_pos + it.beg : nullptr;
-    for (int t = lane; t < k; t += 32) {
-        int j;
-        uint32_t key = 0;
-        if (by_sort) { const unsigned long long kk = s.keys[t]; j = (int)(uint32_t)kk; key = (uint32_t)(kk >> 32); }
-        else { j = all ? t : (int)s.hist[t]; if (need_dist) key = sd[j]; }
-        p.sel_idx[it.off + t] = s.ids[j];
-        if (p.sel_dist) p.sel_dist[it.off + t] = __uint_as_float(key);
-        if (epp) {
-            const int pp = __ldg(epp + j);
-            if (pp >= 0) atomicOr(&s.kbits[pp >> 5], 1u << (pp & 31));
-        }
-        if (it.want_bits) atomicOr(&s.bits[j >> 5], 1u << (j & 31));
-    }
-    __syncwarp();
-    TRACE(4);
-    int m = k;
+    const int d = it.d;
+    if (d <= 32) warp_row<1>(p, it, s, nbr);
+    else if (d <= 64) warp_row<2>(p, it, s, nbr);
+    else if (d <= 128) warp_row<4>(p, it, s, nbr);
+    else if (d <= 256) warp_row<8>(p, it, s, nbr);
+    else warp_row<16>(p, it, s, nbr);
+    int m = it.k;
     if (it.o > 0) m += oversample<32>(p, it, lane, nbr, s.kbits, s.bits, s.hist, s.xw);
     TRACE(6);
     item_finish<32>(p, it, lane, m);
@@ -476,7 +592,7 @@ __device__ void choose_item_warp(const ChooseP& p, int w, WarpSmem& s) {
 // --------------------------------------------------------------------------------- CTA tier
 // One item handled by one CTA (long rows). Kept list in row order.
 __device__ void choose_item_cta(const ChooseP& p, int w, uint32_t* sd, int sd_cap, uint32_t* hist, uint32_t* kbits,
-                                uint32_t* bits_s, int bits_cap_words, uint32_t* bits_g, int* xw) {
+                                uint32_t* cand, uint32_t* bits_s, int bits_cap_words, uint32_t* bits_g, int* xw) {
     constexpr int NT = PCG_LARGE_NT, NW = NT / 32;
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     Item it;
@@ -508,7 +624,7 @@ __device__ void choose_item_cta(const ChooseP& p, int w, uint32_t* sd, int sd_ca
     uint32_t T = 0xffffffffu;
     int need = 0x7fffffff;
     if (k < d) {
-        if (k > 0) radix_select<NT>(get, d, k, hist, xw, tid, T, need);
+        if (k > 0) cta_bitselect<NT>(get, d, k, cand, PCG_CAND_CAP, reinterpret_cast<int*>(hist), xw, tid, T, need);
         else { T = 0; need = 0; }
     }
     TRACE(3);
@@ -575,33 +691,39 @@ __device__ void choose_item_cta(const ChooseP& p, int w, uint32_t* sd, int sd_ca
     TRACE(7);
 }
 
-// Classify items by row length into the warp queue and the CTA queue.
+// Classify items by row length: the warp queue, and the CTA queue with the longest rows (the critical
+// path of the CTA tier) at the front and the other long rows filled in from the back.
 __global__ void k_choose_classify(ChooseP p) {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     const int W = p.R * p.B;
-    bool small = false, large = false;
+    bool small = false, large = false, huge = false;
     if (w < W) {
         const int r = w / p.B, i = w - r * p.B;
         const int64_t row = (int64_t)r * p.n_nodes + p.targets[i];
         const int64_t d = p.indptr[row + 1] - p.indptr[row];
         small = d <= PCG_SMALL_MAX;
-        large = !small;
+        huge = d > PCG_HUGE_MIN;
+        large = !small && !huge;
     }
     const unsigned lt = lanemask_lt();
     const int lane = threadIdx.x & 31;
-    unsigned ms = __ballot_sync(PCG_FULL, small), ml = __ballot_sync(PCG_FULL, large);
-    int bs = 0, bl = 0;
+    const unsigned ms = __ballot_sync(PCG_FULL, small), ml = __ballot_sync(PCG_FULL, large),
+                   mh = __ballot_sync(PCG_FULL, huge);
+    int bs = 0, bl = 0, bh = 0;
     if (lane == 0) {
         if (ms) bs = atomicAdd(&p.status[ST_NSMALL], __popc(ms));
         if (ml) bl = atomicAdd(&p.status[ST_NLARGE], __popc(ml));
+        if (mh) bh = atomicAdd(&p.status[ST_NHUGE], __popc(mh));
     }
     bs = __shfl_sync(PCG_FULL, bs, 0);
     bl = __shfl_sync(PCG_FULL, bl, 0);
+    bh = __shfl_sync(PCG_FULL, bh, 0);
     if (small) p.small_q[bs + __popc(ms & lt)] = w;
-    if (large) p.large_q[bl + __popc(ml & lt)] = w;
+    if (huge) p.large_q[bh + __popc(mh & lt)] = w;
+    if (large) p.large_q[W - 1 - (bl + __popc(ml & lt))] = w;
 }
 
-__global__ void __launch_bounds__(PCG_WARPS_PER_CTA * 32) k_choose_warp(ChooseP p) {
+__global__ void __launch_bounds__(PCG_WARPS_PER_CTA * 32, 3) k_choose_warp(ChooseP p) {
     __shared__ WarpSmem sm[PCG_WARPS_PER_CTA];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpSmem& s = sm[wid];
@@ -619,18 +741,20 @@ __global__ void __launch_bounds__(PCG_LARGE_NT) k_choose_cta(ChooseP p) {
     extern __shared__ uint32_t dyn[];
     __shared__ uint32_t hist[256];
     __shared__ uint32_t kbits[PCG_KB_WORDS_CTA];
+    __shared__ uint32_t cand[PCG_CAND_CAP];
     __shared__ int xw[32];
     __shared__ int s_q;
     uint32_t* sd = dyn;                              // [large_cap]
     uint32_t* bits = dyn + p.large_cap;              // [large_cap / 32]
-    const int n = p.status[ST_NLARGE];
+    const int n_huge = p.status[ST_NHUGE], n = n_huge + p.status[ST_NLARGE];
+    const int W = p.R * p.B;
     for (;;) {
         if (threadIdx.x == 0) s_q = atomicAdd(&p.status[ST_LARGE_CTR], 1);
         __syncthreads();
         const int q = s_q;
         __syncthreads();
         if (q >= n) break;
-        choose_item_cta(p, p.large_q[q], sd, p.large_cap, hist, kbits, bits, p.large_cap / 32,
+        choose_item_cta(p, p.large_q[q < n_huge ? q : W - 1 - (q - n_huge)], sd, p.large_cap, hist, kbits, cand, bits, p.large_cap / 32,
                         p.bits_slab + (int64_t)blockIdx.x * p.slab_words, xw);
     }
 }

@@ -15,6 +15,7 @@
 #define ST_OVERFLOW PCG_ST_OVERFLOW
 #define ST_SMALL_CTR 4
 #define ST_LARGE_CTR 5
+#define ST_NHUGE 6
 
 void pcg_set_error(const char* fmt, ...);
 int pcg_check_launch(const char* what);
