@@ -22,7 +22,7 @@
 
 #define PCG_SMALL_MAX 512      // entries a warp keeps in its shared-memory slice
 #define PCG_WARPS_PER_CTA 8    // warp kernel: 8 items in flight per CTA
-#define PCG_LARGE_NT 512       // CTA kernel threads
+#define PCG_LARGE_NT 1024      // CTA kernel threads (one CTA per SM)
 #define PCG_HUGE_MIN 4096      // rows longer than this are scheduled first
 #define PCG_LARGE_CAP_MAX 32768
 #define PCG_KB_WORDS_WARP 256  // kept-pool bitmap words per warp  (pools up to 8192 positives)
@@ -223,41 +223,102 @@ __device__ __forceinline__ uint32_t pick_digit(int c0, int c1, int c2, int& rema
     return 3u;
 }
 
-// One warp, NE keys per lane in REGISTERS (row position of key[e] is e*32 + lane; vmask marks the valid e).
-// Returns (T, need) like radix_select. ~ (bits that differ)/2 steps of NE*8 ALU ops + 3 warp reductions.
-template <int NE>
-__device__ __forceinline__ void warp_bitselect(const uint32_t (&key)[NE], uint32_t vmask, int kth, uint32_t& T,
-                                               int& need) {
+// Sum of three per-thread counters over the NT threads of the group (NT == 32: one warp reduction each;
+// else warp reductions + one exchange through wsum[3 * NT/32] with two barriers).
+template <int NT>
+__device__ __forceinline__ void grp_sum3(int& c0, int& c1, int& c2, int* wsum, int tid) {
+    c0 = __reduce_add_sync(PCG_FULL, c0);
+    c1 = __reduce_add_sync(PCG_FULL, c1);
+    c2 = __reduce_add_sync(PCG_FULL, c2);
+    if (NT > 32) {
+        constexpr int NW = NT / 32;
+        const int wid = tid >> 5, lane = tid & 31;
+        if (lane == 0) { wsum[wid * 3] = c0; wsum[wid * 3 + 1] = c1; wsum[wid * 3 + 2] = c2; }
+        __syncthreads();
+        c0 = lane < NW ? wsum[lane * 3] : 0;
+        c1 = lane < NW ? wsum[lane * 3 + 1] : 0;
+        c2 = lane < NW ? wsum[lane * 3 + 2] : 0;
+        c0 = __reduce_add_sync(PCG_FULL, c0);
+        c1 = __reduce_add_sync(PCG_FULL, c1);
+        c2 = __reduce_add_sync(PCG_FULL, c2);
+        __syncthreads();
+    }
+}
+
+// NT threads, NE keys per thread in REGISTERS (row position of key[e] is e*NT + tid; vmask marks the valid
+// e). Returns (T, need) like radix_select. A CTA (NT > 32) moves the keys that still match the prefix into
+// the shared list `cand` as soon as they fit, and finishes on that list.
+template <int NT, int NE>
+__device__ __forceinline__ void group_bitselect(const uint32_t (&key)[NE], uint32_t vmask, int n, int kth,
+                                                uint32_t* cand, int cand_cap, int* wsum, int* xw, int tid,
+                                                uint32_t& T, int& need) {
     uint32_t lo = 0xffffffffu, hi = 0u;
 #pragma unroll
     for (int e = 0; e < NE; ++e)
         if ((vmask >> e) & 1u) { lo = min(lo, key[e]); hi = max(hi, key[e]); }
     lo = __reduce_min_sync(PCG_FULL, lo);
     hi = __reduce_max_sync(PCG_FULL, hi);
+    if (NT > 32) {
+        if (tid == 0) { xw[24] = (int)0xffffffffu; xw[25] = 0; }
+        __syncthreads();
+        if ((tid & 31) == 0) { atomicMin((uint32_t*)&xw[24], lo); atomicMax((uint32_t*)&xw[25], hi); }
+        __syncthreads();
+        lo = (uint32_t)xw[24];
+        hi = (uint32_t)xw[25];
+        __syncthreads();
+    }
     if (lo == hi) { T = lo; need = kth; return; }
     int hb = 31 - __clz(lo ^ hi);
     uint32_t mask = hb == 31 ? 0u : ~((2u << hb) - 1u);
     uint32_t prefix = lo & mask;
     int remaining = kth;
+    int n_act = n, n_list = 0;
+    bool listed = false;
     while (hb >= 0) {
         const int shift = max(hb - 1, 0);
         const uint32_t dmask = hb >= 1 ? 3u : 1u;
         int c0 = 0, c1 = 0, c2 = 0;
+        if (!listed) {
 #pragma unroll
-        for (int e = 0; e < NE; ++e) {
-            const bool active = ((vmask >> e) & 1u) && ((key[e] ^ prefix) & mask) == 0u;
-            const uint32_t dg = (key[e] >> shift) & dmask;
-            c0 += active && dg == 0u;
-            c1 += active && dg == 1u;
-            c2 += active && dg == 2u;
+            for (int e = 0; e < NE; ++e) {
+                const bool active = ((vmask >> e) & 1u) && ((key[e] ^ prefix) & mask) == 0u;
+                const uint32_t dg = (key[e] >> shift) & dmask;
+                c0 += active && dg == 0u;
+                c1 += active && dg == 1u;
+                c2 += active && dg == 2u;
+            }
+        } else {
+            for (int j = tid; j < n_list; j += NT) {
+                const uint32_t x = cand[j];
+                const bool active = ((x ^ prefix) & mask) == 0u;
+                const uint32_t dg = (x >> shift) & dmask;
+                c0 += active && dg == 0u;
+                c1 += active && dg == 1u;
+                c2 += active && dg == 2u;
+            }
         }
-        c0 = __reduce_add_sync(PCG_FULL, c0);
-        c1 = __reduce_add_sync(PCG_FULL, c1);
-        c2 = __reduce_add_sync(PCG_FULL, c2);
+        grp_sum3<NT>(c0, c1, c2, wsum, tid);
         const uint32_t dg = pick_digit(c0, c1, c2, remaining);
+        n_act = dg == 0u ? c0 : (dg == 1u ? c1 : (dg == 2u ? c2 : n_act - c0 - c1 - c2));
         prefix |= dg << shift;
         mask |= dmask << shift;
         hb = shift - 1;
+        if (NT > 32 && !listed && hb >= 0 && n_act <= cand_cap) {
+            if (tid == 0) xw[26] = 0;
+            __syncthreads();
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                const bool active = ((vmask >> e) & 1u) && ((key[e] ^ prefix) & mask) == 0u;
+                const unsigned m = __ballot_sync(PCG_FULL, active);
+                int base = 0;
+                if ((tid & 31) == 0 && m) base = atomicAdd(&xw[26], __popc(m));
+                base = __shfl_sync(PCG_FULL, base, 0);
+                if (active) cand[base + __popc(m & lanemask_lt())] = key[e];
+            }
+            __syncthreads();
+            listed = true;
+            n_list = n_act;
+        }
     }
     T = prefix;
     need = remaining;
@@ -279,12 +340,13 @@ __device__ __forceinline__ void cta_bitselect(Get get, int n, int kth, uint32_t*
     uint32_t prefix = kmin & mask;
     int remaining = kth;
     bool listed = false;
+    int n_list = 0;                // length of the candidate list once it exists
     int n_act = n;                 // keys matching the prefix
     while (hb >= 0) {
         const int shift = max(hb - 1, 0);
         const uint32_t dmask = hb >= 1 ? 3u : 1u;
         int c0 = 0, c1 = 0, c2 = 0;
-        const int lim = listed ? n_act : n;
+        const int lim = listed ? n_list : n;
         for (int j = tid; j < lim; j += NT) {
             const uint32_t key = listed ? cand[j] : get(j);
             const bool active = ((key ^ prefix) & mask) == 0u;
@@ -304,10 +366,8 @@ __device__ __forceinline__ void cta_bitselect(Get get, int n, int kth, uint32_t*
         c0 = __reduce_add_sync(PCG_FULL, c0);
         c1 = __reduce_add_sync(PCG_FULL, c1);
         c2 = __reduce_add_sync(PCG_FULL, c2);
-        const int before = remaining;
         const uint32_t dg = pick_digit(c0, c1, c2, remaining);
         const int cnt_dg = dg == 0u ? c0 : (dg == 1u ? c1 : (dg == 2u ? c2 : n_act - c0 - c1 - c2));
-        (void)before;
         prefix |= dg << shift;
         mask |= dmask << shift;
         hb = shift - 1;
@@ -329,6 +389,7 @@ __device__ __forceinline__ void cta_bitselect(Get get, int n, int kth, uint32_t*
             }
             __syncthreads();
             listed = true;
+            n_list = n_act;
         }
     }
     T = prefix;
@@ -489,13 +550,15 @@ struct WarpSmem {
     int xw[32];
 };
 
-// One item handled by one warp with the whole row in registers: NE ids/keys per lane, row position of
-// slot e is e*32 + lane. Two memory round trips (ids, then scores), selection and compaction without
-// shared memory, kept list written in row order.
-template <int NE>
-__device__ __forceinline__ int warp_row(const ChooseP& p, const Item& it, WarpSmem& s, const int32_t* __restrict__ nbr) {
-    const int lane = threadIdx.x & 31;
-    const int tid = lane, w = it.w;
+// One item handled by NT threads with the whole row in REGISTERS: NE ids/keys per thread, row position
+// of slot e is e*NT + tid. Two memory round trips (ids, then scores), selection without histograms, kept
+// list written in row order. kbits/bits: see oversample(); cand/wsum/xw: group scratch (CTA only).
+template <int NT, int NE>
+__device__ __forceinline__ void row_in_regs(const ChooseP& p, const Item& it, const int32_t* __restrict__ nbr,
+                                            uint32_t* kbits, uint32_t* bits, uint32_t* cand, int* wsum, int* xw) {
+    const int tid = NT == 32 ? (threadIdx.x & 31) : threadIdx.x;
+    const int lane = tid & 31;
+    const int w = it.w;
     const int d = it.d, k = it.k;
     const float* __restrict__ escore = p.entry_score ? p.entry_score + it.beg : nullptr;
     const int32_t* __restrict__ epp = it.use_kb ? p.entry_pool_pos + it.beg : nullptr;
@@ -507,7 +570,7 @@ __device__ __forceinline__ int warp_row(const ChooseP& p, const Item& it, WarpSm
     uint32_t vmask = 0;
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
-        const int j = e * 32 + lane;
+        const int j = e * NT + tid;
         const bool valid = j < d;
         vmask |= (uint32_t)valid << e;
         id[e] = valid ? __ldg(nbr + j) : 0;
@@ -515,7 +578,7 @@ __device__ __forceinline__ int warp_row(const ChooseP& p, const Item& it, WarpSm
     }
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
-        const int j = e * 32 + lane;
+        const int j = e * NT + tid;
         uint32_t x = 0u;
         if (((vmask >> e) & 1u) && need_dist) x = dist_bits(it.sv, escore ? escore[j] : __ldg(p.score + id[e]));
         key[e] = x;
@@ -524,38 +587,37 @@ __device__ __forceinline__ int warp_row(const ChooseP& p, const Item& it, WarpSm
     uint32_t T = 0xffffffffu;
     int need = 0x7fffffff;
     if (!all) {
-        if (k > 0) warp_bitselect<NE>(key, vmask, k, T, need);
+        if (k > 0) group_bitselect<NT, NE>(key, vmask, d, k, cand, PCG_CAND_CAP, wsum, xw, tid, T, need);
         else { T = 0; need = 0; }
     }
     TRACE(3);
     int run_less = 0, run_tie = 0;
-    const unsigned lt = lanemask_lt();
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
-        if (e * 32 < d) {                               // warp-uniform
+        if (e * NT < d) {                               // group-uniform
             const bool valid = (vmask >> e) & 1u;
             const bool less = valid && (all || key[e] < T);
             const bool tie = valid && !all && key[e] == T;
-            const unsigned ml = __ballot_sync(PCG_FULL, less), mt = __ballot_sync(PCG_FULL, tie);
-            const int tie_before = run_tie + __popc(mt & lt);
+            int el, et, tl, tt;
+            grp_excl2<NT>(less, tie, tid, xw, el, et, tl, tt);
+            const int tie_before = run_tie + et;
             const bool sel = less || (tie && tie_before < need);
             if (sel) {
-                const int64_t at = it.off + run_less + __popc(ml & lt) + min(tie_before, need);
+                const int64_t at = it.off + run_less + el + min(tie_before, need);
                 p.sel_idx[at] = id[e];
                 if (p.sel_dist) p.sel_dist[at] = __uint_as_float(key[e]);
-                if (pp[e] >= 0) atomicOr(&s.kbits[pp[e] >> 5], 1u << (pp[e] & 31));
+                if (pp[e] >= 0) atomicOr(&kbits[pp[e] >> 5], 1u << (pp[e] & 31));
             }
             if (it.want_bits) {
                 const unsigned sm = __ballot_sync(PCG_FULL, sel);
-                if (lane == 0) s.bits[e] = sm;
+                if (lane == 0) bits[(e * NT + tid) >> 5] = sm;
             }
-            run_less += __popc(ml);
-            run_tie += __popc(mt);
+            run_less += tl;
+            run_tie += tt;
         }
     }
-    __syncwarp();
+    grp_sync<NT>();
     TRACE(4);
-    return 0;
 }
 
 __device__ void choose_item_warp(const ChooseP& p, int w, WarpSmem& s) {
@@ -576,11 +638,11 @@ __device__ void choose_item_warp(const ChooseP& p, int w, WarpSmem& s) {
         __syncwarp();
     }
     const int d = it.d;
-    if (d <= 32) warp_row<1>(p, it, s, nbr);
-    else if (d <= 64) warp_row<2>(p, it, s, nbr);
-    else if (d <= 128) warp_row<4>(p, it, s, nbr);
-    else if (d <= 256) warp_row<8>(p, it, s, nbr);
-    else warp_row<16>(p, it, s, nbr);
+    if (d <= 32) row_in_regs<32, 1>(p, it, nbr, s.kbits, s.bits, nullptr, nullptr, s.xw);
+    else if (d <= 64) row_in_regs<32, 2>(p, it, nbr, s.kbits, s.bits, nullptr, nullptr, s.xw);
+    else if (d <= 128) row_in_regs<32, 4>(p, it, nbr, s.kbits, s.bits, nullptr, nullptr, s.xw);
+    else if (d <= 256) row_in_regs<32, 8>(p, it, nbr, s.kbits, s.bits, nullptr, nullptr, s.xw);
+    else row_in_regs<32, 16>(p, it, nbr, s.kbits, s.bits, nullptr, nullptr, s.xw);
     int m = it.k;
     if (it.o > 0) m += oversample<32>(p, it, lane, nbr, s.kbits, s.bits, s.hist, s.xw);
     TRACE(6);
@@ -609,6 +671,24 @@ __device__ void choose_item_cta(const ChooseP& p, int w, uint32_t* sd, int sd_ca
     const int d = it.d, k = it.k;
     const float sv = it.sv;
     const int32_t* __restrict__ nbr = p.indices + it.beg;
+    uint32_t* bits = (d <= bits_cap_words * 32) ? bits_s : bits_g;
+    if (d <= 16 * NT) {
+        // the row fits the CTA's registers
+        int* wsum = reinterpret_cast<int*>(hist);
+        if (d <= NT) row_in_regs<NT, 1>(p, it, nbr, kbits, bits, cand, wsum, xw);
+        else if (d <= 2 * NT) row_in_regs<NT, 2>(p, it, nbr, kbits, bits, cand, wsum, xw);
+        else if (d <= 4 * NT) row_in_regs<NT, 4>(p, it, nbr, kbits, bits, cand, wsum, xw);
+        else if (d <= 8 * NT) row_in_regs<NT, 8>(p, it, nbr, kbits, bits, cand, wsum, xw);
+        else row_in_regs<NT, 16>(p, it, nbr, kbits, bits, cand, wsum, xw);
+        int m = k;
+        if (it.o > 0) m += oversample<NT>(p, it, tid, nbr, kbits, bits, hist, xw);
+        TRACE(6);
+        item_finish<NT>(p, it, tid, m);
+        __syncthreads();
+        TRACE(7);
+        return;
+    }
+    // ---- longer rows: distances in shared memory (or recomputed per pass beyond its capacity) ----
     const float* __restrict__ escore = p.entry_score ? p.entry_score + it.beg : nullptr;
     const float* __restrict__ score = p.score;
     const bool cached = d <= sd_cap;
@@ -628,7 +708,6 @@ __device__ void choose_item_cta(const ChooseP& p, int w, uint32_t* sd, int sd_ca
         else { T = 0; need = 0; }
     }
     TRACE(3);
-    uint32_t* bits = (d <= bits_cap_words * 32) ? bits_s : bits_g;
     // ---- ordered compaction: every warp owns a contiguous chunk of the row; count, one scan of the
     // per-warp counts, then each warp writes its chunk using ballots only ----
     const int chunk = (((d + NW - 1) / NW) + 31) & ~31;       // multiple of 32 positions per warp
@@ -737,7 +816,7 @@ __global__ void __launch_bounds__(PCG_WARPS_PER_CTA * 32, 3) k_choose_warp(Choos
     }
 }
 
-__global__ void __launch_bounds__(PCG_LARGE_NT) k_choose_cta(ChooseP p) {
+__global__ void __launch_bounds__(PCG_LARGE_NT, 1) k_choose_cta(ChooseP p) {
     extern __shared__ uint32_t dyn[];
     __shared__ uint32_t hist[256];
     __shared__ uint32_t kbits[PCG_KB_WORDS_CTA];
@@ -825,7 +904,7 @@ static WsLayout ws_layout(int B, int R, int64_t max_degree, int sms) {
     WsLayout L;
     size_t W = (size_t)B * R;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    L.grid_large = sms * 2;
+    L.grid_large = sms;
     L.slab_words = max_degree > PCG_LARGE_CAP_MAX ? (max_degree + 31) / 32 : 0;
     size_t o = 0;
     L.small_q = o; o = al(o + W * 4);
@@ -918,7 +997,8 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
     p.large_q = (int32_t*)(ws + L.large_q);
     p.bits_slab = (uint32_t*)(ws + L.bits_slab);
     p.slab_words = L.slab_words;
-    int64_t cap = max_degree < PCG_SMALL_MAX + 1 ? PCG_SMALL_MAX + 1 : max_degree;
+    // shared distance buffer of the CTA tier: only rows beyond 16 * PCG_LARGE_NT entries use it
+    int64_t cap = max_degree <= 16 * PCG_LARGE_NT ? 32 : max_degree;
     if (cap > PCG_LARGE_CAP_MAX) cap = PCG_LARGE_CAP_MAX;
     p.large_cap = (int)((cap + 31) / 32 * 32);
     const int W = R * B;
