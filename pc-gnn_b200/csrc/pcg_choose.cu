@@ -23,7 +23,9 @@
 #define PCG_SMALL_MAX 512      // entries a warp keeps in its shared-memory slice
 #define PCG_WARPS_PER_CTA 8    // warp kernel: 8 items in flight per CTA
 #define PCG_LARGE_NT 1024      // CTA kernel threads (one CTA per SM)
-#define PCG_HUGE_MIN 4096      // rows longer than this are scheduled first
+#define PCG_MID_NT 128         // middle tier threads per CTA
+#define PCG_MID_MAX 2048       // longest row of the middle tier (16 keys per thread)
+#define PCG_CAND_CAP_MID 512   // middle tier: candidate list capacity
 #define PCG_LARGE_CAP_MAX 32768
 #define PCG_KB_WORDS_WARP 256  // kept-pool bitmap words per warp  (pools up to 8192 positives)
 #define PCG_KB_WORDS_CTA 2048  // ... per CTA                      (pools up to 65536 positives)
@@ -56,10 +58,12 @@ struct ChooseP {
     int32_t* it_done;
     int32_t* status;
     int32_t* small_q;
+    int32_t* mid_q;
     int32_t* large_q;
     uint32_t* bits_slab;        // [grid_large, slab_words]
     int64_t slab_words;
     int large_cap;              // entries of the CTA kernel's shared distance buffer
+    int bits_words;             // words of its kept-position bitmask
 };
 
 #ifdef PCG_TRACE
@@ -469,19 +473,33 @@ __device__ __forceinline__ int oversample(const ChooseP& p, const Item& it, int 
     const int w = it.w;
     // split point: first sorted entry with score >= sv; A walks left from it, B right. The distances
     // grow monotonically along both, so the o-th smallest is a k-th-of-two-sorted-sequences search.
-    const int c = warp_partition_point(0, P, [&](int q) { return __ldg(S + q) < sv; });
-    const int nA = c, nB = P - c;
-    auto A = [&](int q) -> uint32_t { return dist_bits(sv, __ldg(S + (c - 1 - q))); };
-    auto Bq = [&](int q) -> uint32_t { return dist_bits(sv, __ldg(S + (c + q))); };
-    const int ia = warp_partition_point(max(0, o - nB), min(o, nA), [&](int m) { return Bq(o - m - 1) > A(m); });
-    const int ib = o - ia;
+    // (first warp of the group searches, the result is broadcast through `hist`)
+    int c = 0, a_less = 0, a_le = 0, b_less = 0, b_le = 0;
     uint32_t Tp = 0;
-    if (ia > 0) Tp = A(ia - 1);
-    if (ib > 0) Tp = max(Tp, Bq(ib - 1));
-    const int a_less = warp_partition_point(0, nA, [&](int q) { return A(q) < Tp; });
-    const int a_le = warp_partition_point(a_less, nA, [&](int q) { return A(q) <= Tp; });
-    const int b_less = warp_partition_point(0, nB, [&](int q) { return Bq(q) < Tp; });
-    const int b_le = warp_partition_point(b_less, nB, [&](int q) { return Bq(q) <= Tp; });
+    if (NT == 32 || tid < 32) {
+        c = warp_partition_point(0, P, [&](int q) { return __ldg(S + q) < sv; });
+        const int nA0 = c, nB0 = P - c;
+        auto A0 = [&](int q) -> uint32_t { return dist_bits(sv, __ldg(S + (c - 1 - q))); };
+        auto B0 = [&](int q) -> uint32_t { return dist_bits(sv, __ldg(S + (c + q))); };
+        const int ia = warp_partition_point(max(0, o - nB0), min(o, nA0), [&](int m) { return B0(o - m - 1) > A0(m); });
+        const int ib = o - ia;
+        if (ia > 0) Tp = A0(ia - 1);
+        if (ib > 0) Tp = max(Tp, B0(ib - 1));
+        a_less = warp_partition_point(0, nA0, [&](int q) { return A0(q) < Tp; });
+        a_le = warp_partition_point(a_less, nA0, [&](int q) { return A0(q) <= Tp; });
+        b_less = warp_partition_point(0, nB0, [&](int q) { return B0(q) < Tp; });
+        b_le = warp_partition_point(b_less, nB0, [&](int q) { return B0(q) <= Tp; });
+    }
+    if (NT > 32) {
+        if (tid == 0) {
+            hist[64] = (uint32_t)c; hist[65] = (uint32_t)a_less; hist[66] = (uint32_t)a_le;
+            hist[67] = (uint32_t)b_less; hist[68] = (uint32_t)b_le; hist[69] = Tp;
+        }
+        __syncthreads();
+        c = (int)hist[64]; a_less = (int)hist[65]; a_le = (int)hist[66];
+        b_less = (int)hist[67]; b_le = (int)hist[68]; Tp = hist[69];
+        __syncthreads();
+    }
     const int cnt_less = a_less + b_less;
     const int tie_a = a_le - a_less, ties = tie_a + (b_le - b_less);
     const int needp = o - cnt_less;            // 1 <= needp <= ties
@@ -587,7 +605,7 @@ __device__ __forceinline__ void row_in_regs(const ChooseP& p, const Item& it, co
     uint32_t T = 0xffffffffu;
     int need = 0x7fffffff;
     if (!all) {
-        if (k > 0) group_bitselect<NT, NE>(key, vmask, d, k, cand, PCG_CAND_CAP, wsum, xw, tid, T, need);
+        if (k > 0) group_bitselect<NT, NE>(key, vmask, d, k, cand, NT == 128 ? PCG_CAND_CAP_MID : PCG_CAND_CAP, wsum, xw, tid, T, need);
         else { T = 0; need = 0; }
     }
     TRACE(3);
@@ -652,13 +670,14 @@ __device__ void choose_item_warp(const ChooseP& p, int w, WarpSmem& s) {
 }
 
 // --------------------------------------------------------------------------------- CTA tier
-// One item handled by one CTA (long rows). Kept list in row order.
+// One item handled by one CTA of NT threads (long rows). Kept list in row order.
+template <int NT, int KBW>
 __device__ void choose_item_cta(const ChooseP& p, int w, uint32_t* sd, int sd_cap, uint32_t* hist, uint32_t* kbits,
                                 uint32_t* cand, uint32_t* bits_s, int bits_cap_words, uint32_t* bits_g, int* xw) {
-    constexpr int NT = PCG_LARGE_NT, NW = NT / 32;
+    constexpr int NW = NT / 32;
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     Item it;
-    item_header(p, w, PCG_KB_WORDS_CTA, it);
+    item_header(p, w, KBW, it);
     TRACE(0); TRACE_VAL(8, it.d); TRACE_VAL(9, it.k); TRACE_VAL(10, it.o);
     if (tid == 0) xw[29] = atomicAdd(&p.status[ST_SLOTS], it.nslots);
     if (it.use_kb)
@@ -689,6 +708,7 @@ __device__ void choose_item_cta(const ChooseP& p, int w, uint32_t* sd, int sd_ca
         return;
     }
     // ---- longer rows: distances in shared memory (or recomputed per pass beyond its capacity) ----
+    if (NT != PCG_LARGE_NT) return;   // the smaller tier never sees such rows
     const float* __restrict__ escore = p.entry_score ? p.entry_score + it.beg : nullptr;
     const float* __restrict__ score = p.score;
     const bool cached = d <= sd_cap;
@@ -770,36 +790,35 @@ __device__ void choose_item_cta(const ChooseP& p, int w, uint32_t* sd, int sd_ca
     TRACE(7);
 }
 
-// Classify items by row length: the warp queue, and the CTA queue with the longest rows (the critical
-// path of the CTA tier) at the front and the other long rows filled in from the back.
+// Classify items by row length into the three tier queues (warp / 128-thread CTA / 1024-thread CTA).
 __global__ void k_choose_classify(ChooseP p) {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     const int W = p.R * p.B;
-    bool small = false, large = false, huge = false;
+    bool small = false, mid = false, big = false;
     if (w < W) {
         const int r = w / p.B, i = w - r * p.B;
         const int64_t row = (int64_t)r * p.n_nodes + p.targets[i];
         const int64_t d = p.indptr[row + 1] - p.indptr[row];
         small = d <= PCG_SMALL_MAX;
-        huge = d > PCG_HUGE_MIN;
-        large = !small && !huge;
+        big = d > PCG_MID_MAX;
+        mid = !small && !big;
     }
     const unsigned lt = lanemask_lt();
     const int lane = threadIdx.x & 31;
-    const unsigned ms = __ballot_sync(PCG_FULL, small), ml = __ballot_sync(PCG_FULL, large),
-                   mh = __ballot_sync(PCG_FULL, huge);
-    int bs = 0, bl = 0, bh = 0;
+    const unsigned ms = __ballot_sync(PCG_FULL, small), mm = __ballot_sync(PCG_FULL, mid),
+                   mb = __ballot_sync(PCG_FULL, big);
+    int bs = 0, bm = 0, bb = 0;
     if (lane == 0) {
         if (ms) bs = atomicAdd(&p.status[ST_NSMALL], __popc(ms));
-        if (ml) bl = atomicAdd(&p.status[ST_NLARGE], __popc(ml));
-        if (mh) bh = atomicAdd(&p.status[ST_NHUGE], __popc(mh));
+        if (mm) bm = atomicAdd(&p.status[ST_NMID], __popc(mm));
+        if (mb) bb = atomicAdd(&p.status[ST_NBIG], __popc(mb));
     }
     bs = __shfl_sync(PCG_FULL, bs, 0);
-    bl = __shfl_sync(PCG_FULL, bl, 0);
-    bh = __shfl_sync(PCG_FULL, bh, 0);
+    bm = __shfl_sync(PCG_FULL, bm, 0);
+    bb = __shfl_sync(PCG_FULL, bb, 0);
     if (small) p.small_q[bs + __popc(ms & lt)] = w;
-    if (huge) p.large_q[bh + __popc(mh & lt)] = w;
-    if (large) p.large_q[W - 1 - (bl + __popc(ml & lt))] = w;
+    if (mid) p.mid_q[bm + __popc(mm & lt)] = w;
+    if (big) p.large_q[bb + __popc(mb & lt)] = w;
 }
 
 __global__ void __launch_bounds__(PCG_WARPS_PER_CTA * 32, 3) k_choose_warp(ChooseP p) {
@@ -816,6 +835,27 @@ __global__ void __launch_bounds__(PCG_WARPS_PER_CTA * 32, 3) k_choose_warp(Choos
     }
 }
 
+// 512 < d <= 2048: one item per 128-thread CTA, many CTAs per SM.
+__global__ void __launch_bounds__(PCG_MID_NT, 6) k_choose_mid(ChooseP p) {
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t kbits[PCG_KB_WORDS_WARP];
+    __shared__ uint32_t cand[PCG_CAND_CAP_MID];
+    __shared__ uint32_t bits[PCG_MID_MAX / 32];
+    __shared__ int xw[32];
+    __shared__ int s_q;
+    const int n = p.status[ST_NMID];
+    for (;;) {
+        if (threadIdx.x == 0) s_q = atomicAdd(&p.status[ST_MID_CTR], 1);
+        __syncthreads();
+        const int q = s_q;
+        __syncthreads();
+        if (q >= n) break;
+        choose_item_cta<PCG_MID_NT, PCG_KB_WORDS_WARP>(p, p.mid_q[q], nullptr, 0, hist, kbits, cand, bits,
+                                                       PCG_MID_MAX / 32, nullptr, xw);
+    }
+}
+
+// d > 2048: one item per 1024-thread CTA, one CTA per SM.
 __global__ void __launch_bounds__(PCG_LARGE_NT, 1) k_choose_cta(ChooseP p) {
     extern __shared__ uint32_t dyn[];
     __shared__ uint32_t hist[256];
@@ -823,18 +863,18 @@ __global__ void __launch_bounds__(PCG_LARGE_NT, 1) k_choose_cta(ChooseP p) {
     __shared__ uint32_t cand[PCG_CAND_CAP];
     __shared__ int xw[32];
     __shared__ int s_q;
-    uint32_t* sd = dyn;                              // [large_cap]
-    uint32_t* bits = dyn + p.large_cap;              // [large_cap / 32]
-    const int n_huge = p.status[ST_NHUGE], n = n_huge + p.status[ST_NLARGE];
-    const int W = p.R * p.B;
+    uint32_t* sd = dyn;                              // [large_cap]   (rows beyond 16 * PCG_LARGE_NT only)
+    uint32_t* bits = dyn + p.large_cap;              // [bits_words]
+    const int n = p.status[ST_NBIG];
     for (;;) {
-        if (threadIdx.x == 0) s_q = atomicAdd(&p.status[ST_LARGE_CTR], 1);
+        if (threadIdx.x == 0) s_q = atomicAdd(&p.status[ST_BIG_CTR], 1);
         __syncthreads();
         const int q = s_q;
         __syncthreads();
         if (q >= n) break;
-        choose_item_cta(p, p.large_q[q < n_huge ? q : W - 1 - (q - n_huge)], sd, p.large_cap, hist, kbits, cand, bits, p.large_cap / 32,
-                        p.bits_slab + (int64_t)blockIdx.x * p.slab_words, xw);
+        choose_item_cta<PCG_LARGE_NT, PCG_KB_WORDS_CTA>(p, p.large_q[q], sd, p.large_cap, hist, kbits, cand, bits,
+                                                        p.bits_words, p.bits_slab + (int64_t)blockIdx.x * p.slab_words,
+                                                        xw);
     }
 }
 
@@ -895,7 +935,7 @@ __global__ void k_entry_pool_pos(const int32_t* __restrict__ indices, int64_t nn
 
 // ------------------------------------------------------------------------------------------- C ABI
 struct WsLayout {
-    size_t small_q, large_q, bits_slab, total;
+    size_t small_q, mid_q, large_q, bits_slab, total;
     int64_t slab_words;
     int grid_large;
 };
@@ -908,6 +948,7 @@ static WsLayout ws_layout(int B, int R, int64_t max_degree, int sms) {
     L.slab_words = max_degree > PCG_LARGE_CAP_MAX ? (max_degree + 31) / 32 : 0;
     size_t o = 0;
     L.small_q = o; o = al(o + W * 4);
+    L.mid_q = o; o = al(o + W * 4);
     L.large_q = o; o = al(o + W * 4);
     L.bits_slab = o; o = al(o + (size_t)L.grid_large * L.slab_words * 4);
     L.total = o;
@@ -955,8 +996,8 @@ extern "C" int pcg_entry_pool_positions(const int32_t* indices, int64_t nnz, con
 }
 
 // second stream + events so the warp tier and the CTA tier run side by side (fork/join; capturable)
-static cudaStream_t g_side = nullptr;
-static cudaEvent_t g_fork = nullptr, g_join = nullptr;
+static cudaStream_t g_side[2] = {nullptr, nullptr};
+static cudaEvent_t g_fork = nullptr, g_join[2] = {nullptr, nullptr};
 
 extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t n_nodes, int R, const float* score,
                           const float* entry_score, const float* center_score, const int32_t* targets,
@@ -994,47 +1035,56 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
     p.it_slot0 = it_slot0; p.it_m = it_m; p.it_base = it_base; p.it_done = it_done; p.status = status;
     char* ws = (char*)workspace;
     p.small_q = (int32_t*)(ws + L.small_q);
+    p.mid_q = (int32_t*)(ws + L.mid_q);
     p.large_q = (int32_t*)(ws + L.large_q);
     p.bits_slab = (uint32_t*)(ws + L.bits_slab);
     p.slab_words = L.slab_words;
-    // shared distance buffer of the CTA tier: only rows beyond 16 * PCG_LARGE_NT entries use it
+    // shared distance buffer of the 1024-thread tier: only rows beyond 16 * PCG_LARGE_NT entries use it
     int64_t cap = max_degree <= 16 * PCG_LARGE_NT ? 32 : max_degree;
     if (cap > PCG_LARGE_CAP_MAX) cap = PCG_LARGE_CAP_MAX;
     p.large_cap = (int)((cap + 31) / 32 * 32);
+    int64_t bw = (max_degree < PCG_LARGE_CAP_MAX ? max_degree : PCG_LARGE_CAP_MAX);
+    p.bits_words = (int)((bw + 31) / 32);
     const int W = R * B;
     k_choose_classify<<<(W + 255) / 256, 256, 0, stream>>>(p);
-    const bool have_large = max_degree > PCG_SMALL_MAX;
-    cudaStream_t s_large = stream;
-    if (have_large) {
-        if (!g_side) {
-            if ((e = cudaStreamCreateWithFlags(&g_side, cudaStreamNonBlocking)) != cudaSuccess ||
-                (e = cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming)) != cudaSuccess ||
-                (e = cudaEventCreateWithFlags(&g_join, cudaEventDisableTiming)) != cudaSuccess) {
+    const bool have_mid = max_degree > PCG_SMALL_MAX, have_big = max_degree > PCG_MID_MAX;
+    if (have_mid && !g_side[0]) {
+        for (int q = 0; q < 2; ++q)
+            if ((e = cudaStreamCreateWithFlags(&g_side[q], cudaStreamNonBlocking)) != cudaSuccess ||
+                (e = cudaEventCreateWithFlags(&g_join[q], cudaEventDisableTiming)) != cudaSuccess) {
                 pcg_set_error("pcg_choose: side stream: %s", cudaGetErrorString(e));
                 return (int)e;
             }
+        if ((e = cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming)) != cudaSuccess) {
+            pcg_set_error("pcg_choose: event: %s", cudaGetErrorString(e));
+            return (int)e;
         }
-        size_t dyn = (size_t)p.large_cap * 4 + (size_t)p.large_cap / 32 * 4;
+    }
+    if (have_mid) cudaEventRecord(g_fork, stream);     // fork: the three tiers run side by side
+    if (have_big) {
+        size_t dyn = (size_t)p.large_cap * 4 + (size_t)p.bits_words * 4;
         static size_t configured = 0;
-        if (dyn > 32 * 1024 && dyn > configured) {
+        if (dyn > 16 * 1024 && dyn > configured) {
             e = cudaFuncSetAttribute(k_choose_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
             if (e != cudaSuccess) { pcg_set_error("pcg_choose: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
             configured = dyn;
         }
-        // fork: the CTA tier (long rows first: they are the critical path) on the side stream
-        cudaEventRecord(g_fork, stream);
-        cudaStreamWaitEvent(g_side, g_fork, 0);
-        s_large = g_side;
+        cudaStreamWaitEvent(g_side[1], g_fork, 0);
         int gl = W < L.grid_large ? W : L.grid_large;
-        k_choose_cta<<<gl, PCG_LARGE_NT, dyn, s_large>>>(p);
+        k_choose_cta<<<gl, PCG_LARGE_NT, dyn, g_side[1]>>>(p);    // longest rows first: they are the critical path
+        cudaEventRecord(g_join[1], g_side[1]);
+    }
+    if (have_mid) {
+        cudaStreamWaitEvent(g_side[0], g_fork, 0);
+        int gm = W < sms * 8 ? W : sms * 8;
+        k_choose_mid<<<gm, PCG_MID_NT, 0, g_side[0]>>>(p);
+        cudaEventRecord(g_join[0], g_side[0]);
     }
     int gw = (W + PCG_WARPS_PER_CTA - 1) / PCG_WARPS_PER_CTA;
     if (gw > sms * 6) gw = sms * 6;
     k_choose_warp<<<gw, PCG_WARPS_PER_CTA * 32, 0, stream>>>(p);
-    if (have_large) {   // join
-        cudaEventRecord(g_join, s_large);
-        cudaStreamWaitEvent(stream, g_join, 0);
-    }
+    if (have_mid) cudaStreamWaitEvent(stream, g_join[0], 0);      // join
+    if (have_big) cudaStreamWaitEvent(stream, g_join[1], 0);
     return pcg_check_launch("pcg_choose");
 }
 

@@ -11,11 +11,12 @@
 // status / counter words (device int32 array, PCG_STATUS_WORDS long)
 #define ST_SLOTS PCG_ST_SLOTS
 #define ST_NSMALL 1
-#define ST_NLARGE 2
+#define ST_NMID 2
 #define ST_OVERFLOW PCG_ST_OVERFLOW
 #define ST_SMALL_CTR 4
-#define ST_LARGE_CTR 5
-#define ST_NHUGE 6
+#define ST_MID_CTR 5
+#define ST_NBIG 6
+#define ST_BIG_CTR 7
 
 void pcg_set_error(const char* fmt, ...);
 int pcg_check_launch(const char* what);
