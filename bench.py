@@ -224,7 +224,7 @@ def main():
     model = build_cuda_pcgnn(data.feat, data.graph, tp, params, rho=RHO, alpha=ALPHA, device=dev)
     inter = model.inter1
     opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=LR, weight_decay=WD,
-                           capturable=True, foreach=True)
+                           capturable=True, fused=True)
     reducer = GradAllReduce(model.parameters()).attach()
     # global batches of batch*world targets, identical on every rank; this rank's contiguous shard
     n_b = W + K
@@ -398,7 +398,7 @@ def main():
                        "parallelism": f"dp{world} (targets sharded, grads all-reduced)" if world > 1 else "single"},
             "e2e": {"value": total_nodes / (ms_e2e / 1e3), "unit": "target-nodes/s", "ms_per_step": ms_e2e / K,
                     "h2d_bytes_per_step": batch * 4 + batch * 8, "d2h_bytes_per_step": 4},
-            "gpu_launches": 9 * K,
+            "gpu_launches": 14 * K,
             "mode": "cuda-graph replay (runtime.GraphedTrainStep)" if use_graph else "eager",
             "roofline": roof, "kernels": kern, "clocks": sampler.result(),
         }

@@ -146,6 +146,30 @@ PCG_API int pcg_aggregate_bwd(const float* d_agg, int64_t ldf, const int32_t* id
                       pcg_stream_t stream);
 
 /*
+ * Fused relation transforms + inter-relation combine, forward:
+ *   cat[i, 0:F]            = feat[targets[i], :F]
+ *   cat[i, F+rE:F+(r+1)E]  = relu([feat[targets[i]], agg[r*B+i]] @ W_r)      (src/layers.py:616-629)
+ *   out[e, i]              = relu(cat[i, :] @ W)[e]                          (src/layers.py:273-289, [E,B])
+ *   w_intra_host  HOST array of R device pointers, each the reference's IntraAgg.weight [2F, E] row-major
+ *   w_inter       device [F+R*E, E]
+ *   cat           fp32 [B, F+R*E] (kept for backward), out fp32 [E, B]
+ */
+PCG_API int pcg_dense_fwd(const float* feat, int64_t ldf, int F, const int32_t* targets, int B, int R, int E,
+                  const float* agg, const float* const* w_intra_host, const float* w_inter, float* cat, float* out,
+                  pcg_stream_t stream);
+
+/*
+ * Backward of pcg_dense_fwd w.r.t. the weights (the reference's features are frozen, src/model_handler.py:85-86,
+ * so these are the only gradients the path produces): d_w_intra_host[r] [2F,E] and d_w_inter [F+R*E,E] are
+ * OVERWRITTEN; the reduction over the batch is split-K with a fixed summation order (deterministic).
+ *   d_out    fp32 [E,B] gradient of `out`;  scratch  pcg_dense_bwd_scratch_floats(B,R,F,E) floats
+ */
+PCG_API size_t pcg_dense_bwd_scratch_floats(int B, int R, int F, int E);
+PCG_API int pcg_dense_bwd(int64_t ldf, int F, int B, int R, int E, const float* agg, const float* w_inter,
+                  const float* cat, const float* out, const float* d_out, float* const* d_w_intra_host,
+                  float* d_w_inter, float* scratch, pcg_stream_t stream);
+
+/*
  * Label-balanced pick step, replay form: out[t] = idx_train[bisect_right(cum, u[t]*total, 0, n-1)],
  * total = cum[n-1]. Bit-compatible with random.choices(idx_train, weights, k) of
  * src/utils.py:274-278 when `u` are the doubles random.random() would have produced and `cum` is

@@ -40,6 +40,9 @@ SIGNATURES = {
     "pcg_select_all": (_i, [_p, _p, _l, _i, _p, _i, _i, _l, _p, _p, _p, _p, _p, _p, _p, _p]),
     "pcg_aggregate": (_i, [_p, _l, _p, _p, _p, _p, _p, _p, _i, _l, _p, _i, _p, _p, _p, _p]),
     "pcg_aggregate_bwd": (_i, [_p, _l, _p, _p, _p, _p, _p, _p, _i, _l, _p, _i, _p, _p]),
+    "pcg_dense_fwd": (_i, [_p, _l, _i, _p, _i, _i, _i, _p, C.POINTER(_p), _p, _p, _p, _p]),
+    "pcg_dense_bwd_scratch_floats": (_z, [_i, _i, _i, _i]),
+    "pcg_dense_bwd": (_i, [_l, _i, _i, _i, _i, _p, _p, _p, _p, _p, C.POINTER(_p), _p, _p, _p]),
     "pcg_pick_step": (_i, [_p, _l, _p, _l, _p, _p, _p]),
     "pcg_pick_step_philox": (_i, [_p, _l, _u64, _u64, _l, _p, _p, _p]),
 }

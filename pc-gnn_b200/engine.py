@@ -299,3 +299,39 @@ class Engine:
                                         feat_grad.data_ptr(), _lib.stream_ptr())
         _lib.check(rc, "pcg_aggregate_bwd")
         return feat_grad
+
+    # ------------------------------------------------------------------ fused dense part
+    def dense_fwd(self, targets, agg, w_intra, w_inter, feat_dim):
+        """(combined [E,B], cat [B, F+R*E]) = relation transforms + inter-relation combine (``pcg_dense_fwd``)."""
+        B = int(targets.shape[0])
+        R = len(w_intra)
+        E = int(w_inter.shape[1])
+        K2 = feat_dim + R * E
+        cat = torch.empty((B, K2), dtype=torch.float32, device=self.device)
+        out = torch.empty((E, B), dtype=torch.float32, device=self.device)
+        ptrs = (C.c_void_p * R)(*[w.data_ptr() for w in w_intra])
+        rc = self.lib.pcg_dense_fwd(self.feat.data_ptr(), self.ldf, feat_dim, targets.data_ptr(), B, R, E,
+                                    agg.data_ptr(), ptrs, w_inter.data_ptr(), cat.data_ptr(), out.data_ptr(),
+                                    _lib.stream_ptr())
+        _lib.check(rc, "pcg_dense_fwd")
+        return out, cat
+
+    def dense_bwd(self, agg, w_inter, cat, out, d_out, feat_dim, n_rel):
+        """Weight gradients of the fused dense part (``pcg_dense_bwd``): (list of dW_r [2F,E], dW [F+R*E,E])."""
+        B = int(cat.shape[0])
+        E = int(w_inter.shape[1])
+        K2 = feat_dim + n_rel * E
+        n = int(self.lib.pcg_dense_bwd_scratch_floats(B, n_rel, feat_dim, E))
+        scratch = torch.empty(n, dtype=torch.float32, device=self.device)
+        # one buffer for all gradients: [dW (K2*E) | dW_1 (2F*E) | ... ]
+        flat = torch.empty(K2 * E + n_rel * 2 * feat_dim * E, dtype=torch.float32, device=self.device)
+        d_inter = flat[:K2 * E].view(K2, E)
+        d_intra = [flat[K2 * E + r * 2 * feat_dim * E: K2 * E + (r + 1) * 2 * feat_dim * E].view(2 * feat_dim, E)
+                   for r in range(n_rel)]
+        ptrs = (C.c_void_p * n_rel)(*[g.data_ptr() for g in d_intra])
+        d_out = d_out.contiguous()
+        rc = self.lib.pcg_dense_bwd(agg.shape[1], feat_dim, B, n_rel, E, agg.data_ptr(), w_inter.data_ptr(),
+                                    cat.data_ptr(), out.data_ptr(), d_out.data_ptr(), ptrs, d_inter.data_ptr(),
+                                    scratch.data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "pcg_dense_bwd")
+        return d_intra, d_inter

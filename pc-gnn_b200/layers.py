@@ -54,6 +54,27 @@ class _AggregateFn(torch.autograd.Function):
         return g[:, :ctx.feat_dim], None, None, None
 
 
+class _DenseFn(torch.autograd.Function):
+    """combined [E,B] = relu(cat(self, relu(cat(self, agg_r) @ W_r) ...) @ W).t() as ONE kernel (``pcg_dense_fwd``),
+    with the weight gradients as the backward (``pcg_dense_bwd``). Used when the feature table is frozen, which
+    is the reference's configuration (model_handler.py:85-86); reference math: layers.py:616-629, 273-289."""
+
+    @staticmethod
+    def forward(ctx, engine, targets, agg, feat_dim, w_inter, *w_intra):
+        w_intra = [w.contiguous() for w in w_intra]
+        w_inter = w_inter.contiguous()
+        out, cat = engine.dense_fwd(targets, agg, w_intra, w_inter, feat_dim)
+        ctx.engine, ctx.feat_dim, ctx.n_rel = engine, feat_dim, len(w_intra)
+        ctx.save_for_backward(agg, w_inter, cat, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        agg, w_inter, cat, out = ctx.saved_tensors
+        d_intra, d_inter = ctx.engine.dense_bwd(agg, w_inter, cat, out, d_out, ctx.feat_dim, ctx.n_rel)
+        return (None, None, None, None, d_inter, *d_intra)
+
+
 def _feature_table(features, n_nodes, device, ids=None):
     """The [N,F] table behind the reference's `features` callable (an nn.Embedding in
     model_handler.py:85; any id->rows callable is accepted)."""
@@ -306,11 +327,14 @@ class InterAgg(nn.Module):
             cap = eng.slots_bound(targets.cpu().numpy(), self.thresholds, rho, train_flag)
         sel = eng.choose(targets, lab, train_flag, self.thresholds, rho, cap)
         self.last_selection = sel
-        if table.requires_grad:
-            agg = _AggregateFn.apply(table, eng, sel, self.feat_dim)
-        else:
-            agg = eng.aggregate(sel)
         B = targets.shape[0]
+        if not table.requires_grad and self.embed_dim <= 256 and B > 0:
+            # frozen features (the reference's setup): aggregation + the whole dense part are two kernels
+            agg = eng.aggregate(sel)
+            combined = _DenseFn.apply(eng, targets, agg, self.feat_dim, self.weight,
+                                      *[ia.weight for ia in self.intra_aggs()])
+            return combined, center_scores
+        agg = _AggregateFn.apply(table, eng, sel, self.feat_dim)
         agg = agg.view(self._R, B, -1)[:, :, :self.feat_dim]
 
         # relation transforms + inter-relation combine: layers.py:625-629, 273-289
