@@ -60,6 +60,23 @@ class GraphedTrainStep:
                             p.grad = torch.zeros_like(p)
                 self._fwd_bwd()
                 # no optimizer step during warm-up: parameters stay as the caller initialised them
+            # Create the optimizer state OUTSIDE the graph: torch builds it lazily in the first step(), and a
+            # captured lazy init would re-zero the moments on every replay. Step once, then undo it.
+            params = [p for g in self.opt.param_groups for p in g["params"] if p.requires_grad]
+            backup = [p.detach().clone() for p in params]
+            had_state = len(self.opt.state) > 0
+            saved = None
+            if had_state:
+                saved = {k: {n: (v.clone() if isinstance(v, torch.Tensor) else v) for n, v in st.items()}
+                         for k, st in self.opt.state.items()}
+            self.opt.step()
+            with torch.no_grad():
+                for p, b in zip(params, backup):
+                    p.copy_(b)
+                for k, st in self.opt.state.items():
+                    for n, v in st.items():
+                        if isinstance(v, torch.Tensor):
+                            v.copy_(saved[k][n]) if had_state else v.zero_()
         torch.cuda.current_stream(self.dev).wait_stream(s)
         torch.cuda.synchronize(self.dev)
         self.g_fb = torch.cuda.CUDAGraph()
