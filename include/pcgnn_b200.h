@@ -170,6 +170,31 @@ PCG_API int pcg_dense_bwd(int64_t ldf, int F, int B, int R, int E, const float* 
                   float* d_w_inter, float* scratch, pcg_stream_t stream);
 
 /*
+ * label_clf similarity head on the batch's targets (src/layers.py:200, :236, :243):
+ *   center[i][c] = dot(feat[targets[i], :F], w[c, :]) + b[c],  w [2,F], b [2] (nn.Linear layout)
+ * and its backward: d_w [2,F], d_b [2] from d_center [B,2] (features are frozen). Deterministic.
+ *   scratch  pcg_head_scratch_floats(B,F,E) floats; ticket: one int32, zero before the first call
+ */
+PCG_API size_t pcg_head_scratch_floats(int B, int F, int E);
+PCG_API int pcg_center_fwd(const float* feat, int64_t ldf, int F, const int32_t* targets, int B, const float* w,
+                   const float* b, float* center, pcg_stream_t stream);
+PCG_API int pcg_center_bwd(const float* feat, int64_t ldf, int F, const int32_t* targets, int B, const float* d_center,
+                   float* d_w, float* d_b, float* scratch, int32_t* ticket, pcg_stream_t stream);
+
+/*
+ * PCALayer head + loss (src/model.py:38, :54-61): logits[i][c] = dot(w[c, :], emb[:, i]) with emb [E,B];
+ * loss = mean_i CE(logits[i], labels[i]) + lambda * mean_i CE(center[i], labels[i]).
+ * p1 / q1 [B] receive the class-1 softmax probabilities of the two heads (inputs of the backward).
+ * Backward: d_emb [E,B], d_center [B,2], d_w [2,E] from the scalar d_loss (device pointer).
+ */
+PCG_API int pcg_head_loss_fwd(const float* emb, int E, int B, const float* w, const float* center,
+                      const int64_t* labels, float lambda, float* logits, float* p1, float* q1, float* loss,
+                      float* scratch, int32_t* ticket, pcg_stream_t stream);
+PCG_API int pcg_head_loss_bwd(const float* emb, int E, int B, const float* w, const int64_t* labels, const float* p1,
+                      const float* q1, float lambda, const float* d_loss, float* d_emb, float* d_center, float* d_w,
+                      float* scratch, int32_t* ticket, pcg_stream_t stream);
+
+/*
  * Label-balanced pick step, replay form: out[t] = idx_train[bisect_right(cum, u[t]*total, 0, n-1)],
  * total = cum[n-1]. Bit-compatible with random.choices(idx_train, weights, k) of
  * src/utils.py:274-278 when `u` are the doubles random.random() would have produced and `cum` is

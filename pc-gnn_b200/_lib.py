@@ -43,6 +43,11 @@ SIGNATURES = {
     "pcg_dense_fwd": (_i, [_p, _l, _i, _p, _i, _i, _i, _p, C.POINTER(_p), _p, _p, _p, _p]),
     "pcg_dense_bwd_scratch_floats": (_z, [_i, _i, _i, _i]),
     "pcg_dense_bwd": (_i, [_l, _i, _i, _i, _i, _p, _p, _p, _p, _p, C.POINTER(_p), _p, _p, _p]),
+    "pcg_head_scratch_floats": (_z, [_i, _i, _i]),
+    "pcg_center_fwd": (_i, [_p, _l, _i, _p, _i, _p, _p, _p, _p]),
+    "pcg_center_bwd": (_i, [_p, _l, _i, _p, _i, _p, _p, _p, _p, _p, _p]),
+    "pcg_head_loss_fwd": (_i, [_p, _i, _i, _p, _p, _p, C.c_float, _p, _p, _p, _p, _p, _p, _p]),
+    "pcg_head_loss_bwd": (_i, [_p, _i, _i, _p, _p, _p, _p, C.c_float, _p, _p, _p, _p, _p, _p, _p]),
     "pcg_pick_step": (_i, [_p, _l, _p, _l, _p, _p, _p]),
     "pcg_pick_step_philox": (_i, [_p, _l, _u64, _u64, _l, _p, _p, _p]),
 }

@@ -335,3 +335,55 @@ class Engine:
                                     scratch.data_ptr(), _lib.stream_ptr())
         _lib.check(rc, "pcg_dense_bwd")
         return d_intra, d_inter
+
+    # ------------------------------------------------------------------ heads
+    def _tickets(self):
+        if getattr(self, "_ticket_buf", None) is None:
+            self._ticket_buf = torch.zeros(8, dtype=torch.int32, device=self.device)
+        return self._ticket_buf
+
+    def center_fwd(self, targets, w, b):
+        """center [B,2] = label_clf on the targets' own features (``pcg_center_fwd``)."""
+        B = int(targets.shape[0])
+        out = torch.empty((B, 2), dtype=torch.float32, device=self.device)
+        rc = self.lib.pcg_center_fwd(self.feat.data_ptr(), self.ldf, self.F, targets.data_ptr(), B, w.data_ptr(),
+                                     b.data_ptr(), out.data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "pcg_center_fwd")
+        return out
+
+    def center_bwd(self, targets, d_center):
+        B = int(targets.shape[0])
+        flat = torch.empty(2 * self.F + 2, dtype=torch.float32, device=self.device)
+        scratch = torch.empty(int(self.lib.pcg_head_scratch_floats(B, self.F, 1)), dtype=torch.float32,
+                              device=self.device)
+        d_center = d_center.contiguous()
+        rc = self.lib.pcg_center_bwd(self.feat.data_ptr(), self.ldf, self.F, targets.data_ptr(), B, d_center.data_ptr(),
+                                     flat.data_ptr(), flat[2 * self.F:].data_ptr(), scratch.data_ptr(),
+                                     self._tickets()[0:].data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "pcg_center_bwd")
+        return flat[:2 * self.F].view(2, self.F), flat[2 * self.F:]
+
+    def head_loss_fwd(self, emb, w, center, labels, lam):
+        E, B = int(emb.shape[0]), int(emb.shape[1])
+        buf = torch.empty(4 * B + 1, dtype=torch.float32, device=self.device)
+        logits, p1, q1, loss = buf[:2 * B].view(B, 2), buf[2 * B:3 * B], buf[3 * B:4 * B], buf[4 * B:]
+        scratch = torch.empty(int(self.lib.pcg_head_scratch_floats(B, 1, E)), dtype=torch.float32, device=self.device)
+        rc = self.lib.pcg_head_loss_fwd(emb.data_ptr(), E, B, w.data_ptr(), center.data_ptr(), labels.data_ptr(),
+                                        float(lam), logits.data_ptr(), p1.data_ptr(), q1.data_ptr(), loss.data_ptr(),
+                                        scratch.data_ptr(), self._tickets()[1:].data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "pcg_head_loss_fwd")
+        return loss.view(()), logits, p1, q1
+
+    def head_loss_bwd(self, emb, w, labels, p1, q1, lam, d_loss):
+        E, B = int(emb.shape[0]), int(emb.shape[1])
+        d_emb = torch.empty((E, B), dtype=torch.float32, device=self.device)
+        d_center = torch.empty((B, 2), dtype=torch.float32, device=self.device)
+        d_w = torch.empty((2, E), dtype=torch.float32, device=self.device)
+        scratch = torch.empty(int(self.lib.pcg_head_scratch_floats(B, 1, E)), dtype=torch.float32, device=self.device)
+        d_loss = d_loss.contiguous()
+        rc = self.lib.pcg_head_loss_bwd(emb.data_ptr(), E, B, w.data_ptr(), labels.data_ptr(), p1.data_ptr(),
+                                        q1.data_ptr(), float(lam), d_loss.data_ptr(), d_emb.data_ptr(),
+                                        d_center.data_ptr(), d_w.data_ptr(), scratch.data_ptr(),
+                                        self._tickets()[2:].data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "pcg_head_loss_bwd")
+        return d_emb, d_center, d_w

@@ -33,7 +33,7 @@ from .engine import Engine, padded_ld
 from .graph import RelGraph
 
 __all__ = ["InterAgg1", "InterAgg3", "InterAgg5", "InterAgg", "IntraAgg", "choose_step_neighs",
-           "choose_step_test"]
+           "choose_step_test", "HeadLossFn"]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -73,6 +73,42 @@ class _DenseFn(torch.autograd.Function):
         agg, w_inter, cat, out = ctx.saved_tensors
         d_intra, d_inter = ctx.engine.dense_bwd(agg, w_inter, cat, out, d_out, ctx.feat_dim, ctx.n_rel)
         return (None, None, None, None, d_inter, *d_intra)
+
+
+class _CenterFn(torch.autograd.Function):
+    """center_scores [B,2] = label_clf(features[batch]) (layers.py:236-243) as one kernel, with label_clf's
+    weight / bias gradients as the backward (the feature table is frozen)."""
+
+    @staticmethod
+    def forward(ctx, engine, targets, weight, bias):
+        weight = weight.contiguous()
+        ctx.engine, ctx.targets = engine, targets
+        return engine.center_fwd(targets, weight, bias)
+
+    @staticmethod
+    def backward(ctx, d_center):
+        d_w, d_b = ctx.engine.center_bwd(ctx.targets, d_center)
+        return None, None, d_w, d_b
+
+
+class HeadLossFn(torch.autograd.Function):
+    """PCALayer's head and loss (model.py:38, :54-61) as one kernel per direction:
+    loss = CE(W @ combined, y) + lambda * CE(center_scores, y)."""
+
+    @staticmethod
+    def forward(ctx, engine, combined, weight, center, labels, lam):
+        combined, weight, center = combined.contiguous(), weight.contiguous(), center.contiguous()
+        loss, logits, p1, q1 = engine.head_loss_fwd(combined, weight, center, labels, lam)
+        ctx.engine, ctx.lam = engine, lam
+        ctx.save_for_backward(combined, weight, labels, p1, q1)
+        ctx.mark_non_differentiable(logits)
+        return loss, logits
+
+    @staticmethod
+    def backward(ctx, d_loss, _d_logits):
+        combined, weight, labels, p1, q1 = ctx.saved_tensors
+        d_emb, d_center, d_w = ctx.engine.head_loss_bwd(combined, weight, labels, p1, q1, ctx.lam, d_loss)
+        return None, d_emb, d_w, d_center, None, None
 
 
 def _feature_table(features, n_nodes, device, ids=None):
@@ -314,9 +350,15 @@ class InterAgg(nn.Module):
             eng.resort_pool()
         else:
             eng.score_table(self.label_clf.weight, self.label_clf.bias)
-        idx = targets.long()
-        self_feats = self.features(idx)
-        center_scores = self.label_clf(self_feats)                   # [B,2], carries grad (layers.py:243)
+        B = targets.shape[0]
+        fused = (not table.requires_grad) and self.embed_dim <= 256 and B > 0 \
+            and isinstance(self.label_clf, nn.Linear) and self.label_clf.bias is not None
+        if fused:   # [B,2] with gradient to label_clf (layers.py:236-243), one kernel
+            center_scores = _CenterFn.apply(eng, targets, self.label_clf.weight, self.label_clf.bias)
+        else:
+            idx = targets.long()
+            self_feats = self.features(idx)
+            center_scores = self.label_clf(self_feats)
 
         # choose (filter + oversample + union) and aggregate: layers.py:246-270, 589-624
         if self.cap_slots_hint is not None:
@@ -327,8 +369,7 @@ class InterAgg(nn.Module):
             cap = eng.slots_bound(targets.cpu().numpy(), self.thresholds, rho, train_flag)
         sel = eng.choose(targets, lab, train_flag, self.thresholds, rho, cap)
         self.last_selection = sel
-        B = targets.shape[0]
-        if not table.requires_grad and self.embed_dim <= 256 and B > 0:
+        if fused:
             # frozen features (the reference's setup): aggregation + the whole dense part are two kernels
             agg = eng.aggregate(sel)
             combined = _DenseFn.apply(eng, targets, agg, self.feat_dim, self.weight,

@@ -32,6 +32,18 @@ class PCALayer(nn.Module):
         return torch.sigmoid(gnn_logits), torch.sigmoid(label_logits)                  # model.py:41-45
 
     def loss(self, nodes, labels, train_flag=True):
+        inter = self.inter1
+        if self.weight.is_cuda and self.weight.shape[0] == 2 and hasattr(inter, "engine") \
+                and isinstance(self.xent, nn.CrossEntropyLoss):
+            # head + both cross-entropies fused into one kernel per direction (same math as below)
+            from .layers import HeadLossFn, _as_device_labels
+
+            embeds1, label_scores = inter(nodes, labels, train_flag)
+            if embeds1.shape[1] > 0:
+                lab = _as_device_labels(labels, embeds1.device)
+                loss, _ = HeadLossFn.apply(inter.engine(), embeds1, self.weight, label_scores, lab,
+                                           float(self.lambda_1))
+                return loss
         gnn_scores, label_scores = self.forward(nodes, labels, train_flag)
         label_loss = self.xent(label_scores, labels.squeeze())                         # model.py:54
         gnn_loss = self.xent(gnn_scores, labels.squeeze())                             # model.py:59
