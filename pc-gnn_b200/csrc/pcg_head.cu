@@ -10,7 +10,7 @@
 // counter) adds them in block order, so results are deterministic run to run.
 #include "pcg_common.cuh"
 
-#define HEAD_BLOCK 256
+#define HEAD_BLOCK 64
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -70,19 +70,29 @@ __global__ void __launch_bounds__(HEAD_BLOCK) k_center_fwd(const float* __restri
 }
 
 // dW[c][f] = sum_i g[i][c] * feat[targets[i]][f];  db[c] = sum_i g[i][c].
-// Block `blk` owns targets [blk*per, (blk+1)*per); thread f owns feature column f.
+// Block `blk` owns targets [blk*per, (blk+1)*per) (per <= CENTER_PER); thread f owns feature column f.
+#define CENTER_PER 32
 __global__ void k_center_bwd(const float* __restrict__ feat, int64_t ldf, int F, const int32_t* __restrict__ targets,
                              int B, const float* __restrict__ g, float* __restrict__ partial, int32_t* ticket,
                              float* __restrict__ dw, float* __restrict__ db) {
+    __shared__ int32_t s_t[CENTER_PER];
+    __shared__ float s_g[CENTER_PER][2];
     const int per = (B + gridDim.x - 1) / gridDim.x;
-    const int ib = blockIdx.x * per, ie = min(B, ib + per);
+    const int ib = blockIdx.x * per, ie = min(B, ib + per), n = max(ie - ib, 0);
+    for (int q = threadIdx.x; q < n; q += blockDim.x) {
+        s_t[q] = targets[ib + q];
+        s_g[q][0] = g[2 * (ib + q)];
+        s_g[q][1] = g[2 * (ib + q) + 1];
+    }
+    __syncthreads();
     const int stride = 2 * F + 2;
     for (int f = threadIdx.x; f < F + 1; f += blockDim.x) {     // column F stands for the bias
         float a0 = 0.f, a1 = 0.f;
-        for (int i = ib; i < ie; ++i) {
-            const float x = f < F ? __ldg(feat + (int64_t)__ldg(targets + i) * ldf + f) : 1.f;
-            a0 = fmaf(g[2 * i], x, a0);
-            a1 = fmaf(g[2 * i + 1], x, a1);
+#pragma unroll 8
+        for (int q = 0; q < n; ++q) {
+            const float x = f < F ? __ldg(feat + (int64_t)s_t[q] * ldf + f) : 1.f;
+            a0 = fmaf(s_g[q][0], x, a0);
+            a1 = fmaf(s_g[q][1], x, a1);
         }
         float* dst = partial + (int64_t)blockIdx.x * stride;
         if (f < F) { dst[f] = a0; dst[F + f] = a1; }
@@ -164,12 +174,13 @@ __global__ void __launch_bounds__(HEAD_BLOCK) k_head_loss_bwd(const float* __res
                                                               float* __restrict__ d_emb, float* __restrict__ d_center,
                                                               float* __restrict__ partial, int32_t* ticket,
                                                               float* __restrict__ dw) {
-    extern __shared__ float sm[];            // [2][E] weights, then [warps][2][E] warp sums
+    extern __shared__ float sm[];            // [2][E] weights, then [HEAD_BLOCK][2] per-target dl
     float* sw = sm;
-    float* wsum = sm + 2 * E;
+    float* dls = sm + 2 * E;
     for (int c = threadIdx.x; c < 2 * E; c += blockDim.x) sw[c] = w[c];
     __syncthreads();
-    const int i = blockIdx.x * HEAD_BLOCK + threadIdx.x;
+    const int i0 = blockIdx.x * HEAD_BLOCK;
+    const int i = i0 + threadIdx.x;
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float s = d_loss[0] / (float)B;
     float dl0 = 0.f, dl1 = 0.f;
@@ -181,22 +192,27 @@ __global__ void __launch_bounds__(HEAD_BLOCK) k_head_loss_bwd(const float* __res
         const float dc1 = lambda * (q - (float)y) * s;
         d_center[2 * i] = -dc1;
         d_center[2 * i + 1] = dc1;
+        for (int e = 0; e < E; ++e) d_emb[(int64_t)e * B + i] = fmaf(sw[e], dl0, sw[E + e] * dl1);
     }
-    for (int e = 0; e < E; ++e) {
-        float x = 0.f;
-        if (i < B) {
-            x = emb[(int64_t)e * B + i];
-            d_emb[(int64_t)e * B + i] = fmaf(sw[e], dl0, sw[E + e] * dl1);
-        }
-        const float a = warp_sum(dl0 * x), b = warp_sum(dl1 * x);
-        if (lane == 0) { wsum[(wid * 2) * E + e] = a; wsum[(wid * 2 + 1) * E + e] = b; }
-    }
+    dls[2 * threadIdx.x] = dl0;
+    dls[2 * threadIdx.x + 1] = dl1;
     __syncthreads();
-    for (int x = threadIdx.x; x < 2 * E; x += blockDim.x) {
-        const int c = x / E, e = x - c * E;
-        float a = 0.f;
-        for (int q = 0; q < HEAD_BLOCK / 32; ++q) a += wsum[(q * 2 + c) * E + e];
-        partial[(int64_t)blockIdx.x * 2 * E + x] = a;
+    // dW partial of this block: warp `wid` owns rows e = wid, wid + 8, ...; lanes run along the batch
+    for (int e = wid; e < E; e += HEAD_BLOCK / 32) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int j = 0; j < HEAD_BLOCK / 32; ++j) {
+            const int t = lane + 32 * j;
+            const float x = i0 + t < B ? emb[(int64_t)e * B + i0 + t] : 0.f;
+            a = fmaf(dls[2 * t], x, a);
+            b = fmaf(dls[2 * t + 1], x, b);
+        }
+        a = warp_sum(a);
+        b = warp_sum(b);
+        if (lane == 0) {
+            partial[(int64_t)blockIdx.x * 2 * E + e] = a;
+            partial[(int64_t)blockIdx.x * 2 * E + E + e] = b;
+        }
     }
     if (!last_block(ticket)) return;
     for (int x = threadIdx.x; x < 2 * E; x += blockDim.x) {
@@ -209,7 +225,7 @@ __global__ void __launch_bounds__(HEAD_BLOCK) k_head_loss_bwd(const float* __res
 // ------------------------------------------------------------------------------------------- C ABI
 extern "C" size_t pcg_head_scratch_floats(int B, int F, int E) {
     const size_t blocks = (size_t)(B + HEAD_BLOCK - 1) / HEAD_BLOCK + 1;
-    size_t a = 64 * (size_t)(2 * F + 2);            // center bwd: up to 64 blocks
+    size_t a = ((size_t)(B + 31) / 32 + 1) * (size_t)(2 * F + 2);   // center bwd: one partial per 32 targets
     size_t b = blocks * 2 * (size_t)(E > 1 ? E : 1);
     return (a > b ? a : b) + 64;
 }
@@ -230,8 +246,7 @@ extern "C" int pcg_center_bwd(const float* feat, int64_t ldf, int F, const int32
                               pcg_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     PCG_REQUIRE(feat && targets && d_center && d_w && d_b && scratch && ticket, "pcg_center_bwd: null pointer");
-    int blocks = (B + 31) / 32;
-    if (blocks > 64) blocks = 64;
+    int blocks = (B + CENTER_PER - 1) / CENTER_PER;       // every block owns <= CENTER_PER targets
     if (blocks < 1) blocks = 1;
     int threads = ((F + 1 + 31) / 32) * 32;
     if (threads > 256) threads = 256;
@@ -260,7 +275,7 @@ extern "C" int pcg_head_loss_bwd(const float* emb, int E, int B, const float* w,
     PCG_REQUIRE(B > 0, "pcg_head_loss_bwd: empty batch");
     PCG_REQUIRE(emb && w && labels && p1 && q1 && d_loss && d_emb && d_center && d_w && scratch && ticket,
                 "pcg_head_loss_bwd: null pointer");
-    const size_t smem = ((size_t)2 * E + (size_t)(HEAD_BLOCK / 32) * 2 * E) * 4;
+    const size_t smem = ((size_t)2 * E + (size_t)HEAD_BLOCK * 2) * 4;
     PCG_REQUIRE(smem <= 48 * 1024, "pcg_head_loss_bwd: embed dim too large");
     const int blocks = (B + HEAD_BLOCK - 1) / HEAD_BLOCK;
     k_head_loss_bwd<<<blocks, HEAD_BLOCK, smem, stream>>>(emb, E, B, w, labels, p1, q1, lambda, d_loss, d_emb, d_center,

@@ -80,13 +80,14 @@ __device__ __forceinline__ uint32_t orderable(float f) {   // float order -> uns
 // shared memory and ranks 32 of them by counting smaller keys, 8 lanes per element; the rank is the
 // element's place in the sorted order. O(P^2) compares spread over P/32 CTAs: a few microseconds and
 // no serial merge chain (a single-CTA bitonic sort of the same pool took ~48 us on B200).
-__global__ void __launch_bounds__(256) k_sort_pool_rank(const float* __restrict__ pool_score,
+// `gather` != 0: pool_score is the whole score table and entry i's score is pool_score[pool[i]].
+__global__ void __launch_bounds__(256) k_sort_pool_rank(const float* __restrict__ pool_score, int gather,
                                                         const int32_t* __restrict__ pool, int P,
                                                         float* __restrict__ ps_score, int32_t* __restrict__ ps_pos,
                                                         int32_t* __restrict__ ps_id) {
     extern __shared__ unsigned long long keys[];
     for (int i = threadIdx.x; i < P; i += blockDim.x)
-        keys[i] = ((unsigned long long)orderable(pool_score[i]) << 32) | (unsigned)i;
+        keys[i] = ((unsigned long long)orderable(pool_score[gather ? pool[i] : i]) << 32) | (unsigned)i;
     __syncthreads();
     const int e = threadIdx.x >> 3, part = threadIdx.x & 7;
     const int i = blockIdx.x * 32 + e;
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(256) k_sort_pool_rank(const float* __restrict_
     cnt += __shfl_xor_sync(PCG_FULL, cnt, 2);
     cnt += __shfl_xor_sync(PCG_FULL, cnt, 4);
     if (part == 0 && i < P) {
-        ps_score[cnt] = pool_score[i];
+        ps_score[cnt] = pool_score[gather ? pool[i] : i];
         ps_pos[cnt] = i;
         ps_id[cnt] = pool[i];
     }
@@ -134,7 +135,7 @@ extern "C" size_t pcg_sort_pool_workspace_bytes(int P) {
     return o;
 }
 
-static int sort_pool_impl(const float* pool_score, const int32_t* pool, int P, float* ps_score, int32_t* ps_pos,
+static int sort_pool_impl(const float* pool_score, int gather, const int32_t* pool, int P, float* ps_score, int32_t* ps_pos,
                           int32_t* ps_id, char* ws, size_t ws_bytes, cudaStream_t stream) {
     if (P <= 0) return 0;
     if (P <= PCG_SORT_SMALL_MAX) {
@@ -146,7 +147,7 @@ static int sort_pool_impl(const float* pool_score, const int32_t* pool, int P, f
             if (e != cudaSuccess) { pcg_set_error("pcg_sort_pool: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
             configured = true;
         }
-        k_sort_pool_rank<<<(P + 31) / 32, 256, smem, stream>>>(pool_score, pool, P, ps_score, ps_pos, ps_id);
+        k_sort_pool_rank<<<(P + 31) / 32, 256, smem, stream>>>(pool_score, gather, pool, P, ps_score, ps_pos, ps_id);
         return 0;
     }
     const size_t a = align256((size_t)P * 4);
@@ -171,7 +172,7 @@ extern "C" int pcg_sort_pool(const float* pool_score, const int32_t* pool, int P
     PCG_REQUIRE(pool_score && pool && ps_score && ps_pos && ps_id, "pcg_sort_pool: null pointer");
     size_t skip = align256((size_t)P * 4);   // the gathered-score slot of the shared layout is unused here
     char* ws = workspace ? (char*)workspace + skip : nullptr;
-    int rc = sort_pool_impl(pool_score, pool, P, ps_score, ps_pos, ps_id, ws,
+    int rc = sort_pool_impl(pool_score, 0, pool, P, ps_score, ps_pos, ps_id, ws,
                             workspace_bytes > skip ? workspace_bytes - skip : 0, stream);
     if (rc) return rc;
     return pcg_check_launch("pcg_sort_pool");
@@ -196,10 +197,15 @@ extern "C" int pcg_score_table(const float* feat, int64_t n_nodes, int F, int64_
         PCG_REQUIRE(ps_score && ps_pos && ps_id, "pcg_score_table: sorted pool outputs missing");
         const size_t skip = align256((size_t)P * 4);
         PCG_REQUIRE(workspace && workspace_bytes >= skip, "pcg_score_table: workspace too small");
-        float* gathered = (float*)workspace;
-        k_gather_pool<<<(P + 255) / 256, 256, 0, stream>>>(score, pool, P, gathered);
-        int rc = sort_pool_impl(gathered, pool, P, ps_score, ps_pos, ps_id, (char*)workspace + skip,
+        int rc;
+        if (P <= PCG_SORT_SMALL_MAX) {      // the rank sort reads score[pool[i]] itself
+            rc = sort_pool_impl(score, 1, pool, P, ps_score, ps_pos, ps_id, nullptr, 0, stream);
+        } else {
+            float* gathered = (float*)workspace;
+            k_gather_pool<<<(P + 255) / 256, 256, 0, stream>>>(score, pool, P, gathered);
+            rc = sort_pool_impl(gathered, 0, pool, P, ps_score, ps_pos, ps_id, (char*)workspace + skip,
                                 workspace_bytes - skip, stream);
+        }
         if (rc) return rc;
     }
     return pcg_check_launch("pcg_score_table");

@@ -21,7 +21,7 @@ from . import _lib
 from .graph import RelGraph
 
 __all__ = ["pick_step", "pick_step_device", "pos_neg_split", "normalize", "sparse_to_adjlist_for_train",
-           "set_seeds", "pick_weights"]
+           "set_seeds", "pick_weights", "test", "load_data", "create_dir", "prob2pred", "conf_gmean"]
 
 
 def _degrees(adj_list, idx_train):
@@ -108,3 +108,73 @@ def set_seeds(seed):
     if torch.cuda.is_available():
         torch.cuda.manual_seed(seed)
         torch.cuda.manual_seed_all(seed)
+
+
+def load_data(data_name, seed: int = 72):
+    """Synthetic stand-in for the reference's dataset loader (utils.py:66-210; the YelpChi / Amazon files are
+    not available offline): (homo, relation_list, feat_data, labels) with ``homo`` / ``relation_list`` as CSR
+    ``RelGraph`` objects, which every consumer in this package accepts in place of dict-of-sets."""
+    from .synth import SPECS, make_graph
+
+    key = {"yelp": "yelp", "amazon": "amazon", "amazon_new": "amazon"}.get(data_name, data_name)
+    if key not in SPECS:
+        raise ValueError(f"no synthetic spec for dataset {data_name!r}")
+    d = make_graph(key, seed=seed)
+    return d.homo, d.graph, d.feat, d.labels
+
+
+def test(test_nodes, labels, model, batch_size, result=None, epoch=None, epoch_best=None, flag=None,
+         print_line=True):
+    """Evaluation loop with the reference's signature and return value (utils.py:280-333): batched
+    ``model.to_prob(nodes, labels, train_flag=False)`` then AUC / recall / macro-F1 / precision."""
+    from sklearn.metrics import f1_score, precision_score, recall_score, roc_auc_score
+
+    labels = np.asarray(labels)
+    pred, anomaly = [], []
+    for start in range(0, len(test_nodes), batch_size):
+        batch_nodes = test_nodes[start:start + batch_size]
+        if len(batch_nodes) == 0:
+            continue
+        out = model.to_prob(batch_nodes, labels[start:start + batch_size], train_flag=False)
+        out = (out[0] if isinstance(out, tuple) else out).data.cpu().numpy()
+        pred.extend(out.argmax(axis=1).tolist())
+        anomaly.extend(out[:, 1].tolist())
+    pred = np.asarray(pred)
+    f1 = f1_score(labels, pred, zero_division=0)
+    f1_macro = f1_score(labels, pred, average="macro", zero_division=0)
+    precision = precision_score(labels, pred, zero_division=0)
+    recall = recall_score(labels, pred, zero_division=0)
+    auc = roc_auc_score(labels, anomaly)
+    line = f"- F1: {f1:.4f}\t- Recall: {recall:.4f}\t- Precision: {precision:.4f}\t- AUC-ROC: {auc:.4f}\t- F1-macro: {f1_macro:.4f}\n"
+    if result is not None:
+        writer = getattr(result, "write_val_log" if flag == "val" else "write_test_log", None)
+        if writer is not None:
+            try:
+                acc = float((pred == labels).mean())
+                pm = precision_score(labels, pred, zero_division=0, average="macro")
+                rm = recall_score(labels, pred, average="macro", zero_division=0)
+                if flag == "val":
+                    writer(epoch, epoch_best, acc, f1, f1_macro, precision, pm, recall, rm, auc, line, print_line)
+                else:
+                    writer(epoch_best, acc, f1, f1_macro, precision, pm, recall, rm, auc, line, print_line)
+            except TypeError:
+                pass
+    elif print_line:
+        print(line, end="")
+    return auc, recall, f1_macro, precision
+
+
+# small helpers other reference modules import from src.utils (result_manager.py:8; utils.py:440-461)
+def create_dir(dir_path):
+    import os
+
+    os.makedirs(dir_path, exist_ok=True)
+
+
+def prob2pred(y_prob, thres=0.5):
+    return (np.asarray(y_prob) >= thres).astype(np.int32)
+
+
+def conf_gmean(conf):
+    tn, fp, fn, tp = np.asarray(conf).ravel()
+    return (tp * tn / ((tp + fn) * (tn + fp))) ** 0.5

@@ -1,0 +1,123 @@
+"""CPU: host-side logic of the product (graph formats, synthetic data, capacity sizing, sampler weights,
+the import shim). No kernels are called."""
+import importlib
+import random
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import ref_harness as H
+from pcgnn_b200.graph import RelGraph, adj_lists_from_csr, csr_from_edges
+from pcgnn_b200.synth import make_graph
+
+
+def test_csr_matches_sparse_to_adjlist_rules():
+    """Self loop on every node, both directions, duplicates merged, rows sorted (utils.py:233-239)."""
+    n = 7
+    src, dst = [0, 0, 3, 3, 5], [1, 1, 4, 0, 5]
+    ip, ix = csr_from_edges(n, src, dst)
+    adj = adj_lists_from_csr(ip, ix)
+    assert adj[0] == {0, 1, 3} and adj[1] == {0, 1} and adj[3] == {0, 3, 4} and adj[6] == {6}
+    for v in range(n):
+        row = ix[ip[v]:ip[v + 1]]
+        assert np.all(np.diff(row) > 0)
+
+
+def test_from_adj_lists_roundtrip_with_numpy_integer_members():
+    d = make_graph("tiny", seed=1)
+    adj = d.graph.to_adj_lists()
+    adj = [{np.int64(k): {np.int32(x) for x in v} for k, v in a.items()} for a in adj]
+    g2 = RelGraph.from_adj_lists(adj, d.graph.n_nodes)
+    assert np.array_equal(g2.indptr, d.graph.indptr) and np.array_equal(g2.indices, d.graph.indices)
+    u = d.graph.union()
+    for v in (0, 5, 77):
+        want = set().union(*[set(d.graph.row(r, v).tolist()) for r in range(3)])
+        assert set(u.row(0, v).tolist()) == want
+
+
+def test_synthetic_shapes_follow_the_spec():
+    d = make_graph("tiny_amz", seed=2)
+    assert d.feat.shape == (900, 25) and d.graph.n_rel == 3
+    assert d.labels[:100].sum() == 0 and min(d.idx_train) >= 100          # unlabeled prefix excluded
+    assert np.allclose(d.feat.sum(1), d.feat.sum(1))                         # finite
+    assert abs(len(d.idx_train) / 800 - 0.4) < 0.02
+    assert set(d.train_pos) == {v for v, y in zip(d.idx_train, d.y_train) if y == 1}
+    assert all(int(d.graph.degrees(r).min()) >= 1 for r in range(3))        # self loops
+
+
+def test_pick_weights_and_replay_equal_random_choices():
+    from pcgnn_b200.utils import pick_weights
+    from oracle import port
+
+    d = make_graph("tiny", seed=4)
+    w = pick_weights(d.idx_train, d.y_train, d.homo)
+    homo = d.homo.to_adj_lists()[0]
+    y = d.y_train
+    lf = (y.sum() - len(y)) * y + len(y)
+    assert np.array_equal(w, np.array([len(homo[v]) for v in d.idx_train]) / lf)
+    random.seed(11)
+    want = random.choices(d.idx_train, weights=w, k=200)
+    random.seed(11)
+    u = [random.random() for _ in range(200)]
+    assert port.pick_step_replay(d.idx_train, w, u) == want
+
+
+def test_slots_bound_is_an_upper_bound_of_the_oracle_sizes():
+    from oracle import c_oracle
+    from pcgnn_b200 import _lib
+
+    d = make_graph("tiny", seed=5, dup_feature_frac=0.2)
+    rng = np.random.default_rng(0)
+    nodes = rng.choice(d.idx_train, 100)
+    score = rng.normal(size=d.feat.shape[0]).astype(np.float32)
+    pool = sorted(d.train_pos)
+    sp, _ = c_oracle.choose(d.graph, score, nodes, np.ones(100, bool), pool=pool, train=True)
+    need = int(((np.diff(sp) + _lib.SLOT - 1) // _lib.SLOT).sum())
+    # same arithmetic as Engine.slots_bound, without constructing an Engine (no GPU here)
+    total = 0
+    for r in range(3):
+        deg = d.graph.degrees(r)[nodes]
+        c = np.ceil(deg * 0.5).astype(np.int64)
+        k = np.where(deg > c + 1, c, deg)
+        o = np.minimum((c * 0.5).astype(np.int64), len(pool))
+        total += int(((k + o + _lib.SLOT - 1) // _lib.SLOT).sum())
+    assert total >= need
+
+
+def test_shim_routes_reference_imports_to_this_package():
+    import pcgnn_b200.shim as shim
+    from pcgnn_b200 import layers, utils
+
+    try:
+        shim.install(reference_root=H.REF_ROOT if H.available() else None)
+        assert importlib.import_module("src.layers") is layers
+        assert importlib.import_module("src.utils").pick_step is utils.pick_step
+        gs = importlib.import_module("src.graphsage")
+        for name in ("nn", "Variable", "torch", "F", "init", "random", "GCN", "GraphSage", "MeanAggregator",
+                     "Encoder", "GCNAggregator", "GCNEncoder"):
+            assert hasattr(gs, name), name                  # model_handler.py gets these via `import *`
+        mod = importlib.import_module("src.model")
+        assert hasattr(mod, "PCALayer")
+        if H.available():
+            assert mod.__file__.startswith(H.REF_ROOT)      # the reference's own model.py, unchanged
+    finally:
+        shim.uninstall()
+
+
+@pytest.mark.skipif(not H.available(), reason="reference tree not present")
+def test_reference_model_handler_imports_through_the_shim():
+    """`from src.model_handler import ModelHandler` resolves every hot-path name to this package."""
+    import pcgnn_b200.shim as shim
+    from pcgnn_b200 import layers
+
+    if H.REF_ROOT not in sys.path:
+        sys.path.insert(0, H.REF_ROOT)
+    try:
+        shim.install(reference_root=H.REF_ROOT)
+        mh = importlib.import_module("src.model_handler")
+        assert mh.InterAgg3 is layers.InterAgg3 and mh.IntraAgg is layers.IntraAgg
+        assert mh.pick_step.__module__.endswith("utils") and "pcgnn" in mh.pick_step.__module__
+        assert mh.PCALayer.__module__ == "src.model"
+    finally:
+        shim.uninstall()
