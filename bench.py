@@ -39,6 +39,15 @@ RHO, ALPHA, LR, WD = 0.5, 2.0, 0.01, 1e-3
 SEED = 72
 
 
+MY_KERNELS_PER_STEP = 20   # score+sort 2, choose 4, aggregate 2, dense fwd 3, center/head fwd 2, head/center bwd 2, dense bwd 3 (+2 when P>8192)
+
+
+def config_dict(desc, batch, world):
+    return {"workload": desc, "global_batch": batch * world, "rho": RHO, "thresholds": 0.5, "optimizer": "Adam",
+            "l2": "flushed between timed steps (256 MiB write)",
+            "parallelism": f"dp{world} (targets sharded, grads all-reduced)" if world > 1 else "single"}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -175,7 +184,7 @@ def run_reference(args):
         "impl": "reference", "metric": "train target-nodes/sec (fwd+bwd)", "value": rate, "unit": "target-nodes/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "rho": RHO, "thresholds": 0.5},
+        "config": config_dict(desc, batch, max(args.gpus, 1)),
         "cpu_baseline": {"value": rate, "unit": "target-nodes/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"full train step of oracle/port.py on the first {sample} targets of each "
                                    f"{batch}-target batch (Python loop per target like the reference; "
@@ -393,12 +402,10 @@ def main():
             "metric": "train target-nodes/sec (fwd+bwd)", "value": total_nodes / (ms_dev / 1e3),
             "unit": "target-nodes/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "global_batch": batch * world, "rho": RHO, "thresholds": 0.5,
-                       "optimizer": "Adam", "l2": "flushed between timed steps (256 MiB write)",
-                       "parallelism": f"dp{world} (targets sharded, grads all-reduced)" if world > 1 else "single"},
+            "config": config_dict(desc, batch, world),
             "e2e": {"value": total_nodes / (ms_e2e / 1e3), "unit": "target-nodes/s", "ms_per_step": ms_e2e / K,
                     "h2d_bytes_per_step": batch * 4 + batch * 8, "d2h_bytes_per_step": 4},
-            "gpu_launches": 14 * K,
+            "gpu_launches": MY_KERNELS_PER_STEP * K,
             "mode": "cuda-graph replay (runtime.GraphedTrainStep)" if use_graph else "eager",
             "roofline": roof, "kernels": kern, "clocks": sampler.result(),
         }
