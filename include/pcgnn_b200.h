@@ -72,9 +72,9 @@ PCG_API int pcg_pool_positions(const int32_t* pool, int P, int64_t n_nodes, int3
 PCG_API int pcg_entry_pool_positions(const int32_t* indices, int64_t nnz, const int32_t* pool_pos_of,
                              int32_t* entry_pool_pos, pcg_stream_t stream);
 
-/* Bytes of scratch pcg_choose needs for B targets x R relations on a graph whose largest row has
- * max_degree entries. */
-PCG_API size_t pcg_choose_workspace_bytes(int B, int R, int64_t max_degree);
+/* Bytes of scratch pcg_choose needs for B targets x R relations on a graph of n_nodes nodes whose largest
+ * row has max_degree entries. */
+PCG_API size_t pcg_choose_workspace_bytes(int B, int R, int64_t max_degree, int64_t n_nodes);
 
 /*
  * Choose step for a batch: per item keep the ceil(d*thresh[r]) neighbours nearest in label score
@@ -102,6 +102,9 @@ PCG_API size_t pcg_choose_workspace_bytes(int B, int R, int64_t max_degree);
  *                included, as in the reference's list; unordered)
  *   slot_item    int32 [cap_slots]  owning item of each handed-out slot, or -1
  *   it_slot0/it_m int32 [R*B], it_base int64 [R*B], it_done int32 [R*B] (zeroed; aggregation tickets)
+ *   it_rep       int32 [R*B]: targets that repeat an earlier id of the batch (pick_step samples with
+ *                replacement) are not processed again; it_rep[w] is the item whose list w shares (w itself
+ *                for first occurrences). pcg_aggregate copies the aggregated row accordingly.
  *   status       int32 [PCG_STATUS_WORDS] (zeroed here)
  */
 PCG_API int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t n_nodes, int R, const float* score,
@@ -110,8 +113,8 @@ PCG_API int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t n_
                const float* ps_score, const int32_t* ps_pos, const int32_t* ps_id, const int32_t* entry_pool_pos, int P,
                int train, int64_t max_degree,
                int32_t* sel_idx, float* sel_dist, int64_t cap_slots, int32_t* slot_item, int32_t* it_slot0,
-               int32_t* it_m, int64_t* it_base, int32_t* it_done, void* workspace, size_t workspace_bytes, int32_t* status,
-               pcg_stream_t stream);
+               int32_t* it_m, int64_t* it_base, int32_t* it_done, int32_t* it_rep, void* workspace,
+               size_t workspace_bytes, int32_t* status, pcg_stream_t stream);
 
 /*
  * Select-all variant for the GraphSAGE / GCN baselines: the item list IS the CSR row (no copy);
@@ -127,13 +130,14 @@ PCG_API int pcg_select_all(const int64_t* indptr, const int32_t* indices, int64_
  * Segmented aggregation: agg[w, :] = norm(sum of feat rows of item w's id list).
  * Replaces the dense-mask matmul of src/layers.py:593-624 and src/graphsage.py:80-95, 212-231.
  *   idx       the id array the items index (sel_idx from pcg_choose, or CSR indices from select_all)
+ *   it_extra / it_rep  from pcg_select_all / pcg_choose, or NULL
  *   partial   fp32 [cap_slots, ldf] scratch, it_done int32 [n_items] tickets zeroed by choose/select
  *   agg       fp32 [n_items, ldf]
  */
 PCG_API int pcg_aggregate(const float* feat, int64_t ldf, const int32_t* idx, const int32_t* slot_item,
                   const int32_t* it_slot0, const int32_t* it_m, const int64_t* it_base, const int32_t* it_extra,
-                  int n_items, int64_t cap_slots, const int32_t* status, int norm, float* partial,
-                  int32_t* it_done, float* agg, pcg_stream_t stream);
+                  const int32_t* it_rep, int n_items, int64_t cap_slots, const int32_t* status, int norm,
+                  float* partial, int32_t* it_done, float* agg, pcg_stream_t stream);
 
 /*
  * Backward of pcg_aggregate w.r.t. the feature table (only needed when `features` is trainable; the

@@ -32,13 +32,13 @@ SIGNATURES = {
     "pcg_score_table": (_i, [_p, _l, _i, _l, _p, _p, _p, _p, _i, _p, _p, _p, _p, _z, _p]),
     "pcg_sort_pool_workspace_bytes": (_z, [_i]),
     "pcg_sort_pool": (_i, [_p, _p, _i, _p, _p, _p, _p, _z, _p]),
-    "pcg_choose_workspace_bytes": (_z, [_i, _i, _l]),
+    "pcg_choose_workspace_bytes": (_z, [_i, _i, _l, _l]),
     "pcg_pool_positions": (_i, [_p, _i, _l, _p, _p]),
     "pcg_entry_pool_positions": (_i, [_p, _l, _p, _p, _p]),
     "pcg_choose": (_i, [_p, _p, _l, _i, _p, _p, _p, _p, _p, _i, C.POINTER(_d), _p, _d, _p, _p, _p, _p, _i, _i, _l,
-                        _p, _p, _l, _p, _p, _p, _p, _p, _p, _z, _p, _p]),
+                        _p, _p, _l, _p, _p, _p, _p, _p, _p, _p, _z, _p, _p]),
     "pcg_select_all": (_i, [_p, _p, _l, _i, _p, _i, _i, _l, _p, _p, _p, _p, _p, _p, _p, _p]),
-    "pcg_aggregate": (_i, [_p, _l, _p, _p, _p, _p, _p, _p, _i, _l, _p, _i, _p, _p, _p, _p]),
+    "pcg_aggregate": (_i, [_p, _l, _p, _p, _p, _p, _p, _p, _p, _i, _l, _p, _i, _p, _p, _p, _p]),
     "pcg_aggregate_bwd": (_i, [_p, _l, _p, _p, _p, _p, _p, _p, _i, _l, _p, _i, _p, _p]),
     "pcg_dense_fwd": (_i, [_p, _l, _i, _p, _i, _i, _i, _p, C.POINTER(_p), _p, _p, _p, _p]),
     "pcg_dense_bwd_scratch_floats": (_z, [_i, _i, _i, _i]),

@@ -128,12 +128,23 @@ __global__ void __launch_bounds__(256) k_aggregate(const float* __restrict__ fea
 }
 
 // Items that own no slot (m == 0, no extra) never reach a warp above: zero their rows first.
-__global__ void k_zero_empty(const int32_t* __restrict__ it_m, const int32_t* __restrict__ it_extra, int n_items,
-                             int64_t ldf, float* __restrict__ agg) {
+__global__ void k_zero_empty(const int32_t* __restrict__ it_m, const int32_t* __restrict__ it_extra,
+                             const int32_t* __restrict__ it_rep, int n_items, int64_t ldf, float* __restrict__ agg) {
     const int w = blockIdx.x;
     if (w >= n_items) return;
+    if (it_rep && it_rep[w] != w) return;                 // duplicates are copied from their representative
     if (it_m[w] > 0 || (it_extra && it_extra[w] >= 0)) return;
     for (int64_t c = threadIdx.x; c < ldf; c += blockDim.x) agg[(int64_t)w * ldf + c] = 0.f;
+}
+
+// agg row of a duplicate item = agg row of its representative (see k_choose_classify).
+__global__ void k_copy_dups(const int32_t* __restrict__ it_rep, int n_items, int64_t ldf, float* __restrict__ agg) {
+    const int w = blockIdx.x;
+    if (w >= n_items) return;
+    const int rep = it_rep[w];
+    if (rep == w) return;
+    for (int64_t c = threadIdx.x * 4; c < ldf; c += blockDim.x * 4)
+        *reinterpret_cast<float4*>(agg + (int64_t)w * ldf + c) = *reinterpret_cast<const float4*>(agg + (int64_t)rep * ldf + c);
 }
 
 // Backward w.r.t. the feature table: feat_grad[id] += d_agg[w] * scale for every id of item w.
@@ -233,8 +244,9 @@ static int dispatch_agg(bool bwd, const float* a0, int64_t ldf, const int32_t* i
 
 extern "C" int pcg_aggregate(const float* feat, int64_t ldf, const int32_t* idx, const int32_t* slot_item,
                              const int32_t* it_slot0, const int32_t* it_m, const int64_t* it_base,
-                             const int32_t* it_extra, int n_items, int64_t cap_slots, const int32_t* status, int norm,
-                             float* partial, int32_t* it_done, float* agg, pcg_stream_t stream_) {
+                             const int32_t* it_extra, const int32_t* it_rep, int n_items, int64_t cap_slots,
+                             const int32_t* status, int norm, float* partial, int32_t* it_done, float* agg,
+                             pcg_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n_items == 0) return 0;
     PCG_REQUIRE(ldf > 0 && ldf % 4 == 0, "pcg_aggregate: ldf=%lld must be a positive multiple of 4", (long long)ldf);
@@ -243,10 +255,11 @@ extern "C" int pcg_aggregate(const float* feat, int64_t ldf, const int32_t* idx,
     PCG_REQUIRE(((uintptr_t)feat & 15) == 0 && ((uintptr_t)agg & 15) == 0 && ((uintptr_t)partial & 15) == 0,
                 "pcg_aggregate: feat/agg/partial must be 16-byte aligned");
     if (n_items == 0 || cap_slots == 0) return 0;
-    k_zero_empty<<<n_items, 64, 0, stream>>>(it_m, it_extra, n_items, ldf, agg);
+    k_zero_empty<<<n_items, 64, 0, stream>>>(it_m, it_extra, it_rep, n_items, ldf, agg);
     int rc = dispatch_agg(false, feat, ldf, idx, slot_item, it_slot0, it_m, it_base, it_extra, cap_slots, status, norm,
                           partial, it_done, agg, stream);
     if (rc) return rc;
+    if (it_rep) k_copy_dups<<<n_items, 32, 0, stream>>>(it_rep, n_items, ldf, agg);
     return pcg_check_launch("pcg_aggregate");
 }
 

@@ -56,6 +56,7 @@ struct ChooseP {
     int32_t* it_m;
     int64_t* it_base;
     int32_t* it_done;
+    int32_t* it_rep;            // representative item of every item (itself unless an earlier target has the same id)
     int32_t* status;
     int32_t* small_q;
     int32_t* mid_q;
@@ -791,17 +792,30 @@ __device__ void choose_item_cta(const ChooseP& p, int w, uint32_t* sd, int sd_ca
 }
 
 // Classify items by row length into the three tier queues (warp / 128-thread CTA / 1024-thread CTA).
-__global__ void k_choose_classify(ChooseP p) {
+// Batches drawn by pick_step are sampled with replacement in proportion to degree, so hub nodes appear
+// several times; an item whose target id already occurred earlier in the batch is not queued at all: it
+// shares the result of that earlier ("representative") item (same node, same relation, same label).
+// first[v] = smallest batch index whose target is node v (table pre-set to 0x7f7f7f7f by a memset)
+__global__ void k_choose_mark(const int32_t* __restrict__ targets, int B, int32_t* __restrict__ first) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) atomicMin(&first[targets[i]], i);
+}
+
+__global__ void k_choose_classify(ChooseP p, const int32_t* __restrict__ first) {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     const int W = p.R * p.B;
     bool small = false, mid = false, big = false;
     if (w < W) {
         const int r = w / p.B, i = w - r * p.B;
-        const int64_t row = (int64_t)r * p.n_nodes + p.targets[i];
-        const int64_t d = p.indptr[row + 1] - p.indptr[row];
-        small = d <= PCG_SMALL_MAX;
-        big = d > PCG_MID_MAX;
-        mid = !small && !big;
+        const int rep = first ? first[p.targets[i]] : i;
+        p.it_rep[w] = r * p.B + rep;
+        if (rep == i) {
+            const int64_t row = (int64_t)r * p.n_nodes + p.targets[i];
+            const int64_t d = p.indptr[row + 1] - p.indptr[row];
+            small = d <= PCG_SMALL_MAX;
+            big = d > PCG_MID_MAX;
+            mid = !small && !big;
+        }
     }
     const unsigned lt = lanemask_lt();
     const int lane = threadIdx.x & 31;
@@ -819,6 +833,18 @@ __global__ void k_choose_classify(ChooseP p) {
     if (small) p.small_q[bs + __popc(ms & lt)] = w;
     if (mid) p.mid_q[bm + __popc(mm & lt)] = w;
     if (big) p.large_q[bb + __popc(mb & lt)] = w;
+}
+
+// Duplicate items take over their representative's list (after all tiers have finished).
+__global__ void k_choose_fixup(ChooseP p) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= p.R * p.B) return;
+    const int rep = p.it_rep[w];
+    if (rep == w) return;
+    p.it_slot0[w] = p.it_slot0[rep];
+    p.it_m[w] = p.it_m[rep];
+    p.it_base[w] = p.it_base[rep];
+    p.it_done[w] = 0;
 }
 
 __global__ void __launch_bounds__(PCG_WARPS_PER_CTA * 32, 3) k_choose_warp(ChooseP p) {
@@ -935,12 +961,12 @@ __global__ void k_entry_pool_pos(const int32_t* __restrict__ indices, int64_t nn
 
 // ------------------------------------------------------------------------------------------- C ABI
 struct WsLayout {
-    size_t small_q, mid_q, large_q, bits_slab, total;
+    size_t small_q, mid_q, large_q, bits_slab, first, total;
     int64_t slab_words;
     int grid_large;
 };
 
-static WsLayout ws_layout(int B, int R, int64_t max_degree, int sms) {
+static WsLayout ws_layout(int B, int R, int64_t max_degree, int64_t n_nodes, int sms) {
     WsLayout L;
     size_t W = (size_t)B * R;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
@@ -951,6 +977,7 @@ static WsLayout ws_layout(int B, int R, int64_t max_degree, int sms) {
     L.mid_q = o; o = al(o + W * 4);
     L.large_q = o; o = al(o + W * 4);
     L.bits_slab = o; o = al(o + (size_t)L.grid_large * L.slab_words * 4);
+    L.first = o; o = al(o + (size_t)n_nodes * 4);
     L.total = o;
     return L;
 }
@@ -973,8 +1000,8 @@ extern "C" __attribute__((visibility("default"))) int pcg_debug_set_trace(long l
 }
 #endif
 
-extern "C" size_t pcg_choose_workspace_bytes(int B, int R, int64_t max_degree) {
-    return ws_layout(B, R, max_degree, 148 * 2).total;   // sized for the largest grid we ever launch
+extern "C" size_t pcg_choose_workspace_bytes(int B, int R, int64_t max_degree, int64_t n_nodes) {
+    return ws_layout(B, R, max_degree, n_nodes, 148 * 2).total;   // sized for the largest grid we ever launch
 }
 
 extern "C" int pcg_pool_positions(const int32_t* pool, int P, int64_t n_nodes, int32_t* pool_pos_of,
@@ -1005,8 +1032,9 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
                           double rho, const float* ps_score, const int32_t* ps_pos, const int32_t* ps_id,
                           const int32_t* entry_pool_pos, int P, int train,
                           int64_t max_degree, int32_t* sel_idx, float* sel_dist, int64_t cap_slots,
-                          int32_t* slot_item, int32_t* it_slot0, int32_t* it_m, int64_t* it_base, int32_t* it_done, void* workspace,
-                          size_t workspace_bytes, int32_t* status, pcg_stream_t stream_) {
+                          int32_t* slot_item, int32_t* it_slot0, int32_t* it_m, int64_t* it_base, int32_t* it_done,
+                          int32_t* it_rep, void* workspace, size_t workspace_bytes, int32_t* status,
+                          pcg_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     PCG_REQUIRE(R >= 1 && R <= PCG_MAX_REL, "pcg_choose: R=%d outside [1,%d]", R, PCG_MAX_REL);
     PCG_REQUIRE(B >= 0, "pcg_choose: negative batch");
@@ -1016,10 +1044,11 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
     }
     PCG_REQUIRE(score || (entry_score && center_score), "pcg_choose: need a score table or explicit scores");
     PCG_REQUIRE(!(train && P > 0) || (ps_score && ps_pos && ps_id), "pcg_choose: sorted pool arrays missing");
-    PCG_REQUIRE(indptr && indices && targets && sel_idx && slot_item && it_slot0 && it_m && it_base && it_done && status,
+    PCG_REQUIRE(indptr && indices && targets && sel_idx && slot_item && it_slot0 && it_m && it_base && it_done &&
+                    it_rep && status,
                 "pcg_choose: null pointer");
     const int sms = device_sms();
-    WsLayout L = ws_layout(B, R, max_degree, sms);
+    WsLayout L = ws_layout(B, R, max_degree, n_nodes, sms);
     PCG_REQUIRE(workspace && workspace_bytes >= L.total, "pcg_choose: workspace too small (%zu < %zu)", workspace_bytes,
                 L.total);
     cudaError_t e = cudaMemsetAsync(status, 0, PCG_STATUS_WORDS * sizeof(int32_t), stream);
@@ -1032,7 +1061,7 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
     p.P = (train && ps_score) ? P : 0; p.train = train;
     for (int r = 0; r < PCG_MAX_REL; ++r) p.thresh[r] = r < R ? thresh_host[r] : 0.5;
     p.rho = rho; p.sel_idx = sel_idx; p.sel_dist = sel_dist; p.cap_slots = cap_slots; p.slot_item = slot_item;
-    p.it_slot0 = it_slot0; p.it_m = it_m; p.it_base = it_base; p.it_done = it_done; p.status = status;
+    p.it_slot0 = it_slot0; p.it_m = it_m; p.it_base = it_base; p.it_done = it_done; p.it_rep = it_rep; p.status = status;
     char* ws = (char*)workspace;
     p.small_q = (int32_t*)(ws + L.small_q);
     p.mid_q = (int32_t*)(ws + L.mid_q);
@@ -1046,7 +1075,16 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
     int64_t bw = (max_degree < PCG_LARGE_CAP_MAX ? max_degree : PCG_LARGE_CAP_MAX);
     p.bits_words = (int)((bw + 31) / 32);
     const int W = R * B;
-    k_choose_classify<<<(W + 255) / 256, 256, 0, stream>>>(p);
+    // duplicate targets are folded when ids come from a score table (explicit per-target lists are all distinct)
+    const bool dedup = score != nullptr && entry_score == nullptr;
+    int32_t* first = nullptr;
+    if (dedup) {
+        first = (int32_t*)(ws + L.first);
+        e = cudaMemsetAsync(first, 0x7f, (size_t)n_nodes * 4, stream);
+        if (e != cudaSuccess) { pcg_set_error("pcg_choose: memset: %s", cudaGetErrorString(e)); return (int)e; }
+        k_choose_mark<<<(B + 255) / 256, 256, 0, stream>>>(targets, B, first);
+    }
+    k_choose_classify<<<(W + 255) / 256, 256, 0, stream>>>(p, first);
     const bool have_mid = max_degree > PCG_SMALL_MAX, have_big = max_degree > PCG_MID_MAX;
     if (have_mid && !g_side[0]) {
         for (int q = 0; q < 2; ++q)
@@ -1085,6 +1123,7 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
     k_choose_warp<<<gw, PCG_WARPS_PER_CTA * 32, 0, stream>>>(p);
     if (have_mid) cudaStreamWaitEvent(stream, g_join[0], 0);      // join
     if (have_big) cudaStreamWaitEvent(stream, g_join[1], 0);
+    if (dedup) k_choose_fixup<<<(W + 255) / 256, 256, 0, stream>>>(p);
     return pcg_check_launch("pcg_choose");
 }
 

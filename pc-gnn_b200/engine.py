@@ -28,7 +28,7 @@ def padded_ld(feat_dim: int) -> int:
 class Selection:
     """Result of a choose / select-all call: per item w = r*B + i an id list inside ``idx``."""
 
-    __slots__ = ("B", "R", "idx", "slot_item", "it_slot0", "it_m", "it_base", "it_extra", "it_done",
+    __slots__ = ("B", "R", "idx", "slot_item", "it_slot0", "it_m", "it_base", "it_extra", "it_done", "it_rep",
                  "status", "cap_slots", "norm", "_blob")
 
     def lists(self):
@@ -200,7 +200,7 @@ class Engine:
         dev = self.device
         # one allocation, carved into typed views (int64 part first for alignment)
         n64 = W
-        n32 = (cap_slots * _lib.SLOT if with_sel_idx else 0) + cap_slots + 3 * W + (W if with_extra else 0) \
+        n32 = (cap_slots * _lib.SLOT if with_sel_idx else 0) + cap_slots + 4 * W + (W if with_extra else 0) \
             + _lib.STATUS_WORDS
         blob = torch.empty(n64 * 2 + n32, dtype=torch.int32, device=dev)
         s = Selection()
@@ -221,6 +221,7 @@ class Engine:
         s.it_m = take(W)
         s.it_done = take(W)
         s.it_extra = take(W) if with_extra else None
+        s.it_rep = take(W) if with_sel_idx else None
         s.status = take(_lib.STATUS_WORDS)
         s.norm = _lib.NORM_MEAN
         return s
@@ -238,7 +239,7 @@ class Engine:
         R = self.R if n_rel is None else n_rel
         s = self._new_selection(B, R, cap_slots, True, False)
         maxdeg = self.max_degree if max_degree is None else max_degree
-        ws_bytes = self.lib.pcg_choose_workspace_bytes(B, R, maxdeg)
+        ws_bytes = self.lib.pcg_choose_workspace_bytes(B, R, maxdeg, self.N if n_nodes is None else n_nodes)
         if self._ws is None or self._ws.numel() < ws_bytes:
             self._ws = torch.empty(int(ws_bytes), dtype=torch.uint8, device=self.device)
         th = (C.c_double * R)(*[float(x) for x in thresh])
@@ -257,7 +258,8 @@ class Engine:
             _lib.ptr(ps), _lib.ptr(pp), _lib.ptr(pi), _lib.ptr(self.entry_pool_pos) if use_table else None, P,
             int(bool(train)), maxdeg, s.idx.data_ptr(), _lib.ptr(dist),
             cap_slots, s.slot_item.data_ptr(), s.it_slot0.data_ptr(), s.it_m.data_ptr(), s.it_base.data_ptr(),
-            s.it_done.data_ptr(), self._ws.data_ptr(), int(ws_bytes), s.status.data_ptr(), _lib.stream_ptr())
+            s.it_done.data_ptr(), s.it_rep.data_ptr(), self._ws.data_ptr(), int(ws_bytes), s.status.data_ptr(),
+            _lib.stream_ptr())
         _lib.check(rc, "pcg_choose")
         return (s, dist) if want_dist else s
 
@@ -283,8 +285,9 @@ class Engine:
         partial = torch.empty((sel.cap_slots, ldf), dtype=torch.float32, device=self.device)
         rc = self.lib.pcg_aggregate(feat.data_ptr(), ldf, sel.idx.data_ptr(), sel.slot_item.data_ptr(),
                                     sel.it_slot0.data_ptr(), sel.it_m.data_ptr(), sel.it_base.data_ptr(),
-                                    _lib.ptr(sel.it_extra), W, sel.cap_slots, sel.status.data_ptr(), sel.norm,
-                                    partial.data_ptr(), sel.it_done.data_ptr(), agg.data_ptr(), _lib.stream_ptr())
+                                    _lib.ptr(sel.it_extra), _lib.ptr(sel.it_rep), W, sel.cap_slots,
+                                    sel.status.data_ptr(), sel.norm, partial.data_ptr(), sel.it_done.data_ptr(),
+                                    agg.data_ptr(), _lib.stream_ptr())
         _lib.check(rc, "pcg_aggregate")
         return agg
 
@@ -293,6 +296,10 @@ class Engine:
         ldf = feat_grad.shape[1]
         W = sel.B * sel.R
         d_agg = d_agg.contiguous()
+        if sel.it_rep is not None:      # duplicates' gradients flow through their representative's list
+            folded = torch.zeros_like(d_agg)
+            folded.index_add_(0, sel.it_rep.long(), d_agg)
+            d_agg = folded
         rc = self.lib.pcg_aggregate_bwd(d_agg.data_ptr(), ldf, sel.idx.data_ptr(), sel.slot_item.data_ptr(),
                                         sel.it_slot0.data_ptr(), sel.it_m.data_ptr(), sel.it_base.data_ptr(),
                                         _lib.ptr(sel.it_extra), W, sel.cap_slots, sel.status.data_ptr(), sel.norm,

@@ -298,3 +298,79 @@ def test_pick_step_replays_random_choices():
     w = pick_weights(d.idx_train, d.y_train, d.homo)
     pos_mass = w[d.y_train == 1].sum() / w.sum()
     assert abs(d.labels[a].mean() - pos_mass) < 0.02
+
+
+def test_graphed_train_step_equals_eager_steps():
+    """runtime.GraphedTrainStep (two CUDA graphs, static buffers) follows the same parameter trajectory as
+    eager model.loss / backward / Adam.step over several batches, including duplicated targets."""
+    from pcgnn_b200.parallel import GradAllReduce
+    from pcgnn_b200.runtime import GraphedTrainStep
+    from pcgnn_b200.synth import make_graph
+
+    d = make_graph("tiny_amz", seed=51, dup_feature_frac=0.1)
+    rng = np.random.default_rng(4)
+    params = random_params(rng, d.feat.shape[1], 16, 3)
+    tp = sorted(d.train_pos)
+    B = 128
+    batches = []
+    for _ in range(5):
+        nodes = rng.choice(d.idx_train, B)           # with replacement: duplicates inside a batch
+        batches.append((nodes, d.labels[nodes]))
+
+    def make():
+        m = build_cuda_pcgnn(d.feat, d.graph, tp, params)
+        o = torch.optim.Adam([p for p in m.parameters() if p.requires_grad], lr=0.01, weight_decay=1e-3,
+                             capturable=True, fused=True)
+        return m, o
+
+    eager, opt_e = make()
+    losses_e = []
+    for nodes, labels in batches:
+        opt_e.zero_grad()
+        loss = eager.loss(nodes.tolist(), torch.from_numpy(labels).cuda())
+        loss.backward()
+        opt_e.step()
+        losses_e.append(loss.item())
+
+    graphed, opt_g = make()
+    red = GradAllReduce(graphed.parameters()).attach()
+    eng = graphed.inter1.engine()
+    eng.set_features(graphed.inter1.features.weight)
+    cap = GraphedTrainStep.plan(eng, [n for n, _ in batches], graphed.inter1.thresholds, 0.5)
+    step = GraphedTrainStep(graphed, opt_g, B, cap, reducer=red, warmup_batch=batches[0])
+    losses_g = [step.run(nodes, labels).item() for nodes, labels in batches]
+    assert not step.overflowed()
+    assert np.allclose(losses_g, losses_e, rtol=1e-5, atol=1e-6), (losses_g, losses_e)
+    for (k, a), (_, b) in zip(eager.named_parameters(), graphed.named_parameters()):
+        assert rel_err(b.detach().cpu().numpy(), a.detach().cpu().numpy()) <= 1e-4, k
+
+
+def test_duplicate_targets_share_their_representative():
+    from pcgnn_b200.synth import make_graph
+
+    d = make_graph("tiny", seed=53)
+    rng = np.random.default_rng(5)
+    params = random_params(rng, d.feat.shape[1], 8, 3)
+    tp = sorted(d.train_pos)
+    base = rng.choice(d.idx_train, 40, replace=False)
+    nodes = np.concatenate([base, base[:15], base[5:10]]).tolist()     # every duplicate pattern
+    labels = d.labels[nodes]
+    model = build_cuda_pcgnn(d.feat, d.graph, tp, params)
+    pm = port.PortPCGNN(d.feat, d.graph, tp, params)
+    ref = pm.step_loss_backward(nodes, labels)
+    model.inter1.score_override = pm.last["score_table"].detach()[:, 0].contiguous().cuda()
+    loss = model.loss(nodes, torch.from_numpy(labels).cuda())
+    loss.backward()
+    sel = model.inter1.last_selection
+    rep = sel.it_rep.cpu().numpy()
+    B = len(nodes)
+    assert (rep != np.arange(3 * B)).sum() == 3 * 20                    # 20 duplicates per relation
+    got = sel.lists()
+    for r in range(3):
+        for i in range(B):
+            assert got[r * B + i].tolist() == pm.last["sel"][r][i]
+    assert abs(loss.item() - ref) <= 1e-5 * abs(ref)
+    grads = pm.named_grads()
+    for k, p in model.named_parameters():
+        if p.grad is not None and "label_clf" not in k:
+            assert rel_err(p.grad.cpu().numpy(), grads[k]) <= GTOL, k
