@@ -34,6 +34,7 @@ WORKLOADS = {
     "yelp": ("yelp", 1024, 64, "C2 YelpChi-shaped N=45954 F=32 R=3 ~4.0M edges, emb 64, batch 1024/GPU"),
     "amazon": ("amazon", 1024, 64, "C1 Amazon-shaped N=11944 F=25 R=3 ~4.8M edges, emb 64, batch 1024/GPU"),
     "yelp100": ("yelp100", 4096, 128, "C3 YelpChi-shaped F=100, emb 128, batch 4096/GPU"),
+    "amazon_gcn": ("amazon", 1024, 64, "C4 GCN baseline on the Amazon-shaped union graph, emb 64, batch 1024/GPU"),
 }
 RHO, ALPHA, LR, WD = 0.5, 2.0, 0.01, 1e-3
 SEED = 72
@@ -80,7 +81,8 @@ def init_params(feat_dim, embed, n_rel, seed):
         return rng.uniform(-a, a, size=(r, c)).astype(np.float32)
 
     return dict(intra=[xavier(2 * feat_dim, embed) for _ in range(n_rel)], inter=xavier(feat_dim + n_rel * embed, embed),
-                clf_w=xavier(2, feat_dim), clf_b=np.zeros(2, np.float32), head=xavier(2, embed))
+                clf_w=xavier(2, feat_dim), clf_b=np.zeros(2, np.float32), head=xavier(2, embed),
+                enc=xavier(embed, feat_dim))      # enc: GCNEncoder weight [E,F] (C4 only)
 
 
 class ClockSampler(threading.Thread):
@@ -126,20 +128,26 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
-def cpu_port_rate(data, params, batches, sample, steps, warmup):
+def cpu_port_rate(data, params, batches, sample, steps, warmup, gcn=False):
     """Oracle port (CPU restatement of the reference's structure): full train steps on `sample` targets."""
     import torch
     from oracle import port
 
     tp = sorted(data.train_pos)
-    pm = port.PortPCGNN(data.feat, data.graph, tp, params, rho=RHO, alpha=ALPHA)
+    if gcn:
+        pm = port.PortGCN(data.feat, data.homo, params["enc"], params["head"])
+    else:
+        pm = port.PortPCGNN(data.feat, data.graph, tp, params, rho=RHO, alpha=ALPHA)
     opt = torch.optim.Adam(pm.parameters(), lr=LR, weight_decay=WD)
     times = []
     for s in range(warmup + steps):
         nodes, labels = batches[s % len(batches)]
         t0 = time.perf_counter()
         opt.zero_grad()
-        loss = pm.loss(nodes[:sample].tolist(), labels[:sample], True, shared_table=False)
+        if gcn:
+            loss = pm.loss(nodes[:sample].tolist(), labels[:sample])
+        else:
+            loss = pm.loss(nodes[:sample].tolist(), labels[:sample], True, shared_table=False)
         loss.backward()
         opt.step()
         dt = time.perf_counter() - t0
@@ -166,6 +174,133 @@ def c_port_rate(data, batches, reps=3):
     return len(batches[0][0]) / best
 
 
+GCN_KERNELS_PER_STEP = 2   # select-all + aggregate (the GCN encoder/head are torch library GEMMs, as in the reference)
+
+
+def build_cuda_gcn(data, params, dev):
+    """GCN(GCNEncoder(GCNAggregator)) of the product on the union graph (model_handler.py:99-101, 119-120)."""
+    import torch
+    import torch.nn as nn
+    from pcgnn_b200 import graphsage as gs
+
+    F_ = data.feat.shape[1]
+    E = params["enc"].shape[0]
+    features = nn.Embedding(*data.feat.shape)
+    features.weight = nn.Parameter(torch.from_numpy(np.ascontiguousarray(data.feat)), requires_grad=False)
+    features = features.to(dev)
+    enc = gs.GCNEncoder(features, F_, E, data.homo, gs.GCNAggregator(features, cuda=True), cuda=True)
+    model = gs.GCN(2, enc)
+    with torch.no_grad():
+        enc.weight.copy_(torch.from_numpy(params["enc"]))
+        model.weight.copy_(torch.from_numpy(params["head"]))
+    return model.to(dev)
+
+
+def _roof(kern, dom, extra=None):
+    peak, peak_src = measured_peaks()
+    r = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s",
+         "frac": kern[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src}
+    r.update(extra or {})
+    return r
+
+
+def hot_kernels_pcgnn(eng, inter, data, shards, dev_nodes, dev_labels, cap, W, K, flush, dev, batch):
+    import torch
+
+    R, F_ = data.graph.n_rel, data.feat.shape[1]
+    t_choose = t_agg = t_score = 0.0
+    alg_choose = alg_agg = 0.0
+    P = eng.P
+    st_nodes = dev_nodes[W].clone()
+    st_labels = dev_labels[W].clone()
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            eng.score_table(inter.label_clf.weight, inter.label_clf.bias)
+            sel = eng.choose(st_nodes, st_labels, True, inter.thresholds, RHO, cap)
+            eng.aggregate(sel)
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize()
+    g_score, g_choose, g_agg = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g_score):
+        eng.score_table(inter.label_clf.weight, inter.label_clf.bias)
+    with torch.cuda.graph(g_choose):
+        sel = eng.choose(st_nodes, st_labels, True, inter.thresholds, RHO, cap)
+    with torch.cuda.graph(g_agg):
+        eng.aggregate(sel)
+    for s in range(K):
+        i = W + s
+        st_nodes.copy_(dev_nodes[i])
+        st_labels.copy_(dev_labels[i])
+        flush.zero_()
+        e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+        e0.record()
+        g_score.replay()
+        e1.record()
+        g_choose.replay()
+        e2.record()
+        g_agg.replay()
+        e3.record()
+        torch.cuda.synchronize()
+        t_score += e0.elapsed_time(e1)
+        t_choose += e1.elapsed_time(e2)
+        t_agg += e2.elapsed_time(e3)
+        nodes, labels = shards[i]
+        n_pos = int((labels == 1).sum())
+        sum_d = sum(int(data.graph.degrees(r)[nodes].sum()) for r in range(R))
+        m_tot = int(sel.it_m.sum().item())
+        alg_choose += 8.0 * sum_d + R * batch * 16 + 4 * batch + 4.0 * P * n_pos * R + 4.0 * m_tot
+        alg_agg += (4.0 * F_ + 4.0) * m_tot + 4.0 * F_ * R * batch
+        assert not sel.overflowed()
+    kern = {
+        "choose": {"ms": t_choose / K, "alg_bytes": alg_choose / K, "gbs": alg_choose / t_choose / 1e6,
+                   "launches_per_step": 6},
+        "aggregate": {"ms": t_agg / K, "alg_bytes": alg_agg / K, "gbs": alg_agg / t_agg / 1e6,
+                      "launches_per_step": 2},
+        "score_table_and_pool_sort": {"ms": t_score / K, "launches_per_step": 2},
+    }
+    dom = "choose" if t_choose >= t_agg else "aggregate"
+    return kern, _roof(kern, dom, {"filter_plus_aggregate_gbs": (alg_choose + alg_agg) / (t_choose + t_agg) / 1e6})
+
+
+def hot_kernels_gcn(eng, agg_mod, data, shards, dev_nodes, cap, W, K, flush, dev):
+    """C4: select-all + aggregate (rsqrt norm, self union) alone; bytes = (4F + 4) per neighbour row + output."""
+    import torch
+    from pcgnn_b200 import _lib
+
+    F_ = data.feat.shape[1]
+    st_nodes = dev_nodes[W].clone()
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            eng.aggregate(eng.select_all(st_nodes, True, cap, _lib.NORM_RSQRT))
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        sel = eng.select_all(st_nodes, True, cap, _lib.NORM_RSQRT)
+        eng.aggregate(sel)
+    t = alg = 0.0
+    for s in range(K):
+        i = W + s
+        st_nodes.copy_(dev_nodes[i])
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        t += e0.elapsed_time(e1)
+        nodes, _ = shards[i]
+        sum_d = int(data.homo.degrees(0)[nodes].sum())
+        alg += (4.0 * F_ + 4.0) * sum_d + 16.0 * len(nodes) + 4.0 * F_ * len(nodes)
+        assert not sel.overflowed()
+    kern = {"aggregate": {"ms": t / K, "alg_bytes": alg / K, "gbs": alg / t / 1e6, "launches_per_step": 2}}
+    return kern, _roof(kern, "aggregate")
+
+
 def run_reference(args):
     """--impl reference: the oracle port on the host cores, same config/metric/unit."""
     rank = int(os.environ.get("RANK", "0"))
@@ -179,7 +314,8 @@ def run_reference(args):
     params = init_params(data.feat.shape[1], embed, data.graph.n_rel, SEED)
     batches = make_batches(data, 4, batch, SEED)
     sample = min(args.cpu_sample, batch)
-    rate, sec = cpu_port_rate(data, params, batches, sample, args.steps, args.warmup)
+    rate, sec = cpu_port_rate(data, params, batches, sample, args.steps, args.warmup,
+                              gcn=args.workload.endswith("_gcn"))
     line = {
         "impl": "reference", "metric": "train target-nodes/sec (fwd+bwd)", "value": rate, "unit": "target-nodes/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
@@ -230,8 +366,13 @@ def main():
     F_, R = data.feat.shape[1], data.graph.n_rel
     params = init_params(F_, embed, R, SEED)
     tp = sorted(data.train_pos)
-    model = build_cuda_pcgnn(data.feat, data.graph, tp, params, rho=RHO, alpha=ALPHA, device=dev)
-    inter = model.inter1
+    is_gcn = args.workload.endswith("_gcn")
+    if is_gcn:
+        model = build_cuda_gcn(data, params, dev)
+        inter = model.enc.aggregator             # the module that owns the engine / slot capacity
+    else:
+        model = build_cuda_pcgnn(data.feat, data.graph, tp, params, rho=RHO, alpha=ALPHA, device=dev)
+        inter = model.inter1
     opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=LR, weight_decay=WD,
                            capturable=True, fused=True)
     reducer = GradAllReduce(model.parameters()).attach()
@@ -243,9 +384,14 @@ def main():
     dev_labels = [torch.from_numpy(l).to(dev) for _, l in shards]
     host_nodes = [n.tolist() for n, _ in shards]
     host_labels = [l for _, l in shards]
-    eng = inter.engine()
-    eng.set_features(inter.features.weight)
-    cap = max(eng.slots_bound(n.astype(np.int32), inter.thresholds, RHO, True) for n, _ in shards)
+    if is_gcn:
+        eng = inter._get_engine()
+        eng.set_features(inter.features.weight)
+        cap = max(inter.slots_bound(n) for n, _ in shards)
+    else:
+        eng = inter.engine()
+        eng.set_features(inter.features.weight)
+        cap = max(eng.slots_bound(n.astype(np.int32), inter.thresholds, RHO, True) for n, _ in shards)
     inter.cap_slots_hint = cap
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
@@ -338,63 +484,8 @@ def main():
 
     # ---- hot-path kernels alone (roofline), same batches. Each group is captured into its own CUDA graph
     # (static input buffers) so the events bracket GPU work only, not the host's launch calls. ----
-    t_choose = t_agg = t_score = 0.0
-    alg_choose = alg_agg = 0.0
-    P = eng.P
-    st_nodes = dev_nodes[W].clone()
-    st_labels = dev_labels[W].clone()
-    side = torch.cuda.Stream(device=dev)
-    side.wait_stream(torch.cuda.current_stream(dev))
-    with torch.cuda.stream(side):
-        for _ in range(2):
-            eng.score_table(inter.label_clf.weight, inter.label_clf.bias)
-            sel = eng.choose(st_nodes, st_labels, True, inter.thresholds, RHO, cap)
-            eng.aggregate(sel)
-    torch.cuda.current_stream(dev).wait_stream(side)
-    torch.cuda.synchronize()
-    g_score, g_choose, g_agg = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g_score):
-        eng.score_table(inter.label_clf.weight, inter.label_clf.bias)
-    with torch.cuda.graph(g_choose):
-        sel = eng.choose(st_nodes, st_labels, True, inter.thresholds, RHO, cap)
-    with torch.cuda.graph(g_agg):
-        agg_out = eng.aggregate(sel)
-    for s in range(K):
-        i = W + s
-        st_nodes.copy_(dev_nodes[i])
-        st_labels.copy_(dev_labels[i])
-        flush.zero_()
-        e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
-        e0.record()
-        g_score.replay()
-        e1.record()
-        g_choose.replay()
-        e2.record()
-        g_agg.replay()
-        e3.record()
-        torch.cuda.synchronize()
-        t_score += e0.elapsed_time(e1)
-        t_choose += e1.elapsed_time(e2)
-        t_agg += e2.elapsed_time(e3)
-        nodes, labels = shards[i]
-        n_pos = int((labels == 1).sum())
-        sum_d = sum(int(data.graph.degrees(r)[nodes].sum()) for r in range(R))
-        m_tot = int(sel.it_m.sum().item())
-        alg_choose += 8.0 * sum_d + R * batch * 16 + 4 * batch + 4.0 * P * n_pos * R + 4.0 * m_tot
-        alg_agg += (4.0 * F_ + 4.0) * m_tot + 4.0 * F_ * R * batch
-        assert not sel.overflowed()
-    peak, peak_src = measured_peaks()
-    kern = {
-        "choose": {"ms": t_choose / K, "alg_bytes": alg_choose / K, "gbs": alg_choose / t_choose / 1e6,
-                   "launches_per_step": 4},
-        "aggregate": {"ms": t_agg / K, "alg_bytes": alg_agg / K, "gbs": alg_agg / t_agg / 1e6,
-                      "launches_per_step": 2},
-    }
-    kern["score_table_and_pool_sort"] = {"ms": t_score / K, "launches_per_step": 3}
-    dom = "choose" if t_choose >= t_agg else "aggregate"
-    roof = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s",
-            "frac": kern[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
-            "filter_plus_aggregate_gbs": (alg_choose + alg_agg) / (t_choose + t_agg) / 1e6}
+    kern, roof = hot_kernels_gcn(eng, inter, data, shards, dev_nodes, cap, W, K, flush, dev) if is_gcn else \
+        hot_kernels_pcgnn(eng, inter, data, shards, dev_nodes, dev_labels, cap, W, K, flush, dev, batch)
 
     if rank == 0:
         total_nodes = batch * world * K
@@ -405,7 +496,7 @@ def main():
             "config": config_dict(desc, batch, world),
             "e2e": {"value": total_nodes / (ms_e2e / 1e3), "unit": "target-nodes/s", "ms_per_step": ms_e2e / K,
                     "h2d_bytes_per_step": batch * 4 + batch * 8, "d2h_bytes_per_step": 4},
-            "gpu_launches": MY_KERNELS_PER_STEP * K,
+            "gpu_launches": (GCN_KERNELS_PER_STEP if is_gcn else MY_KERNELS_PER_STEP) * K,
             "mode": "cuda-graph replay (runtime.GraphedTrainStep)" if use_graph else "eager",
             "roofline": roof, "kernels": kern, "clocks": sampler.result(),
         }
@@ -415,12 +506,14 @@ def main():
                                                "call": "model.loss(list_of_ids, cuda_labels); backward; Adam.step; loss.item()"}
         if world == 1 and not args.no_cpu_baseline:
             sample = min(args.cpu_sample, batch)
-            rate, sec = cpu_port_rate(data, params, global_batches, sample, 6, 1)
+            rate, sec = cpu_port_rate(data, params, global_batches, sample, 6, 1, gcn=is_gcn)
             line["cpu_baseline"] = {
                 "value": rate, "unit": "target-nodes/s", "cores": torch.get_num_threads(), "kind": "port",
                 "sample": f"6 full train steps of oracle/port.py on the first {sample} targets of a batch "
                           f"({sec * 1e3:.0f} ms each; host has {os.cpu_count()} cpus)",
-                "c_port_choose_aggregate_nodes_per_s": c_port_rate(data, global_batches)}
+                }
+            if not is_gcn:
+                line["cpu_baseline"]["c_port_choose_aggregate_nodes_per_s"] = c_port_rate(data, global_batches)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

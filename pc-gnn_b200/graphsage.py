@@ -48,6 +48,8 @@ class _RowAggregator(nn.Module):
         self._graph = None
         self._graph_src = None
         self._engine = None
+        self.cap_slots_hint = None      # fixed slot capacity (CUDA-graph use); else sized from the host ids
+        self.last_selection = None
 
     def bind_graph(self, adj_lists):
         """Give the aggregator the graph its rows come from (the encoders call this once)."""
@@ -71,8 +73,10 @@ class _RowAggregator(nn.Module):
     def _run(self, eng, targets, degrees, add_self, n_table=None):
         table = _feature_table(self.features, eng.N if n_table is None else n_table, eng.device)
         eng.set_features(table)
-        cap = int(np.maximum((degrees + _lib.SLOT - 1) // _lib.SLOT, 1).sum())
+        cap = int(np.maximum((degrees + _lib.SLOT - 1) // _lib.SLOT, 1).sum()) if degrees is not None \
+            else int(self.cap_slots_hint)
         sel = eng.select_all(targets, add_self, cap, self._norm)
+        self.last_selection = sel
         agg = _AggregateFn.apply(table, eng, sel, table.shape[1]) if table.requires_grad else eng.aggregate(sel)
         return agg[:, :table.shape[1]]
 
@@ -81,10 +85,19 @@ class _RowAggregator(nn.Module):
             return self._aggregate_lists(nodes, to_neighs, add_self)
         eng = self._get_engine()
         targets, host = eng.upload_targets(nodes)
+        if self.cap_slots_hint is not None:
+            return self._run(eng, targets, None, add_self)
         if host is None:
             host = targets.cpu().numpy()
         t = host.astype(np.int64)
         return self._run(eng, targets, eng.graph.indptr[t + 1] - eng.graph.indptr[t], add_self)
+
+    def slots_bound(self, nodes) -> int:
+        """Slot capacity that covers a batch of node ids (host arithmetic on the CSR offsets)."""
+        g = self._get_engine().graph
+        t = np.asarray(nodes, dtype=np.int64)
+        d = g.indptr[t + 1] - g.indptr[t]
+        return int(np.maximum((d + _lib.SLOT - 1) // _lib.SLOT, 1).sum())
 
     def _aggregate_lists(self, nodes, to_neighs, add_self):
         """Explicit neighbour sets (stand-alone aggregator use, or sub-sampled rows): a one-off graph

@@ -17,17 +17,18 @@ __all__ = ["GraphedTrainStep"]
 
 
 class GraphedTrainStep:
-    """model: pcgnn_b200.model.PCALayer (or any module with .loss(nodes, labels) whose hot path is an
-    InterAgg at ``model.inter1``); optimizer must be capturable (e.g. Adam(capturable=True))."""
+    """model: pcgnn_b200.model.PCALayer (hot path: the InterAgg at ``model.inter1``) or graphsage.GCN / GraphSage
+    (hot path: ``model.enc.aggregator``); optimizer must be capturable (e.g. Adam(capturable=True, fused=True))."""
 
     def __init__(self, model, optimizer, batch_size: int, cap_slots: int, reducer=None, world: int = 1,
                  warmup_batch=None):
         self.model, self.opt, self.B = model, optimizer, int(batch_size)
         self.reducer, self.world = reducer, world
-        inter = model.inter1
-        dev = inter.weight.device
+        # the module that sizes the per-step slot buffer: InterAgg for PC-GNN, the row aggregator for GCN / SAGE
+        self._sizer = model.inter1 if hasattr(model, "inter1") else model.enc.aggregator
+        dev = next(p for p in model.parameters() if p.requires_grad).device
         self.dev = dev
-        inter.cap_slots_hint = int(cap_slots)
+        self._sizer.cap_slots_hint = int(cap_slots)
         self.cap_slots = int(cap_slots)
         self.nodes = torch.zeros(self.B, dtype=torch.int32, device=dev)
         self.labels = torch.zeros(self.B, dtype=torch.int64, device=dev)
@@ -112,7 +113,7 @@ class GraphedTrainStep:
     def overflowed(self) -> bool:
         """True if some replay needed more slots than the captured capacity (results then incomplete:
         re-plan with a larger capacity). Syncs."""
-        sel = self.model.inter1.last_selection
+        sel = self._sizer.last_selection
         return bool(sel is not None and sel.overflowed())
 
     @staticmethod

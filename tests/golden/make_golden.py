@@ -101,6 +101,41 @@ def run_case(name, graph, feat, labels, train_pos, nodes, E, rho, seed):
     print(name, os.path.getsize(path), "bytes")
 
 
+def run_homo_case(name, kind, data, nodes, E, seed):
+    """GCN / GraphSAGE train step of the live reference on the union graph (model_handler.py:96-101, 118-120)."""
+    import torch
+
+    rng = np.random.default_rng(seed)
+    F_ = data.feat.shape[1]
+    enc_w = port.xavier(rng, E, F_)
+    head = port.xavier(rng, 2, E)
+    ns = H.load(False)
+    G = ns.graphsage
+    features = torch.nn.Embedding(*data.feat.shape)
+    features.weight = torch.nn.Parameter(torch.from_numpy(data.feat), requires_grad=False)
+    adj = data.homo.to_adj_lists()[0]
+    if kind == "GCN":
+        enc = G.GCNEncoder(features, F_, E, adj, G.GCNAggregator(features, cuda=False), cuda=False)
+        model = G.GCN(2, enc)
+    else:
+        enc = G.Encoder(features, F_, E, adj, G.MeanAggregator(features, cuda=False), gcn=True, cuda=False)
+        model = G.GraphSage(2, enc)
+    with torch.no_grad():
+        enc.weight.copy_(torch.from_numpy(enc_w))
+        model.weight.copy_(torch.from_numpy(head))
+    lab = torch.from_numpy(data.labels[np.asarray(nodes)])
+    loss = model.loss([int(v) for v in nodes], lab)
+    loss.backward()
+    with torch.no_grad():
+        emb = enc([int(v) for v in nodes])
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), indptr=data.homo.indptr, indices=data.homo.indices,
+                        n_nodes=data.homo.n_nodes, feat=data.feat, labels=data.labels,
+                        nodes=np.asarray(nodes, dtype=np.int32), E=E, enc_w=enc_w, head=head,
+                        loss=np.float64(loss.item()), emb=emb.numpy(), grad_enc=enc.weight.grad.numpy(),
+                        grad_head=model.weight.grad.numpy())
+    print(name, "loss", loss.item())
+
+
 def main():
     assert H.available(), "needs /root/reference"
     # 1. hand-made edge cases: every node once + duplicates, as one batch
@@ -122,6 +157,12 @@ def main():
     rng = np.random.default_rng(13)
     nodes = rng.choice(d.idx_train, 48).tolist()
     run_case("one_rel", d.graph, d.feat, d.labels, d.train_pos, nodes, 8, 0.5, 4)
+    # 5./6. GCN and GraphSAGE baselines on the union graph
+    d = make_graph("tiny_amz", seed=47)
+    rng = np.random.default_rng(14)
+    nodes = rng.choice(d.idx_train, 90).tolist()
+    run_homo_case("homo_gcn", "GCN", d, nodes, 16, 5)
+    run_homo_case("homo_sage", "SAGE", d, nodes, 16, 6)
 
 
 if __name__ == "__main__":

@@ -374,3 +374,36 @@ def test_duplicate_targets_share_their_representative():
     for k, p in model.named_parameters():
         if p.grad is not None and "label_clf" not in k:
             assert rel_err(p.grad.cpu().numpy(), grads[k]) <= GTOL, k
+
+
+@pytest.mark.parametrize("kind", ["gcn", "sage"])
+def test_homo_baselines_match_golden(kind):
+    """GCN / GraphSAGE modules against the live reference's golden train step."""
+    import torch.nn as nn
+    from pcgnn_b200 import graphsage as gs
+    from pcgnn_b200.graph import RelGraph
+
+    g = load_golden("homo_" + kind)
+    graph = RelGraph(int(g["n_nodes"]), [g["indptr"]], [g["indices"]])
+    F_, E = g["feat"].shape[1], int(g["E"])
+    features = nn.Embedding(*g["feat"].shape)
+    features.weight = nn.Parameter(torch.from_numpy(g["feat"]), requires_grad=False)
+    features = features.cuda()
+    if kind == "gcn":
+        enc = gs.GCNEncoder(features, F_, E, graph, gs.GCNAggregator(features, cuda=True), cuda=True)
+        model = gs.GCN(2, enc)
+    else:
+        enc = gs.Encoder(features, F_, E, graph, gs.MeanAggregator(features, cuda=True), gcn=True, cuda=True)
+        model = gs.GraphSage(2, enc)
+    with torch.no_grad():
+        enc.weight.copy_(torch.from_numpy(g["enc_w"]))
+        model.weight.copy_(torch.from_numpy(g["head"]))
+    model = model.cuda()
+    nodes = g["nodes"].tolist()
+    loss = model.loss(nodes, torch.from_numpy(g["labels"][g["nodes"]]).cuda())
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= TOL * abs(float(g["loss"]))
+    with torch.no_grad():
+        assert rel_err(enc(nodes).cpu().numpy(), g["emb"]) <= TOL
+    assert rel_err(enc.weight.grad.cpu().numpy(), g["grad_enc"]) <= GTOL
+    assert rel_err(model.weight.grad.cpu().numpy(), g["grad_head"]) <= GTOL

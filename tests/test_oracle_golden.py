@@ -95,3 +95,21 @@ def test_edge_case_fixture_covers_the_documented_cases():
                 added += len(set(tr[r][i]) - set(ev[r][i]))
                 kept_in_pool += len(set(ev[r][i]) & pool)
     assert added > 0 and kept_in_pool > 0
+
+
+@pytest.mark.parametrize("kind", ["gcn", "sage"])
+def test_homo_ports_match_golden(kind):
+    """GCN / GraphSAGE restatements against the live reference's train step on the union graph."""
+    from pcgnn_b200.graph import RelGraph
+
+    g = load_golden("homo_" + kind)
+    graph = RelGraph(int(g["n_nodes"]), [g["indptr"]], [g["indices"]])
+    cls = port.PortGCN if kind == "gcn" else port.PortSAGE
+    pm = cls(g["feat"], graph, g["enc_w"], g["head"])
+    nodes = g["nodes"].tolist()
+    loss = pm.loss(nodes, g["labels"][g["nodes"]])
+    loss.backward()
+    assert abs(float(loss.detach()) - float(g["loss"])) <= TOL * abs(float(g["loss"]))
+    assert rel_err(pm.last["combined"].detach().numpy(), g["emb"]) <= TOL
+    assert rel_err(pm.enc_w.grad.numpy(), g["grad_enc"]) <= 1e-4
+    assert rel_err(pm.head.grad.numpy(), g["grad_head"]) <= 1e-4
