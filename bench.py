@@ -249,13 +249,13 @@ def hot_kernels_pcgnn(eng, inter, data, shards, dev_nodes, dev_labels, cap, W, K
         nodes, labels = shards[i]
         n_pos = int((labels == 1).sum())
         sum_d = sum(int(data.graph.degrees(r)[nodes].sum()) for r in range(R))
-        m_tot = int(sel.it_m.sum().item())
+        m_tot = int(sel.it_m[sel.it_rep.long()].sum().item())
         alg_choose += 8.0 * sum_d + R * batch * 16 + 4 * batch + 4.0 * P * n_pos * R + 4.0 * m_tot
         alg_agg += (4.0 * F_ + 4.0) * m_tot + 4.0 * F_ * R * batch
         assert not sel.overflowed()
     kern = {
         "choose": {"ms": t_choose / K, "alg_bytes": alg_choose / K, "gbs": alg_choose / t_choose / 1e6,
-                   "launches_per_step": 6},
+                   "launches_per_step": 4},
         "aggregate": {"ms": t_agg / K, "alg_bytes": alg_agg / K, "gbs": alg_agg / t_agg / 1e6,
                       "launches_per_step": 2},
         "score_table_and_pool_sort": {"ms": t_score / K, "launches_per_step": 2},

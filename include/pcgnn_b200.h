@@ -73,8 +73,11 @@ PCG_API int pcg_entry_pool_positions(const int32_t* indices, int64_t nnz, const 
                              int32_t* entry_pool_pos, pcg_stream_t stream);
 
 /* Bytes of scratch pcg_choose needs for B targets x R relations on a graph of n_nodes nodes whose largest
- * row has max_degree entries. */
+ * row has max_degree entries. The first n_nodes*4 bytes hold a per-node table that carries state between
+ * calls (all bytes 0x7f between calls; pcg_choose restores it): call pcg_choose_workspace_init once after
+ * allocating the buffer, and again if the same buffer is later used with another n_nodes. */
 PCG_API size_t pcg_choose_workspace_bytes(int B, int R, int64_t max_degree, int64_t n_nodes);
+PCG_API int pcg_choose_workspace_init(void* workspace, size_t workspace_bytes, int64_t n_nodes, pcg_stream_t stream);
 
 /*
  * Choose step for a batch: per item keep the ceil(d*thresh[r]) neighbours nearest in label score
@@ -104,8 +107,11 @@ PCG_API size_t pcg_choose_workspace_bytes(int B, int R, int64_t max_degree, int6
  *   it_slot0/it_m int32 [R*B], it_base int64 [R*B], it_done int32 [R*B] (zeroed; aggregation tickets)
  *   it_rep       int32 [R*B]: targets that repeat an earlier id of the batch (pick_step samples with
  *                replacement) are not processed again; it_rep[w] is the item whose list w shares (w itself
- *                for first occurrences). pcg_aggregate copies the aggregated row accordingly.
- *   status       int32 [PCG_STATUS_WORDS] (zeroed here)
+ *                for first occurrences). Only representatives (it_rep[w] == w) carry it_slot0/it_m/it_base;
+ *                pcg_aggregate copies the aggregated row of a repeated target from its representative.
+ *   status       int32 [PCG_STATUS_WORDS] (every word written here)
+ * The slots of the items are handed out by a prefix sum in item order, so the layout of sel_idx is the same
+ * on every run.
  */
 PCG_API int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t n_nodes, int R, const float* score,
                const float* entry_score, const float* center_score, const int32_t* targets,

@@ -4,10 +4,8 @@
 // two .tolist() host syncs per target per relation) by an exact k-smallest selection on the key
 // (|s_v - s_u| as fp32 bits, position in the id-sorted row):
 //   1. the k-th smallest distance T (and how many elements equal to T are still needed) is found by a
-//      bit-serial selection: two key bits per step, decided from counts obtained by warp reductions
-//      (no atomics, no histogram); bits all keys share are skipped. Rows of <= 512 entries live in the
-//      REGISTERS of one warp; longer rows in the shared memory of one CTA, which switches to a short
-//      candidate list once few keys still match the prefix,
+//      bit-serial selection over keys held in REGISTERS: two key bits per step, decided from counts
+//      obtained by warp reductions (no atomics, no histogram); bits all keys share are skipped,
 //   2. an ORDERED compaction writes every element with d < T plus the first `need` elements with
 //      d == T (row order == id order, which is the reference's stable-sort tie rule),
 //   3. for positive targets the o nearest train positives come from the score-sorted pool
@@ -15,21 +13,34 @@
 //      the o-th smallest distance is a k-th-of-two-sorted-sequences search done with warp-wide
 //      32-ary probes; pool members that are already kept (a per-item bitmap over pool positions,
 //      filled during the compaction) are dropped: the set union of src/layers.py:690-694.
-// Rows up to PCG_SMALL_MAX entries are handled one per warp, longer rows one per CTA; both kernels
-// are persistent, pull items from queues filled by a classification kernel and run concurrently on
-// two streams.
+//
+// Work decomposition (every thread holds at most a few row entries, so an item's latency is a handful of
+// dependent memory round trips plus ~15 selection steps, whatever its length):
+//   prep     one CTA: folds repeated targets (pick_step samples with replacement), computes every item's
+//            sizes, hands out the output slots by a prefix sum (deterministic layout, no atomics on the
+//            item path) and sorts the items into four tier queues,
+//   warp     d <= 128          one warp per item,
+//   cta      128 < d <= 1024   one 256-thread CTA per item,
+//   cluster  1024 < d <= 32768 one thread-block CLUSTER of 8 x 256 threads per item; the per-step counts
+//            and the compaction offsets are exchanged through distributed shared memory,
+//   big      d > 32768         one 1024-thread CTA, distances recomputed per pass (rare hub rows).
+// The tier kernels run side by side on forked streams (CUDA-graph capturable).
 #include "pcg_common.cuh"
 
-#define PCG_SMALL_MAX 512      // entries a warp keeps in its shared-memory slice
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+#define PCG_SMALL_MAX 128      // warp tier: <= 4 entries per lane
 #define PCG_WARPS_PER_CTA 8    // warp kernel: 8 items in flight per CTA
-#define PCG_LARGE_NT 1024      // CTA kernel threads (one CTA per SM)
-#define PCG_MID_NT 128         // middle tier threads per CTA
-#define PCG_MID_MAX 2048       // longest row of the middle tier (16 keys per thread)
-#define PCG_CAND_CAP_MID 512   // middle tier: candidate list capacity
-#define PCG_LARGE_CAP_MAX 32768
-#define PCG_KB_WORDS_WARP 256  // kept-pool bitmap words per warp  (pools up to 8192 positives)
-#define PCG_KB_WORDS_CTA 2048  // ... per CTA                      (pools up to 65536 positives)
-#define PCG_CAND_CAP 2048      // CTA-tier selection: candidate keys kept in shared memory once they fit
+#define PCG_GRP_NT 256         // cta / cluster tiers: threads per CTA
+#define PCG_GRP_NW (PCG_GRP_NT / 32)
+#define PCG_CTA_MAX 1024       // cta tier: <= 4 entries per thread
+#define PCG_CL 8               // cluster tier: CTAs per item
+#define PCG_CL_MAX 32768       // ... 8 x 256 threads x 16 entries
+#define PCG_LARGE_NT 1024      // big tier threads (one CTA per SM)
+#define PCG_KB_WORDS 256       // kept-pool bitmap words per item (pools up to 8192 positives; else row-position bits)
+#define PCG_CAND_CAP 2048      // big tier: candidate keys kept in shared memory once they fit
+#define PCG_PREP_NT 1024
 
 struct ChooseP {
     const int64_t* indptr;
@@ -58,25 +69,29 @@ struct ChooseP {
     int32_t* it_done;
     int32_t* it_rep;            // representative item of every item (itself unless an earlier target has the same id)
     int32_t* status;
-    int32_t* small_q;
-    int32_t* mid_q;
-    int32_t* large_q;
-    uint32_t* bits_slab;        // [grid_large, slab_words]
+    int32_t* first;             // [n_nodes] smallest batch index per node id (0x7f7f7f7f when absent); NULL: no folding
+    int32_t* q_warp;
+    int32_t* q_cta;
+    int32_t* q_cl;
+    int32_t* q_big;
+    uint32_t* bits_slab;        // [grid_big, slab_words] kept-position bitmasks of the big tier
     int64_t slab_words;
-    int large_cap;              // entries of the CTA kernel's shared distance buffer
-    int bits_words;             // words of its kept-position bitmask
 };
 
 #ifdef PCG_TRACE
 // Debug build only (make EXTRA=-DPCG_TRACE): per-item phase timestamps, 12 int64 per item.
 __device__ long long* g_trace = nullptr;
-#define TRACE(slot) do { if (g_trace && tid == 0) g_trace[(int64_t)w * 12 + (slot)] = clock64(); } while (0)
+__device__ __forceinline__ long long trace_now() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define TRACE(slot) do { if (g_trace && tid == 0 && (blockIdx.x % 8 == 0 || blockDim.x != 256 || gridDim.x % 8 != 0 || true)) g_trace[(int64_t)w * 12 + (slot)] = trace_now(); } while (0)
 #define TRACE_VAL(slot, val) do { if (g_trace && tid == 0) g_trace[(int64_t)w * 12 + (slot)] = (val); } while (0)
 #else
 #define TRACE(slot) do {} while (0)
 #define TRACE_VAL(slot, val) do {} while (0)
 #endif
-
 template <int NT>
 __device__ __forceinline__ void grp_sync() {
     if (NT == 32) __syncwarp(); else __syncthreads();
@@ -138,7 +153,6 @@ __device__ __forceinline__ void grp_minmax(Get get, int n, int tid, int* xw, uin
     kmin = lo;
     kmax = hi;
 }
-
 // k-th smallest (kth is 1-based) of get(0..n-1) as (T, need): T = that value, need = how many of
 // the elements equal to T belong to the kth smallest (in position order).
 // Digits are cut from the highest bit in which min and max differ (bits every key shares need no
@@ -249,7 +263,6 @@ __device__ __forceinline__ void grp_sum3(int& c0, int& c1, int& c2, int* wsum, i
         __syncthreads();
     }
 }
-
 // NT threads, NE keys per thread in REGISTERS (row position of key[e] is e*NT + tid; vmask marks the valid
 // e). Returns (T, need) like radix_select. A CTA (NT > 32) moves the keys that still match the prefix into
 // the shared list `cand` as soon as they fit, and finishes on that list.
@@ -400,7 +413,6 @@ __device__ __forceinline__ void cta_bitselect(Get get, int n, int kth, uint32_t*
     T = prefix;
     need = remaining;
 }
-
 // First index in [lo, hi) where pred turns false (pred is true on a prefix), found with warp-wide
 // 32-ary probes: ceil(log32(range)) rounds of one predicate evaluation per lane. Every warp of the
 // group runs it redundantly (same addresses -> broadcast loads), so no block barrier is needed.
@@ -420,8 +432,7 @@ __device__ __forceinline__ int warp_partition_point(int lo, int hi, Pred pred) {
     }
     return lo;
 }
-
-// Per-item header shared by both tiers.
+// Per-item header shared by all tiers.
 struct Item {
     int w, r, i, d, k, o, nslots, slot0;
     int32_t v;
@@ -430,7 +441,7 @@ struct Item {
     bool use_kb, want_bits;
 };
 
-__device__ __forceinline__ void item_header(const ChooseP& p, int w, int kb_words, Item& it) {
+__device__ __forceinline__ void item_header(const ChooseP& p, int w, Item& it) {
     it.w = w;
     it.r = w / p.B;
     it.i = w - it.r * p.B;
@@ -443,21 +454,10 @@ __device__ __forceinline__ void item_header(const ChooseP& p, int w, int kb_word
     item_counts(it.d, p.thresh[it.r], p.rho, positive, p.P, p.k_override ? p.k_override[w] : 0, p.k_override != nullptr,
                 it.k, it.o);
     it.nslots = (it.k + it.o + PCG_SLOT - 1) / PCG_SLOT;
-    it.use_kb = it.o > 0 && p.entry_pool_pos != nullptr && p.P <= kb_words * 32;
+    it.slot0 = p.it_slot0[w];                       // handed out by k_choose_prep
+    it.off = (int64_t)it.slot0 * PCG_SLOT;
+    it.use_kb = it.o > 0 && p.entry_pool_pos != nullptr && p.P <= PCG_KB_WORDS * 32;
     it.want_bits = it.o > 0 && !it.use_kb;
-}
-
-// Slot buffer too small: flag, emit nothing for this item (group-uniform decision).
-template <int NT>
-__device__ __forceinline__ bool item_overflow(const ChooseP& p, const Item& it, int tid) {
-    if ((int64_t)it.slot0 + it.nslots <= p.cap_slots) return false;
-    if (tid == 0) {
-        atomicExch(&p.status[ST_OVERFLOW], 1);
-        p.it_slot0[it.w] = 0; p.it_m[it.w] = 0; p.it_base[it.w] = 0; p.it_done[it.w] = 0;
-    }
-    for (int c = tid; c < it.nslots; c += NT)
-        if ((int64_t)it.slot0 + c < p.cap_slots) p.slot_item[it.slot0 + c] = -1;
-    return true;
 }
 
 // Minority oversampling for one positive item: the o nearest train positives (score-sorted pool)
@@ -560,11 +560,11 @@ __device__ __forceinline__ void item_finish(const ChooseP& p, const Item& it, in
     }
     for (int c = tid; c < it.nslots; c += NT) p.slot_item[it.slot0 + c] = (c * PCG_SLOT < m) ? it.w : -1;
 }
-
+// --------------------------------------------------------------------------------- warp tier
 // --------------------------------------------------------------------------------- warp tier
 struct WarpSmem {
     uint32_t hist[256];                       // pool phase: radix histogram (equal-distance pool ties)
-    uint32_t kbits[PCG_KB_WORDS_WARP];        // kept neighbours that are pool members, by pool position
+    uint32_t kbits[PCG_KB_WORDS];        // kept neighbours that are pool members, by pool position
     uint32_t bits[PCG_SMALL_MAX / 32];        // kept row positions (fallback membership test)
     int xw[32];
 };
@@ -606,7 +606,7 @@ __device__ __forceinline__ void row_in_regs(const ChooseP& p, const Item& it, co
     uint32_t T = 0xffffffffu;
     int need = 0x7fffffff;
     if (!all) {
-        if (k > 0) group_bitselect<NT, NE>(key, vmask, d, k, cand, NT == 128 ? PCG_CAND_CAP_MID : PCG_CAND_CAP, wsum, xw, tid, T, need);
+        if (k > 0) group_bitselect<NT, NE>(key, vmask, d, k, cand, PCG_CAND_CAP, wsum, xw, tid, T, need);
         else { T = 0; need = 0; }
     }
     TRACE(3);
@@ -638,18 +638,12 @@ __device__ __forceinline__ void row_in_regs(const ChooseP& p, const Item& it, co
     grp_sync<NT>();
     TRACE(4);
 }
-
 __device__ void choose_item_warp(const ChooseP& p, int w, WarpSmem& s) {
     const int lane = threadIdx.x & 31;
     const int tid = lane;
     Item it;
-    item_header(p, w, PCG_KB_WORDS_WARP, it);
+    item_header(p, w, it);
     TRACE(0); TRACE_VAL(8, it.d); TRACE_VAL(9, it.k); TRACE_VAL(10, it.o);
-    int slot0 = 0;
-    if (lane == 0) slot0 = atomicAdd(&p.status[ST_SLOTS], it.nslots);
-    it.slot0 = __shfl_sync(PCG_FULL, slot0, 0);
-    it.off = (int64_t)it.slot0 * PCG_SLOT;
-    if (item_overflow<32>(p, it, lane)) { __syncwarp(); return; }
     TRACE(1);
     const int32_t* __restrict__ nbr = p.indices + it.beg;
     if (it.use_kb) {
@@ -659,9 +653,7 @@ __device__ void choose_item_warp(const ChooseP& p, int w, WarpSmem& s) {
     const int d = it.d;
     if (d <= 32) row_in_regs<32, 1>(p, it, nbr, s.kbits, s.bits, nullptr, nullptr, s.xw);
     else if (d <= 64) row_in_regs<32, 2>(p, it, nbr, s.kbits, s.bits, nullptr, nullptr, s.xw);
-    else if (d <= 128) row_in_regs<32, 4>(p, it, nbr, s.kbits, s.bits, nullptr, nullptr, s.xw);
-    else if (d <= 256) row_in_regs<32, 8>(p, it, nbr, s.kbits, s.bits, nullptr, nullptr, s.xw);
-    else row_in_regs<32, 16>(p, it, nbr, s.kbits, s.bits, nullptr, nullptr, s.xw);
+    else row_in_regs<32, 4>(p, it, nbr, s.kbits, s.bits, nullptr, nullptr, s.xw);
     int m = it.k;
     if (it.o > 0) m += oversample<32>(p, it, lane, nbr, s.kbits, s.bits, s.hist, s.xw);
     TRACE(6);
@@ -670,46 +662,288 @@ __device__ void choose_item_warp(const ChooseP& p, int w, WarpSmem& s) {
     TRACE(7);
 }
 
-// --------------------------------------------------------------------------------- CTA tier
-// One item handled by one CTA of NT threads (long rows). Kept list in row order.
-template <int NT, int KBW>
-__device__ void choose_item_cta(const ChooseP& p, int w, uint32_t* sd, int sd_cap, uint32_t* hist, uint32_t* kbits,
-                                uint32_t* cand, uint32_t* bits_s, int bits_cap_words, uint32_t* bits_g, int* xw) {
-    constexpr int NW = NT / 32;
+// d <= 128: one item per warp.
+__global__ void __launch_bounds__(PCG_WARPS_PER_CTA * 32, 3) k_choose_warp(ChooseP p) {
+    __shared__ WarpSmem sm[PCG_WARPS_PER_CTA];
+    const int wid = threadIdx.x >> 5;
+    WarpSmem& s = sm[wid];
+    const int n = p.status[ST_NSMALL];
+    const int n_warps = gridDim.x * PCG_WARPS_PER_CTA;
+    for (int q = blockIdx.x * PCG_WARPS_PER_CTA + wid; q < n; q += n_warps) choose_item_warp(p, p.q_warp[q], s);
+}
+
+// ------------------------------------------------------------------------ cta / cluster tiers
+// One item handled by a GROUP of CL CTAs x 256 threads (CL == 1: a plain CTA, CL == 8: a thread-block
+// cluster). CTA `rank` owns the contiguous positions [rank*NE*256, (rank+1)*NE*256) of the row, NE
+// entries per thread in registers (position of entry e: rank*NE*256 + e*256 + tid). Everything the
+// CTAs have to agree on (min/max, the three counts of every selection step, the compaction totals) is
+// written by the producing warp straight into EVERY CTA's shared memory (distributed shared memory)
+// and read locally after one group barrier, so a selection step costs one barrier.
+struct GrpSmem {
+    uint32_t xchg[2][PCG_CL * PCG_GRP_NW];   // packed step counts of every warp of the group (parity double buffer)
+    uint32_t mm[2][PCG_CL * PCG_GRP_NW];     // per-warp min / max keys
+    int cnt[16 * PCG_GRP_NW];                // compaction: per (round, warp) counts, less | tie << 16
+    int pre[16 * PCG_GRP_NW];                // their exclusive scan
+    int ctot[PCG_CL];                        // per-CTA totals, same packing
+    uint32_t hist[256];                      // oversampling: radix histogram / broadcast words
+    uint32_t kbits[PCG_KB_WORDS];            // rank 0: kept neighbours that are pool members, by pool position
+    uint32_t bits[PCG_CL_MAX / 32];          // rank 0: kept row positions (fallback membership test)
+    int xw[32];
+};
+
+template <int CL>
+__device__ __forceinline__ void grp_barrier() {
+    if (CL == 1) __syncthreads();
+    else cg::this_cluster().sync();
+}
+
+// pointer to the same shared-memory object in CTA `rank` of the group
+template <int CL, class T>
+__device__ __forceinline__ T* grp_peer(T* own, int rank) {
+    if (CL == 1) return own;
+    return cg::this_cluster().map_shared_rank(own, rank);
+}
+
+// k-th smallest (1-based) of the group's keys as (T, need); all threads of all CTAs return the same pair.
+template <int NE, int CL>
+__device__ __forceinline__ void grp_select(const uint32_t (&key)[NE], uint32_t vmask, int kth, GrpSmem& s, int rank,
+                                           int& par, uint32_t& T, int& need) {
+    constexpr int NW = PCG_GRP_NW, NS = CL * NW;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int slot = rank * NW + wid;
+    uint32_t lo = 0xffffffffu, hi = 0u;
+#pragma unroll
+    for (int e = 0; e < NE; ++e)
+        if ((vmask >> e) & 1u) { lo = min(lo, key[e]); hi = max(hi, key[e]); }
+    lo = __reduce_min_sync(PCG_FULL, lo);
+    hi = __reduce_max_sync(PCG_FULL, hi);
+    if (lane < CL) {
+        *grp_peer<CL>(&s.mm[0][slot], lane) = lo;
+        *grp_peer<CL>(&s.mm[1][slot], lane) = hi;
+    }
+    grp_barrier<CL>();
+    lo = 0xffffffffu; hi = 0u;
+#pragma unroll
+    for (int q = lane; q < NS; q += 32) { lo = min(lo, s.mm[0][q]); hi = max(hi, s.mm[1][q]); }
+    lo = __reduce_min_sync(PCG_FULL, lo);
+    hi = __reduce_max_sync(PCG_FULL, hi);
+    if (lo == hi) { T = lo; need = kth; return; }
+    int hb = 31 - __clz(lo ^ hi);
+    uint32_t mask = hb == 31 ? 0u : ~((2u << hb) - 1u);
+    uint32_t prefix = lo & mask;
+    int remaining = kth;
+    while (hb >= 0) {
+        const int shift = max(hb - 1, 0);
+        const uint32_t dmask = hb >= 1 ? 3u : 1u;
+        int c0 = 0, c1 = 0, c2 = 0;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            const bool active = ((vmask >> e) & 1u) && ((key[e] ^ prefix) & mask) == 0u;
+            const uint32_t dg = (key[e] >> shift) & dmask;
+            c0 += active && dg == 0u;
+            c1 += active && dg == 1u;
+            c2 += active && dg == 2u;
+        }
+        c0 = __reduce_add_sync(PCG_FULL, c0);
+        c1 = __reduce_add_sync(PCG_FULL, c1);
+        c2 = __reduce_add_sync(PCG_FULL, c2);
+        // a warp counts at most 32 * 16 = 512 keys: 10 bits per counter
+        if (lane < CL) *grp_peer<CL>(&s.xchg[par][slot], lane) = (uint32_t)c0 | ((uint32_t)c1 << 10) | ((uint32_t)c2 << 20);
+        grp_barrier<CL>();
+        c0 = c1 = c2 = 0;
+#pragma unroll
+        for (int q = lane; q < NS; q += 32) {
+            const uint32_t x = s.xchg[par][q];
+            c0 += (int)(x & 1023u);
+            c1 += (int)((x >> 10) & 1023u);
+            c2 += (int)(x >> 20);
+        }
+        c0 = __reduce_add_sync(PCG_FULL, c0);
+        c1 = __reduce_add_sync(PCG_FULL, c1);
+        c2 = __reduce_add_sync(PCG_FULL, c2);
+        par ^= 1;
+        const uint32_t dg = pick_digit(c0, c1, c2, remaining);
+        prefix |= dg << shift;
+        mask |= dmask << shift;
+        hb = shift - 1;
+    }
+    T = prefix;
+    need = remaining;
+}
+
+template <int NE, int CL>
+__device__ __forceinline__ void grp_body(const ChooseP& p, const Item& it, GrpSmem& s, int rank, int& par) {
+    constexpr int NT = PCG_GRP_NT, NW = PCG_GRP_NW;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int w = it.w;
+    const int d = it.d, k = it.k;
+    const int32_t* __restrict__ nbr = p.indices + it.beg;
+    const float* __restrict__ escore = p.entry_score ? p.entry_score + it.beg : nullptr;
+    const bool all = k >= d;
+    const bool need_dist = !all || p.sel_dist != nullptr;
+    const int pos0 = rank * (NE * NT) + tid;
+    uint32_t key[NE];
+    uint32_t vmask = 0;
+    {
+        int32_t id[NE];
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            const int j = pos0 + e * NT;
+            const bool valid = j < d;
+            vmask |= (uint32_t)valid << e;
+            id[e] = (valid && !escore) ? __ldg(nbr + j) : 0;
+        }
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            const int j = pos0 + e * NT;
+            uint32_t x = 0u;
+            if (((vmask >> e) & 1u) && need_dist) x = dist_bits(it.sv, escore ? escore[j] : __ldg(p.score + id[e]));
+            key[e] = x;
+        }
+    }
+    TRACE(2);
+    uint32_t T = 0xffffffffu;
+    int need = 0x7fffffff;
+    if (!all) {
+        if (k > 0) grp_select<NE, CL>(key, vmask, k, s, rank, par, T, need);
+        else { T = 0; need = 0; }
+    }
+    TRACE(3);
+    // ---- ordered compaction: counts per (round, warp) -> one scan by warp 0 -> totals to every CTA ----
+    const unsigned lt = lanemask_lt();
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        const bool valid = (vmask >> e) & 1u;
+        const unsigned ml = __ballot_sync(PCG_FULL, valid && (all || key[e] < T));
+        const unsigned mt = __ballot_sync(PCG_FULL, valid && !all && key[e] == T);
+        if (lane == 0) s.cnt[e * NW + wid] = __popc(ml) | (__popc(mt) << 16);
+    }
+    __syncthreads();
+    if (wid == 0) {
+        constexpr int PER = (NE * NW + 31) / 32;       // entries per lane (1..4), consecutive
+        int v[PER], sum = 0;
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const int at = lane * PER + q;
+            v[q] = at < NE * NW ? s.cnt[at] : 0;
+            sum += v[q];
+        }
+        int incl = sum;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(PCG_FULL, incl, off);
+            if (lane >= off) incl += t;
+        }
+        int run = incl - sum;
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const int at = lane * PER + q;
+            if (at < NE * NW) s.pre[at] = run;
+            run += v[q];
+        }
+        const int total = __shfl_sync(PCG_FULL, incl, 31);
+        if (lane < CL) *grp_peer<CL>(&s.ctot[rank], lane) = total;
+    }
+    grp_barrier<CL>();
+    int base_less = 0, base_tie = 0;
+#pragma unroll
+    for (int c = 0; c < CL; ++c)
+        if (c < rank) { const int t = s.ctot[c]; base_less += t & 0xffff; base_tie += t >> 16; }
+    const int32_t* __restrict__ epp = it.use_kb ? p.entry_pool_pos + it.beg : nullptr;
+    uint32_t* kbits0 = grp_peer<CL>(&s.kbits[0], 0);
+    uint32_t* bits0 = grp_peer<CL>(&s.bits[0], 0);
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        const int j = pos0 + e * NT;
+        const bool valid = (vmask >> e) & 1u;
+        const bool less = valid && (all || key[e] < T);
+        const bool tie = valid && !all && key[e] == T;
+        const unsigned ml = __ballot_sync(PCG_FULL, less), mt = __ballot_sync(PCG_FULL, tie);
+        const int pl = s.pre[e * NW + wid];
+        const int tie_before = base_tie + (pl >> 16) + __popc(mt & lt);
+        const bool sel = less || (tie && tie_before < need);
+        if (sel) {
+            const int64_t at = it.off + base_less + (pl & 0xffff) + __popc(ml & lt) + min(tie_before, need);
+            p.sel_idx[at] = __ldg(nbr + j);
+            if (p.sel_dist) p.sel_dist[at] = __uint_as_float(key[e]);
+            if (epp) {
+                const int pp = __ldg(epp + j);
+                if (pp >= 0) atomicOr(&kbits0[pp >> 5], 1u << (pp & 31));
+            }
+        }
+        if (it.want_bits) {
+            const unsigned sm = __ballot_sync(PCG_FULL, sel);
+            if (lane == 0 && (j - lane) < d) bits0[j >> 5] = sm;
+        }
+    }
+    TRACE(4);
+}
+
+template <int CL>
+__device__ __forceinline__ void grp_item(const ChooseP& p, int w, GrpSmem& s, int rank, int& par) {
+    constexpr int NT = PCG_GRP_NT;
+    const int tid = threadIdx.x;
+    Item it;
+    item_header(p, w, it);
+    TRACE(0); TRACE_VAL(8, it.d); TRACE_VAL(9, it.k); TRACE_VAL(10, it.o);
+    // rank 0 clears its kept-pool bitmap; the compaction's group barrier orders this before any remote OR
+    if (rank == 0 && it.use_kb)
+        for (int q = tid; q < (p.P + 31) >> 5; q += NT) s.kbits[q] = 0u;
+    TRACE(1);
+    const int per = (it.d + CL * NT - 1) / (CL * NT);
+    if (per <= 1) grp_body<1, CL>(p, it, s, rank, par);
+    else if (per <= 2) grp_body<2, CL>(p, it, s, rank, par);
+    else if (per <= 4 || CL == 1) grp_body<4, CL>(p, it, s, rank, par);
+    else if (per <= 8) grp_body<(CL == 1 ? 4 : 8), CL>(p, it, s, rank, par);
+    else grp_body<(CL == 1 ? 4 : 16), CL>(p, it, s, rank, par);
+    if (it.o > 0) grp_barrier<CL>();      // kept bitmaps complete (remote ORs) before rank 0 reads them
+    else if (CL == 1) __syncthreads();
+    if (rank != 0) return;
+    int m = it.k;
+    if (it.o > 0) m += oversample<NT>(p, it, tid, p.indices + it.beg, s.kbits, s.bits, s.hist, s.xw);
+    TRACE(6);
+    item_finish<NT>(p, it, tid, m);
+    __syncthreads();
+    TRACE(7);
+}
+
+// 128 < d <= 1024: one item per 256-thread CTA.
+__global__ void __launch_bounds__(PCG_GRP_NT, 4) k_choose_cta(ChooseP p) {
+    __shared__ GrpSmem s;
+    const int n = p.status[ST_NMID];
+    int par = 0;
+    for (int q = blockIdx.x; q < n; q += gridDim.x) grp_item<1>(p, p.q_cta[q], s, 0, par);
+}
+
+// 1024 < d <= 32768: one item per cluster of 8 CTAs.
+__global__ void __cluster_dims__(PCG_CL, 1, 1) __launch_bounds__(PCG_GRP_NT, 2) k_choose_cluster(ChooseP p) {
+    __shared__ GrpSmem s;
+    cg::cluster_group cl = cg::this_cluster();
+    const int rank = (int)cl.block_rank();
+    const int n = p.status[ST_NCL];
+    const int n_cl = gridDim.x / PCG_CL, cid = blockIdx.x / PCG_CL;
+    int par = 0;
+    for (int q = cid; q < n; q += n_cl) grp_item<PCG_CL>(p, p.q_cl[q], s, rank, par);
+    cl.sync();          // nobody leaves while a peer may still address its shared memory
+}
+
+// --------------------------------------------------------------------------------- big tier
+// Rows beyond PCG_CL_MAX entries (rare hubs): one 1024-thread CTA per item; distances live in shared memory
+// up to `sd_cap` entries and are recomputed per pass beyond; kept-position bits in a global slab.
+__device__ void choose_item_big(const ChooseP& p, int w, uint32_t* sd, int sd_cap, uint32_t* hist, uint32_t* kbits,
+                                uint32_t* cand, uint32_t* bits, int* xw) {
+    constexpr int NT = PCG_LARGE_NT, NW = NT / 32;
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     Item it;
-    item_header(p, w, KBW, it);
+    item_header(p, w, it);
     TRACE(0); TRACE_VAL(8, it.d); TRACE_VAL(9, it.k); TRACE_VAL(10, it.o);
-    if (tid == 0) xw[29] = atomicAdd(&p.status[ST_SLOTS], it.nslots);
     if (it.use_kb)
         for (int q = tid; q < (p.P + 31) >> 5; q += NT) kbits[q] = 0u;
     __syncthreads();
-    it.slot0 = xw[29];
-    it.off = (int64_t)it.slot0 * PCG_SLOT;
-    if (item_overflow<NT>(p, it, tid)) { __syncthreads(); return; }
     TRACE(1);
     const int d = it.d, k = it.k;
     const float sv = it.sv;
     const int32_t* __restrict__ nbr = p.indices + it.beg;
-    uint32_t* bits = (d <= bits_cap_words * 32) ? bits_s : bits_g;
-    if (d <= 16 * NT) {
-        // the row fits the CTA's registers
-        int* wsum = reinterpret_cast<int*>(hist);
-        if (d <= NT) row_in_regs<NT, 1>(p, it, nbr, kbits, bits, cand, wsum, xw);
-        else if (d <= 2 * NT) row_in_regs<NT, 2>(p, it, nbr, kbits, bits, cand, wsum, xw);
-        else if (d <= 4 * NT) row_in_regs<NT, 4>(p, it, nbr, kbits, bits, cand, wsum, xw);
-        else if (d <= 8 * NT) row_in_regs<NT, 8>(p, it, nbr, kbits, bits, cand, wsum, xw);
-        else row_in_regs<NT, 16>(p, it, nbr, kbits, bits, cand, wsum, xw);
-        int m = k;
-        if (it.o > 0) m += oversample<NT>(p, it, tid, nbr, kbits, bits, hist, xw);
-        TRACE(6);
-        item_finish<NT>(p, it, tid, m);
-        __syncthreads();
-        TRACE(7);
-        return;
-    }
-    // ---- longer rows: distances in shared memory (or recomputed per pass beyond its capacity) ----
-    if (NT != PCG_LARGE_NT) return;   // the smaller tier never sees such rows
     const float* __restrict__ escore = p.entry_score ? p.entry_score + it.beg : nullptr;
     const float* __restrict__ score = p.score;
     const bool cached = d <= sd_cap;
@@ -791,117 +1025,111 @@ __device__ void choose_item_cta(const ChooseP& p, int w, uint32_t* sd, int sd_ca
     TRACE(7);
 }
 
-// Classify items by row length into the three tier queues (warp / 128-thread CTA / 1024-thread CTA).
-// Batches drawn by pick_step are sampled with replacement in proportion to degree, so hub nodes appear
-// several times; an item whose target id already occurred earlier in the batch is not queued at all: it
-// shares the result of that earlier ("representative") item (same node, same relation, same label).
-// first[v] = smallest batch index whose target is node v (table pre-set to 0x7f7f7f7f by a memset)
-__global__ void k_choose_mark(const int32_t* __restrict__ targets, int B, int32_t* __restrict__ first) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < B) atomicMin(&first[targets[i]], i);
-}
-
-__global__ void k_choose_classify(ChooseP p, const int32_t* __restrict__ first) {
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    const int W = p.R * p.B;
-    bool small = false, mid = false, big = false;
-    if (w < W) {
-        const int r = w / p.B, i = w - r * p.B;
-        const int rep = first ? first[p.targets[i]] : i;
-        p.it_rep[w] = r * p.B + rep;
-        if (rep == i) {
-            const int64_t row = (int64_t)r * p.n_nodes + p.targets[i];
-            const int64_t d = p.indptr[row + 1] - p.indptr[row];
-            small = d <= PCG_SMALL_MAX;
-            big = d > PCG_MID_MAX;
-            mid = !small && !big;
-        }
-    }
-    const unsigned lt = lanemask_lt();
-    const int lane = threadIdx.x & 31;
-    const unsigned ms = __ballot_sync(PCG_FULL, small), mm = __ballot_sync(PCG_FULL, mid),
-                   mb = __ballot_sync(PCG_FULL, big);
-    int bs = 0, bm = 0, bb = 0;
-    if (lane == 0) {
-        if (ms) bs = atomicAdd(&p.status[ST_NSMALL], __popc(ms));
-        if (mm) bm = atomicAdd(&p.status[ST_NMID], __popc(mm));
-        if (mb) bb = atomicAdd(&p.status[ST_NBIG], __popc(mb));
-    }
-    bs = __shfl_sync(PCG_FULL, bs, 0);
-    bm = __shfl_sync(PCG_FULL, bm, 0);
-    bb = __shfl_sync(PCG_FULL, bb, 0);
-    if (small) p.small_q[bs + __popc(ms & lt)] = w;
-    if (mid) p.mid_q[bm + __popc(mm & lt)] = w;
-    if (big) p.large_q[bb + __popc(mb & lt)] = w;
-}
-
-// Duplicate items take over their representative's list (after all tiers have finished).
-__global__ void k_choose_fixup(ChooseP p) {
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= p.R * p.B) return;
-    const int rep = p.it_rep[w];
-    if (rep == w) return;
-    p.it_slot0[w] = p.it_slot0[rep];
-    p.it_m[w] = p.it_m[rep];
-    p.it_base[w] = p.it_base[rep];
-    p.it_done[w] = 0;
-}
-
-__global__ void __launch_bounds__(PCG_WARPS_PER_CTA * 32, 3) k_choose_warp(ChooseP p) {
-    __shared__ WarpSmem sm[PCG_WARPS_PER_CTA];
-    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    WarpSmem& s = sm[wid];
-    const int n = p.status[ST_NSMALL];
-    for (;;) {
-        int q = 0;
-        if (lane == 0) q = atomicAdd(&p.status[ST_SMALL_CTR], 1);
-        q = __shfl_sync(PCG_FULL, q, 0);
-        if (q >= n) break;
-        choose_item_warp(p, p.small_q[q], s);
-    }
-}
-
-// 512 < d <= 2048: one item per 128-thread CTA, many CTAs per SM.
-__global__ void __launch_bounds__(PCG_MID_NT, 6) k_choose_mid(ChooseP p) {
+// d > 32768: one item per 1024-thread CTA, one CTA per SM.
+__global__ void __launch_bounds__(PCG_LARGE_NT, 1) k_choose_big(ChooseP p, int sd_cap) {
+    extern __shared__ uint32_t dyn[];                // [sd_cap] distance cache
     __shared__ uint32_t hist[256];
-    __shared__ uint32_t kbits[PCG_KB_WORDS_WARP];
-    __shared__ uint32_t cand[PCG_CAND_CAP_MID];
-    __shared__ uint32_t bits[PCG_MID_MAX / 32];
-    __shared__ int xw[32];
-    __shared__ int s_q;
-    const int n = p.status[ST_NMID];
-    for (;;) {
-        if (threadIdx.x == 0) s_q = atomicAdd(&p.status[ST_MID_CTR], 1);
-        __syncthreads();
-        const int q = s_q;
-        __syncthreads();
-        if (q >= n) break;
-        choose_item_cta<PCG_MID_NT, PCG_KB_WORDS_WARP>(p, p.mid_q[q], nullptr, 0, hist, kbits, cand, bits,
-                                                       PCG_MID_MAX / 32, nullptr, xw);
-    }
-}
-
-// d > 2048: one item per 1024-thread CTA, one CTA per SM.
-__global__ void __launch_bounds__(PCG_LARGE_NT, 1) k_choose_cta(ChooseP p) {
-    extern __shared__ uint32_t dyn[];
-    __shared__ uint32_t hist[256];
-    __shared__ uint32_t kbits[PCG_KB_WORDS_CTA];
+    __shared__ uint32_t kbits[PCG_KB_WORDS];
     __shared__ uint32_t cand[PCG_CAND_CAP];
     __shared__ int xw[32];
-    __shared__ int s_q;
-    uint32_t* sd = dyn;                              // [large_cap]   (rows beyond 16 * PCG_LARGE_NT only)
-    uint32_t* bits = dyn + p.large_cap;              // [bits_words]
     const int n = p.status[ST_NBIG];
-    for (;;) {
-        if (threadIdx.x == 0) s_q = atomicAdd(&p.status[ST_BIG_CTR], 1);
+    for (int q = blockIdx.x; q < n; q += gridDim.x)
+        choose_item_big(p, p.q_big[q], dyn, sd_cap, hist, kbits, cand, p.bits_slab + (int64_t)blockIdx.x * p.slab_words, xw);
+}
+
+// ------------------------------------------------------------------------------------ prep
+// One CTA. (1) Batches drawn by pick_step are sampled with replacement in proportion to degree, so hub
+// nodes appear several times: an item whose target id already occurred earlier in the batch is not
+// processed, it shares the result of that earlier ("representative") item (same node, same relation,
+// same label). first[v] = smallest batch index whose target is node v; the table lives in the workspace,
+// is all 0x7f7f7f7f between calls and is restored before this kernel ends. (2) Sizes k, o of every
+// representative item in the reference's arithmetic; its output slots by an exclusive prefix sum in item
+// order (so the slot layout is deterministic); items that do not fit `cap_slots` are dropped and flagged.
+// (3) Tier queues by row length.
+__global__ void __launch_bounds__(PCG_PREP_NT, 1) k_choose_prep(ChooseP p) {
+    __shared__ int s_wsum[32];
+    __shared__ int s_n[4];
+    constexpr int NT = PCG_PREP_NT;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int W = p.R * p.B;
+    int32_t* first = p.first;
+    if (first)
+        for (int i = tid; i < p.B; i += NT) atomicMin(&first[p.targets[i]], i);
+    if (tid < 4) s_n[tid] = 0;
+    __syncthreads();
+    int run = 0;                       // slots handed out so far (same value in every thread)
+    bool overflow = false;
+    int32_t* const queues[4] = {p.q_warp, p.q_cta, p.q_cl, p.q_big};
+    for (int base = 0; base < W; base += NT) {
+        const int w = base + tid;
+        int nslots = 0, tier = -1;
+        if (w < W) {
+            const int r = w / p.B, i = w - r * p.B;
+            const int32_t v = p.targets[i];
+            const int rep = first ? __ldcg(first + v) : i;
+            p.it_rep[w] = r * p.B + rep;
+            if (rep == i) {
+                const int64_t row = (int64_t)r * p.n_nodes + v;
+                const int64_t d = p.indptr[row + 1] - p.indptr[row];
+                const bool positive = p.train && p.labels && p.labels[i] == 1;
+                int k, o;
+                item_counts(d, p.thresh[r], p.rho, positive, p.P, p.k_override ? p.k_override[w] : 0,
+                            p.k_override != nullptr, k, o);
+                nslots = (k + o + PCG_SLOT - 1) / PCG_SLOT;
+                tier = d <= PCG_SMALL_MAX ? 0 : (d <= PCG_CTA_MAX ? 1 : (d <= PCG_CL_MAX ? 2 : 3));
+            }
+        }
+        int incl = nslots;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(PCG_FULL, incl, off);
+            if (lane >= off) incl += t;
+        }
+        if (lane == 31) s_wsum[wid] = incl;
         __syncthreads();
-        const int q = s_q;
-        __syncthreads();
-        if (q >= n) break;
-        choose_item_cta<PCG_LARGE_NT, PCG_KB_WORDS_CTA>(p, p.large_q[q], sd, p.large_cap, hist, kbits, cand, bits,
-                                                        p.bits_words, p.bits_slab + (int64_t)blockIdx.x * p.slab_words,
-                                                        xw);
+        const int ws = s_wsum[lane];
+        int wincl = ws;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(PCG_FULL, wincl, off);
+            if (lane >= off) wincl += t;
+        }
+        const int slot0 = run + __shfl_sync(PCG_FULL, wincl - ws, wid) + incl - nslots;
+        run += __shfl_sync(PCG_FULL, wincl, 31);
+        if (tier >= 0) {
+            if ((int64_t)slot0 + nslots > p.cap_slots) {       // does not fit: flag, emit nothing for this item
+                overflow = true;
+                tier = -1;
+                p.it_slot0[w] = 0; p.it_m[w] = 0; p.it_base[w] = 0; p.it_done[w] = 0;
+                for (int c = 0; c < nslots; ++c)
+                    if ((int64_t)slot0 + c < p.cap_slots) p.slot_item[slot0 + c] = -1;
+            } else {
+                p.it_slot0[w] = slot0;
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const unsigned m = __ballot_sync(PCG_FULL, tier == t);
+            if (m) {
+                int b = 0;
+                if (lane == 0) b = atomicAdd(&s_n[t], __popc(m));
+                b = __shfl_sync(PCG_FULL, b, 0);
+                if (tier == t) queues[t][b + __popc(m & lanemask_lt())] = w;
+            }
+        }
+        __syncthreads();               // s_wsum is rewritten by the next round
     }
+    const int any_overflow = __syncthreads_or(overflow);
+    if (tid == 0) {
+        p.status[ST_SLOTS] = run;
+        p.status[ST_NSMALL] = s_n[0];
+        p.status[ST_NMID] = s_n[1];
+        p.status[ST_OVERFLOW] = any_overflow ? 1 : 0;
+        p.status[ST_NCL] = s_n[2];
+        p.status[ST_NBIG] = s_n[3];
+    }
+    if (first)
+        for (int i = tid; i < p.B; i += NT) first[p.targets[i]] = 0x7f7f7f7f;
 }
 
 // Select-all (GraphSAGE / GCN): the item list is the CSR row itself. One warp per item.
@@ -958,26 +1186,27 @@ __global__ void k_entry_pool_pos(const int32_t* __restrict__ indices, int64_t nn
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e < nnz) out[e] = pool_pos_of[indices[e]];
 }
-
 // ------------------------------------------------------------------------------------------- C ABI
 struct WsLayout {
-    size_t small_q, mid_q, large_q, bits_slab, first, total;
+    size_t first, bits_slab, q_warp, q_cta, q_cl, q_big, total;
     int64_t slab_words;
-    int grid_large;
+    int grid_big;
 };
 
+// `first` comes first: its place must not depend on the batch size (it carries state between calls)
 static WsLayout ws_layout(int B, int R, int64_t max_degree, int64_t n_nodes, int sms) {
     WsLayout L;
     size_t W = (size_t)B * R;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    L.grid_large = sms;
-    L.slab_words = max_degree > PCG_LARGE_CAP_MAX ? (max_degree + 31) / 32 : 0;
+    L.grid_big = sms;
+    L.slab_words = max_degree > PCG_CL_MAX ? (max_degree + 31) / 32 : 0;
     size_t o = 0;
-    L.small_q = o; o = al(o + W * 4);
-    L.mid_q = o; o = al(o + W * 4);
-    L.large_q = o; o = al(o + W * 4);
-    L.bits_slab = o; o = al(o + (size_t)L.grid_large * L.slab_words * 4);
     L.first = o; o = al(o + (size_t)n_nodes * 4);
+    L.bits_slab = o; o = al(o + (size_t)L.grid_big * L.slab_words * 4);
+    L.q_warp = o; o = al(o + W * 4);
+    L.q_cta = o; o = al(o + W * 4);
+    L.q_cl = o; o = al(o + W * 4);
+    L.q_big = o; o = al(o + W * 4);
     L.total = o;
     return L;
 }
@@ -1004,6 +1233,14 @@ extern "C" size_t pcg_choose_workspace_bytes(int B, int R, int64_t max_degree, i
     return ws_layout(B, R, max_degree, n_nodes, 148 * 2).total;   // sized for the largest grid we ever launch
 }
 
+extern "C" int pcg_choose_workspace_init(void* workspace, size_t workspace_bytes, int64_t n_nodes, pcg_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PCG_REQUIRE(workspace && workspace_bytes >= (size_t)n_nodes * 4, "pcg_choose_workspace_init: workspace too small");
+    cudaError_t e = cudaMemsetAsync(workspace, 0x7f, (size_t)n_nodes * 4, stream);
+    if (e != cudaSuccess) { pcg_set_error("pcg_choose_workspace_init: memset: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
+
 extern "C" int pcg_pool_positions(const int32_t* pool, int P, int64_t n_nodes, int32_t* pool_pos_of,
                                   pcg_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -1022,9 +1259,10 @@ extern "C" int pcg_entry_pool_positions(const int32_t* indices, int64_t nnz, con
     return pcg_check_launch("pcg_entry_pool_positions");
 }
 
-// second stream + events so the warp tier and the CTA tier run side by side (fork/join; capturable)
-static cudaStream_t g_side[2] = {nullptr, nullptr};
-static cudaEvent_t g_fork = nullptr, g_join[2] = {nullptr, nullptr};
+// side streams + events so the tiers run side by side (fork/join; capturable)
+#define PCG_N_SIDE 3
+static cudaStream_t g_side[PCG_N_SIDE] = {nullptr, nullptr, nullptr};
+static cudaEvent_t g_fork = nullptr, g_join[PCG_N_SIDE] = {nullptr, nullptr, nullptr};
 
 extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t n_nodes, int R, const float* score,
                           const float* entry_score, const float* center_score, const int32_t* targets,
@@ -1051,8 +1289,7 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
     WsLayout L = ws_layout(B, R, max_degree, n_nodes, sms);
     PCG_REQUIRE(workspace && workspace_bytes >= L.total, "pcg_choose: workspace too small (%zu < %zu)", workspace_bytes,
                 L.total);
-    cudaError_t e = cudaMemsetAsync(status, 0, PCG_STATUS_WORDS * sizeof(int32_t), stream);
-    if (e != cudaSuccess) { pcg_set_error("pcg_choose: memset: %s", cudaGetErrorString(e)); return (int)e; }
+    cudaError_t e;
     ChooseP p;
     p.indptr = indptr; p.indices = indices; p.score = score; p.entry_score = entry_score;
     p.center_score = center_score; p.targets = targets; p.labels = labels; p.k_override = k_override;
@@ -1063,31 +1300,19 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
     p.rho = rho; p.sel_idx = sel_idx; p.sel_dist = sel_dist; p.cap_slots = cap_slots; p.slot_item = slot_item;
     p.it_slot0 = it_slot0; p.it_m = it_m; p.it_base = it_base; p.it_done = it_done; p.it_rep = it_rep; p.status = status;
     char* ws = (char*)workspace;
-    p.small_q = (int32_t*)(ws + L.small_q);
-    p.mid_q = (int32_t*)(ws + L.mid_q);
-    p.large_q = (int32_t*)(ws + L.large_q);
+    // duplicate targets are folded when ids come from a score table (explicit per-target lists are all distinct)
+    p.first = (score != nullptr && entry_score == nullptr) ? (int32_t*)(ws + L.first) : nullptr;
+    p.q_warp = (int32_t*)(ws + L.q_warp);
+    p.q_cta = (int32_t*)(ws + L.q_cta);
+    p.q_cl = (int32_t*)(ws + L.q_cl);
+    p.q_big = (int32_t*)(ws + L.q_big);
     p.bits_slab = (uint32_t*)(ws + L.bits_slab);
     p.slab_words = L.slab_words;
-    // shared distance buffer of the 1024-thread tier: only rows beyond 16 * PCG_LARGE_NT entries use it
-    int64_t cap = max_degree <= 16 * PCG_LARGE_NT ? 32 : max_degree;
-    if (cap > PCG_LARGE_CAP_MAX) cap = PCG_LARGE_CAP_MAX;
-    p.large_cap = (int)((cap + 31) / 32 * 32);
-    int64_t bw = (max_degree < PCG_LARGE_CAP_MAX ? max_degree : PCG_LARGE_CAP_MAX);
-    p.bits_words = (int)((bw + 31) / 32);
     const int W = R * B;
-    // duplicate targets are folded when ids come from a score table (explicit per-target lists are all distinct)
-    const bool dedup = score != nullptr && entry_score == nullptr;
-    int32_t* first = nullptr;
-    if (dedup) {
-        first = (int32_t*)(ws + L.first);
-        e = cudaMemsetAsync(first, 0x7f, (size_t)n_nodes * 4, stream);
-        if (e != cudaSuccess) { pcg_set_error("pcg_choose: memset: %s", cudaGetErrorString(e)); return (int)e; }
-        k_choose_mark<<<(B + 255) / 256, 256, 0, stream>>>(targets, B, first);
-    }
-    k_choose_classify<<<(W + 255) / 256, 256, 0, stream>>>(p, first);
-    const bool have_mid = max_degree > PCG_SMALL_MAX, have_big = max_degree > PCG_MID_MAX;
-    if (have_mid && !g_side[0]) {
-        for (int q = 0; q < 2; ++q)
+    k_choose_prep<<<1, PCG_PREP_NT, 0, stream>>>(p);
+    const bool have_cta = max_degree > PCG_SMALL_MAX, have_cl = max_degree > PCG_CTA_MAX, have_big = max_degree > PCG_CL_MAX;
+    if (have_cta && !g_fork) {
+        for (int q = 0; q < PCG_N_SIDE; ++q)
             if ((e = cudaStreamCreateWithFlags(&g_side[q], cudaStreamNonBlocking)) != cudaSuccess ||
                 (e = cudaEventCreateWithFlags(&g_join[q], cudaEventDisableTiming)) != cudaSuccess) {
                 pcg_set_error("pcg_choose: side stream: %s", cudaGetErrorString(e));
@@ -1098,32 +1323,38 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
             return (int)e;
         }
     }
-    if (have_mid) cudaEventRecord(g_fork, stream);     // fork: the three tiers run side by side
+    if (have_cta) cudaEventRecord(g_fork, stream);     // fork: the tiers run side by side, longest rows first
     if (have_big) {
-        size_t dyn = (size_t)p.large_cap * 4 + (size_t)p.bits_words * 4;
+        int64_t cap = max_degree > 49152 ? 49152 : (max_degree + 31) / 32 * 32;
+        size_t dyn = (size_t)cap * 4;
         static size_t configured = 0;
-        if (dyn > 16 * 1024 && dyn > configured) {
-            e = cudaFuncSetAttribute(k_choose_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (dyn > configured) {
+            e = cudaFuncSetAttribute(k_choose_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
             if (e != cudaSuccess) { pcg_set_error("pcg_choose: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
             configured = dyn;
         }
+        cudaStreamWaitEvent(g_side[2], g_fork, 0);
+        k_choose_big<<<W < L.grid_big ? W : L.grid_big, PCG_LARGE_NT, dyn, g_side[2]>>>(p, (int)cap);
+        cudaEventRecord(g_join[2], g_side[2]);
+    }
+    if (have_cl) {
         cudaStreamWaitEvent(g_side[1], g_fork, 0);
-        int gl = W < L.grid_large ? W : L.grid_large;
-        k_choose_cta<<<gl, PCG_LARGE_NT, dyn, g_side[1]>>>(p);    // longest rows first: they are the critical path
+        int n_cl = W < 64 ? W : 64;
+        k_choose_cluster<<<n_cl * PCG_CL, PCG_GRP_NT, 0, g_side[1]>>>(p);
         cudaEventRecord(g_join[1], g_side[1]);
     }
-    if (have_mid) {
+    if (have_cta) {
         cudaStreamWaitEvent(g_side[0], g_fork, 0);
-        int gm = W < sms * 8 ? W : sms * 8;
-        k_choose_mid<<<gm, PCG_MID_NT, 0, g_side[0]>>>(p);
+        int gm = W < sms * 4 ? W : sms * 4;
+        k_choose_cta<<<gm, PCG_GRP_NT, 0, g_side[0]>>>(p);
         cudaEventRecord(g_join[0], g_side[0]);
     }
     int gw = (W + PCG_WARPS_PER_CTA - 1) / PCG_WARPS_PER_CTA;
-    if (gw > sms * 6) gw = sms * 6;
+    if (gw > sms * 3) gw = sms * 3;
     k_choose_warp<<<gw, PCG_WARPS_PER_CTA * 32, 0, stream>>>(p);
-    if (have_mid) cudaStreamWaitEvent(stream, g_join[0], 0);      // join
-    if (have_big) cudaStreamWaitEvent(stream, g_join[1], 0);
-    if (dedup) k_choose_fixup<<<(W + 255) / 256, 256, 0, stream>>>(p);
+    if (have_cta) cudaStreamWaitEvent(stream, g_join[0], 0);      // join
+    if (have_cl) cudaStreamWaitEvent(stream, g_join[1], 0);
+    if (have_big) cudaStreamWaitEvent(stream, g_join[2], 0);
     return pcg_check_launch("pcg_choose");
 }
 

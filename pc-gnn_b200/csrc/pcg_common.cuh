@@ -10,13 +10,11 @@
 
 // status / counter words (device int32 array, PCG_STATUS_WORDS long)
 #define ST_SLOTS PCG_ST_SLOTS
-#define ST_NSMALL 1
-#define ST_NMID 2
+#define ST_NSMALL 1      // items queued for the warp tier
+#define ST_NMID 2        // ... the cta tier
 #define ST_OVERFLOW PCG_ST_OVERFLOW
-#define ST_SMALL_CTR 4
-#define ST_MID_CTR 5
-#define ST_NBIG 6
-#define ST_BIG_CTR 7
+#define ST_NCL 4         // ... the cluster tier
+#define ST_NBIG 6        // ... the big tier
 
 void pcg_set_error(const char* fmt, ...);
 int pcg_check_launch(const char* what);

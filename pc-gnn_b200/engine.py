@@ -33,8 +33,7 @@ class Selection:
 
     def lists(self):
         """Host copy: list over items of sorted id arrays (tests / compat API only: syncs)."""
-        m = self.it_m.cpu().numpy()
-        base = self.it_base.cpu().numpy()
+        m, base = self.item_sizes()
         idx = self.idx.cpu().numpy()
         extra = self.it_extra.cpu().numpy() if self.it_extra is not None else None
         out = []
@@ -44,6 +43,16 @@ class Selection:
                 ids = np.append(ids, extra[w])
             out.append(np.sort(ids))
         return out
+
+    def item_sizes(self):
+        """Host copies of (m, base) per item. Only representative items carry sizes on the device
+        (``it_rep``: repeated targets share the list of their first occurrence); resolved here."""
+        m = self.it_m.cpu().numpy()
+        base = self.it_base.cpu().numpy()
+        if self.it_rep is not None:
+            rep = self.it_rep.cpu().numpy()
+            m, base = m[rep], base[rep]
+        return m, base
 
     def overflowed(self) -> bool:
         return bool(self.status[_lib.ST_OVERFLOW].item())
@@ -78,6 +87,7 @@ class Engine:
         self.P = 0
         self._pin = None
         self._ws = None
+        self._ws_nodes = None
 
     # ------------------------------------------------------------------ resident tables
     def set_features(self, weight: torch.Tensor):
@@ -239,9 +249,16 @@ class Engine:
         R = self.R if n_rel is None else n_rel
         s = self._new_selection(B, R, cap_slots, True, False)
         maxdeg = self.max_degree if max_degree is None else max_degree
-        ws_bytes = self.lib.pcg_choose_workspace_bytes(B, R, maxdeg, self.N if n_nodes is None else n_nodes)
-        if self._ws is None or self._ws.numel() < ws_bytes:
-            self._ws = torch.empty(int(ws_bytes), dtype=torch.uint8, device=self.device)
+        nn_ = self.N if n_nodes is None else n_nodes
+        ws_bytes = self.lib.pcg_choose_workspace_bytes(B, R, maxdeg, nn_)
+        if self._ws is None or self._ws.numel() < ws_bytes or self._ws_nodes != nn_:
+            # the head of the workspace is the per-node "first occurrence" table, which the kernels expect
+            # (and leave) all-0x7f: initialise it whenever the buffer or the node count behind it changes
+            if self._ws is None or self._ws.numel() < ws_bytes:
+                self._ws = torch.empty(int(ws_bytes), dtype=torch.uint8, device=self.device)
+            _lib.check(self.lib.pcg_choose_workspace_init(self._ws.data_ptr(), self._ws.numel(), nn_, _lib.stream_ptr()),
+                       "pcg_choose_workspace_init")
+            self._ws_nodes = nn_
         th = (C.c_double * R)(*[float(x) for x in thresh])
         use_table = entry_score is None
         if sorted_pool is None and self.sorted_pool is not None and use_table:

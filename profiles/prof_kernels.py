@@ -32,4 +32,4 @@ for nodes, labels in batches:
     sel = eng.choose(t, lab, True, [0.5] * 3, 0.5, cap)
     agg = eng.aggregate(sel)
     torch.cuda.synchronize()
-print("ok", float(agg.sum()), int(sel.it_m.sum()))
+print("ok", float(agg.sum()), int(sel.it_m[sel.it_rep.long()].sum()))

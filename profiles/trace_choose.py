@@ -1,6 +1,6 @@
-"""Debug-build tracer: per-item phase cycle counts of the choose kernels (needs a library built with
--DPCG_TRACE: make -C pc-gnn_b200/csrc clean all EXTRA=-DPCG_TRACE). Prints where the time of the slowest
-items goes. Usage: python profiles/trace_choose.py [workload]"""
+"""Debug-build tracer: per-item phase timestamps (ns, %globaltimer) of the choose kernels (needs a library built
+with -DPCG_TRACE: make -C pc-gnn_b200/csrc clean all EXTRA=-DPCG_TRACE). Prints where the time of the slowest
+items goes and when each tier starts/ends relative to the first item. Usage: python profiles/trace_choose.py [workload]"""
 import ctypes
 import os
 import sys
@@ -35,6 +35,7 @@ for it, (nodes, labels) in enumerate(batches):
     lab = torch.from_numpy(labels).cuda()
     cap = eng.slots_bound(host, [0.5] * R, 0.5, True)
     eng.score_table(w, b)
+    trace.zero_()
     flush.zero_()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -42,22 +43,34 @@ for it, (nodes, labels) in enumerate(batches):
     e1.record()
     torch.cuda.synchronize()
     tr = trace.cpu().numpy().reshape(-1, 12)
+    done = tr[:, 7] > 0
+    tr = tr[done]
     ts = tr[:, :8].astype(np.float64)
     d, k, o = tr[:, 8], tr[:, 9], tr[:, 10]
     start = ts[:, 0].min()
     dur = ts[:, 7] - ts[:, 0]
-    names = ["slot-alloc", "load-dist", "select", "compact", "pool-search", "pool-emit", "finish"]
-    print(f"iter {it}: choose {e0.elapsed_time(e1) * 1e3:.1f} us; last item ends at {ts[:, 7].max() - start:.0f} cycles "
-          f"(global clock domain per SM differs; treat as approximate)")
-    for tier, mask in (("warp tier (d<=512)", d <= 512), ("cta tier", d > 512)):
+    names = ["header", "load-dist", "select", "compact", "pool-search", "pool-emit", "finish"]
+    print(f"iter {it}: choose {e0.elapsed_time(e1) * 1e3:.1f} us (eager launch, events); {done.sum()} representative items; "
+          f"last item ends {(ts[:, 7].max() - start) / 1e3:.1f} us after the first item starts")
+    for tier, mask in (("warp tier (d<=128)", d <= 128), ("cta tier (<=1024)", (d > 128) & (d <= 1024)),
+                       ("cluster tier (<=32768)", (d > 1024) & (d <= 32768)), ("big tier", d > 32768)):
         if not mask.any():
             continue
         idx = np.nonzero(mask)[0]
-        ph = np.diff(ts[idx], axis=1)
-        print(f"  {tier}: {len(idx)} items, mean {dur[idx].mean():.0f} cyc, p99 {np.percentile(dur[idx], 99):.0f}, "
-              f"max {dur[idx].max():.0f}; begin-time p50 {np.median(ts[idx, 0] - start):.0f} max {(ts[idx, 0] - start).max():.0f}")
-        print("    mean per phase: " + ", ".join(f"{n}={v:.0f}" for n, v in zip(names, ph.mean(0))))
-        worst = idx[np.argsort(-dur[idx])[:5]]
+        tsi = ts[idx].copy()
+        # phases 5 (pool-search) is only stamped for positive items: fall back to the previous stamp
+        for c in range(1, 8):
+            tsi[:, c] = np.where(tsi[:, c] > 0, tsi[:, c], tsi[:, c - 1])
+        ph = np.diff(tsi, axis=1)
+        print(f"  {tier}: {len(idx)} items, mean {dur[idx].mean():.0f} ns, p99 {np.percentile(dur[idx], 99):.0f}, "
+              f"max {dur[idx].max():.0f}; first starts +{(ts[idx, 0].min() - start) / 1e3:.1f} us, "
+              f"median start +{(np.median(ts[idx, 0]) - start) / 1e3:.1f} us, last start +{(ts[idx, 0].max() - start) / 1e3:.1f} us, "
+              f"last end +{(ts[idx, 7].max() - start) / 1e3:.1f} us")
+        print("    mean ns per phase: " + ", ".join(f"{n}={v:.0f}" for n, v in zip(names, ph.mean(0))))
+        worst = idx[np.argsort(-dur[idx])[:4]]
         for wi in worst:
-            print(f"    slow item d={d[wi]} k={k[wi]} o={o[wi]} total={dur[wi]:.0f}: " +
-                  ", ".join(f"{n}={v:.0f}" for n, v in zip(names, np.diff(ts[wi]))))
+            row = ts[wi].copy()
+            for c in range(1, 8):
+                row[c] = row[c] if row[c] > 0 else row[c - 1]
+            print(f"    slow item d={d[wi]} k={k[wi]} o={o[wi]} total={dur[wi]:.0f} ns (start +{(ts[wi, 0] - start) / 1e3:.1f} us): " +
+                  ", ".join(f"{n}={v:.0f}" for n, v in zip(names, np.diff(row))))
