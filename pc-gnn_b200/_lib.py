@@ -9,7 +9,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libpcgnn_b200.so")
+# PCG_LIB_VARIANT=trace selects the per-item phase tracer build (profiles/trace_choose.py; `make trace`)
+SO_PATH = os.path.join(_HERE, "libpcgnn_b200_trace.so" if os.environ.get("PCG_LIB_VARIANT") == "trace"
+                       else "libpcgnn_b200.so")
 
 SLOT = 64            # PCG_SLOT
 MAX_REL = 8          # PCG_MAX_REL

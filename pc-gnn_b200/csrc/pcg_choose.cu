@@ -4,8 +4,8 @@
 // two .tolist() host syncs per target per relation) by an exact k-smallest selection on the key
 // (|s_v - s_u| as fp32 bits, position in the id-sorted row):
 //   1. the k-th smallest distance T (and how many elements equal to T are still needed) is found by a
-//      bit-serial selection over keys held in REGISTERS: two key bits per step, decided from counts
-//      obtained by warp reductions (no atomics, no histogram); bits all keys share are skipped,
+//      radix selection over keys held in REGISTERS: 8 key bits per step counted into per-warp shared-memory
+//      histograms (the skewed exponent digit is peeled with ballots first), at most 4 steps, usually 2,
 //   2. an ORDERED compaction writes every element with d < T plus the first `need` elements with
 //      d == T (row order == id order, which is the reference's stable-sort tie rule),
 //   3. for positive targets the o nearest train positives come from the score-sorted pool
@@ -15,29 +15,32 @@
 //      filled during the compaction) are dropped: the set union of src/layers.py:690-694.
 //
 // Work decomposition (every thread holds at most a few row entries, so an item's latency is a handful of
-// dependent memory round trips plus ~15 selection steps, whatever its length):
+// dependent memory round trips plus 2-4 selection steps, whatever its length):
 //   prep     one CTA: folds repeated targets (pick_step samples with replacement), computes every item's
 //            sizes, hands out the output slots by a prefix sum (deterministic layout, no atomics on the
 //            item path) and sorts the items into four tier queues,
 //   warp     d <= 128          one warp per item,
 //   cta      128 < d <= 1024   one 256-thread CTA per item,
-//   cluster  1024 < d <= 32768 one thread-block CLUSTER of 8 x 256 threads per item; the per-step counts
-//            and the compaction offsets are exchanged through distributed shared memory,
-//   big      d > 32768         one 1024-thread CTA, distances recomputed per pass (rare hub rows).
+//   wide     1024 < d <= 16384 one thread-block CLUSTER of 8 x 256 threads per item (launched first: the longest
+//            rows are the critical path); the CTAs' histograms and compaction totals are exchanged through
+//            distributed shared memory, one cluster barrier per selection step,
+//   big      d > 16384         one 1024-thread CTA, distances in shared memory / recomputed per pass (rare hubs).
 // The tier kernels run side by side on forked streams (CUDA-graph capturable).
 #include "pcg_common.cuh"
 
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
+
+
+
 #define PCG_SMALL_MAX 128      // warp tier: <= 4 entries per lane
 #define PCG_WARPS_PER_CTA 8    // warp kernel: 8 items in flight per CTA
-#define PCG_GRP_NT 256         // cta / cluster tiers: threads per CTA
-#define PCG_GRP_NW (PCG_GRP_NT / 32)
+#define PCG_GRP_NT 256         // cta tier: threads per CTA
 #define PCG_CTA_MAX 1024       // cta tier: <= 4 entries per thread
-#define PCG_CL 8               // cluster tier: CTAs per item
-#define PCG_CL_MAX 32768       // ... 8 x 256 threads x 16 entries
-#define PCG_LARGE_NT 1024      // big tier threads (one CTA per SM)
+#define PCG_LARGE_NT 1024      // wide and big tiers: threads per CTA (one CTA per SM)
+#define PCG_CL 8               // wide tier: CTAs per cluster
+#define PCG_CL_MAX 16384       // wide tier: 8 x 256 threads x <= 8 entries
 #define PCG_KB_WORDS 256       // kept-pool bitmap words per item (pools up to 8192 positives; else row-position bits)
 #define PCG_CAND_CAP 2048      // big tier: candidate keys kept in shared memory once they fit
 #define PCG_PREP_NT 1024
@@ -413,6 +416,163 @@ __device__ __forceinline__ void cta_bitselect(Get get, int n, int kth, uint32_t*
     T = prefix;
     need = remaining;
 }
+// ---- histogram selection: 8 key bits per step, at most 4 steps (bit 31 of a distance is always 0) ----
+// k-th smallest (kth is 1-based) of the keys held in registers by a group of NT threads (NT == 32: one warp,
+// else a whole CTA), as (T, need). Every step counts the digit [shift, shift+8) of the keys that still match
+// the prefix into shared-memory histograms (one per warp for NT <= 256, one per 4 warps above: no two lanes
+// of a warp collide unless their digits are equal), the histograms are merged bin-per-thread, scanned, and the
+// bin holding the k-th key extends the prefix. The first digit is the fp32 exponent, where most keys share two
+// or three values: those are peeled off with ballots so one lane adds the whole count. The loop ends as soon
+// as a single key matches the prefix (typically after two steps).
+//   hist: NH*256 words, all ZERO on entry and on exit (NH = 1 for a warp, 8 for a CTA);  xw: >= 24 ints
+// CL > 1: the group is a thread-block cluster of CL CTAs; every CTA publishes its merged histogram in its own
+// shared memory (chist, parity double buffer `par`), one cluster barrier, then every thread adds up its bin
+// over the CL CTAs through distributed shared memory: all CTAs scan the same totals and agree on the digit.
+template <int NT, int NE, int CL = 1>
+__device__ __forceinline__ void hist_select(const uint32_t (&key)[NE], uint32_t vmask, int kth, uint32_t* hist, int* xw,
+                                            int tid, uint32_t& T, int& need, uint32_t* chist = nullptr,
+                                            int* par = nullptr) {
+    static_assert(CL == 1 || NT == 256, "cluster exchange is written for 256-thread CTAs");
+    constexpr int NH = NT == 32 ? 1 : 8;
+    const int lane = tid & 31, wid = tid >> 5;
+    uint32_t* myh = hist + (NT == 32 ? 0 : (wid & (NH - 1)) * 256);
+    uint32_t prefix = 0u, mask = 0u;
+    int remaining = kth;
+#pragma unroll 1
+    for (int step = 0; step < 4; ++step) {
+        const int shift = step == 3 ? 0 : 23 - 8 * step;
+        const uint32_t dmask = step == 3 ? 0x7fu : 0xffu;
+        if (step == 0) {
+            // exponent digit: most keys of a warp share two or three values. The three most frequent digits of
+            // the warp's first row are counted in registers over all NE rows and added by one lane each.
+            uint32_t pd[3];
+            {
+                const bool a0 = vmask & 1u;
+                const uint32_t dg0 = key[0] >> 23;
+                unsigned rem = __ballot_sync(PCG_FULL, a0);
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const int ldr = rem ? __ffs(rem) - 1 : 0;
+                    pd[q] = rem ? __shfl_sync(PCG_FULL, dg0, ldr) : 0xffffffffu;     // 0xffffffff never matches
+                    rem &= ~__ballot_sync(PCG_FULL, a0 && dg0 == pd[q]);
+                }
+            }
+            int pc0 = 0, pc1 = 0, pc2 = 0;
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                const bool active = (vmask >> e) & 1u;
+                const uint32_t digit = key[e] >> 23;
+                const bool m0 = active && digit == pd[0], m1 = active && digit == pd[1], m2 = active && digit == pd[2];
+                pc0 += m0; pc1 += m1; pc2 += m2;
+                if (active && !(m0 || m1 || m2)) atomicAdd(&myh[digit], 1u);
+            }
+            pc0 = __reduce_add_sync(PCG_FULL, pc0);
+            pc1 = __reduce_add_sync(PCG_FULL, pc1);
+            pc2 = __reduce_add_sync(PCG_FULL, pc2);
+            if (lane == 0 && pc0) atomicAdd(&myh[pd[0]], (uint32_t)pc0);
+            if (lane == 1 && pc1) atomicAdd(&myh[pd[1]], (uint32_t)pc1);
+            if (lane == 2 && pc2) atomicAdd(&myh[pd[2]], (uint32_t)pc2);
+        } else {
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                const bool active = ((vmask >> e) & 1u) && ((key[e] ^ prefix) & mask) == 0u;
+                if (active) atomicAdd(&myh[(key[e] >> shift) & dmask], 1u);
+            }
+        }
+        grp_sync<NT>();
+        // merge (and clear) the histograms, scan, find the bin of the k-th key
+        int dg = -1, rem_in = 0, cnt_in = 0;
+        if (NT == 32) {
+            uint32_t c[8];
+            int s = 0;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) { c[b] = hist[lane * 8 + b]; hist[lane * 8 + b] = 0u; s += (int)c[b]; }
+            int incl = s;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int t = __shfl_up_sync(PCG_FULL, incl, off);
+                if (lane >= off) incl += t;
+            }
+            int run = incl - s;
+            if (run < remaining && remaining <= incl) {
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    if (dg < 0 && run + (int)c[b] >= remaining) { dg = lane * 8 + b; rem_in = remaining - run; cnt_in = (int)c[b]; }
+                    run += (int)c[b];
+                }
+            }
+            const unsigned who = __ballot_sync(PCG_FULL, dg >= 0);
+            const int src = __ffs(who) - 1;
+            dg = __shfl_sync(PCG_FULL, dg, src);
+            rem_in = __shfl_sync(PCG_FULL, rem_in, src);
+            cnt_in = __shfl_sync(PCG_FULL, cnt_in, src);
+        } else {
+            int c = 0, incl = 0;
+            if (tid < 256) {
+#pragma unroll
+                for (int h = 0; h < NH; ++h) { c += (int)hist[h * 256 + tid]; hist[h * 256 + tid] = 0u; }
+            }
+            if (CL > 1) {
+                cg::cluster_group cl = cg::this_cluster();
+                uint32_t* mine_h = chist + *par * 256 + tid;
+                *mine_h = (uint32_t)c;
+                cl.sync();
+                c = 0;
+#pragma unroll
+                for (int r = 0; r < CL; ++r) c += (int)*cl.map_shared_rank(mine_h, r);
+                *par ^= 1;
+            }
+            if (tid < 256) {
+                incl = c;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const int t = __shfl_up_sync(PCG_FULL, incl, off);
+                    if (lane >= off) incl += t;
+                }
+                if (lane == 31) xw[wid] = incl;
+            }
+            __syncthreads();
+            if (tid < 256) {
+                int base = 0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) base += q < wid ? xw[q] : 0;
+                const int excl = base + incl - c;
+                if (excl < remaining && remaining <= excl + c) { xw[16] = tid; xw[17] = remaining - excl; xw[18] = c; }
+            }
+            __syncthreads();
+            dg = xw[16]; rem_in = xw[17]; cnt_in = xw[18];
+        }
+        remaining = rem_in;
+        prefix |= (uint32_t)dg << shift;
+        mask |= dmask << shift;
+        if (cnt_in == 1 && step < 3) {
+            // a single key matches the prefix: it is the k-th
+            uint32_t mine = 0u;
+            bool have = false;
+#pragma unroll
+            for (int e = 0; e < NE; ++e)
+                if (((vmask >> e) & 1u) && ((key[e] ^ prefix) & mask) == 0u) { mine = key[e]; have = true; }
+            if (NT == 32) {
+                const unsigned who = __ballot_sync(PCG_FULL, have);
+                prefix = __shfl_sync(PCG_FULL, mine, __ffs(who) - 1);
+            } else if (CL == 1) {
+                if (have) xw[19] = (int)mine;
+                __syncthreads();
+                prefix = (uint32_t)xw[19];
+            } else {
+                cg::cluster_group cl = cg::this_cluster();
+                if (have)
+                    for (int r = 0; r < CL; ++r) *cl.map_shared_rank(&xw[19], r) = (int)mine;
+                cl.sync();
+                prefix = (uint32_t)xw[19];
+            }
+            break;
+        }
+    }
+    T = prefix;
+    need = remaining;
+}
+
 // First index in [lo, hi) where pred turns false (pred is true on a prefix), found with warp-wide
 // 32-ary probes: ceil(log32(range)) rounds of one predicate evaluation per lane. Every warp of the
 // group runs it redundantly (same addresses -> broadcast loads), so no block barrier is needed.
@@ -561,8 +721,8 @@ __device__ __forceinline__ void item_finish(const ChooseP& p, const Item& it, in
     for (int c = tid; c < it.nslots; c += NT) p.slot_item[it.slot0 + c] = (c * PCG_SLOT < m) ? it.w : -1;
 }
 // --------------------------------------------------------------------------------- warp tier
-// --------------------------------------------------------------------------------- warp tier
 struct WarpSmem {
+    uint32_t shist[256];                      // selection histogram (zero between uses)
     uint32_t hist[256];                       // pool phase: radix histogram (equal-distance pool ties)
     uint32_t kbits[PCG_KB_WORDS];        // kept neighbours that are pool members, by pool position
     uint32_t bits[PCG_SMALL_MAX / 32];        // kept row positions (fallback membership test)
@@ -574,7 +734,7 @@ struct WarpSmem {
 // list written in row order. kbits/bits: see oversample(); cand/wsum/xw: group scratch (CTA only).
 template <int NT, int NE>
 __device__ __forceinline__ void row_in_regs(const ChooseP& p, const Item& it, const int32_t* __restrict__ nbr,
-                                            uint32_t* kbits, uint32_t* bits, uint32_t* cand, int* wsum, int* xw) {
+                                            uint32_t* kbits, uint32_t* bits, uint32_t* hist, int* xw) {
     const int tid = NT == 32 ? (threadIdx.x & 31) : threadIdx.x;
     const int lane = tid & 31;
     const int w = it.w;
@@ -606,7 +766,7 @@ __device__ __forceinline__ void row_in_regs(const ChooseP& p, const Item& it, co
     uint32_t T = 0xffffffffu;
     int need = 0x7fffffff;
     if (!all) {
-        if (k > 0) group_bitselect<NT, NE>(key, vmask, d, k, cand, PCG_CAND_CAP, wsum, xw, tid, T, need);
+        if (k > 0) hist_select<NT, NE>(key, vmask, k, hist, xw, tid, T, need);
         else { T = 0; need = 0; }
     }
     TRACE(3);
@@ -651,9 +811,9 @@ __device__ void choose_item_warp(const ChooseP& p, int w, WarpSmem& s) {
         __syncwarp();
     }
     const int d = it.d;
-    if (d <= 32) row_in_regs<32, 1>(p, it, nbr, s.kbits, s.bits, nullptr, nullptr, s.xw);
-    else if (d <= 64) row_in_regs<32, 2>(p, it, nbr, s.kbits, s.bits, nullptr, nullptr, s.xw);
-    else row_in_regs<32, 4>(p, it, nbr, s.kbits, s.bits, nullptr, nullptr, s.xw);
+    if (d <= 32) row_in_regs<32, 1>(p, it, nbr, s.kbits, s.bits, s.shist, s.xw);
+    else if (d <= 64) row_in_regs<32, 2>(p, it, nbr, s.kbits, s.bits, s.shist, s.xw);
+    else row_in_regs<32, 4>(p, it, nbr, s.kbits, s.bits, s.shist, s.xw);
     int m = it.k;
     if (it.o > 0) m += oversample<32>(p, it, lane, nbr, s.kbits, s.bits, s.hist, s.xw);
     TRACE(6);
@@ -667,149 +827,74 @@ __global__ void __launch_bounds__(PCG_WARPS_PER_CTA * 32, 3) k_choose_warp(Choos
     __shared__ WarpSmem sm[PCG_WARPS_PER_CTA];
     const int wid = threadIdx.x >> 5;
     WarpSmem& s = sm[wid];
+    for (int b = threadIdx.x & 31; b < 256; b += 32) s.shist[b] = 0u;
+    __syncwarp();
     const int n = p.status[ST_NSMALL];
     const int n_warps = gridDim.x * PCG_WARPS_PER_CTA;
     for (int q = blockIdx.x * PCG_WARPS_PER_CTA + wid; q < n; q += n_warps) choose_item_warp(p, p.q_warp[q], s);
 }
 
-// ------------------------------------------------------------------------ cta / cluster tiers
-// One item handled by a GROUP of CL CTAs x 256 threads (CL == 1: a plain CTA, CL == 8: a thread-block
-// cluster). CTA `rank` owns the contiguous positions [rank*NE*256, (rank+1)*NE*256) of the row, NE
-// entries per thread in registers (position of entry e: rank*NE*256 + e*256 + tid). Everything the
-// CTAs have to agree on (min/max, the three counts of every selection step, the compaction totals) is
-// written by the producing warp straight into EVERY CTA's shared memory (distributed shared memory)
-// and read locally after one group barrier, so a selection step costs one barrier.
-struct GrpSmem {
-    uint32_t xchg[2][PCG_CL * PCG_GRP_NW];   // packed step counts of every warp of the group (parity double buffer)
-    uint32_t mm[2][PCG_CL * PCG_GRP_NW];     // per-warp min / max keys
-    int cnt[16 * PCG_GRP_NW];                // compaction: per (round, warp) counts, less | tie << 16
-    int pre[16 * PCG_GRP_NW];                // their exclusive scan
-    int ctot[PCG_CL];                        // per-CTA totals, same packing
-    uint32_t hist[256];                      // oversampling: radix histogram / broadcast words
-    uint32_t kbits[PCG_KB_WORDS];            // rank 0: kept neighbours that are pool members, by pool position
-    uint32_t bits[PCG_CL_MAX / 32];          // rank 0: kept row positions (fallback membership test)
+// ------------------------------------------------------------------------ CTA tiers
+// One item handled by one CTA of NT threads (256 or 1024) with the row in REGISTERS: NE keys per thread,
+// position of entry e = e*NT + tid. Two memory round trips (ids, then scores), histogram selection, then an
+// ordered compaction whose offsets come from ONE scan over the per-(round, warp) counts.
+template <int NT>
+struct CtaSmem {
+    uint32_t hist[8 * 256];                  // selection histograms (zero between uses)
+    uint32_t chist[2 * 256];                 // cluster tier: this CTA's merged histogram (parity double buffer)
+    int ctot;                                // cluster tier: this CTA's compaction totals
+    int cnt[16 * (NT / 32)];                 // compaction: per (round, warp) counts, less | tie << 16
+    int pre[16 * (NT / 32)];                 // their exclusive scan
+    uint32_t ohist[256];                     // oversampling: radix histogram / broadcast words
+    uint32_t kbits[PCG_KB_WORDS];            // kept neighbours that are pool members, by pool position
+    uint32_t bits[PCG_CL_MAX / 32];          // kept row positions (fallback membership test; rank 0 of a cluster holds the row's)
     int xw[32];
 };
 
-template <int CL>
-__device__ __forceinline__ void grp_barrier() {
-    if (CL == 1) __syncthreads();
-    else cg::this_cluster().sync();
-}
-
-// pointer to the same shared-memory object in CTA `rank` of the group
-template <int CL, class T>
-__device__ __forceinline__ T* grp_peer(T* own, int rank) {
-    if (CL == 1) return own;
-    return cg::this_cluster().map_shared_rank(own, rank);
-}
-
-// k-th smallest (1-based) of the group's keys as (T, need); all threads of all CTAs return the same pair.
-template <int NE, int CL>
-__device__ __forceinline__ void grp_select(const uint32_t (&key)[NE], uint32_t vmask, int kth, GrpSmem& s, int rank,
-                                           int& par, uint32_t& T, int& need) {
-    constexpr int NW = PCG_GRP_NW, NS = CL * NW;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int slot = rank * NW + wid;
-    uint32_t lo = 0xffffffffu, hi = 0u;
-#pragma unroll
-    for (int e = 0; e < NE; ++e)
-        if ((vmask >> e) & 1u) { lo = min(lo, key[e]); hi = max(hi, key[e]); }
-    lo = __reduce_min_sync(PCG_FULL, lo);
-    hi = __reduce_max_sync(PCG_FULL, hi);
-    if (lane < CL) {
-        *grp_peer<CL>(&s.mm[0][slot], lane) = lo;
-        *grp_peer<CL>(&s.mm[1][slot], lane) = hi;
-    }
-    grp_barrier<CL>();
-    lo = 0xffffffffu; hi = 0u;
-#pragma unroll
-    for (int q = lane; q < NS; q += 32) { lo = min(lo, s.mm[0][q]); hi = max(hi, s.mm[1][q]); }
-    lo = __reduce_min_sync(PCG_FULL, lo);
-    hi = __reduce_max_sync(PCG_FULL, hi);
-    if (lo == hi) { T = lo; need = kth; return; }
-    int hb = 31 - __clz(lo ^ hi);
-    uint32_t mask = hb == 31 ? 0u : ~((2u << hb) - 1u);
-    uint32_t prefix = lo & mask;
-    int remaining = kth;
-    while (hb >= 0) {
-        const int shift = max(hb - 1, 0);
-        const uint32_t dmask = hb >= 1 ? 3u : 1u;
-        int c0 = 0, c1 = 0, c2 = 0;
-#pragma unroll
-        for (int e = 0; e < NE; ++e) {
-            const bool active = ((vmask >> e) & 1u) && ((key[e] ^ prefix) & mask) == 0u;
-            const uint32_t dg = (key[e] >> shift) & dmask;
-            c0 += active && dg == 0u;
-            c1 += active && dg == 1u;
-            c2 += active && dg == 2u;
-        }
-        c0 = __reduce_add_sync(PCG_FULL, c0);
-        c1 = __reduce_add_sync(PCG_FULL, c1);
-        c2 = __reduce_add_sync(PCG_FULL, c2);
-        // a warp counts at most 32 * 16 = 512 keys: 10 bits per counter
-        if (lane < CL) *grp_peer<CL>(&s.xchg[par][slot], lane) = (uint32_t)c0 | ((uint32_t)c1 << 10) | ((uint32_t)c2 << 20);
-        grp_barrier<CL>();
-        c0 = c1 = c2 = 0;
-#pragma unroll
-        for (int q = lane; q < NS; q += 32) {
-            const uint32_t x = s.xchg[par][q];
-            c0 += (int)(x & 1023u);
-            c1 += (int)((x >> 10) & 1023u);
-            c2 += (int)(x >> 20);
-        }
-        c0 = __reduce_add_sync(PCG_FULL, c0);
-        c1 = __reduce_add_sync(PCG_FULL, c1);
-        c2 = __reduce_add_sync(PCG_FULL, c2);
-        par ^= 1;
-        const uint32_t dg = pick_digit(c0, c1, c2, remaining);
-        prefix |= dg << shift;
-        mask |= dmask << shift;
-        hb = shift - 1;
-    }
-    T = prefix;
-    need = remaining;
-}
-
-template <int NE, int CL>
-__device__ __forceinline__ void grp_body(const ChooseP& p, const Item& it, GrpSmem& s, int rank, int& par) {
-    constexpr int NT = PCG_GRP_NT, NW = PCG_GRP_NW;
+// sid / spp: per-position stash of the ids and pool positions for the 1024-thread tier (each thread reads back
+// only what it wrote: a register spill space that keeps the tier at 64 registers); NULL: kept in registers.
+template <int NT, int NE, int CL>
+__device__ __forceinline__ void cta_body(const ChooseP& p, const Item& it, CtaSmem<NT>& s, int32_t* sid, int16_t* spp,
+                                         int rank, int* par) {
+    constexpr int NW = NT / 32;
+    constexpr bool STASH = NT > PCG_GRP_NT;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int w = it.w;
     const int d = it.d, k = it.k;
     const int32_t* __restrict__ nbr = p.indices + it.beg;
     const float* __restrict__ escore = p.entry_score ? p.entry_score + it.beg : nullptr;
+    const int32_t* __restrict__ epp = it.use_kb ? p.entry_pool_pos + it.beg : nullptr;
     const bool all = k >= d;
     const bool need_dist = !all || p.sel_dist != nullptr;
-    const int pos0 = rank * (NE * NT) + tid;
+    const int pos0 = rank * (NE * NT) + tid;     // CTA `rank` of a cluster owns NE*NT consecutive positions
     uint32_t key[NE];
+    int32_t id[NE];
+    int pp[NE];
     uint32_t vmask = 0;
-    {
-        int32_t id[NE];
 #pragma unroll
-        for (int e = 0; e < NE; ++e) {
-            const int j = pos0 + e * NT;
-            const bool valid = j < d;
-            vmask |= (uint32_t)valid << e;
-            id[e] = (valid && !escore) ? __ldg(nbr + j) : 0;
-        }
+    for (int e = 0; e < NE; ++e) {
+        const int j = pos0 + e * NT;
+        const bool valid = j < d;
+        vmask |= (uint32_t)valid << e;
+        id[e] = valid ? __ldg(nbr + j) : 0;
+        pp[e] = (valid && epp) ? __ldg(epp + j) : -1;
+    }
 #pragma unroll
-        for (int e = 0; e < NE; ++e) {
-            const int j = pos0 + e * NT;
-            uint32_t x = 0u;
-            if (((vmask >> e) & 1u) && need_dist) x = dist_bits(it.sv, escore ? escore[j] : __ldg(p.score + id[e]));
-            key[e] = x;
-        }
+    for (int e = 0; e < NE; ++e) {
+        const int j = pos0 + e * NT;
+        uint32_t x = 0u;
+        if (((vmask >> e) & 1u) && need_dist) x = dist_bits(it.sv, escore ? escore[j] : __ldg(p.score + id[e]));
+        key[e] = x;
+        if (STASH) { sid[j] = id[e]; spp[j] = (int16_t)pp[e]; }
     }
     TRACE(2);
     uint32_t T = 0xffffffffu;
     int need = 0x7fffffff;
     if (!all) {
-        if (k > 0) grp_select<NE, CL>(key, vmask, k, s, rank, par, T, need);
+        if (k > 0) hist_select<NT, NE, CL>(key, vmask, k, s.hist, s.xw, tid, T, need, s.chist, par);
         else { T = 0; need = 0; }
     }
     TRACE(3);
-    // ---- ordered compaction: counts per (round, warp) -> one scan by warp 0 -> totals to every CTA ----
     const unsigned lt = lanemask_lt();
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
@@ -820,7 +905,7 @@ __device__ __forceinline__ void grp_body(const ChooseP& p, const Item& it, GrpSm
     }
     __syncthreads();
     if (wid == 0) {
-        constexpr int PER = (NE * NW + 31) / 32;       // entries per lane (1..4), consecutive
+        constexpr int PER = (NE * NW + 31) / 32;       // consecutive entries per lane
         int v[PER], sum = 0;
 #pragma unroll
         for (int q = 0; q < PER; ++q) {
@@ -841,17 +926,24 @@ __device__ __forceinline__ void grp_body(const ChooseP& p, const Item& it, GrpSm
             if (at < NE * NW) s.pre[at] = run;
             run += v[q];
         }
-        const int total = __shfl_sync(PCG_FULL, incl, 31);
-        if (lane < CL) *grp_peer<CL>(&s.ctot[rank], lane) = total;
+        if (CL > 1 && lane == 31) s.ctot = incl;
     }
-    grp_barrier<CL>();
     int base_less = 0, base_tie = 0;
-#pragma unroll
-    for (int c = 0; c < CL; ++c)
-        if (c < rank) { const int t = s.ctot[c]; base_less += t & 0xffff; base_tie += t >> 16; }
-    const int32_t* __restrict__ epp = it.use_kb ? p.entry_pool_pos + it.beg : nullptr;
-    uint32_t* kbits0 = grp_peer<CL>(&s.kbits[0], 0);
-    uint32_t* bits0 = grp_peer<CL>(&s.bits[0], 0);
+    uint32_t* kbits0 = s.kbits;
+    uint32_t* bits0 = s.bits;
+    if (CL > 1) {
+        cg::cluster_group cl = cg::this_cluster();
+        cl.sync();
+        for (int c = 0; c < rank; ++c) {
+            const int t = *cl.map_shared_rank(&s.ctot, c);
+            base_less += t & 0xffff;
+            base_tie += t >> 16;
+        }
+        kbits0 = cl.map_shared_rank(&s.kbits[0], 0);
+        bits0 = cl.map_shared_rank(&s.bits[0], 0);
+    } else {
+        __syncthreads();
+    }
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
         const int j = pos0 + e * NT;
@@ -864,43 +956,43 @@ __device__ __forceinline__ void grp_body(const ChooseP& p, const Item& it, GrpSm
         const bool sel = less || (tie && tie_before < need);
         if (sel) {
             const int64_t at = it.off + base_less + (pl & 0xffff) + __popc(ml & lt) + min(tie_before, need);
-            p.sel_idx[at] = __ldg(nbr + j);
+            p.sel_idx[at] = STASH ? sid[j] : id[e];
             if (p.sel_dist) p.sel_dist[at] = __uint_as_float(key[e]);
-            if (epp) {
-                const int pp = __ldg(epp + j);
-                if (pp >= 0) atomicOr(&kbits0[pp >> 5], 1u << (pp & 31));
-            }
+            const int q = STASH ? (int)spp[j] : pp[e];
+            if (q >= 0) atomicOr(&kbits0[q >> 5], 1u << (q & 31));
         }
         if (it.want_bits) {
             const unsigned sm = __ballot_sync(PCG_FULL, sel);
-            if (lane == 0 && (j - lane) < d) bits0[j >> 5] = sm;
+            if (lane == 0 && j < d) bits0[j >> 5] = sm;
         }
     }
     TRACE(4);
 }
 
-template <int CL>
-__device__ __forceinline__ void grp_item(const ChooseP& p, int w, GrpSmem& s, int rank, int& par) {
-    constexpr int NT = PCG_GRP_NT;
+template <int NT, int CL>
+__device__ __forceinline__ void cta_item(const ChooseP& p, int w, CtaSmem<NT>& s, int32_t* sid, int16_t* spp, int rank,
+                                         int* par) {
     const int tid = threadIdx.x;
     Item it;
     item_header(p, w, it);
     TRACE(0); TRACE_VAL(8, it.d); TRACE_VAL(9, it.k); TRACE_VAL(10, it.o);
-    // rank 0 clears its kept-pool bitmap; the compaction's group barrier orders this before any remote OR
     if (rank == 0 && it.use_kb)
-        for (int q = tid; q < (p.P + 31) >> 5; q += NT) s.kbits[q] = 0u;
+        for (int q = tid; q < (p.P + 31) >> 5; q += NT) s.kbits[q] = 0u;   // ordered before the ORs by the compaction's barriers
     TRACE(1);
     const int per = (it.d + CL * NT - 1) / (CL * NT);
-    if (per <= 1) grp_body<1, CL>(p, it, s, rank, par);
-    else if (per <= 2) grp_body<2, CL>(p, it, s, rank, par);
-    else if (per <= 4 || CL == 1) grp_body<4, CL>(p, it, s, rank, par);
-    else if (per <= 8) grp_body<(CL == 1 ? 4 : 8), CL>(p, it, s, rank, par);
-    else grp_body<(CL == 1 ? 4 : 16), CL>(p, it, s, rank, par);
-    if (it.o > 0) grp_barrier<CL>();      // kept bitmaps complete (remote ORs) before rank 0 reads them
-    else if (CL == 1) __syncthreads();
-    if (rank != 0) return;
+    constexpr int NE_MAX = NT == PCG_GRP_NT ? (CL == 1 ? 4 : 8) : 16;
+    if (per <= 1) cta_body<NT, 1, CL>(p, it, s, sid, spp, rank, par);
+    else if (per <= 2) cta_body<NT, 2, CL>(p, it, s, sid, spp, rank, par);
+    else if (per <= 4 || NE_MAX == 4) cta_body<NT, 4, CL>(p, it, s, sid, spp, rank, par);
+    else if (per <= 8 || NE_MAX == 8) cta_body<NT, (NE_MAX < 8 ? NE_MAX : 8), CL>(p, it, s, sid, spp, rank, par);
+    else cta_body<NT, NE_MAX, CL>(p, it, s, sid, spp, rank, par);
+    if (CL > 1) {
+        if (it.o > 0) cg::this_cluster().sync();      // kept bitmaps complete (remote ORs) before rank 0 reads them
+        if (rank != 0) return;
+    }
+    __syncthreads();                      // kept bitmaps complete
     int m = it.k;
-    if (it.o > 0) m += oversample<NT>(p, it, tid, p.indices + it.beg, s.kbits, s.bits, s.hist, s.xw);
+    if (it.o > 0) m += oversample<NT>(p, it, tid, p.indices + it.beg, s.kbits, s.bits, s.ohist, s.xw);
     TRACE(6);
     item_finish<NT>(p, it, tid, m);
     __syncthreads();
@@ -909,21 +1001,25 @@ __device__ __forceinline__ void grp_item(const ChooseP& p, int w, GrpSmem& s, in
 
 // 128 < d <= 1024: one item per 256-thread CTA.
 __global__ void __launch_bounds__(PCG_GRP_NT, 4) k_choose_cta(ChooseP p) {
-    __shared__ GrpSmem s;
+    __shared__ CtaSmem<PCG_GRP_NT> s;
+    for (int b = threadIdx.x; b < 8 * 256; b += PCG_GRP_NT) s.hist[b] = 0u;
+    __syncthreads();
     const int n = p.status[ST_NMID];
-    int par = 0;
-    for (int q = blockIdx.x; q < n; q += gridDim.x) grp_item<1>(p, p.q_cta[q], s, 0, par);
+    for (int q = blockIdx.x; q < n; q += gridDim.x) cta_item<PCG_GRP_NT, 1>(p, p.q_cta[q], s, nullptr, nullptr, 0, nullptr);
 }
 
-// 1024 < d <= 32768: one item per cluster of 8 CTAs.
-__global__ void __cluster_dims__(PCG_CL, 1, 1) __launch_bounds__(PCG_GRP_NT, 2) k_choose_cluster(ChooseP p) {
-    __shared__ GrpSmem s;
+// 1024 < d <= 16384: one item per CLUSTER of 8 CTAs x 256 threads (<= 8 entries per thread): the longest rows are
+// the critical path of the step, so they get 8 SMs each and are launched first.
+__global__ void __cluster_dims__(PCG_CL, 1, 1) __launch_bounds__(PCG_GRP_NT, 3) k_choose_wide(ChooseP p) {
+    __shared__ CtaSmem<PCG_GRP_NT> s;
     cg::cluster_group cl = cg::this_cluster();
     const int rank = (int)cl.block_rank();
+    for (int b = threadIdx.x; b < 8 * 256; b += PCG_GRP_NT) s.hist[b] = 0u;
+    __syncthreads();
     const int n = p.status[ST_NCL];
     const int n_cl = gridDim.x / PCG_CL, cid = blockIdx.x / PCG_CL;
     int par = 0;
-    for (int q = cid; q < n; q += n_cl) grp_item<PCG_CL>(p, p.q_cl[q], s, rank, par);
+    for (int q = cid; q < n; q += n_cl) cta_item<PCG_GRP_NT, PCG_CL>(p, p.q_cl[q], s, nullptr, nullptr, rank, &par);
     cl.sync();          // nobody leaves while a peer may still address its shared memory
 }
 
@@ -1043,43 +1139,61 @@ __global__ void __launch_bounds__(PCG_LARGE_NT, 1) k_choose_big(ChooseP p, int s
 // processed, it shares the result of that earlier ("representative") item (same node, same relation,
 // same label). first[v] = smallest batch index whose target is node v; the table lives in the workspace,
 // is all 0x7f7f7f7f between calls and is restored before this kernel ends. (2) Sizes k, o of every
-// representative item in the reference's arithmetic; its output slots by an exclusive prefix sum in item
-// order (so the slot layout is deterministic); items that do not fit `cap_slots` are dropped and flagged.
-// (3) Tier queues by row length.
+// representative item in the reference's arithmetic; its output slots by an exclusive prefix sum in
+// (target, relation) order (so the slot layout is deterministic); items that do not fit `cap_slots` are
+// dropped and flagged. (3) Tier queues by row length.
+// A thread owns one target and its R items; the row offsets of all relations are requested before the
+// barrier that completes the first-occurrence table, so a round costs three dependent memory round trips.
 __global__ void __launch_bounds__(PCG_PREP_NT, 1) k_choose_prep(ChooseP p) {
     __shared__ int s_wsum[32];
     __shared__ int s_n[4];
     constexpr int NT = PCG_PREP_NT;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int W = p.R * p.B;
+    const int B = p.B, R = p.R;
     int32_t* first = p.first;
-    if (first)
-        for (int i = tid; i < p.B; i += NT) atomicMin(&first[p.targets[i]], i);
     if (tid < 4) s_n[tid] = 0;
-    __syncthreads();
     int run = 0;                       // slots handed out so far (same value in every thread)
     bool overflow = false;
     int32_t* const queues[4] = {p.q_warp, p.q_cta, p.q_cl, p.q_big};
-    for (int base = 0; base < W; base += NT) {
-        const int w = base + tid;
-        int nslots = 0, tier = -1;
-        if (w < W) {
-            const int r = w / p.B, i = w - r * p.B;
-            const int32_t v = p.targets[i];
-            const int rep = first ? __ldcg(first + v) : i;
-            p.it_rep[w] = r * p.B + rep;
-            if (rep == i) {
+    for (int base = 0; base < B; base += NT) {
+        const int i = base + tid;
+        const bool valid = i < B;
+        const int32_t v = valid ? p.targets[i] : 0;
+        if (valid && first) atomicMin(&first[v], i);
+        int64_t beg[PCG_MAX_REL], end[PCG_MAX_REL];
+#pragma unroll
+        for (int r = 0; r < PCG_MAX_REL; ++r) {
+            if (valid && r < R) {
                 const int64_t row = (int64_t)r * p.n_nodes + v;
-                const int64_t d = p.indptr[row + 1] - p.indptr[row];
-                const bool positive = p.train && p.labels && p.labels[i] == 1;
-                int k, o;
-                item_counts(d, p.thresh[r], p.rho, positive, p.P, p.k_override ? p.k_override[w] : 0,
-                            p.k_override != nullptr, k, o);
-                nslots = (k + o + PCG_SLOT - 1) / PCG_SLOT;
-                tier = d <= PCG_SMALL_MAX ? 0 : (d <= PCG_CTA_MAX ? 1 : (d <= PCG_CL_MAX ? 2 : 3));
+                beg[r] = __ldg(p.indptr + row);
+                end[r] = __ldg(p.indptr + row + 1);
+            } else {
+                beg[r] = end[r] = 0;
             }
         }
-        int incl = nslots;
+        const bool positive = valid && p.train && p.labels && p.labels[i] == 1;
+        __syncthreads();               // every earlier occurrence of v (smaller i) has been recorded
+        const int rep = !valid ? -1 : (first ? __ldcg(first + v) : i);
+        int nsl[PCG_MAX_REL], tier[PCG_MAX_REL], mine = 0;
+#pragma unroll
+        for (int r = 0; r < PCG_MAX_REL; ++r) {
+            nsl[r] = 0;
+            tier[r] = -1;
+            if (valid && r < R) {
+                const int w = r * B + i;
+                p.it_rep[w] = r * B + rep;
+                if (rep == i) {
+                    const int64_t d = end[r] - beg[r];
+                    int k, o;
+                    item_counts(d, p.thresh[r], p.rho, positive, p.P, p.k_override ? p.k_override[w] : 0,
+                                p.k_override != nullptr, k, o);
+                    nsl[r] = (k + o + PCG_SLOT - 1) / PCG_SLOT;
+                    tier[r] = d <= PCG_SMALL_MAX ? 0 : (d <= PCG_CTA_MAX ? 1 : (d <= PCG_CL_MAX ? 2 : 3));
+                    mine += nsl[r];
+                }
+            }
+        }
+        int incl = mine;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
             const int t = __shfl_up_sync(PCG_FULL, incl, off);
@@ -1094,32 +1208,41 @@ __global__ void __launch_bounds__(PCG_PREP_NT, 1) k_choose_prep(ChooseP p) {
             const int t = __shfl_up_sync(PCG_FULL, wincl, off);
             if (lane >= off) wincl += t;
         }
-        const int slot0 = run + __shfl_sync(PCG_FULL, wincl - ws, wid) + incl - nslots;
+        int slot0 = run + __shfl_sync(PCG_FULL, wincl - ws, wid) + incl - mine;
         run += __shfl_sync(PCG_FULL, wincl, 31);
-        if (tier >= 0) {
-            if ((int64_t)slot0 + nslots > p.cap_slots) {       // does not fit: flag, emit nothing for this item
-                overflow = true;
-                tier = -1;
-                p.it_slot0[w] = 0; p.it_m[w] = 0; p.it_base[w] = 0; p.it_done[w] = 0;
-                for (int c = 0; c < nslots; ++c)
-                    if ((int64_t)slot0 + c < p.cap_slots) p.slot_item[slot0 + c] = -1;
-            } else {
-                p.it_slot0[w] = slot0;
-            }
-        }
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const unsigned m = __ballot_sync(PCG_FULL, tier == t);
-            if (m) {
-                int b = 0;
-                if (lane == 0) b = atomicAdd(&s_n[t], __popc(m));
-                b = __shfl_sync(PCG_FULL, b, 0);
-                if (tier == t) queues[t][b + __popc(m & lanemask_lt())] = w;
+        for (int r = 0; r < PCG_MAX_REL; ++r) {
+            if (r < R) {                                         // uniform
+                const int w = r * B + i;
+                if (tier[r] >= 0) {
+                    if ((int64_t)slot0 + nsl[r] > p.cap_slots) {  // does not fit: flag, emit nothing for this item
+                        overflow = true;
+                        tier[r] = -1;
+                        p.it_slot0[w] = 0; p.it_m[w] = 0; p.it_base[w] = 0; p.it_done[w] = 0;
+                        for (int c = 0; c < nsl[r]; ++c)
+                            if ((int64_t)slot0 + c < p.cap_slots) p.slot_item[slot0 + c] = -1;
+                    } else {
+                        p.it_slot0[w] = slot0;
+                    }
+                    slot0 += nsl[r];
+                }
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const unsigned m = __ballot_sync(PCG_FULL, tier[r] == t);
+                    if (m) {
+                        int b = 0;
+                        if (lane == 0) b = atomicAdd(&s_n[t], __popc(m));
+                        b = __shfl_sync(PCG_FULL, b, 0);
+                        if (tier[r] == t) queues[t][b + __popc(m & lanemask_lt())] = w;
+                    }
+                }
             }
         }
         __syncthreads();               // s_wsum is rewritten by the next round
     }
     const int any_overflow = __syncthreads_or(overflow);
+    if (first)                          // restore the table (all reads are behind the barrier above)
+        for (int i = tid; i < B; i += NT) first[p.targets[i]] = 0x7f7f7f7f;
     if (tid == 0) {
         p.status[ST_SLOTS] = run;
         p.status[ST_NSMALL] = s_n[0];
@@ -1128,8 +1251,6 @@ __global__ void __launch_bounds__(PCG_PREP_NT, 1) k_choose_prep(ChooseP p) {
         p.status[ST_NCL] = s_n[2];
         p.status[ST_NBIG] = s_n[3];
     }
-    if (first)
-        for (int i = tid; i < p.B; i += NT) first[p.targets[i]] = 0x7f7f7f7f;
 }
 
 // Select-all (GraphSAGE / GCN): the item list is the CSR row itself. One warp per item.
@@ -1339,8 +1460,8 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
     }
     if (have_cl) {
         cudaStreamWaitEvent(g_side[1], g_fork, 0);
-        int n_cl = W < 64 ? W : 64;
-        k_choose_cluster<<<n_cl * PCG_CL, PCG_GRP_NT, 0, g_side[1]>>>(p);
+        const int n_cl = W < 56 ? W : 56;
+        k_choose_wide<<<n_cl * PCG_CL, PCG_GRP_NT, 0, g_side[1]>>>(p);
         cudaEventRecord(g_join[1], g_side[1]);
     }
     if (have_cta) {

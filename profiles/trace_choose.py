@@ -53,7 +53,7 @@ for it, (nodes, labels) in enumerate(batches):
     print(f"iter {it}: choose {e0.elapsed_time(e1) * 1e3:.1f} us (eager launch, events); {done.sum()} representative items; "
           f"last item ends {(ts[:, 7].max() - start) / 1e3:.1f} us after the first item starts")
     for tier, mask in (("warp tier (d<=128)", d <= 128), ("cta tier (<=1024)", (d > 128) & (d <= 1024)),
-                       ("cluster tier (<=32768)", (d > 1024) & (d <= 32768)), ("big tier", d > 32768)):
+                       ("wide tier (<=16384)", (d > 1024) & (d <= 16384)), ("big tier", d > 16384)):
         if not mask.any():
             continue
         idx = np.nonzero(mask)[0]
