@@ -70,36 +70,51 @@ __global__ void __launch_bounds__(HEAD_BLOCK) k_center_fwd(const float* __restri
 }
 
 // dW[c][f] = sum_i g[i][c] * feat[targets[i]][f];  db[c] = sum_i g[i][c].
-// Block `blk` owns targets [blk*per, (blk+1)*per) (per <= CENTER_PER); thread f owns feature column f.
+// Block `blk` owns CENTER_PER targets: thread (j, f) = (tid / 32, tid % 32 + 32*c) multiplies target j's row
+// (one coalesced row read per warp, all warps' loads in flight together), the CENTER_PER partial rows are then
+// added in target order by the first warps; the last block to arrive adds the blocks in block order.
 #define CENTER_PER 32
-__global__ void k_center_bwd(const float* __restrict__ feat, int64_t ldf, int F, const int32_t* __restrict__ targets,
-                             int B, const float* __restrict__ g, float* __restrict__ partial, int32_t* ticket,
-                             float* __restrict__ dw, float* __restrict__ db) {
-    __shared__ int32_t s_t[CENTER_PER];
-    __shared__ float s_g[CENTER_PER][2];
-    const int per = (B + gridDim.x - 1) / gridDim.x;
-    const int ib = blockIdx.x * per, ie = min(B, ib + per), n = max(ie - ib, 0);
-    for (int q = threadIdx.x; q < n; q += blockDim.x) {
-        s_t[q] = targets[ib + q];
-        s_g[q][0] = g[2 * (ib + q)];
-        s_g[q][1] = g[2 * (ib + q) + 1];
+#define CENTER_NT 1024
+__global__ void __launch_bounds__(CENTER_NT) k_center_bwd(const float* __restrict__ feat, int64_t ldf, int F,
+                                                          const int32_t* __restrict__ targets, int B,
+                                                          const float* __restrict__ g, float* __restrict__ partial,
+                                                          int32_t* ticket, float* __restrict__ dw,
+                                                          float* __restrict__ db) {
+    extern __shared__ float sp[];               // [CENTER_PER][2][ldf] products, then reused
+    const int j = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * CENTER_PER + j;
+    const int stride = 2 * F + 2;
+    float g0 = 0.f, g1 = 0.f;
+    const float* rowp = feat;
+    if (i < B) {
+        g0 = g[2 * i];
+        g1 = g[2 * i + 1];
+        rowp = feat + (int64_t)targets[i] * ldf;
+    }
+    for (int f = lane; f < ldf; f += 32) {
+        const float x = (i < B && f < F) ? __ldg(rowp + f) : 0.f;
+        sp[(j * 2 + 0) * ldf + f] = g0 * x;
+        sp[(j * 2 + 1) * ldf + f] = g1 * x;
     }
     __syncthreads();
-    const int stride = 2 * F + 2;
-    for (int f = threadIdx.x; f < F + 1; f += blockDim.x) {     // column F stands for the bias
-        float a0 = 0.f, a1 = 0.f;
+    float* dst = partial + (int64_t)blockIdx.x * stride;
+    for (int x = threadIdx.x; x < 2 * F; x += CENTER_NT) {
+        const int c = x / F, f = x - c * F;
+        float a = 0.f;
 #pragma unroll 8
-        for (int q = 0; q < n; ++q) {
-            const float x = f < F ? __ldg(feat + (int64_t)s_t[q] * ldf + f) : 1.f;
-            a0 = fmaf(s_g[q][0], x, a0);
-            a1 = fmaf(s_g[q][1], x, a1);
+        for (int q = 0; q < CENTER_PER; ++q) a += sp[(q * 2 + c) * ldf + f];
+        dst[x] = a;
+    }
+    if (threadIdx.x < 2) {                       // bias gradient of this block (target order)
+        float a = 0.f;
+        for (int q = 0; q < CENTER_PER; ++q) {
+            const int t = blockIdx.x * CENTER_PER + q;
+            if (t < B) a += g[2 * t + threadIdx.x];
         }
-        float* dst = partial + (int64_t)blockIdx.x * stride;
-        if (f < F) { dst[f] = a0; dst[F + f] = a1; }
-        else { dst[2 * F] = a0; dst[2 * F + 1] = a1; }
+        dst[2 * F + threadIdx.x] = a;
     }
     if (!last_block(ticket)) return;
-    for (int x = threadIdx.x; x < stride; x += blockDim.x) {
+    for (int x = threadIdx.x; x < stride; x += CENTER_NT) {
         float s = 0.f;
         for (int q = 0; q < (int)gridDim.x; ++q) s += __ldcg(partial + (int64_t)q * stride + x);
         if (x < 2 * F) dw[x] = s; else db[x - 2 * F] = s;
@@ -107,55 +122,67 @@ __global__ void k_center_bwd(const float* __restrict__ feat, int64_t ldf, int F,
 }
 
 // ------------------------------------------------------------------------------------ head + loss
-// One thread per target. p1[i] / q1[i] = softmax probability of class 1 (GNN head / label head), kept for
-// the backward pass.
-__global__ void __launch_bounds__(HEAD_BLOCK) k_head_loss_fwd(const float* __restrict__ emb, int E, int B,
-                                                              const float* __restrict__ w, const float* __restrict__ center,
-                                                              const int64_t* __restrict__ labels, float lambda,
-                                                              float* __restrict__ logits, float* __restrict__ p1,
-                                                              float* __restrict__ q1, float* __restrict__ partial,
-                                                              int32_t* ticket, float* __restrict__ loss) {
+// HEAD_TB targets per block of 256 threads: thread (g, t) = (tid / 32, tid % 32) covers the embedding rows
+// e = g, g + 8, ... of target t (coalesced along the batch, every load independent), the 8 partial sums are
+// added in g order. p1[i] / q1[i] = softmax probability of class 1 (GNN head / label head), kept for the
+// backward pass.
+#define HEAD_TB 32
+#define HEAD_NT 256
+__global__ void __launch_bounds__(HEAD_NT) k_head_loss_fwd(const float* __restrict__ emb, int E, int B,
+                                                           const float* __restrict__ w, const float* __restrict__ center,
+                                                           const int64_t* __restrict__ labels, float lambda,
+                                                           float* __restrict__ logits, float* __restrict__ p1,
+                                                           float* __restrict__ q1, float* __restrict__ partial,
+                                                           int32_t* ticket, float* __restrict__ loss) {
     extern __shared__ float sw[];            // [2][E]
-    __shared__ float red[2][HEAD_BLOCK / 32];
+    __shared__ float ps[HEAD_NT / 32][HEAD_TB][2];
     for (int c = threadIdx.x; c < 2 * E; c += blockDim.x) sw[c] = w[c];
     __syncthreads();
-    const int i = blockIdx.x * HEAD_BLOCK + threadIdx.x;
-    float lg = 0.f, ll = 0.f;
+    const int g = threadIdx.x >> 5, t = threadIdx.x & 31;
+    const int i = blockIdx.x * HEAD_TB + t;
+    float g0 = 0.f, g1 = 0.f;
     if (i < B) {
-        float g0 = 0.f, g1 = 0.f;
-        for (int e = 0; e < E; ++e) {
-            const float x = emb[(int64_t)e * B + i];
+#pragma unroll 8
+        for (int e = g; e < E; e += HEAD_NT / 32) {
+            const float x = __ldg(emb + (int64_t)e * B + i);
             g0 = fmaf(sw[e], x, g0);
             g1 = fmaf(sw[E + e], x, g1);
         }
-        logits[2 * i] = g0;
-        logits[2 * i + 1] = g1;
-        const int y = labels[i] == 1 ? 1 : 0;
-        {   // cross entropy = logsumexp - logit[y], computed like log_softmax (shift by the max)
-            const float m = fmaxf(g0, g1);
-            const float e0 = expf(g0 - m), e1 = expf(g1 - m);
-            const float lse = m + logf(e0 + e1);
-            lg = lse - (y ? g1 : g0);
-            p1[i] = e1 / (e0 + e1);
-        }
-        {
-            const float c0 = center[2 * i], c1 = center[2 * i + 1];
-            const float m = fmaxf(c0, c1);
-            const float e0 = expf(c0 - m), e1 = expf(c1 - m);
-            const float lse = m + logf(e0 + e1);
-            ll = lse - (y ? c1 : c0);
-            q1[i] = e1 / (e0 + e1);
-        }
     }
-    lg = warp_sum(lg);
-    ll = warp_sum(ll);
-    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = lg; red[1][threadIdx.x >> 5] = ll; }
+    ps[g][t][0] = g0;
+    ps[g][t][1] = g1;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        float a = 0.f, c = 0.f;
-        for (int q = 0; q < HEAD_BLOCK / 32; ++q) { a += red[0][q]; c += red[1][q]; }
-        partial[2 * blockIdx.x] = a;
-        partial[2 * blockIdx.x + 1] = c;
+    if (g == 0) {
+        float lg = 0.f, ll = 0.f;
+        if (i < B) {
+            g0 = g1 = 0.f;
+#pragma unroll
+            for (int q = 0; q < HEAD_NT / 32; ++q) { g0 += ps[q][t][0]; g1 += ps[q][t][1]; }
+            logits[2 * i] = g0;
+            logits[2 * i + 1] = g1;
+            const int y = labels[i] == 1 ? 1 : 0;
+            {   // cross entropy = logsumexp - logit[y], computed like log_softmax (shift by the max)
+                const float m = fmaxf(g0, g1);
+                const float e0 = expf(g0 - m), e1 = expf(g1 - m);
+                const float lse = m + logf(e0 + e1);
+                lg = lse - (y ? g1 : g0);
+                p1[i] = e1 / (e0 + e1);
+            }
+            {
+                const float c0 = center[2 * i], c1 = center[2 * i + 1];
+                const float m = fmaxf(c0, c1);
+                const float e0 = expf(c0 - m), e1 = expf(c1 - m);
+                const float lse = m + logf(e0 + e1);
+                ll = lse - (y ? c1 : c0);
+                q1[i] = e1 / (e0 + e1);
+            }
+        }
+        lg = warp_sum(lg);
+        ll = warp_sum(ll);
+        if (t == 0) {
+            partial[2 * blockIdx.x] = lg;
+            partial[2 * blockIdx.x + 1] = ll;
+        }
     }
     if (!last_block(ticket)) return;
     if (threadIdx.x == 0) {
@@ -166,22 +193,19 @@ __global__ void __launch_bounds__(HEAD_BLOCK) k_head_loss_fwd(const float* __res
 }
 
 // d_emb[e][i] = sum_c W[c][e] * dl[i][c];  d_center[i][c] = lambda * (q - onehot) * s;  dW[c][e] = sum_i dl[i][c] * emb[e][i]
-// with dl[i][c] = (p - onehot) * s and s = d_loss / B.
-__global__ void __launch_bounds__(HEAD_BLOCK) k_head_loss_bwd(const float* __restrict__ emb, int E, int B,
-                                                              const float* __restrict__ w, const int64_t* __restrict__ labels,
-                                                              const float* __restrict__ p1, const float* __restrict__ q1,
-                                                              float lambda, const float* __restrict__ d_loss,
-                                                              float* __restrict__ d_emb, float* __restrict__ d_center,
-                                                              float* __restrict__ partial, int32_t* ticket,
-                                                              float* __restrict__ dw) {
-    extern __shared__ float sm[];            // [2][E] weights, then [HEAD_BLOCK][2] per-target dl
-    float* sw = sm;
-    float* dls = sm + 2 * E;
+// with dl[i][c] = (p - onehot) * s and s = d_loss / B. Same (g, t) layout as the forward kernel: warp g owns the
+// embedding rows e = g, g + 8, ...; lanes run along the block's HEAD_TB targets.
+__global__ void __launch_bounds__(HEAD_NT) k_head_loss_bwd(const float* __restrict__ emb, int E, int B,
+                                                           const float* __restrict__ w, const int64_t* __restrict__ labels,
+                                                           const float* __restrict__ p1, const float* __restrict__ q1,
+                                                           float lambda, const float* __restrict__ d_loss,
+                                                           float* __restrict__ d_emb, float* __restrict__ d_center,
+                                                           float* __restrict__ partial, int32_t* ticket,
+                                                           float* __restrict__ dw) {
+    extern __shared__ float sw[];            // [2][E]
     for (int c = threadIdx.x; c < 2 * E; c += blockDim.x) sw[c] = w[c];
-    __syncthreads();
-    const int i0 = blockIdx.x * HEAD_BLOCK;
-    const int i = i0 + threadIdx.x;
-    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = threadIdx.x >> 5, t = threadIdx.x & 31;
+    const int i = blockIdx.x * HEAD_TB + t;
     const float s = d_loss[0] / (float)B;
     float dl0 = 0.f, dl1 = 0.f;
     if (i < B) {
@@ -189,30 +213,20 @@ __global__ void __launch_bounds__(HEAD_BLOCK) k_head_loss_bwd(const float* __res
         const float p = p1[i], q = q1[i];
         dl1 = (p - (float)y) * s;
         dl0 = -dl1;                                   // (1-p) - (1-y) = -(p - y)
-        const float dc1 = lambda * (q - (float)y) * s;
-        d_center[2 * i] = -dc1;
-        d_center[2 * i + 1] = dc1;
-        for (int e = 0; e < E; ++e) d_emb[(int64_t)e * B + i] = fmaf(sw[e], dl0, sw[E + e] * dl1);
+        if (g == 0) {
+            const float dc1 = lambda * (q - (float)y) * s;
+            d_center[2 * i] = -dc1;
+            d_center[2 * i + 1] = dc1;
+        }
     }
-    dls[2 * threadIdx.x] = dl0;
-    dls[2 * threadIdx.x + 1] = dl1;
     __syncthreads();
-    // dW partial of this block: warp `wid` owns rows e = wid, wid + 8, ...; lanes run along the batch
-    for (int e = wid; e < E; e += HEAD_BLOCK / 32) {
-        float a = 0.f, b = 0.f;
-#pragma unroll
-        for (int j = 0; j < HEAD_BLOCK / 32; ++j) {
-            const int t = lane + 32 * j;
-            const float x = i0 + t < B ? emb[(int64_t)e * B + i0 + t] : 0.f;
-            a = fmaf(dls[2 * t], x, a);
-            b = fmaf(dls[2 * t + 1], x, b);
-        }
-        a = warp_sum(a);
-        b = warp_sum(b);
-        if (lane == 0) {
-            partial[(int64_t)blockIdx.x * 2 * E + e] = a;
-            partial[(int64_t)blockIdx.x * 2 * E + E + e] = b;
-        }
+    float* dst = partial + (int64_t)blockIdx.x * 2 * E;
+#pragma unroll 4
+    for (int e = g; e < E; e += HEAD_NT / 32) {
+        const float x = i < B ? __ldg(emb + (int64_t)e * B + i) : 0.f;
+        if (i < B) d_emb[(int64_t)e * B + i] = fmaf(sw[e], dl0, sw[E + e] * dl1);
+        const float a = warp_sum(dl0 * x), b = warp_sum(dl1 * x);
+        if (t == 0) { dst[e] = a; dst[E + e] = b; }
     }
     if (!last_block(ticket)) return;
     for (int x = threadIdx.x; x < 2 * E; x += blockDim.x) {
@@ -224,7 +238,7 @@ __global__ void __launch_bounds__(HEAD_BLOCK) k_head_loss_bwd(const float* __res
 
 // ------------------------------------------------------------------------------------------- C ABI
 extern "C" size_t pcg_head_scratch_floats(int B, int F, int E) {
-    const size_t blocks = (size_t)(B + HEAD_BLOCK - 1) / HEAD_BLOCK + 1;
+    const size_t blocks = (size_t)(B + HEAD_TB - 1) / HEAD_TB + 1;
     size_t a = ((size_t)(B + 31) / 32 + 1) * (size_t)(2 * F + 2);   // center bwd: one partial per 32 targets
     size_t b = blocks * 2 * (size_t)(E > 1 ? E : 1);
     return (a > b ? a : b) + 64;
@@ -248,9 +262,15 @@ extern "C" int pcg_center_bwd(const float* feat, int64_t ldf, int F, const int32
     PCG_REQUIRE(feat && targets && d_center && d_w && d_b && scratch && ticket, "pcg_center_bwd: null pointer");
     int blocks = (B + CENTER_PER - 1) / CENTER_PER;       // every block owns <= CENTER_PER targets
     if (blocks < 1) blocks = 1;
-    int threads = ((F + 1 + 31) / 32) * 32;
-    if (threads > 256) threads = 256;
-    k_center_bwd<<<blocks, threads, 0, stream>>>(feat, ldf, F, targets, B, d_center, scratch, ticket, d_w, d_b);
+    const size_t smem = (size_t)CENTER_PER * 2 * ldf * 4;
+    PCG_REQUIRE(smem <= 200 * 1024, "pcg_center_bwd: feature rows too wide (ldf=%lld)", (long long)ldf);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_center_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { pcg_set_error("pcg_center_bwd: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+        configured = smem;
+    }
+    k_center_bwd<<<blocks, CENTER_NT, smem, stream>>>(feat, ldf, F, targets, B, d_center, scratch, ticket, d_w, d_b);
     return pcg_check_launch("pcg_center_bwd");
 }
 
@@ -262,8 +282,8 @@ extern "C" int pcg_head_loss_fwd(const float* emb, int E, int B, const float* w,
     PCG_REQUIRE(emb && w && center && labels && logits && p1 && q1 && loss && scratch && ticket,
                 "pcg_head_loss_fwd: null pointer");
     PCG_REQUIRE((size_t)2 * E * 4 <= 40 * 1024, "pcg_head_loss_fwd: embed dim too large");
-    const int blocks = (B + HEAD_BLOCK - 1) / HEAD_BLOCK;
-    k_head_loss_fwd<<<blocks, HEAD_BLOCK, (size_t)2 * E * 4, stream>>>(emb, E, B, w, center, labels, lambda, logits, p1,
+    const int blocks = (B + HEAD_TB - 1) / HEAD_TB;
+    k_head_loss_fwd<<<blocks, HEAD_NT, (size_t)2 * E * 4, stream>>>(emb, E, B, w, center, labels, lambda, logits, p1,
                                                                       q1, scratch, ticket, loss);
     return pcg_check_launch("pcg_head_loss_fwd");
 }
@@ -275,10 +295,10 @@ extern "C" int pcg_head_loss_bwd(const float* emb, int E, int B, const float* w,
     PCG_REQUIRE(B > 0, "pcg_head_loss_bwd: empty batch");
     PCG_REQUIRE(emb && w && labels && p1 && q1 && d_loss && d_emb && d_center && d_w && scratch && ticket,
                 "pcg_head_loss_bwd: null pointer");
-    const size_t smem = ((size_t)2 * E + (size_t)HEAD_BLOCK * 2) * 4;
+    const size_t smem = (size_t)2 * E * 4;
     PCG_REQUIRE(smem <= 48 * 1024, "pcg_head_loss_bwd: embed dim too large");
-    const int blocks = (B + HEAD_BLOCK - 1) / HEAD_BLOCK;
-    k_head_loss_bwd<<<blocks, HEAD_BLOCK, smem, stream>>>(emb, E, B, w, labels, p1, q1, lambda, d_loss, d_emb, d_center,
+    const int blocks = (B + HEAD_TB - 1) / HEAD_TB;
+    k_head_loss_bwd<<<blocks, HEAD_NT, smem, stream>>>(emb, E, B, w, labels, p1, q1, lambda, d_loss, d_emb, d_center,
                                                           scratch, ticket, d_w);
     return pcg_check_launch("pcg_head_loss_bwd");
 }

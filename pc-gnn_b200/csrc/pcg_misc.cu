@@ -76,29 +76,48 @@ __device__ __forceinline__ uint32_t orderable(float f) {   // float order -> uns
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
+__device__ __forceinline__ uint32_t unorderable(uint32_t k) {   // inverse of orderable (bit pattern of the float)
+    return (k & 0x80000000u) ? (k ^ 0x80000000u) : ~k;
+}
 // P <= 8192: rank sort. Every CTA stages all P keys (orderable(score) << 32 | position, unique) in
-// shared memory and ranks 32 of them by counting smaller keys, 8 lanes per element; the rank is the
+// shared memory and ranks 32 of them by counting smaller keys, 16 lanes per element; the rank is the
 // element's place in the sorted order. O(P^2) compares spread over P/32 CTAs: a few microseconds and
 // no serial merge chain (a single-CTA bitonic sort of the same pool took ~48 us on B200).
 // `gather` != 0: pool_score is the whole score table and entry i's score is pool_score[pool[i]].
-__global__ void __launch_bounds__(256) k_sort_pool_rank(const float* __restrict__ pool_score, int gather,
-                                                        const int32_t* __restrict__ pool, int P,
-                                                        float* __restrict__ ps_score, int32_t* __restrict__ ps_pos,
-                                                        int32_t* __restrict__ ps_id) {
+#define RANK_NT 512
+#define RANK_PER 32      // elements ranked per CTA: 16 threads each
+__global__ void __launch_bounds__(RANK_NT) k_sort_pool_rank(const float* __restrict__ pool_score, int gather,
+                                                            const int32_t* __restrict__ pool, int P,
+                                                            float* __restrict__ ps_score, int32_t* __restrict__ ps_pos,
+                                                            int32_t* __restrict__ ps_id) {
     extern __shared__ unsigned long long keys[];
-    for (int i = threadIdx.x; i < P; i += blockDim.x)
-        keys[i] = ((unsigned long long)orderable(pool_score[gather ? pool[i] : i]) << 32) | (unsigned)i;
+    // stage all keys: ids first, then the dependent score gathers, 8 of each in flight per thread
+    for (int base = 0; base < P; base += RANK_NT * 8) {
+        int32_t id[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = base + u * RANK_NT + threadIdx.x;
+            id[u] = (i < P && gather) ? __ldg(pool + i) : i;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = base + u * RANK_NT + threadIdx.x;
+            if (i < P) keys[i] = ((unsigned long long)orderable(__ldg(pool_score + id[u])) << 32) | (unsigned)i;
+        }
+    }
     __syncthreads();
-    const int e = threadIdx.x >> 3, part = threadIdx.x & 7;
-    const int i = blockIdx.x * 32 + e;
+    const int e = threadIdx.x >> 4, part = threadIdx.x & 15;
+    const int i = blockIdx.x * RANK_PER + e;
     const unsigned long long mine = i < P ? keys[i] : ~0ull;
     int cnt = 0;
-    for (int j = part; j < P; j += 8) cnt += keys[j] < mine;
+#pragma unroll 4
+    for (int j = part; j < P; j += 16) cnt += keys[j] < mine;
     cnt += __shfl_xor_sync(PCG_FULL, cnt, 1);
     cnt += __shfl_xor_sync(PCG_FULL, cnt, 2);
     cnt += __shfl_xor_sync(PCG_FULL, cnt, 4);
+    cnt += __shfl_xor_sync(PCG_FULL, cnt, 8);
     if (part == 0 && i < P) {
-        ps_score[cnt] = pool_score[gather ? pool[i] : i];
+        ps_score[cnt] = __uint_as_float(unorderable((uint32_t)(mine >> 32)));
         ps_pos[cnt] = i;
         ps_id[cnt] = pool[i];
     }
@@ -147,7 +166,7 @@ static int sort_pool_impl(const float* pool_score, int gather, const int32_t* po
             if (e != cudaSuccess) { pcg_set_error("pcg_sort_pool: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
             configured = true;
         }
-        k_sort_pool_rank<<<(P + 31) / 32, 256, smem, stream>>>(pool_score, gather, pool, P, ps_score, ps_pos, ps_id);
+        k_sort_pool_rank<<<(P + RANK_PER - 1) / RANK_PER, RANK_NT, smem, stream>>>(pool_score, gather, pool, P, ps_score, ps_pos, ps_id);
         return 0;
     }
     const size_t a = align256((size_t)P * 4);
