@@ -16,6 +16,106 @@
 #define DENSE_MAX_E 256
 
 // ------------------------------------------------------------------------------------------------
+// C[M,N] = A[M,K] * B[K,N] for the skinny shapes of this path (N = E or R*E, K <= a few hundred, M = the
+// batch): TM x 64 output tiles (TM = 16 / 32 / 64 by batch size, so that a 1024-target batch still spreads
+// over 64+ CTAs), K in chunks of 32 through a 3-stage cp.async pipeline. The operands are functors:
+// addr(z, row, k) / addr(z, k, col) give the element's address (4-byte cp.async, zero fill out of range), so
+// the concatenations, gathers and transposes of the reference's cat / index / .t() calls cost nothing; an
+// A operand that must be COMPUTED (A_REG) is loaded through registers instead. A_MC / B_NC say which index
+// is contiguous in memory so that the tile loads coalesce.
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc, bool ok) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int n = ok ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int TM, bool A_REG, bool A_MC, bool B_NC, class AL, class BL, class EP>
+__global__ void __launch_bounds__(256) k_gemm_p(int M, int N, int K, AL al, BL bl, EP ep) {
+    constexpr int KC = 32, ST = 3, RPT = TM / 16;
+    __shared__ __align__(16) float As[ST][KC][TM + 4];   // [k][m]
+    __shared__ __align__(16) float Bs[ST][KC][64 + 4];   // [k][n]
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int m0 = blockIdx.x * TM, n0 = blockIdx.y * 64, z = blockIdx.z;
+    al.bind(z); bl.bind(z); ep.bind(z);  // resolve per-z pointers / offsets once (z is block-uniform)
+    if (ep.skip(z, m0)) return;
+    int kb, ke;
+    ep.k_range(z, K, kb, ke);
+    const int nt = (ke - kb + KC - 1) / KC;
+    auto issue = [&](int t) {
+        const int buf = t % ST, k0 = kb + t * KC;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {                    // B tile: 32 x 64
+            const int nn = B_NC ? (tid & 63) : (tid >> 5) + 8 * j;
+            const int kk = B_NC ? (tid >> 6) + 4 * j : (tid & 31);
+            const bool ok = n0 + nn < N && k0 + kk < ke;
+            cp_async4(&Bs[buf][kk][nn], ok ? bl.addr(z, k0 + kk, n0 + nn) : bl.any(), ok);
+        }
+#pragma unroll
+        for (int j = 0; j < TM * KC / 256; ++j) {        // A tile: TM x 32
+            const int mm = A_MC ? (tid % TM) : (tid >> 5) + 8 * j;
+            const int kk = A_MC ? (tid / TM) + (256 / TM) * j : (tid & 31);
+            const bool ok = m0 + mm < M && k0 + kk < ke;
+            if constexpr (A_REG) As[buf][kk][mm] = ok ? al(z, m0 + mm, k0 + kk) : 0.f;
+            else cp_async4(&As[buf][kk][mm], ok ? al.addr(z, m0 + mm, k0 + kk) : al.any(), ok);
+        }
+    };
+    float acc[RPT][4];
+#pragma unroll
+    for (int a = 0; a < RPT; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+#pragma unroll
+    for (int s = 0; s < ST - 1; ++s) {
+        if (s < nt) issue(s);
+        cp_async_commit();
+    }
+    for (int t = 0; t < nt; ++t) {
+        cp_async_wait<ST - 2>();          // this thread's copies of stage t have landed
+        __syncthreads();                  // ... everybody's; and stage t-1 is no longer being read
+        if (t + ST - 1 < nt) issue(t + ST - 1);
+        cp_async_commit();                // (possibly empty: keeps the group count uniform)
+        const int cur = t % ST;
+#pragma unroll
+        for (int kk = 0; kk < KC; ++kk) {
+            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[cur][kk][tx * 4]);
+            float av[RPT];
+#pragma unroll
+            for (int a = 0; a < RPT; ++a) av[a] = As[cur][kk][ty * RPT + a];
+#pragma unroll
+            for (int a = 0; a < RPT; ++a) {
+                acc[a][0] = fmaf(av[a], b4.x, acc[a][0]);
+                acc[a][1] = fmaf(av[a], b4.y, acc[a][1]);
+                acc[a][2] = fmaf(av[a], b4.z, acc[a][2]);
+                acc[a][3] = fmaf(av[a], b4.w, acc[a][3]);
+            }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < RPT; ++a) {
+        const int m = m0 + ty * RPT + a;
+        if (m >= M) continue;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int n = n0 + tx * 4 + b;
+            if (n < N) ep(z, m, n, acc[a][b]);
+        }
+    }
+}
+
+// rows of the batch per CTA: small batches need small tiles to fill the GPU
+static int pick_tm(int M) { return M <= 2048 ? 16 : 64; }
+#define PCG_GEMM(A_REG, A_MC, B_NC, tm, grid_m_rows, gy, gz, M, N, K, a, b, ep)                                   \
+    do {                                                                                                          \
+        const int tm_ = (tm);                                                                                     \
+        dim3 g_((unsigned)(((grid_m_rows) + tm_ - 1) / tm_), (unsigned)(gy), (unsigned)(gz));                      \
+        if (tm_ == 16) k_gemm_p<16, A_REG, A_MC, B_NC><<<g_, 256, 0, stream>>>(M, N, K, a, b, ep);                \
+        else k_gemm64<A_MC, B_NC><<<g_, 256, 0, stream>>>(M, N, K, a, b, ep);                                     \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
 // C[M,N] = A[M,K] * B[K,N], 64x64x16 tiles, 256 threads, 4x4 outputs per thread, register-prefetched
 // double buffering. A and B are functors (z, row, k) -> float / (z, k, col) -> float, only called in
 // range; A_MC / B_NC say which index is contiguous in memory so the tile loads coalesce.
@@ -114,15 +214,18 @@ __global__ void __launch_bounds__(256) k_gemm64(int M, int N, int K, AL al, BL b
 struct FwdRelA {    // A(r, i, k) = [feat[targets[i]] | agg[r*B + i]][k]
     const float* feat; const float* agg; const int32_t* targets; int64_t ldf; int B, F;
     __device__ void bind(int) {}
-    __device__ float operator()(int r, int i, int k) const {
-        return k < F ? __ldg(feat + (int64_t)__ldg(targets + i) * ldf + k)
-                     : __ldg(agg + ((int64_t)r * B + i) * ldf + (k - F));
+    __device__ const float* any() const { return feat; }
+    __device__ const float* addr(int r, int i, int k) const {
+        return k < F ? feat + (int64_t)__ldg(targets + i) * ldf + k : agg + ((int64_t)r * B + i) * ldf + (k - F);
     }
+    __device__ float operator()(int r, int i, int k) const { return __ldg(addr(r, i, k)); }
 };
 struct FwdRelB {    // B(r, k, n) = W_r[k][n]
     const float* w[PCG_MAX_REL]; int E; const float* cur;
     __device__ void bind(int r) { cur = w[r]; }
-    __device__ float operator()(int, int k, int n) const { return __ldg(cur + (int64_t)k * E + n); }
+    __device__ const float* any() const { return cur; }
+    __device__ const float* addr(int, int k, int n) const { return cur + (int64_t)k * E + n; }
+    __device__ float operator()(int r, int k, int n) const { return __ldg(addr(r, k, n)); }
 };
 struct FwdRelEp {   // cat[i][F + r*E + n] = relu(v)
     float* cat; int K2, F, E;
@@ -143,12 +246,16 @@ __global__ void k_copy_self(const float* __restrict__ feat, int64_t ldf, const i
 struct CombA {      // A(_, i, k) = cat[i][k]
     const float* cat; int K2;
     __device__ void bind(int) {}
-    __device__ float operator()(int, int i, int k) const { return cat[(int64_t)i * K2 + k]; }
+    __device__ const float* any() const { return cat; }
+    __device__ const float* addr(int, int i, int k) const { return cat + (int64_t)i * K2 + k; }
+    __device__ float operator()(int z, int i, int k) const { return *addr(z, i, k); }
 };
 struct CombB {
     const float* w; int E;
     __device__ void bind(int) {}
-    __device__ float operator()(int, int k, int n) const { return __ldg(w + (int64_t)k * E + n); }
+    __device__ const float* any() const { return w; }
+    __device__ const float* addr(int, int k, int n) const { return w + (int64_t)k * E + n; }
+    __device__ float operator()(int z, int k, int n) const { return __ldg(addr(z, k, n)); }
 };
 struct CombEp {     // out[n][i] = relu(v)   ([E,B], the reference's transposed layout, layers.py:289)
     float* out; int B;
@@ -171,7 +278,9 @@ struct BwdHA {      // A(_, i, e) = dZ[i][e] = d_out[e][i] * (out[e][i] > 0); al
 struct BwdHB {      // B(_, e, c) = W[F + c][e]
     const float* w; int F, E;
     __device__ void bind(int) {}
-    __device__ float operator()(int, int e, int c) const { return __ldg(w + (int64_t)(F + c) * E + e); }
+    __device__ const float* any() const { return w; }
+    __device__ const float* addr(int, int e, int c) const { return w + (int64_t)(F + c) * E + e; }
+    __device__ float operator()(int z, int e, int c) const { return __ldg(addr(z, e, c)); }
 };
 struct BwdHEp {     // dH[i][c] = v * (cat[i][F + c] > 0)
     const float* cat; float* dh; int K2, F, RE;
@@ -186,18 +295,25 @@ struct BwdHEp {     // dH[i][c] = v * (cat[i][F + c] > 0)
 struct WgA {        // A(z, m, i) = X_job[i][m]
     const float* cat; const float* agg; int64_t ldf; int B, F, K2, S; int job;
     __device__ void bind(int z) { job = z / S; }
-    __device__ float operator()(int, int m, int i) const {
-        if (job == 0) return m < K2 ? cat[(int64_t)i * K2 + m] : 0.f;
-        if (m >= 2 * F) return 0.f;
-        return m < F ? cat[(int64_t)i * K2 + m] : __ldg(agg + ((int64_t)(job - 1) * B + i) * ldf + (m - F));
+    __device__ const float* any() const { return cat; }
+    __device__ const float* addr(int, int m, int i) const {      // rows beyond the job's matrix are dropped by WgEp
+        if (job == 0) return m < K2 ? cat + (int64_t)i * K2 + m : cat;
+        if (m >= 2 * F) return cat;
+        return m < F ? cat + (int64_t)i * K2 + m : agg + ((int64_t)(job - 1) * B + i) * ldf + (m - F);
+    }
+    __device__ float operator()(int z, int m, int i) const {
+        if ((job == 0 && m >= K2) || (job > 0 && m >= 2 * F)) return 0.f;
+        return *addr(z, m, i);
     }
 };
 struct WgB {        // B(z, i, n) = dZ[i][n] (job 0) or dH[i][r*E + n]
     const float* dz; const float* dh; int E, RE, S; int job;
     __device__ void bind(int z) { job = z / S; }
-    __device__ float operator()(int, int i, int n) const {
-        return job == 0 ? dz[(int64_t)i * E + n] : dh[(int64_t)i * RE + (job - 1) * E + n];
+    __device__ const float* any() const { return dz; }
+    __device__ const float* addr(int, int i, int n) const {
+        return job == 0 ? dz + (int64_t)i * E + n : dh + (int64_t)i * RE + (job - 1) * E + n;
     }
+    __device__ float operator()(int z, int i, int n) const { return *addr(z, i, n); }
 };
 struct WgEp {       // part[job][split][m][n] = v over the split's slice of the batch
     float* part; int64_t off[PCG_MAX_REL + 1]; int rows[PCG_MAX_REL + 1]; int E, S, B;
@@ -272,13 +388,12 @@ extern "C" int pcg_dense_fwd(const float* feat, int64_t ldf, int F, const int32_
     b.E = E; b.cur = nullptr;
     FwdRelEp ep{cat, K2, F, E};
     k_copy_self<<<(unsigned)(((int64_t)B * F + 255) / 256), 256, 0, stream>>>(feat, ldf, targets, B, F, K2, cat);
-    dim3 g1((B + 63) / 64, (E + 63) / 64, R);
-    k_gemm64<false, true><<<g1, 256, 0, stream>>>(B, E, 2 * F, a, b, ep);
+    const int tm = pick_tm(B);
+    PCG_GEMM(false, false, true, tm, B, (E + 63) / 64, R, B, E, 2 * F, a, b, ep);
     CombA ca{cat, K2};
     CombB cb{w_inter, E};
     CombEp ce{out, B};
-    dim3 g2((B + 63) / 64, (E + 63) / 64, 1);
-    k_gemm64<false, true><<<g2, 256, 0, stream>>>(B, E, K2, ca, cb, ce);
+    PCG_GEMM(false, false, true, tm, B, (E + 63) / 64, 1, B, E, K2, ca, cb, ce);
     return pcg_check_launch("pcg_dense_fwd");
 }
 
@@ -298,8 +413,7 @@ extern "C" int pcg_dense_bwd(int64_t ldf, int F, int B, int R, int E, const floa
         BwdHA a{d_out, out, dz, B, E};
         BwdHB b{w_inter, F, E};
         BwdHEp ep{cat, dh, K2, F, RE};
-        dim3 g((B + 63) / 64, (RE + 63) / 64, 1);
-        k_gemm64<true, false><<<g, 256, 0, stream>>>(B, RE, E, a, b, ep);
+        PCG_GEMM(true, true, false, pick_tm(B), B, (RE + 63) / 64, 1, B, RE, E, a, b, ep);
     }
     WgA wa{cat, agg, ldf, B, F, K2, S, 0};
     WgB wb{dz, dh, E, RE, S, 0};
@@ -316,8 +430,7 @@ extern "C" int pcg_dense_bwd(int64_t ldf, int F, int B, int R, int E, const floa
         off += (int64_t)S * M * E;
     }
     const int Mw = K2 > 2 * F ? K2 : 2 * F;          // R == 1 with F > E: the relation weight has more rows
-    dim3 gw((Mw + 63) / 64, (E + 63) / 64, (R + 1) * S);
-    k_gemm64<true, true><<<gw, 256, 0, stream>>>(Mw, E, B, wa, wb, we);
+    PCG_GEMM(false, true, true, 64, Mw, (E + 63) / 64, (R + 1) * S, Mw, E, B, wa, wb, we);
     dim3 rg((unsigned)(((int64_t)Mw * E + 255) / 256), R + 1);
     k_dense_reduce<<<rg, 256, 0, stream>>>(rp);
     return pcg_check_launch("pcg_dense_bwd");
