@@ -91,7 +91,9 @@ __device__ __forceinline__ long long trace_now() {
 }
 #define TRACE(slot) do { if (g_trace && tid == 0 && (blockIdx.x % 8 == 0 || blockDim.x != 256 || gridDim.x % 8 != 0 || true)) g_trace[(int64_t)w * 12 + (slot)] = trace_now(); } while (0)
 #define TRACE_VAL(slot, val) do { if (g_trace && tid == 0) g_trace[(int64_t)w * 12 + (slot)] = (val); } while (0)
+#define PTRACE(slot) do { if (g_trace && threadIdx.x == 0) g_trace[(int64_t)p.R * p.B * 12 + (slot)] = trace_now(); } while (0)
 #else
+#define PTRACE(slot) do {} while (0)
 #define TRACE(slot) do {} while (0)
 #define TRACE_VAL(slot, val) do {} while (0)
 #endif
@@ -1134,123 +1136,168 @@ __global__ void __launch_bounds__(PCG_LARGE_NT, 1) k_choose_big(ChooseP p, int s
 }
 
 // ------------------------------------------------------------------------------------ prep
-// One CTA. (1) Batches drawn by pick_step are sampled with replacement in proportion to degree, so hub
+// (1) Batches drawn by pick_step are sampled with replacement in proportion to degree, so hub
 // nodes appear several times: an item whose target id already occurred earlier in the batch is not
 // processed, it shares the result of that earlier ("representative") item (same node, same relation,
 // same label). first[v] = smallest batch index whose target is node v; the table lives in the workspace,
 // is all 0x7f7f7f7f between calls and is restored before this kernel ends. (2) Sizes k, o of every
 // representative item in the reference's arithmetic; its output slots by an exclusive prefix sum in
-// (target, relation) order (so the slot layout is deterministic); items that do not fit `cap_slots` are
+// item order (so the slot layout is deterministic); items that do not fit `cap_slots` are
 // dropped and flagged. (3) Tier queues by row length.
-// A thread owns one target and its R items; the row offsets of all relations are requested before the
-// barrier that completes the first-occurrence table, so a round costs three dependent memory round trips.
-__global__ void __launch_bounds__(PCG_PREP_NT, 1) k_choose_prep(ChooseP p) {
+// The items are split into contiguous chunks over up to #SMs co-resident CTAs which meet at two grid barriers
+// (table complete / chunk totals published). Phase A computes the sizes of a CTA's items with four items per
+// thread in flight and parks them in shared memory; phase B is a prefix sum over contiguous runs (slot order
+// = item order w = r*B + i).
+#define PCG_PREP_CHUNK 512       // items per CTA when the batch is small (more CTAs = shorter critical path)
+#define PCG_PREP_ITEMS 8192      // most items one CTA stages (32 KB of shared memory)
+
+// Barrier over the co-resident CTAs of the prep grid (grid <= #SMs, one CTA fits every SM): bar[0] counts
+// arrivals of the current launch, the last CTA to leave the kernel resets the words (prep_exit).
+__device__ __forceinline__ void prep_grid_barrier(int32_t* bar, int target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(&bar[0], 1);
+        while (*(volatile int32_t*)&bar[0] < target) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(PCG_PREP_NT, 1) k_choose_prep(ChooseP p, int chunk, int32_t* bar, int32_t* totals) {
+    __shared__ int s_info[PCG_PREP_ITEMS];   // per item of the CTA: nslots << 3 | (tier + 1), 0 for repeated targets
     __shared__ int s_wsum[32];
-    __shared__ int s_n[4];
+    __shared__ int s_base;
     constexpr int NT = PCG_PREP_NT;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int B = p.B, R = p.R;
+    const int B = p.B, W = p.R * p.B, G = gridDim.x;
     int32_t* first = p.first;
-    if (tid < 4) s_n[tid] = 0;
-    int run = 0;                       // slots handed out so far (same value in every thread)
+    PTRACE(0);
+    if (first)
+        for (int i = blockIdx.x * NT + tid; i < B; i += G * NT) atomicMin(&first[__ldg(p.targets + i)], i);
+    if (blockIdx.x == 0 && tid < PCG_STATUS_WORDS) p.status[tid] = 0;
+    prep_grid_barrier(bar, G);               // the first-occurrence table is complete, the status words are zero
+    PTRACE(1);
+    const int w0 = min(W, blockIdx.x * chunk), n_items = min(W, w0 + chunk) - w0;
+    // ---- phase A: sizes of every item, four items per thread in flight (loads first, then the arithmetic)
+    for (int q0 = tid; q0 < n_items; q0 += 4 * NT) {
+        int rr[4], ii[4], rep[4];
+        int64_t beg[4], end[4];
+        bool pos[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int q = q0 + u * NT;
+            const int w = w0 + q;
+            rr[u] = w / B;
+            ii[u] = w - rr[u] * B;
+            rep[u] = -1;
+            beg[u] = end[u] = 0;
+            pos[u] = false;
+            if (q < n_items) {
+                const int32_t v = __ldg(p.targets + ii[u]);
+                rep[u] = first ? __ldcg(first + v) : ii[u];
+                const int64_t row = (int64_t)rr[u] * p.n_nodes + v;
+                beg[u] = __ldg(p.indptr + row);
+                end[u] = __ldg(p.indptr + row + 1);
+                pos[u] = p.train && p.labels && __ldg(p.labels + ii[u]) == 1;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int q = q0 + u * NT;
+            if (q < n_items) {
+                const int w = w0 + q;
+                int info = 0;
+                p.it_rep[w] = rr[u] * B + rep[u];
+                if (rep[u] == ii[u]) {
+                    const int64_t d = end[u] - beg[u];
+                    int k, o;
+                    item_counts(d, p.thresh[rr[u]], p.rho, pos[u], p.P, p.k_override ? p.k_override[w] : 0,
+                                p.k_override != nullptr, k, o);
+                    const int tier = d <= PCG_SMALL_MAX ? 0 : (d <= PCG_CTA_MAX ? 1 : (d <= PCG_CL_MAX ? 2 : 3));
+                    info = (((k + o + PCG_SLOT - 1) / PCG_SLOT) << 3) | (tier + 1);
+                }
+                s_info[q] = info;
+            }
+        }
+    }
+    __syncthreads();
+    PTRACE(2);
+    // ---- phase B: exclusive prefix sum of the slot counts in item order; every thread owns a contiguous run
+    const int per = (n_items + NT - 1) / NT;
+    const int c0 = min(n_items, tid * per), c1 = min(n_items, c0 + per);
+    int mine = 0;
+    for (int q = c0; q < c1; ++q) mine += s_info[q] >> 3;
+    int incl = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(PCG_FULL, incl, off);
+        if (lane >= off) incl += t;
+    }
+    if (lane == 31) s_wsum[wid] = incl;
+    __syncthreads();
+    const int ws = s_wsum[lane];
+    int wincl = ws;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(PCG_FULL, wincl, off);
+        if (lane >= off) wincl += t;
+    }
+    const int cta_total = __shfl_sync(PCG_FULL, wincl, 31);
+    if (tid == 0) totals[blockIdx.x] = cta_total;
+    prep_grid_barrier(bar, 2 * G);           // every CTA's total is published (and every read of `first` is done)
+    if (wid == 0) {                          // slots of the CTAs before this one, added in CTA order
+        int acc = 0;
+        for (int c = lane; c < (int)blockIdx.x; c += 32) acc += __ldcg(totals + c);
+        acc = __reduce_add_sync(PCG_FULL, acc);
+        if (lane == 0) s_base = acc;
+    }
+    __syncthreads();
+    int slot0 = s_base + __shfl_sync(PCG_FULL, wincl - ws, wid) + incl - mine;
     bool overflow = false;
     int32_t* const queues[4] = {p.q_warp, p.q_cta, p.q_cl, p.q_big};
-    for (int base = 0; base < B; base += NT) {
-        const int i = base + tid;
-        const bool valid = i < B;
-        const int32_t v = valid ? p.targets[i] : 0;
-        if (valid && first) atomicMin(&first[v], i);
-        int64_t beg[PCG_MAX_REL], end[PCG_MAX_REL];
-#pragma unroll
-        for (int r = 0; r < PCG_MAX_REL; ++r) {
-            if (valid && r < R) {
-                const int64_t row = (int64_t)r * p.n_nodes + v;
-                beg[r] = __ldg(p.indptr + row);
-                end[r] = __ldg(p.indptr + row + 1);
-            } else {
-                beg[r] = end[r] = 0;
+    const int counters[4] = {ST_NSMALL, ST_NMID, ST_NCL, ST_NBIG};
+    for (int c = 0; c < per; ++c) {                          // uniform trip count (ballots inside)
+        const int q = c0 + c;
+        int tier = -1;
+        if (q < c1) {
+            const int info = s_info[q];
+            if (info) {
+                const int w = w0 + q, nsl = info >> 3;
+                tier = (info & 7) - 1;
+                if ((int64_t)slot0 + nsl > p.cap_slots) {    // does not fit: flag, emit nothing for this item
+                    overflow = true;
+                    tier = -1;
+                    p.it_slot0[w] = 0; p.it_m[w] = 0; p.it_base[w] = 0; p.it_done[w] = 0;
+                    for (int x = 0; x < nsl; ++x)
+                        if ((int64_t)slot0 + x < p.cap_slots) p.slot_item[slot0 + x] = -1;
+                } else {
+                    p.it_slot0[w] = slot0;
+                }
+                slot0 += nsl;
             }
         }
-        const bool positive = valid && p.train && p.labels && p.labels[i] == 1;
-        __syncthreads();               // every earlier occurrence of v (smaller i) has been recorded
-        const int rep = !valid ? -1 : (first ? __ldcg(first + v) : i);
-        int nsl[PCG_MAX_REL], tier[PCG_MAX_REL], mine = 0;
 #pragma unroll
-        for (int r = 0; r < PCG_MAX_REL; ++r) {
-            nsl[r] = 0;
-            tier[r] = -1;
-            if (valid && r < R) {
-                const int w = r * B + i;
-                p.it_rep[w] = r * B + rep;
-                if (rep == i) {
-                    const int64_t d = end[r] - beg[r];
-                    int k, o;
-                    item_counts(d, p.thresh[r], p.rho, positive, p.P, p.k_override ? p.k_override[w] : 0,
-                                p.k_override != nullptr, k, o);
-                    nsl[r] = (k + o + PCG_SLOT - 1) / PCG_SLOT;
-                    tier[r] = d <= PCG_SMALL_MAX ? 0 : (d <= PCG_CTA_MAX ? 1 : (d <= PCG_CL_MAX ? 2 : 3));
-                    mine += nsl[r];
-                }
+        for (int t = 0; t < 4; ++t) {
+            const unsigned m = __ballot_sync(PCG_FULL, tier == t);
+            if (m) {
+                int b = 0;
+                if (lane == 0) b = atomicAdd(&p.status[counters[t]], __popc(m));
+                b = __shfl_sync(PCG_FULL, b, 0);
+                if (tier == t) queues[t][b + __popc(m & lanemask_lt())] = w0 + q;
             }
         }
-        int incl = mine;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const int t = __shfl_up_sync(PCG_FULL, incl, off);
-            if (lane >= off) incl += t;
-        }
-        if (lane == 31) s_wsum[wid] = incl;
-        __syncthreads();
-        const int ws = s_wsum[lane];
-        int wincl = ws;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const int t = __shfl_up_sync(PCG_FULL, wincl, off);
-            if (lane >= off) wincl += t;
-        }
-        int slot0 = run + __shfl_sync(PCG_FULL, wincl - ws, wid) + incl - mine;
-        run += __shfl_sync(PCG_FULL, wincl, 31);
-#pragma unroll
-        for (int r = 0; r < PCG_MAX_REL; ++r) {
-            if (r < R) {                                         // uniform
-                const int w = r * B + i;
-                if (tier[r] >= 0) {
-                    if ((int64_t)slot0 + nsl[r] > p.cap_slots) {  // does not fit: flag, emit nothing for this item
-                        overflow = true;
-                        tier[r] = -1;
-                        p.it_slot0[w] = 0; p.it_m[w] = 0; p.it_base[w] = 0; p.it_done[w] = 0;
-                        for (int c = 0; c < nsl[r]; ++c)
-                            if ((int64_t)slot0 + c < p.cap_slots) p.slot_item[slot0 + c] = -1;
-                    } else {
-                        p.it_slot0[w] = slot0;
-                    }
-                    slot0 += nsl[r];
-                }
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const unsigned m = __ballot_sync(PCG_FULL, tier[r] == t);
-                    if (m) {
-                        int b = 0;
-                        if (lane == 0) b = atomicAdd(&s_n[t], __popc(m));
-                        b = __shfl_sync(PCG_FULL, b, 0);
-                        if (tier[r] == t) queues[t][b + __popc(m & lanemask_lt())] = w;
-                    }
-                }
-            }
-        }
-        __syncthreads();               // s_wsum is rewritten by the next round
     }
-    const int any_overflow = __syncthreads_or(overflow);
-    if (first)                          // restore the table (all reads are behind the barrier above)
-        for (int i = tid; i < B; i += NT) first[p.targets[i]] = 0x7f7f7f7f;
+    PTRACE(3);
+    if (__syncthreads_or(overflow) && tid == 0) atomicExch(&p.status[ST_OVERFLOW], 1);
+    if (first)                               // restore the table (all its reads are behind the second barrier)
+        for (int i = blockIdx.x * NT + tid; i < B; i += G * NT) first[__ldg(p.targets + i)] = 0x7f7f7f7f;
     if (tid == 0) {
-        p.status[ST_SLOTS] = run;
-        p.status[ST_NSMALL] = s_n[0];
-        p.status[ST_NMID] = s_n[1];
-        p.status[ST_OVERFLOW] = any_overflow ? 1 : 0;
-        p.status[ST_NCL] = s_n[2];
-        p.status[ST_NBIG] = s_n[3];
+        if (blockIdx.x == G - 1) p.status[ST_SLOTS] = s_base + cta_total;
+        __threadfence();
+        if (atomicAdd(&bar[1], 1) == G - 1) { bar[0] = 0; bar[1] = 0; }   // last CTA out re-arms the barrier
     }
+    PTRACE(4);
 }
 
 // Select-all (GraphSAGE / GCN): the item list is the CSR row itself. One warp per item.
@@ -1309,7 +1356,7 @@ __global__ void k_entry_pool_pos(const int32_t* __restrict__ indices, int64_t nn
 }
 // ------------------------------------------------------------------------------------------- C ABI
 struct WsLayout {
-    size_t first, bits_slab, q_warp, q_cta, q_cl, q_big, total;
+    size_t first, bar, totals, bits_slab, q_warp, q_cta, q_cl, q_big, total;
     int64_t slab_words;
     int grid_big;
 };
@@ -1323,6 +1370,8 @@ static WsLayout ws_layout(int B, int R, int64_t max_degree, int64_t n_nodes, int
     L.slab_words = max_degree > PCG_CL_MAX ? (max_degree + 31) / 32 : 0;
     size_t o = 0;
     L.first = o; o = al(o + (size_t)n_nodes * 4);
+    L.bar = o; o = al(o + 8);                    // prep grid barrier words (zero between calls)
+    L.totals = o; o = al(o + 1024 * 4);          // per-CTA slot totals of the prep kernel
     L.bits_slab = o; o = al(o + (size_t)L.grid_big * L.slab_words * 4);
     L.q_warp = o; o = al(o + W * 4);
     L.q_cta = o; o = al(o + W * 4);
@@ -1356,8 +1405,10 @@ extern "C" size_t pcg_choose_workspace_bytes(int B, int R, int64_t max_degree, i
 
 extern "C" int pcg_choose_workspace_init(void* workspace, size_t workspace_bytes, int64_t n_nodes, pcg_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    PCG_REQUIRE(workspace && workspace_bytes >= (size_t)n_nodes * 4, "pcg_choose_workspace_init: workspace too small");
+    WsLayout L = ws_layout(1, 1, 0, n_nodes, 148);
+    PCG_REQUIRE(workspace && workspace_bytes >= L.bar + 8, "pcg_choose_workspace_init: workspace too small");
     cudaError_t e = cudaMemsetAsync(workspace, 0x7f, (size_t)n_nodes * 4, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync((char*)workspace + L.bar, 0, 8, stream);
     if (e != cudaSuccess) { pcg_set_error("pcg_choose_workspace_init: memset: %s", cudaGetErrorString(e)); return (int)e; }
     return 0;
 }
@@ -1430,7 +1481,14 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
     p.bits_slab = (uint32_t*)(ws + L.bits_slab);
     p.slab_words = L.slab_words;
     const int W = R * B;
-    k_choose_prep<<<1, PCG_PREP_NT, 0, stream>>>(p);
+    {
+        // contiguous chunks of items over at most #SMs CTAs (they meet at grid barriers: all must be resident)
+        int chunk = PCG_PREP_CHUNK;
+        if ((W + chunk - 1) / chunk > sms) chunk = (W + sms - 1) / sms;
+        PCG_REQUIRE(chunk <= PCG_PREP_ITEMS, "pcg_choose: batch too large (%d items; at most %d)", W, PCG_PREP_ITEMS * sms);
+        k_choose_prep<<<(W + chunk - 1) / chunk, PCG_PREP_NT, 0, stream>>>(p, chunk, (int32_t*)(ws + L.bar),
+                                                                         (int32_t*)(ws + L.totals));
+    }
     const bool have_cta = max_degree > PCG_SMALL_MAX, have_cl = max_degree > PCG_CTA_MAX, have_big = max_degree > PCG_CL_MAX;
     if (have_cta && !g_fork) {
         for (int q = 0; q < PCG_N_SIDE; ++q)

@@ -23,7 +23,7 @@ eng.set_features(torch.from_numpy(data.feat).cuda())
 eng.set_pool(sorted(data.train_pos))
 L = _lib.lib()
 R = data.graph.n_rel
-trace = torch.zeros(batch * R * 12, dtype=torch.int64, device="cuda")
+trace = torch.zeros(batch * R * 12 + 16, dtype=torch.int64, device="cuda")
 L.pcg_debug_set_trace.argtypes = [ctypes.c_void_p]
 assert L.pcg_debug_set_trace(trace.data_ptr()) == 0
 rng = np.random.default_rng(0)
@@ -42,7 +42,11 @@ for it, (nodes, labels) in enumerate(batches):
     sel = eng.choose(t, lab, True, [0.5] * R, 0.5, cap)
     e1.record()
     torch.cuda.synchronize()
-    tr = trace.cpu().numpy().reshape(-1, 12)
+    raw = trace.cpu().numpy()
+    pt = raw[batch * R * 12:batch * R * 12 + 5].astype(np.float64)
+    print("  prep kernel phases (ns): first-table=%d sizes=%d scan+queues=%d tail=%d; first item starts %+d ns after prep ends"
+          % (pt[1] - pt[0], pt[2] - pt[1], pt[3] - pt[2], pt[4] - pt[3], raw[:batch * R * 12].reshape(-1, 12)[:, 0][raw[:batch * R * 12].reshape(-1, 12)[:, 7] > 0].min() - pt[4]))
+    tr = raw[:batch * R * 12].reshape(-1, 12)
     done = tr[:, 7] > 0
     tr = tr[done]
     ts = tr[:, :8].astype(np.float64)
