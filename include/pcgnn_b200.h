@@ -86,6 +86,10 @@ PCG_API int pcg_choose_workspace_init(void* workspace, size_t workspace_bytes, i
  * Replaces src/layers.py:216-227 (neighbour lookup), :246-262 (per-relation prep),
  * :633-697 choose_step_neighs, :700-738 choose_step_test and the set-union of :594/:694.
  *
+ *   indptr/indices  stacked CSR of R relations over n_nodes ROWS each (row r*n_nodes + (v - row_lo)); a row
+ *                partition of a larger graph passes its first global node id as row_lo (else 0); neighbour
+ *                ids, targets, the score table and the pool always use GLOBAL node ids. A target outside
+ *                [row_lo, row_lo + n_nodes) yields an empty item and status[PCG_ST_OVERFLOW] = 2.
  *   score        [N] table, or NULL with entry_score/center_score given (explicit scores, the
  *                IntraAgg.forward calling convention of src/layers.py:562)
  *   entry_score  per CSR entry (same indexing as `indices`) or NULL
@@ -113,7 +117,8 @@ PCG_API int pcg_choose_workspace_init(void* workspace, size_t workspace_bytes, i
  * The slots of the items are handed out by a prefix sum in item order, so the layout of sel_idx is the same
  * on every run.
  */
-PCG_API int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t n_nodes, int R, const float* score,
+PCG_API int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t n_nodes, int64_t row_lo, int R,
+               const float* score,
                const float* entry_score, const float* center_score, const int32_t* targets,
                const int64_t* labels, int B, const double* thresh_host, const int32_t* k_override, double rho,
                const float* ps_score, const int32_t* ps_pos, const int32_t* ps_id, const int32_t* entry_pool_pos, int P,

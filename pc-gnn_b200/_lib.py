@@ -18,6 +18,7 @@ MAX_REL = 8          # PCG_MAX_REL
 STATUS_WORDS = 8     # PCG_STATUS_WORDS
 ST_SLOTS, ST_OVERFLOW = 0, 3
 NORM_MEAN, NORM_RSQRT = 0, 1
+KB_MAX_POOL = 8192   # PCG_KB_WORDS * 32: pools up to this size use the per-item kept-pool bitmap
 
 _p = C.c_void_p
 _i = C.c_int
@@ -38,7 +39,7 @@ SIGNATURES = {
     "pcg_choose_workspace_init": (_i, [_p, _z, _l, _p]),
     "pcg_pool_positions": (_i, [_p, _i, _l, _p, _p]),
     "pcg_entry_pool_positions": (_i, [_p, _l, _p, _p, _p]),
-    "pcg_choose": (_i, [_p, _p, _l, _i, _p, _p, _p, _p, _p, _i, C.POINTER(_d), _p, _d, _p, _p, _p, _p, _i, _i, _l,
+    "pcg_choose": (_i, [_p, _p, _l, _l, _i, _p, _p, _p, _p, _p, _i, C.POINTER(_d), _p, _d, _p, _p, _p, _p, _i, _i, _l,
                         _p, _p, _l, _p, _p, _p, _p, _p, _p, _p, _z, _p, _p]),
     "pcg_select_all": (_i, [_p, _p, _l, _i, _p, _i, _i, _l, _p, _p, _p, _p, _p, _p, _p, _p]),
     "pcg_aggregate": (_i, [_p, _l, _p, _p, _p, _p, _p, _p, _p, _i, _l, _p, _i, _p, _p, _p, _p]),

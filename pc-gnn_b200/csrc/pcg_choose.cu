@@ -58,7 +58,8 @@ struct ChooseP {
     const int32_t* ps_pos;      // pool position of each sorted entry
     const int32_t* ps_id;       // node id of each sorted entry
     const int32_t* entry_pool_pos; // [nnz] pool position of every CSR entry's node, or -1 (NULL: binary-search fallback)
-    int64_t n_nodes;
+    int64_t n_nodes;            // rows per relation of THIS CSR (a row partition holds rows [row_lo, row_lo + n_nodes))
+    int64_t row_lo;             // global id of local row 0 (0 for an unpartitioned graph)
     int R, B, P, train;
     double thresh[PCG_MAX_REL];
     double rho;
@@ -608,7 +609,7 @@ __device__ __forceinline__ void item_header(const ChooseP& p, int w, Item& it) {
     it.r = w / p.B;
     it.i = w - it.r * p.B;
     it.v = p.targets[it.i];
-    const int64_t row = (int64_t)it.r * p.n_nodes + it.v;
+    const int64_t row = (int64_t)it.r * p.n_nodes + (it.v - p.row_lo);
     it.beg = p.indptr[row];
     it.d = (int)(p.indptr[row + 1] - it.beg);
     it.sv = p.center_score ? p.center_score[it.i] : p.score[it.v];
@@ -1174,7 +1175,10 @@ __global__ void __launch_bounds__(PCG_PREP_NT, 1) k_choose_prep(ChooseP p, int c
     int32_t* first = p.first;
     PTRACE(0);
     if (first)
-        for (int i = blockIdx.x * NT + tid; i < B; i += G * NT) atomicMin(&first[__ldg(p.targets + i)], i);
+        for (int i = blockIdx.x * NT + tid; i < B; i += G * NT) {
+            const int64_t lv = (int64_t)__ldg(p.targets + i) - p.row_lo;
+            if (lv >= 0 && lv < p.n_nodes) atomicMin(&first[lv], i);
+        }
     if (blockIdx.x == 0 && tid < PCG_STATUS_WORDS) p.status[tid] = 0;
     prep_grid_barrier(bar, G);               // the first-occurrence table is complete, the status words are zero
     PTRACE(1);
@@ -1194,12 +1198,16 @@ __global__ void __launch_bounds__(PCG_PREP_NT, 1) k_choose_prep(ChooseP p, int c
             beg[u] = end[u] = 0;
             pos[u] = false;
             if (q < n_items) {
-                const int32_t v = __ldg(p.targets + ii[u]);
-                rep[u] = first ? __ldcg(first + v) : ii[u];
-                const int64_t row = (int64_t)rr[u] * p.n_nodes + v;
-                beg[u] = __ldg(p.indptr + row);
-                end[u] = __ldg(p.indptr + row + 1);
-                pos[u] = p.train && p.labels && __ldg(p.labels + ii[u]) == 1;
+                const int64_t lv = (int64_t)__ldg(p.targets + ii[u]) - p.row_lo;
+                if (lv >= 0 && lv < p.n_nodes) {
+                    rep[u] = first ? __ldcg(first + lv) : ii[u];
+                    const int64_t row = (int64_t)rr[u] * p.n_nodes + lv;
+                    beg[u] = __ldg(p.indptr + row);
+                    end[u] = __ldg(p.indptr + row + 1);
+                    pos[u] = p.train && p.labels && __ldg(p.labels + ii[u]) == 1;
+                } else {
+                    rep[u] = -2;             // a target whose row this CSR does not hold: flagged below
+                }
             }
         }
 #pragma unroll
@@ -1208,7 +1216,11 @@ __global__ void __launch_bounds__(PCG_PREP_NT, 1) k_choose_prep(ChooseP p, int c
             if (q < n_items) {
                 const int w = w0 + q;
                 int info = 0;
-                p.it_rep[w] = rr[u] * B + rep[u];
+                p.it_rep[w] = rep[u] >= 0 ? rr[u] * B + rep[u] : w;
+                if (rep[u] == -2) {          // not our row: empty item, error flag
+                    p.it_slot0[w] = 0; p.it_m[w] = 0; p.it_base[w] = 0; p.it_done[w] = 0;
+                    atomicExch(&p.status[ST_OVERFLOW], 2);
+                }
                 if (rep[u] == ii[u]) {
                     const int64_t d = end[u] - beg[u];
                     int k, o;
@@ -1291,7 +1303,10 @@ __global__ void __launch_bounds__(PCG_PREP_NT, 1) k_choose_prep(ChooseP p, int c
     PTRACE(3);
     if (__syncthreads_or(overflow) && tid == 0) atomicExch(&p.status[ST_OVERFLOW], 1);
     if (first)                               // restore the table (all its reads are behind the second barrier)
-        for (int i = blockIdx.x * NT + tid; i < B; i += G * NT) first[__ldg(p.targets + i)] = 0x7f7f7f7f;
+        for (int i = blockIdx.x * NT + tid; i < B; i += G * NT) {
+            const int64_t lv = (int64_t)__ldg(p.targets + i) - p.row_lo;
+            if (lv >= 0 && lv < p.n_nodes) first[lv] = 0x7f7f7f7f;
+        }
     if (tid == 0) {
         if (blockIdx.x == G - 1) p.status[ST_SLOTS] = s_base + cta_total;
         __threadfence();
@@ -1436,7 +1451,8 @@ extern "C" int pcg_entry_pool_positions(const int32_t* indices, int64_t nnz, con
 static cudaStream_t g_side[PCG_N_SIDE] = {nullptr, nullptr, nullptr};
 static cudaEvent_t g_fork = nullptr, g_join[PCG_N_SIDE] = {nullptr, nullptr, nullptr};
 
-extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t n_nodes, int R, const float* score,
+extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t n_nodes, int64_t row_lo, int R,
+                          const float* score,
                           const float* entry_score, const float* center_score, const int32_t* targets,
                           const int64_t* labels, int B, const double* thresh_host, const int32_t* k_override,
                           double rho, const float* ps_score, const int32_t* ps_pos, const int32_t* ps_id,
@@ -1466,7 +1482,7 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
     p.indptr = indptr; p.indices = indices; p.score = score; p.entry_score = entry_score;
     p.center_score = center_score; p.targets = targets; p.labels = labels; p.k_override = k_override;
     p.ps_score = ps_score; p.ps_pos = ps_pos; p.ps_id = ps_id; p.entry_pool_pos = entry_pool_pos;
-    p.n_nodes = n_nodes; p.R = R; p.B = B;
+    p.n_nodes = n_nodes; p.row_lo = row_lo; p.R = R; p.B = B;
     p.P = (train && ps_score) ? P : 0; p.train = train;
     for (int r = 0; r < PCG_MAX_REL; ++r) p.thresh[r] = r < R ? thresh_host[r] : 0.5;
     p.rho = rho; p.sel_idx = sel_idx; p.sel_dist = sel_dist; p.cap_slots = cap_slots; p.slot_item = slot_item;
@@ -1486,8 +1502,19 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
         int chunk = PCG_PREP_CHUNK;
         if ((W + chunk - 1) / chunk > sms) chunk = (W + sms - 1) / sms;
         PCG_REQUIRE(chunk <= PCG_PREP_ITEMS, "pcg_choose: batch too large (%d items; at most %d)", W, PCG_PREP_ITEMS * sms);
-        k_choose_prep<<<(W + chunk - 1) / chunk, PCG_PREP_NT, 0, stream>>>(p, chunk, (int32_t*)(ws + L.bar),
-                                                                         (int32_t*)(ws + L.totals));
+        // cooperative launch: the CTAs wait on one another at the grid barriers, so all must be resident
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)((W + chunk - 1) / chunk));
+        cfg.blockDim = dim3(PCG_PREP_NT);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, k_choose_prep, p, chunk, (int32_t*)(ws + L.bar), (int32_t*)(ws + L.totals));
+        if (e != cudaSuccess) { pcg_set_error("pcg_choose: prep launch: %s", cudaGetErrorString(e)); return (int)e; }
     }
     const bool have_cta = max_degree > PCG_SMALL_MAX, have_cl = max_degree > PCG_CTA_MAX, have_big = max_degree > PCG_CL_MAX;
     if (have_cta && !g_fork) {

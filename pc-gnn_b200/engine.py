@@ -65,15 +65,18 @@ class Engine:
         self.lib = _lib.lib()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.graph = graph
+        self.row_lo = 0
         if graph is not None:
+            # N: rows held here; N_global: nodes of the whole graph (ids, features, scores and the pool are global)
             self.N, self.R = graph.n_nodes, graph.n_rel
+            self.row_lo, self.N_global = graph.row_lo, graph.n_global
             if self.R > _lib.MAX_REL:
                 raise ValueError(f"at most {_lib.MAX_REL} relations are supported")
             self.indptr, self.indices = graph.device(self.device)
             deg = np.diff(graph.indptr)
             self.max_degree = int(deg.max()) if deg.size else 0
         else:   # explicit-list use only (IntraAgg.forward / choose_step_* compat calls)
-            self.N = self.R = self.max_degree = 0
+            self.N = self.N_global = self.R = self.max_degree = 0
             self.indptr = self.indices = None
         self.strict_rows = True     # feature table must have exactly one row per graph node
         self._feat_key = None
@@ -88,6 +91,7 @@ class Engine:
         self._pin = None
         self._ws = None
         self._ws_nodes = None
+        self.score_group = None     # torch.distributed group over which the score slices are all-gathered (C5)
 
     # ------------------------------------------------------------------ resident tables
     def set_features(self, weight: torch.Tensor):
@@ -96,8 +100,8 @@ class Engine:
         if key == self._feat_key:
             return self.feat
         w = weight.detach()
-        if self.graph is not None and self.strict_rows and w.shape[0] != self.N:
-            raise ValueError(f"feature table has {w.shape[0]} rows, graph has {self.N} nodes")
+        if self.graph is not None and self.strict_rows and w.shape[0] != self.N_global:
+            raise ValueError(f"feature table has {w.shape[0]} rows, graph has {self.N_global} nodes")
         F_ = w.shape[1]
         ld = padded_ld(F_)
         if ld == F_ and w.is_contiguous() and w.dtype == torch.float32 and w.device == self.device \
@@ -109,26 +113,31 @@ class Engine:
         self.feat, self.F, self.ldf = feat, F_, ld
         self._feat_key = key
         if self.score is None and self.graph is not None:
-            self.score = torch.empty(self.N, dtype=torch.float32, device=self.device)
+            self.score = torch.empty(self.N_global, dtype=torch.float32, device=self.device)
         return feat
 
     def set_pool(self, train_pos):
-        """Train-positive pool (order preserved: ties are broken by pool position, src/layers.py:687-690)."""
-        arr = np.asarray(list(train_pos), dtype=np.int32)
-        self.pool = torch.from_numpy(arr).to(self.device)
-        self.P = int(arr.shape[0])
+        """Train-positive pool (order preserved: ties are broken by pool position, src/layers.py:687-690).
+        A list / array of global node ids, or an int32 device tensor (C5: ~4e5 ids made on the GPU)."""
+        if isinstance(train_pos, torch.Tensor):
+            self.pool = train_pos.to(self.device, torch.int32).contiguous()
+        else:
+            self.pool = torch.from_numpy(np.asarray(list(train_pos), dtype=np.int32)).to(self.device)
+        self.P = int(self.pool.shape[0])
         self.sorted_pool = self._alloc_sorted_pool(self.P)
         self.pool_pos_of = None
+        self.entry_pool_pos = None
         if self.graph is not None:
-            self.pool_pos_of = torch.empty(self.N, dtype=torch.int32, device=self.device)
-            rc = self.lib.pcg_pool_positions(self.pool.data_ptr(), self.P, self.N, self.pool_pos_of.data_ptr(),
+            self.pool_pos_of = torch.empty(self.N_global, dtype=torch.int32, device=self.device)
+            rc = self.lib.pcg_pool_positions(self.pool.data_ptr(), self.P, self.N_global, self.pool_pos_of.data_ptr(),
                                              _lib.stream_ptr())
             _lib.check(rc, "pcg_pool_positions")
-            self.entry_pool_pos = torch.empty(max(self.indices.shape[0], 1), dtype=torch.int32, device=self.device)
-            rc = self.lib.pcg_entry_pool_positions(self.indices.data_ptr(), self.indices.shape[0],
-                                                   self.pool_pos_of.data_ptr(), self.entry_pool_pos.data_ptr(),
-                                                   _lib.stream_ptr())
-            _lib.check(rc, "pcg_entry_pool_positions")
+            if self.P <= _lib.KB_MAX_POOL:      # larger pools use the row-position test, not the per-item bitmap
+                self.entry_pool_pos = torch.empty(max(self.indices.shape[0], 1), dtype=torch.int32, device=self.device)
+                rc = self.lib.pcg_entry_pool_positions(self.indices.data_ptr(), self.indices.shape[0],
+                                                       self.pool_pos_of.data_ptr(), self.entry_pool_pos.data_ptr(),
+                                                       _lib.stream_ptr())
+                _lib.check(rc, "pcg_entry_pool_positions")
 
     def _alloc_sorted_pool(self, P):
         n = max(P, 1)
@@ -147,13 +156,31 @@ class Engine:
         return ps, pp, pi
 
     def score_table(self, clf_weight: torch.Tensor, clf_bias: torch.Tensor):
-        """score[v] = <feat[v], clf_weight[0]> + clf_bias[0] for all nodes, then the pool sorted by it."""
+        """score[v] = <feat[v], clf_weight[0]> + clf_bias[0] for all nodes, then the pool sorted by it.
+
+        Row-partitioned graph with ``score_group`` set (C5): every rank scores only the nodes whose rows it
+        holds and the slices are all-gathered (the halo exchange of the partitioned path: neighbours' scores
+        outside the rank's node range come from their owners), then the pool is sorted from the full table."""
         w = clf_weight.detach()
         b = clf_bias.detach()
         if not w.is_contiguous():
             w = w.contiguous()
         ps, pp, pi, ws = self.sorted_pool if self.pool is not None else (None, None, None, None)
-        rc = self.lib.pcg_score_table(self.feat.data_ptr(), self.N, self.F, self.ldf, w.data_ptr(), b.data_ptr(),
+        if self.score_group is not None:
+            import torch.distributed as dist
+
+            world = dist.get_world_size(self.score_group)
+            if world * self.N != self.N_global:
+                raise ValueError("score exchange needs equal row ranges (n_global == world * rows per rank)")
+            lo = self.row_lo
+            rc = self.lib.pcg_score_table(self.feat.data_ptr() + lo * self.ldf * 4, self.N, self.F, self.ldf,
+                                          w.data_ptr(), b.data_ptr(), self.score.data_ptr() + lo * 4, None, 0, None,
+                                          None, None, None, 0, _lib.stream_ptr())
+            _lib.check(rc, "pcg_score_table")
+            dist.all_gather_into_tensor(self.score, self.score[lo:lo + self.N], group=self.score_group)
+            self.resort_pool()
+            return self.score
+        rc = self.lib.pcg_score_table(self.feat.data_ptr(), self.N_global, self.F, self.ldf, w.data_ptr(), b.data_ptr(),
                                       self.score.data_ptr(), _lib.ptr(self.pool), self.P, _lib.ptr(ps), _lib.ptr(pp),
                                       _lib.ptr(pi), _lib.ptr(ws), 0 if ws is None else ws.numel(), _lib.stream_ptr())
         _lib.check(rc, "pcg_score_table")
@@ -186,7 +213,7 @@ class Engine:
     def slots_bound(self, host_targets, thresh, rho, train, *, k_override=None) -> int:
         """Upper bound of the slots a batch needs, from the host copy of the CSR offsets (every
         target counted as positive when training, since labels may live on the device)."""
-        t = host_targets.astype(np.int64)
+        t = host_targets.astype(np.int64) - self.row_lo
         total = 0
         for r in range(self.R):
             rows = r * self.N + t
@@ -269,7 +296,7 @@ class Engine:
         rc = self.lib.pcg_choose(
             (self.indptr if indptr is None else indptr).data_ptr(),
             (self.indices if indices is None else indices).data_ptr(),
-            self.N if n_nodes is None else n_nodes, R,
+            self.N if n_nodes is None else n_nodes, self.row_lo if n_nodes is None else 0, R,
             self.score.data_ptr() if use_table else None, _lib.ptr(entry_score), _lib.ptr(center_score),
             targets.data_ptr(), _lib.ptr(labels) if train else None, B, th, _lib.ptr(k_override), float(rho),
             _lib.ptr(ps), _lib.ptr(pp), _lib.ptr(pi), _lib.ptr(self.entry_pool_pos) if use_table else None, P,
@@ -282,6 +309,8 @@ class Engine:
 
     def select_all(self, targets, add_self: bool, cap_slots: int, norm: int) -> Selection:
         """GraphSAGE / GCN selection: whole rows (∪ self), no copy (``pcg_select_all``)."""
+        if self.graph is not None and self.graph.partitioned:
+            raise NotImplementedError("select-all runs on unpartitioned graphs only")
         B = int(targets.shape[0])
         s = self._new_selection(B, self.R, cap_slots, False, True)
         s.norm = norm

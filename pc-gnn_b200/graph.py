@@ -65,10 +65,18 @@ def adj_lists_from_csr(indptr, indices, rows=None):
 
 
 class RelGraph:
-    """R stacked relations over N nodes (host numpy + lazily made device copy)."""
+    """R stacked relations over N nodes (host numpy + lazily made device copy).
 
-    def __init__(self, n_nodes: int, indptr_list, indices_list):
+    A ROW PARTITION of a larger graph (config C5: CSR rows split by node range over the GPUs) is the same
+    object with ``row_lo`` / ``n_global`` set: it holds the rows of nodes [row_lo, row_lo + n_nodes) of a graph
+    with ``n_global`` nodes; neighbour ids stay global."""
+
+    def __init__(self, n_nodes: int, indptr_list, indices_list, row_lo: int = 0, n_global: int | None = None):
         self.n_nodes = int(n_nodes)
+        self.row_lo = int(row_lo)
+        self.n_global = int(n_global) if n_global is not None else self.n_nodes + self.row_lo
+        if self.row_lo < 0 or self.row_lo + self.n_nodes > self.n_global:
+            raise ValueError("row range outside the global graph")
         self.n_rel = len(indptr_list)
         if self.n_rel == 0:
             raise ValueError("at least one relation is required")
@@ -146,9 +154,40 @@ class RelGraph:
         return ip, self.indices[lo:self.rel_offsets[r + 1]]
 
     def row(self, r: int, v: int):
-        b = self.indptr[r * self.n_nodes + v]
-        e = self.indptr[r * self.n_nodes + v + 1]
+        """Neighbour ids of GLOBAL node v under relation r (v must lie in this partition)."""
+        lv = v - self.row_lo
+        b = self.indptr[r * self.n_nodes + lv]
+        e = self.indptr[r * self.n_nodes + lv + 1]
         return self.indices[b:e]
+
+    @property
+    def partitioned(self) -> bool:
+        return self.row_lo != 0 or self.n_global != self.n_nodes
+
+    def row_partition(self, lo: int, hi: int):
+        """The rows [lo, hi) of this (unpartitioned) graph as a partition object (copies)."""
+        if self.partitioned:
+            raise ValueError("already a partition")
+        ips, ixs = [], []
+        for r in range(self.n_rel):
+            ip, ix = self.relation(r)
+            ips.append(ip[lo:hi + 1] - ip[lo])
+            ixs.append(ix[ip[lo]:ip[hi]])
+        return RelGraph(hi - lo, ips, ixs, row_lo=lo, n_global=self.n_nodes)
+
+    @classmethod
+    def from_device_csr(cls, n_rows: int, n_rel: int, indptr, indices, row_lo: int = 0, n_global: int | None = None):
+        """Wrap a stacked CSR that already lives on a device (torch tensors: indptr int64 [R*n_rows + 1],
+        indices int32 [nnz]) without a host copy of the indices (C5: ~10^9 entries generated on the GPU)."""
+        g = cls.__new__(cls)
+        g.n_nodes, g.n_rel = int(n_rows), int(n_rel)
+        g.row_lo = int(row_lo)
+        g.n_global = int(n_global) if n_global is not None else g.n_nodes + g.row_lo
+        g.indptr = indptr.cpu().numpy()
+        g.indices = None                      # device only
+        g.rel_offsets = g.indptr[::g.n_nodes][:g.n_rel + 1].copy() if g.n_nodes else np.zeros(n_rel + 1, np.int64)
+        g._dev = {_device_key(indices.device): (indptr, indices)}
+        return g
 
     def degrees(self, r: int):
         n = self.n_nodes
@@ -175,8 +214,19 @@ class RelGraph:
         """(indptr, indices) torch tensors on ``device`` (cached)."""
         import torch
 
-        key = str(torch.device(device))
+        key = _device_key(device)
         if key not in self._dev:
+            if self.indices is None:
+                raise ValueError(f"this graph lives on {list(self._dev)} only")
             self._dev[key] = (torch.from_numpy(self.indptr).to(device),
                               torch.from_numpy(self.indices).to(device))
         return self._dev[key]
+
+
+def _device_key(device) -> str:
+    import torch
+
+    d = torch.device(device)
+    if d.type == "cuda" and d.index is None:
+        d = torch.device("cuda", torch.cuda.current_device())
+    return str(d)

@@ -338,7 +338,7 @@ class InterAgg(nn.Module):
     def forward(self, nodes, labels, train_flag=True):
         eng = self.engine()
         dev = eng.device
-        table = _feature_table(self.features, eng.N, dev)
+        table = _feature_table(self.features, eng.N_global, dev)
         eng.set_features(table)
         targets, host = eng.upload_targets(nodes)
         rho = self.intra_agg1.rho

@@ -121,3 +121,29 @@ def test_reference_model_handler_imports_through_the_shim():
         assert mh.PCALayer.__module__ == "src.model"
     finally:
         shim.uninstall()
+
+
+def test_big_graph_generator_is_partition_independent():
+    """C5 generator: any rank can make any row range; labels, split, pool and features agree everywhere."""
+    import torch
+    from pcgnn_b200.synth_big import BigSpec, make_partition
+
+    mk = lambda rows, rank, world: make_partition(BigSpec(nodes_per_rank=rows, feat_dim=4, rel_mean_deg=(2.0, 5.0, 9.0),
+                                                          max_degree=5000, seed=3), rank, world, "cpu")
+    full = mk(6000, 0, 1)
+    ipf, ixf = full.graph.device("cpu")
+    parts = [mk(2000, r, 3) for r in range(3)]
+    for part in parts:
+        assert torch.equal(part.train_pos, full.train_pos) and torch.equal(part.labels, full.labels)
+        assert torch.equal(part.feat, full.feat)
+        ip, ix = part.graph.device("cpu")
+        lo, n = part.row_lo, part.graph.n_nodes
+        for r in range(3):
+            a = ixf[ipf[r * 6000 + lo]:ipf[r * 6000 + lo + n]]
+            b = ix[ip[r * n]:ip[(r + 1) * n]]
+            assert torch.equal(a, b)
+        nodes, lab = part.sample_batches(1, 512, seed=1)[0]
+        assert int(nodes.min()) >= lo and int(nodes.max()) < lo + n
+        assert 0.35 < float(lab.float().mean()) < 0.65          # label-balanced like pick_step
+    rows = ixf[ipf[5]:ipf[6]]
+    assert 5 in rows.tolist() and bool((rows[1:] > rows[:-1]).all())   # self loop, ascending ids
