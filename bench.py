@@ -35,6 +35,8 @@ WORKLOADS = {
     "amazon": ("amazon", 1024, 64, "C1 Amazon-shaped N=11944 F=25 R=3 ~4.8M edges, emb 64, batch 1024/GPU"),
     "yelp100": ("yelp100", 4096, 128, "C3 YelpChi-shaped F=100, emb 128, batch 4096/GPU"),
     "amazon_gcn": ("amazon", 1024, 64, "C4 GCN baseline on the Amazon-shaped union graph, emb 64, batch 1024/GPU"),
+    "big": ("big", 1024, 64, "C5 power-law fraud graph, 1.25M nodes and ~1.25e8 CSR entries PER GPU (10M / 1e9 at 8 GPUs), "
+                             "F=64, R=3, 10% positives, CSR row-partitioned by node range, emb 64, batch 1024/GPU"),
 }
 RHO, ALPHA, LR, WD = 0.5, 2.0, 0.01, 1e-3
 SEED = 72
@@ -177,6 +179,31 @@ def c_port_rate(data, batches, reps=3):
 GCN_KERNELS_PER_STEP = 2   # select-all + aggregate (the GCN encoder/head are torch library GEMMs, as in the reference)
 
 
+def build_cuda_pcgnn_device(feat_dev, graph, train_pos_dev, params, dev):
+    """PCALayer(InterAgg3(IntraAgg x3)) over tables that already live on the device (workload big)."""
+    import torch
+    import torch.nn as nn
+
+    from pcgnn_b200.layers import InterAgg3, IntraAgg
+    from pcgnn_b200.model import PCALayer
+
+    F_, E = feat_dev.shape[1], params["inter"].shape[1]
+    features = nn.Embedding(1, 1)
+    features.weight = nn.Parameter(feat_dev, requires_grad=False)          # no copy of the 2.56 GB table
+    features.num_embeddings, features.embedding_dim = feat_dev.shape
+    intras = [IntraAgg(features, F_, E, train_pos_dev, RHO, cuda=True) for _ in range(graph.n_rel)]
+    inter = InterAgg3(features, F_, E, train_pos_dev, graph, intras, cuda=True)
+    model = PCALayer(2, inter, ALPHA)
+    with torch.no_grad():
+        for ia, w in zip(intras, params["intra"]):
+            ia.weight.copy_(torch.from_numpy(np.asarray(w)))
+        inter.weight.copy_(torch.from_numpy(params["inter"]))
+        inter.label_clf.weight.copy_(torch.from_numpy(params["clf_w"]))
+        inter.label_clf.bias.copy_(torch.from_numpy(params["clf_b"]))
+        model.weight.copy_(torch.from_numpy(params["head"]))
+    return model.to(dev)
+
+
 def build_cuda_gcn(data, params, dev):
     """GCN(GCNEncoder(GCNAggregator)) of the product on the union graph (model_handler.py:99-101, 119-120)."""
     import torch
@@ -223,8 +250,12 @@ def hot_kernels_pcgnn(eng, inter, data, shards, dev_nodes, dev_labels, cap, W, K
     torch.cuda.current_stream(dev).wait_stream(side)
     torch.cuda.synchronize()
     g_score, g_choose, g_agg = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+    exchange = eng.score_group is not None          # partitioned graph: the all-gather stays outside the graphs
     with torch.cuda.graph(g_score):
-        eng.score_table(inter.label_clf.weight, inter.label_clf.bias)
+        if exchange:
+            eng.score_local(inter.label_clf.weight, inter.label_clf.bias)
+        else:
+            eng.score_table(inter.label_clf.weight, inter.label_clf.bias)
     with torch.cuda.graph(g_choose):
         sel = eng.choose(st_nodes, st_labels, True, inter.thresholds, RHO, cap)
     with torch.cuda.graph(g_agg):
@@ -237,6 +268,9 @@ def hot_kernels_pcgnn(eng, inter, data, shards, dev_nodes, dev_labels, cap, W, K
         e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
         e0.record()
         g_score.replay()
+        if exchange:
+            eng.score_exchange()
+            eng.resort_pool()
         e1.record()
         g_choose.replay()
         e2.record()
@@ -248,7 +282,7 @@ def hot_kernels_pcgnn(eng, inter, data, shards, dev_nodes, dev_labels, cap, W, K
         t_agg += e2.elapsed_time(e3)
         nodes, labels = shards[i]
         n_pos = int((labels == 1).sum())
-        sum_d = sum(int(data.graph.degrees(r)[nodes].sum()) for r in range(R))
+        sum_d = sum(int(data.graph.degrees(r)[nodes - data.graph.row_lo].sum()) for r in range(R))
         m_tot = int(sel.it_m[sel.it_rep.long()].sum().item())
         alg_choose += 8.0 * sum_d + R * batch * 16 + 4 * batch + 4.0 * P * n_pos * R + 4.0 * m_tot
         alg_agg += (4.0 * F_ + 4.0) * m_tot + 4.0 * F_ * R * batch
@@ -310,6 +344,10 @@ def run_reference(args):
     from pcgnn_b200.synth import make_graph
 
     spec, batch, embed, desc = WORKLOADS[args.workload]
+    if args.workload == "big":
+        print(json.dumps({"impl": "reference", "unavailable": "workload big: the graph exists only as a device-side CSR "
+                          "(1e9 entries); the CPU arm is measured on the yelp / amazon workloads"}))
+        return
     data = make_graph(spec, seed=SEED)
     params = init_params(data.feat.shape[1], embed, data.graph.n_rel, SEED)
     batches = make_batches(data, 4, batch, SEED)
@@ -341,6 +379,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="do not use CUDA graphs for the device-resident step")
+    ap.add_argument("--nodes-per-gpu", type=int, default=1_250_000, help="workload big: rows of the CSR held per GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -362,24 +401,56 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     K, W = args.steps, max(args.warmup, 3)
     spec, batch, embed, desc = WORKLOADS[args.workload]
-    data = make_graph(spec, seed=SEED)
-    F_, R = data.feat.shape[1], data.graph.n_rel
-    params = init_params(F_, embed, R, SEED)
-    tp = sorted(data.train_pos)
     is_gcn = args.workload.endswith("_gcn")
-    if is_gcn:
+    is_big = args.workload == "big"
+    n_b = W + K
+    if is_big:
+        # C5: every rank generates and holds only its own row range of the CSR; features, scores and the pool
+        # are global. Each rank draws its share of the global batch from its own nodes (targets live with
+        # their rows), so the only exchanges per step are the score-slice all-gather and the gradient sum.
+        from pcgnn_b200.synth_big import BigSpec, make_partition
+
+        part = make_partition(BigSpec(nodes_per_rank=args.nodes_per_gpu, seed=SEED), rank, world, dev)
+        data = part
+        F_, R = part.feat.shape[1], part.graph.n_rel
+        params = init_params(F_, embed, R, SEED)
+        model = build_cuda_pcgnn_device(part.feat, part.graph, part.train_pos, params, dev)
+        inter = model.inter1
+        if world > 1:
+            # self-check of the exchange: slice kernel + all-gather must equal the whole table computed locally
+            e_ = inter.engine()
+            e_.set_features(inter.features.weight)
+            e_.score_table(inter.label_clf.weight, inter.label_clf.bias)
+            whole = e_.score.clone()
+            e_.score.zero_()
+            e_.score_group = dist.group.WORLD
+            e_.score_table(inter.label_clf.weight, inter.label_clf.bias)
+            assert torch.equal(whole, e_.score), "score exchange differs from the locally computed table"
+            del whole
+        drawn = part.sample_batches(n_b, batch, SEED + rank)
+        shards = [(n.cpu().numpy().astype(np.int64), l.cpu().numpy()) for n, l in drawn]
+        global_batches = None
+        torch.cuda.synchronize()
+        desc += f"; this run: {part.n_global} nodes, {int(part.graph.indptr[-1]) * world / 1e6:.0f}M CSR entries, pool {int(part.train_pos.shape[0])}"
+    elif is_gcn:
+        data = make_graph(spec, seed=SEED)
+        F_, R = data.feat.shape[1], data.graph.n_rel
+        params = init_params(F_, embed, R, SEED)
         model = build_cuda_gcn(data, params, dev)
         inter = model.enc.aggregator             # the module that owns the engine / slot capacity
     else:
-        model = build_cuda_pcgnn(data.feat, data.graph, tp, params, rho=RHO, alpha=ALPHA, device=dev)
+        data = make_graph(spec, seed=SEED)
+        F_, R = data.feat.shape[1], data.graph.n_rel
+        params = init_params(F_, embed, R, SEED)
+        model = build_cuda_pcgnn(data.feat, data.graph, sorted(data.train_pos), params, rho=RHO, alpha=ALPHA, device=dev)
         inter = model.inter1
     opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=LR, weight_decay=WD,
                            capturable=True, fused=True)
     reducer = GradAllReduce(model.parameters()).attach()
-    # global batches of batch*world targets, identical on every rank; this rank's contiguous shard
-    n_b = W + K
-    global_batches = make_batches(data, n_b, batch * world, SEED)
-    shards = [(n[rank * batch:(rank + 1) * batch], l[rank * batch:(rank + 1) * batch]) for n, l in global_batches]
+    if not is_big:
+        # global batches of batch*world targets, identical on every rank; this rank's contiguous shard
+        global_batches = make_batches(data, n_b, batch * world, SEED)
+        shards = [(n[rank * batch:(rank + 1) * batch], l[rank * batch:(rank + 1) * batch]) for n, l in global_batches]
     dev_nodes = [torch.from_numpy(n.astype(np.int32)).to(dev) for n, _ in shards]
     dev_labels = [torch.from_numpy(l).to(dev) for _, l in shards]
     host_nodes = [n.tolist() for n, _ in shards]
@@ -474,6 +545,8 @@ def main():
     ms_e2e = max_over_ranks(ms_e2e)
     ms_api = None
     if use_graph:      # the reference-facing eager call model.loss(list, labels) for comparison
+        if hasattr(inter, "scores_external"):
+            inter.scores_external = False      # the eager call computes (and exchanges) the scores itself
         for s in range(W):
             step_host_eager(s)
         barrier()
@@ -504,7 +577,7 @@ def main():
             line["e2e_reference_api_eager"] = {"value": total_nodes / (ms_api / 1e3), "unit": "target-nodes/s",
                                                "ms_per_step": ms_api / K,
                                                "call": "model.loss(list_of_ids, cuda_labels); backward; Adam.step; loss.item()"}
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not is_big:
             sample = min(args.cpu_sample, batch)
             rate, sec = cpu_port_rate(data, params, global_batches, sample, 6, 1, gcn=is_gcn)
             line["cpu_baseline"] = {

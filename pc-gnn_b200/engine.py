@@ -167,17 +167,8 @@ class Engine:
             w = w.contiguous()
         ps, pp, pi, ws = self.sorted_pool if self.pool is not None else (None, None, None, None)
         if self.score_group is not None:
-            import torch.distributed as dist
-
-            world = dist.get_world_size(self.score_group)
-            if world * self.N != self.N_global:
-                raise ValueError("score exchange needs equal row ranges (n_global == world * rows per rank)")
-            lo = self.row_lo
-            rc = self.lib.pcg_score_table(self.feat.data_ptr() + lo * self.ldf * 4, self.N, self.F, self.ldf,
-                                          w.data_ptr(), b.data_ptr(), self.score.data_ptr() + lo * 4, None, 0, None,
-                                          None, None, None, 0, _lib.stream_ptr())
-            _lib.check(rc, "pcg_score_table")
-            dist.all_gather_into_tensor(self.score, self.score[lo:lo + self.N], group=self.score_group)
+            self.score_local(w, b)
+            self.score_exchange()
             self.resort_pool()
             return self.score
         rc = self.lib.pcg_score_table(self.feat.data_ptr(), self.N_global, self.F, self.ldf, w.data_ptr(), b.data_ptr(),
@@ -185,6 +176,23 @@ class Engine:
                                       _lib.ptr(pi), _lib.ptr(ws), 0 if ws is None else ws.numel(), _lib.stream_ptr())
         _lib.check(rc, "pcg_score_table")
         return self.score
+
+    def score_local(self, w: torch.Tensor, b: torch.Tensor):
+        """Partitioned graph: scores of the nodes whose rows live here, written into their slice of the table."""
+        lo = self.row_lo
+        rc = self.lib.pcg_score_table(self.feat.data_ptr() + lo * self.ldf * 4, self.N, self.F, self.ldf,
+                                      w.detach().data_ptr(), b.detach().data_ptr(), self.score.data_ptr() + lo * 4,
+                                      None, 0, None, None, None, None, 0, _lib.stream_ptr())
+        _lib.check(rc, "pcg_score_table")
+
+    def score_exchange(self):
+        """All-gather of the score slices over ``score_group`` (the halo exchange of the partitioned path)."""
+        import torch.distributed as dist
+
+        world = dist.get_world_size(self.score_group)
+        if world * self.N != self.N_global:
+            raise ValueError("score exchange needs equal row ranges (n_global == world * rows per rank)")
+        dist.all_gather_into_tensor(self.score, self.score[self.row_lo:self.row_lo + self.N], group=self.score_group)
 
     def resort_pool(self):
         """Re-sort the resident pool after ``self.score`` was written by someone else (tests inject a table)."""

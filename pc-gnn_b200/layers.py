@@ -317,6 +317,8 @@ class InterAgg(nn.Module):
         self._engine = None
         self.cap_slots_hint = None      # set to a fixed capacity to avoid sizing from host ids
         self.score_override = None      # tests: inject an [N] score table (identical score bits)
+        self.scores_external = False    # the caller refreshes eng.score itself (runtime.GraphedTrainStep on a
+        #                                 partitioned graph: slice kernel -> all-gather -> this forward)
         self.last_selection = None
 
     # -- plumbing ---------------------------------------------------------------------------
@@ -347,6 +349,8 @@ class InterAgg(nn.Module):
         # label-aware scores for every node (column 0 only) + the pool's: layers.py:231-237
         if self.score_override is not None:
             eng.score.copy_(self.score_override)
+            eng.resort_pool()
+        elif self.scores_external:
             eng.resort_pool()
         else:
             eng.score_table(self.label_clf.weight, self.label_clf.bias)

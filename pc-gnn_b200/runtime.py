@@ -30,18 +30,33 @@ class GraphedTrainStep:
         self.dev = dev
         self._sizer.cap_slots_hint = int(cap_slots)
         self.cap_slots = int(cap_slots)
+        if hasattr(model, "inter1") and model.inter1.engine().score_group is not None:
+            model.inter1.scores_external = True
         self.nodes = torch.zeros(self.B, dtype=torch.int32, device=dev)
         self.labels = torch.zeros(self.B, dtype=torch.int64, device=dev)
         self.pin_nodes = torch.zeros(self.B, dtype=torch.int32, pin_memory=True)
         self.pin_labels = torch.zeros(self.B, dtype=torch.int64, pin_memory=True)
         self.loss = None
+        # row-partitioned graph: the score slices are exchanged by an eager all-gather BETWEEN two graphs
+        # (slice kernel | all-gather | everything else), so no collective is captured
+        eng = model.inter1.engine() if hasattr(model, "inter1") else None
+        self._xeng = eng if (eng is not None and eng.score_group is not None) else None
+        self.g_pre = None
         if warmup_batch is not None:
             self.nodes.copy_(torch.as_tensor(np.asarray(warmup_batch[0], dtype=np.int32)))
             self.labels.copy_(torch.as_tensor(np.asarray(warmup_batch[1], dtype=np.int64)))
         self._capture()
 
     # -- one eager step on the static buffers (also what gets captured) -------------------------
+    def _score_pre(self):
+        inter = self.model.inter1
+        self._xeng.set_features(inter.features.weight)
+        self._xeng.score_local(inter.label_clf.weight, inter.label_clf.bias)
+
     def _fwd_bwd(self):
+        if self._xeng is not None and not torch.cuda.is_current_stream_capturing():
+            self._score_pre()                      # eager warm-up steps: slice, exchange, then the forward
+            self._xeng.score_exchange()
         if self.reducer is not None:
             self.reducer.zero()
         else:
@@ -80,6 +95,10 @@ class GraphedTrainStep:
                             v.copy_(saved[k][n]) if had_state else v.zero_()
         torch.cuda.current_stream(self.dev).wait_stream(s)
         torch.cuda.synchronize(self.dev)
+        if self._xeng is not None:
+            self.g_pre = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_pre):
+                self._score_pre()
         self.g_fb = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.g_fb):
             self.loss = self._fwd_bwd()
@@ -88,6 +107,9 @@ class GraphedTrainStep:
             self.opt.step()
 
     def _replay(self):
+        if self.g_pre is not None:
+            self.g_pre.replay()
+            self._xeng.score_exchange()
         self.g_fb.replay()
         if self.world > 1 and self.reducer is not None:
             self.reducer()                       # one NCCL all-reduce of the flat gradient
