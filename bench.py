@@ -379,6 +379,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="do not use CUDA graphs for the device-resident step")
+    ap.add_argument("--torch-adam", action="store_true",
+                    help="NCCL all-reduce + torch.optim.Adam instead of the fused peer-memory exchange + Adam kernel")
     ap.add_argument("--nodes-per-gpu", type=int, default=1_250_000, help="workload big: rows of the CSR held per GPU")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -388,7 +390,7 @@ def main():
     import torch.distributed as dist
 
     from pcgnn_b200 import _lib
-    from pcgnn_b200.parallel import GradAllReduce
+    from pcgnn_b200.parallel import FusedAdam, GradAllReduce, PeerComm
     from pcgnn_b200.synth import make_graph
     from tests.helpers import build_cuda_pcgnn
 
@@ -444,9 +446,13 @@ def main():
         params = init_params(F_, embed, R, SEED)
         model = build_cuda_pcgnn(data.feat, data.graph, sorted(data.train_pos), params, rho=RHO, alpha=ALPHA, device=dev)
         inter = model.inter1
-    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=LR, weight_decay=WD,
-                           capturable=True, fused=True)
     reducer = GradAllReduce(model.parameters()).attach()
+    if args.torch_adam:     # NCCL all-reduce between two CUDA graphs + torch's fused Adam (the baseline arrangement)
+        opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=LR, weight_decay=WD,
+                               capturable=True, fused=True)
+    else:                   # gradient exchange over NVLink peer memory + Adam in one kernel inside the step graph
+        opt = FusedAdam(reducer, lr=LR, weight_decay=WD, comm=PeerComm(reducer.flat.numel()))
+    fused = not args.torch_adam
     if not is_big:
         # global batches of batch*world targets, identical on every rank; this rank's contiguous shard
         global_batches = make_batches(data, n_b, batch * world, SEED)
@@ -466,25 +472,28 @@ def main():
     inter.cap_slots_hint = cap
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
+    def finish_step():
+        if not fused:
+            reducer()
+            if world > 1:
+                reducer.flat.div_(world)
+        opt.step()                                               # fused: exchange + Adam + gradient clear
+
     def step_device_eager(i):
-        reducer.zero()
+        if not fused:
+            reducer.zero()
         loss = model.loss(dev_nodes[i], dev_labels[i])
         loss.backward()
-        reducer()
-        if world > 1:
-            reducer.flat.div_(world)
-        opt.step()
+        finish_step()
         return loss
 
     def step_host_eager(i):
-        reducer.zero()
+        if not fused:
+            reducer.zero()
         lab = torch.from_numpy(host_labels[i]).to(dev)          # model_handler.py:150 (cuda LongTensor of labels)
         loss = model.loss(host_nodes[i], lab)
         loss.backward()
-        reducer()
-        if world > 1:
-            reducer.flat.div_(world)
-        opt.step()
+        finish_step()
         return loss.item()                                       # D2H of the step's result
 
     use_graph = not args.no_graph

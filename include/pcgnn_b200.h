@@ -222,6 +222,30 @@ PCG_API int pcg_pick_step(const double* cum, int64_t n, const double* u, int64_t
 PCG_API int pcg_pick_step_philox(const double* cum, int64_t n, uint64_t seed, uint64_t offset, int64_t k,
                          const int32_t* idx_train, int32_t* out, pcg_stream_t stream);
 
+/*
+ * Data-parallel gradient exchange + Adam step as one kernel over NVLink peer memory (new design: the
+ * reference is single-GPU, model_handler.py:87, and steps with torch.optim.Adam, model_handler.py:124,153).
+ * Every rank owns a REGION of pcg_comm_region_bytes(n) bytes allocated with pcg_comm_alloc (cudaMalloc, zeroed),
+ * exported with pcg_comm_export (64-byte CUDA IPC handle) and mapped by the peers with pcg_comm_import.
+ * pcg_allreduce_adam(grad, param, m, v, n, regions[world] (HOST array of this process's mappings, own region
+ * at [rank]), rank, world, epoch, ticket, lr, beta1, beta2, eps, weight_decay, do_adam, stream):
+ *   grad <- mean over ranks of grad (summed in rank order: bit-identical on every rank); with do_adam the
+ *   torch.optim.Adam update (L2 weight decay, bias correction with step = *epoch + 1) is applied to param / m / v
+ *   and grad is cleared. epoch (uint32, zero before the first step) and ticket (int32, zero) live in device
+ *   memory so that CUDA-graph replays advance them. n must be a multiple of 4; world <= 8. All ranks must call
+ *   it the same number of times (the kernels wait for one another through flags in the regions).
+ */
+PCG_API size_t pcg_comm_region_bytes(int64_t n_params);
+PCG_API int pcg_comm_alloc(void** ptr, size_t bytes);
+PCG_API int pcg_comm_free(void* ptr);
+PCG_API int pcg_comm_export(void* ptr, unsigned char* handle64);
+PCG_API int pcg_comm_import(const unsigned char* handle64, void** ptr);
+PCG_API int pcg_comm_unmap(void* ptr);
+PCG_API int pcg_allreduce_adam(float* grad, float* param, float* m, float* v, int64_t n_params,
+                       void* const* peer_regions_host, int rank, int world, uint32_t* epoch, int32_t* ticket,
+                       float lr, float beta1, float beta2, float eps, float weight_decay, int do_adam,
+                       pcg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

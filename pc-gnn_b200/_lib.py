@@ -52,6 +52,14 @@ SIGNATURES = {
     "pcg_center_bwd": (_i, [_p, _l, _i, _p, _i, _p, _p, _p, _p, _p, _p]),
     "pcg_head_loss_fwd": (_i, [_p, _i, _i, _p, _p, _p, C.c_float, _p, _p, _p, _p, _p, _p, _p]),
     "pcg_head_loss_bwd": (_i, [_p, _i, _i, _p, _p, _p, _p, C.c_float, _p, _p, _p, _p, _p, _p, _p]),
+    "pcg_comm_region_bytes": (_z, [_l]),
+    "pcg_comm_alloc": (_i, [C.POINTER(_p), _z]),
+    "pcg_comm_free": (_i, [_p]),
+    "pcg_comm_export": (_i, [_p, C.c_char_p]),
+    "pcg_comm_import": (_i, [C.c_char_p, C.POINTER(_p)]),
+    "pcg_comm_unmap": (_i, [_p]),
+    "pcg_allreduce_adam": (_i, [_p, _p, _p, _p, _l, C.POINTER(_p), _i, _i, _p, _p, C.c_float, C.c_float, C.c_float,
+                                C.c_float, C.c_float, _i, _p]),
     "pcg_pick_step": (_i, [_p, _l, _p, _l, _p, _p, _p]),
     "pcg_pick_step_philox": (_i, [_p, _l, _u64, _u64, _l, _p, _p, _p]),
 }

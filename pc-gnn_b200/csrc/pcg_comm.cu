@@ -1,0 +1,182 @@
+// Gradient exchange + optimizer step of the data-parallel train step as ONE kernel over NVLink peer memory.
+//
+// The reference has no distributed code; its optimizer step is torch.optim.Adam on ~27 k
+// parameters (/root/reference/src/model_handler.py:124, 153). Data parallel over the batch's targets needs one
+// exchange per step: the sum of the small parameter gradient. With NCCL that is a separate, latency-bound
+// collective between two CUDA graphs plus torch's multi-tensor Adam; here every rank
+//   1. copies its flat gradient into a send buffer that all peers have mapped (CUDA IPC, NVLink / NVSwitch),
+//   2. raises a per-CTA flag in every peer's flag area (st.release.sys) and waits for the peers' flags,
+//   3. reads the peers' chunks straight over NVLink, adds them in RANK ORDER (every rank computes bit-identical
+//      sums, so the replicas never drift) and divides by the world size,
+//   4. applies the Adam update (same formula as torch.optim.Adam with L2 weight decay) to its replica of the
+//      parameters and clears the gradient for the next step,
+// all inside the captured step graph. world == 1 runs steps 4 only.
+#include "pcg_common.cuh"
+
+#define COMM_MAX_WORLD 8
+#define COMM_NT 256
+#define COMM_PER_CTA (COMM_NT * 4)
+
+struct CommP {
+    float* grad;
+    float* param;
+    float* m;
+    float* v;
+    int n;
+    int64_t n_pad;                        // floats per send buffer (two of them, double buffered by step parity)
+    float* peer_send[COMM_MAX_WORLD];     // every rank's send area, as mapped HERE
+    uint32_t* peer_flags[COMM_MAX_WORLD]; // every rank's flag area [n_cta][COMM_MAX_WORLD]
+    uint32_t* epoch;                      // steps completed so far (device counter, so graph replays advance it)
+    int32_t* ticket;
+    int rank, world;
+    float lr, b1, b2, eps, wd;
+    int do_adam;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(COMM_NT) k_allreduce_adam(CommP p) {
+    __shared__ float s_c[2];              // step size, 1 / sqrt(bias correction 2)
+    const int tid = threadIdx.x, c = blockIdx.x;
+    const uint32_t e = *(volatile uint32_t*)p.epoch + 1u;      // this step's number (1-based)
+    const int i0 = c * COMM_PER_CTA + tid * 4;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool in = i0 < p.n;             // n is padded to a multiple of 4 by the caller
+    if (in) g = *reinterpret_cast<const float4*>(p.grad + i0);
+    if (p.world > 1) {
+        const int64_t boff = (int64_t)(e & 1u) * p.n_pad;
+        if (in) *reinterpret_cast<float4*>(p.peer_send[p.rank] + boff + i0) = g;
+        __syncthreads();
+        if (tid < p.world) {
+            __threadfence_system();
+            st_release_sys(p.peer_flags[tid] + (int64_t)c * COMM_MAX_WORLD + p.rank, e);
+            const uint32_t* mine = p.peer_flags[p.rank] + (int64_t)c * COMM_MAX_WORLD + tid;
+            while ((int32_t)(ld_acquire_sys(mine) - e) < 0) { }
+        }
+        __syncthreads();
+        if (in) {
+            g = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = 0; r < p.world; ++r) {                 // rank order: identical sums everywhere
+                const float4 x = __ldcv(reinterpret_cast<const float4*>(p.peer_send[r] + boff + i0));
+                g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
+            }
+            const float inv = 1.0f / (float)p.world;
+            g.x *= inv; g.y *= inv; g.z *= inv; g.w *= inv;
+        }
+    }
+    if (p.do_adam) {
+        if (tid == 0) {
+            const double bc1 = 1.0 - pow((double)p.b1, (double)e), bc2 = 1.0 - pow((double)p.b2, (double)e);
+            s_c[0] = (float)((double)p.lr / bc1);
+            s_c[1] = (float)(1.0 / sqrt(bc2));
+        }
+        __syncthreads();
+        if (in) {
+            const float step = s_c[0], rs2 = s_c[1];
+            float4 w = *reinterpret_cast<float4*>(p.param + i0);
+            float4 m = *reinterpret_cast<float4*>(p.m + i0);
+            float4 v = *reinterpret_cast<float4*>(p.v + i0);
+#define PCG_ADAM1(W, M, V, G)                                           \
+            {                                                           \
+                const float gg = fmaf(p.wd, W, G);                      \
+                M = fmaf(1.0f - p.b1, gg - M, M);                       \
+                V = fmaf(1.0f - p.b2, gg * gg - V, V);                  \
+                W -= step * M / (sqrtf(V) * rs2 + p.eps);               \
+            }
+            PCG_ADAM1(w.x, m.x, v.x, g.x) PCG_ADAM1(w.y, m.y, v.y, g.y)
+            PCG_ADAM1(w.z, m.z, v.z, g.z) PCG_ADAM1(w.w, m.w, v.w, g.w)
+#undef PCG_ADAM1
+            *reinterpret_cast<float4*>(p.param + i0) = w;
+            *reinterpret_cast<float4*>(p.m + i0) = m;
+            *reinterpret_cast<float4*>(p.v + i0) = v;
+            *reinterpret_cast<float4*>(p.grad + i0) = make_float4(0.f, 0.f, 0.f, 0.f);   // ready for the next backward
+        }
+    } else if (in) {
+        *reinterpret_cast<float4*>(p.grad + i0) = g;
+    }
+    // last CTA out advances the step counter (every CTA has read it long before)
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(p.ticket, 1) == (int)gridDim.x - 1) {
+            *p.ticket = 0;
+            *(volatile uint32_t*)p.epoch = e;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------- C ABI
+extern "C" int pcg_comm_alloc(void** ptr, size_t bytes) {
+    PCG_REQUIRE(ptr && bytes > 0, "pcg_comm_alloc: bad arguments");
+    cudaError_t e = cudaMalloc(ptr, bytes);
+    if (e == cudaSuccess) e = cudaMemset(*ptr, 0, bytes);
+    if (e != cudaSuccess) { pcg_set_error("pcg_comm_alloc: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
+
+extern "C" int pcg_comm_free(void* ptr) {
+    cudaError_t e = cudaFree(ptr);
+    if (e != cudaSuccess) { pcg_set_error("pcg_comm_free: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
+
+extern "C" int pcg_comm_export(void* ptr, unsigned char* handle64) {
+    PCG_REQUIRE(ptr && handle64, "pcg_comm_export: null pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, ptr);
+    if (e != cudaSuccess) { pcg_set_error("pcg_comm_export: %s", cudaGetErrorString(e)); return (int)e; }
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+
+extern "C" int pcg_comm_import(const unsigned char* handle64, void** ptr) {
+    PCG_REQUIRE(ptr && handle64, "pcg_comm_import: null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { pcg_set_error("pcg_comm_import: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
+
+extern "C" int pcg_comm_unmap(void* ptr) {
+    cudaError_t e = cudaIpcCloseMemHandle(ptr);
+    if (e != cudaSuccess) { pcg_set_error("pcg_comm_unmap: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
+
+extern "C" size_t pcg_comm_region_bytes(int64_t n_params) {
+    const int64_t n_pad = (n_params + COMM_PER_CTA - 1) / COMM_PER_CTA * COMM_PER_CTA;
+    const int64_t n_cta = n_pad / COMM_PER_CTA;
+    return (size_t)(2 * n_pad * 4 + n_cta * COMM_MAX_WORLD * 4 + 256);
+}
+
+extern "C" int pcg_allreduce_adam(float* grad, float* param, float* m, float* v, int64_t n_params,
+                                  void* const* peer_regions_host, int rank, int world, uint32_t* epoch, int32_t* ticket,
+                                  float lr, float beta1, float beta2, float eps, float weight_decay, int do_adam,
+                                  pcg_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PCG_REQUIRE(grad && epoch && ticket && n_params > 0 && n_params % 4 == 0, "pcg_allreduce_adam: bad arguments");
+    PCG_REQUIRE(!do_adam || (param && m && v), "pcg_allreduce_adam: optimizer state missing");
+    PCG_REQUIRE(world >= 1 && world <= COMM_MAX_WORLD && rank >= 0 && rank < world, "pcg_allreduce_adam: bad rank/world");
+    PCG_REQUIRE(world == 1 || peer_regions_host, "pcg_allreduce_adam: peer regions missing");
+    CommP p;
+    p.grad = grad; p.param = param; p.m = m; p.v = v; p.n = (int)n_params;
+    p.n_pad = (n_params + COMM_PER_CTA - 1) / COMM_PER_CTA * COMM_PER_CTA;
+    for (int r = 0; r < COMM_MAX_WORLD; ++r) {
+        char* base = (world > 1 && r < world) ? (char*)peer_regions_host[r] : nullptr;
+        p.peer_send[r] = (float*)base;
+        p.peer_flags[r] = base ? (uint32_t*)(base + 2 * p.n_pad * 4) : nullptr;
+    }
+    p.epoch = epoch; p.ticket = ticket; p.rank = rank; p.world = world;
+    p.lr = lr; p.b1 = beta1; p.b2 = beta2; p.eps = eps; p.wd = weight_decay; p.do_adam = do_adam;
+    k_allreduce_adam<<<(unsigned)(p.n_pad / COMM_PER_CTA), COMM_NT, 0, stream>>>(p);
+    return pcg_check_launch("pcg_allreduce_adam");
+}

@@ -11,7 +11,7 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_range", "shard_batch", "GradAllReduce", "global_mean_loss_scale"]
+__all__ = ["shard_range", "shard_batch", "GradAllReduce", "global_mean_loss_scale", "PeerComm", "FusedAdam"]
 
 
 def shard_range(n: int, rank: int, world: int):
@@ -42,8 +42,9 @@ class GradAllReduce:
         self.params = [p for p in params if p.requires_grad]
         self.group = group
         n = sum(p.numel() for p in self.params)
+        self.n = n
         dev = self.params[0].device if self.params else torch.device("cpu")
-        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.flat = torch.zeros((n + 3) // 4 * 4, dtype=torch.float32, device=dev)   # padded: float4 kernels
         self.views = []
         o = 0
         for p in self.params:
@@ -68,3 +69,96 @@ class GradAllReduce:
                     p.grad = v
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
         return self.flat
+
+
+class PeerComm:
+    """One region of device memory per rank that every peer of the node has mapped (CUDA IPC over NVLink /
+    NVSwitch): send buffers + flags of the fused gradient exchange (csrc/pcg_comm.cu). world == 1: no region."""
+
+    def __init__(self, n_params: int, group=None):
+        import ctypes as C
+
+        from . import _lib
+
+        self.lib = _lib.lib()
+        self.group = group
+        on = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if on else 1
+        self.rank = dist.get_rank(group) if on else 0
+        self.regions = None
+        self._own = self._mapped = None
+        if self.world == 1:
+            return
+        if self.world > 8:
+            raise ValueError("the peer-memory exchange is written for one node (<= 8 GPUs)")
+        nbytes = int(self.lib.pcg_comm_region_bytes(n_params))
+        own = C.c_void_p()
+        _lib.check(self.lib.pcg_comm_alloc(C.byref(own), nbytes), "pcg_comm_alloc")
+        self._own = own.value
+        buf = C.create_string_buffer(64)
+        _lib.check(self.lib.pcg_comm_export(self._own, buf), "pcg_comm_export")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(buf.raw), group=group)
+        ptrs, self._mapped = [], []
+        for r in range(self.world):
+            if r == self.rank:
+                ptrs.append(self._own)
+                continue
+            q = C.c_void_p()
+            _lib.check(self.lib.pcg_comm_import(handles[r], C.byref(q)), "pcg_comm_import")
+            ptrs.append(q.value)
+            self._mapped.append(q.value)
+        self.regions = (C.c_void_p * self.world)(*ptrs)
+        dist.barrier(group=group)      # nobody signals into a region that is not mapped everywhere yet
+
+    def close(self):
+        if self._mapped:
+            for q in self._mapped:
+                self.lib.pcg_comm_unmap(q)
+            self._mapped = None
+        if self._own:
+            self.lib.pcg_comm_free(self._own)
+            self._own = None
+
+
+class FusedAdam:
+    """torch.optim.Adam(lr, betas, eps, weight_decay) on a flat replica of the parameters, fused with the
+    data-parallel gradient mean into one kernel (``pcg_allreduce_adam``). The parameters' ``.data`` and
+    ``.grad`` become views into flat buffers; ``step()`` is CUDA-graph capturable (the step count lives on
+    the device) and leaves the gradients zeroed for the next backward."""
+
+    def __init__(self, reducer: GradAllReduce, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, comm=None):
+        from . import _lib
+
+        self.lib = _lib.lib()
+        self.reducer, self.comm = reducer, comm
+        self.lr, self.betas, self.eps, self.wd = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
+        flat = reducer.flat
+        self.param = torch.zeros_like(flat)
+        o = 0
+        with torch.no_grad():
+            for p in reducer.params:
+                n = p.numel()
+                self.param[o:o + n].copy_(p.data.reshape(-1))
+                p.data = self.param[o:o + n].view_as(p)
+                o += n
+        self.m = torch.zeros_like(flat)
+        self.v = torch.zeros_like(flat)
+        self.state = torch.zeros(2, dtype=torch.int32, device=flat.device)      # [step count, ticket]
+
+    @property
+    def steps(self) -> int:
+        return int(self.state[0].item())
+
+    def step(self, do_adam: bool = True):
+        from . import _lib
+
+        c = self.comm
+        world = c.world if c is not None else 1
+        rc = self.lib.pcg_allreduce_adam(self.reducer.flat.data_ptr(), self.param.data_ptr(), self.m.data_ptr(),
+                                         self.v.data_ptr(), self.reducer.flat.numel(),
+                                         c.regions if (c is not None and world > 1) else None,
+                                         c.rank if c is not None else 0, world, self.state.data_ptr(),
+                                         self.state[1:].data_ptr(), self.lr, self.betas[0], self.betas[1], self.eps,
+                                         self.wd, int(do_adam), _lib.stream_ptr())
+        _lib.check(rc, "pcg_allreduce_adam")

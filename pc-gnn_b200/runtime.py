@@ -22,6 +22,11 @@ class GraphedTrainStep:
 
     def __init__(self, model, optimizer, batch_size: int, cap_slots: int, reducer=None, world: int = 1,
                  warmup_batch=None):
+        """optimizer: a capturable torch optimizer (gradient mean over ranks by NCCL between two graphs), or a
+        ``parallel.FusedAdam`` (gradient exchange over peer memory + Adam inside the one step graph)."""
+        from .parallel import FusedAdam
+
+        self.fused = isinstance(optimizer, FusedAdam)
         self.model, self.opt, self.B = model, optimizer, int(batch_size)
         self.reducer, self.world = reducer, world
         # the module that sizes the per-step slot buffer: InterAgg for PC-GNN, the row aggregator for GCN / SAGE
@@ -57,7 +62,9 @@ class GraphedTrainStep:
         if self._xeng is not None and not torch.cuda.is_current_stream_capturing():
             self._score_pre()                      # eager warm-up steps: slice, exchange, then the forward
             self._xeng.score_exchange()
-        if self.reducer is not None:
+        if self.fused:
+            pass                                   # the fused step leaves the gradients zeroed
+        elif self.reducer is not None:
             self.reducer.zero()
         else:
             self.opt.zero_grad(set_to_none=False)
@@ -75,7 +82,24 @@ class GraphedTrainStep:
                         if p.requires_grad and p.grad is None:
                             p.grad = torch.zeros_like(p)
                 self._fwd_bwd()
+                if self.fused:
+                    self.reducer.zero()
                 # no optimizer step during warm-up: parameters stay as the caller initialised them
+            if self.fused:
+                torch.cuda.current_stream(self.dev).wait_stream(s)
+        if self.fused:
+            torch.cuda.synchronize(self.dev)
+            if self._xeng is not None:
+                self.g_pre = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.g_pre):
+                    self._score_pre()
+            self.g_fb = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_fb):
+                self.loss = self._fwd_bwd()
+                self.opt.step()                    # gradient mean over the ranks + Adam, one kernel
+            self.g_opt = None
+            return
+        with torch.cuda.stream(s):
             # Create the optimizer state OUTSIDE the graph: torch builds it lazily in the first step(), and a
             # captured lazy init would re-zero the moments on every replay. Step once, then undo it.
             params = [p for g in self.opt.param_groups for p in g["params"] if p.requires_grad]
@@ -111,6 +135,8 @@ class GraphedTrainStep:
             self.g_pre.replay()
             self._xeng.score_exchange()
         self.g_fb.replay()
+        if self.fused:
+            return self.loss
         if self.world > 1 and self.reducer is not None:
             self.reducer()                       # one NCCL all-reduce of the flat gradient
             self.reducer.flat.div_(self.world)

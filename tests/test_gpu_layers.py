@@ -407,3 +407,63 @@ def test_homo_baselines_match_golden(kind):
         assert rel_err(enc(nodes).cpu().numpy(), g["emb"]) <= TOL
     assert rel_err(enc.weight.grad.cpu().numpy(), g["grad_enc"]) <= GTOL
     assert rel_err(model.weight.grad.cpu().numpy(), g["grad_head"]) <= GTOL
+
+
+def test_fused_adam_kernel_matches_torch_adam_on_the_same_gradients():
+    """pcg_allreduce_adam (world 1) against torch.optim.Adam fed with identical gradients, 12 steps."""
+    import torch.nn as nn
+    from pcgnn_b200.parallel import FusedAdam, GradAllReduce
+
+    torch.manual_seed(0)
+    shapes = [(217, 64), (50, 64), (2, 25), (2,), (2, 64), (7,)]          # 17,307 floats: not a multiple of 4
+    ref = [nn.Parameter(torch.randn(*s, device="cuda")) for s in shapes]
+    mine = [nn.Parameter(p.detach().clone()) for p in ref]
+    opt_ref = torch.optim.Adam(ref, lr=0.01, weight_decay=1e-3)
+    reducer = GradAllReduce(mine).attach()
+    opt = FusedAdam(reducer, lr=0.01, weight_decay=1e-3)
+    for step in range(12):
+        grads = [torch.randn(*s, device="cuda") * (10.0 ** (step % 4 - 2)) for s in shapes]
+        for p, q, g in zip(ref, mine, grads):
+            p.grad = g.clone()
+            q.grad.copy_(g)
+        opt_ref.step()
+        opt.step()
+        assert float(reducer.flat.abs().max()) == 0.0                       # gradients cleared for the next backward
+    assert opt.steps == 12
+    for p, q in zip(ref, mine):
+        assert rel_err(q.detach().cpu().numpy(), p.detach().cpu().numpy()) <= 2e-6
+
+
+def test_fused_adam_train_step_follows_torch_adam():
+    """parallel.FusedAdam inside the step graph against torch.optim.Adam on the same batches: same losses
+    (individual weights with vanishing gradients may differ: Adam's m / sqrt(v) amplifies rounding there)."""
+    from pcgnn_b200.parallel import FusedAdam, GradAllReduce
+    from pcgnn_b200.runtime import GraphedTrainStep
+    from pcgnn_b200.synth import make_graph
+
+    d = make_graph("tiny", seed=11)
+    rng = np.random.default_rng(4)
+    params = random_params(rng, d.feat.shape[1], 16, 3)
+    tp = sorted(d.train_pos)
+    batches = [rng.choice(d.idx_train, 64) for _ in range(6)]
+    results = []
+    for fused in (False, True):
+        model = build_cuda_pcgnn(d.feat, d.graph, tp, params)
+        reducer = GradAllReduce(model.parameters()).attach()
+        if fused:
+            opt = FusedAdam(reducer, lr=0.01, weight_decay=1e-3)
+        else:
+            opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=0.01, weight_decay=1e-3,
+                                   capturable=True)
+        eng = model.inter1.engine()
+        eng.set_features(model.inter1.features.weight)
+        cap = max(eng.slots_bound(np.asarray(b, dtype=np.int32), [0.5] * 3, 0.5, True) for b in batches)
+        g = GraphedTrainStep(model, opt, 64, cap, reducer=reducer, warmup_batch=(batches[0], d.labels[batches[0]]))
+        losses = [float(g.run(b, d.labels[b]).item()) for b in batches]
+        assert not g.overflowed()
+        results.append((losses, {k: v.detach().cpu().numpy().copy() for k, v in model.named_parameters()
+                                 if v.requires_grad}))
+    (l0, p0), (l1, p1) = results
+    assert np.allclose(l0, l1, rtol=5e-5, atol=0)
+    for k in p0:
+        assert rel_err(p1[k], p0[k]) <= 5e-3, k
