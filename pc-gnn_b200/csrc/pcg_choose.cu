@@ -825,17 +825,6 @@ __device__ void choose_item_warp(const ChooseP& p, int w, WarpSmem& s) {
     TRACE(7);
 }
 
-// d <= 128: one item per warp.
-__global__ void __launch_bounds__(PCG_WARPS_PER_CTA * 32, 3) k_choose_warp(ChooseP p) {
-    __shared__ WarpSmem sm[PCG_WARPS_PER_CTA];
-    const int wid = threadIdx.x >> 5;
-    WarpSmem& s = sm[wid];
-    for (int b = threadIdx.x & 31; b < 256; b += 32) s.shist[b] = 0u;
-    __syncwarp();
-    const int n = p.status[ST_NSMALL];
-    const int n_warps = gridDim.x * PCG_WARPS_PER_CTA;
-    for (int q = blockIdx.x * PCG_WARPS_PER_CTA + wid; q < n; q += n_warps) choose_item_warp(p, p.q_warp[q], s);
-}
 
 // ------------------------------------------------------------------------ CTA tiers
 // One item handled by one CTA of NT threads (256 or 1024) with the row in REGISTERS: NE keys per thread,
@@ -1002,13 +991,47 @@ __device__ __forceinline__ void cta_item(const ChooseP& p, int w, CtaSmem<NT>& s
     TRACE(7);
 }
 
-// 128 < d <= 1024: one item per 256-thread CTA.
-__global__ void __launch_bounds__(PCG_GRP_NT, 4) k_choose_cta(ChooseP p) {
-    __shared__ CtaSmem<PCG_GRP_NT> s;
-    for (int b = threadIdx.x; b < 8 * 256; b += PCG_GRP_NT) s.hist[b] = 0u;
-    __syncthreads();
-    const int n = p.status[ST_NMID];
-    for (int q = blockIdx.x; q < n; q += gridDim.x) cta_item<PCG_GRP_NT, 1>(p, p.q_cta[q], s, nullptr, nullptr, 0, nullptr);
+// d <= 1024: one kernel of 256-thread CTAs serves both short tiers from two device-side queues: first the
+// rows of 128 < d <= 1024 (one per CTA), then the rows of d <= 128 (one per warp), so CTAs that get no
+// (or short) CTA-tier rows take more of the warp-tier rows and no tier waits for the other's registers.
+__global__ void __launch_bounds__(PCG_GRP_NT, 3) k_choose_small(ChooseP p) {
+    constexpr size_t SM_BYTES = sizeof(CtaSmem<PCG_GRP_NT>) > sizeof(WarpSmem) * PCG_WARPS_PER_CTA
+                                    ? sizeof(CtaSmem<PCG_GRP_NT>) : sizeof(WarpSmem) * PCG_WARPS_PER_CTA;
+    __shared__ __align__(16) unsigned char raw[SM_BYTES];
+    __shared__ int s_q;
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // half of the CTAs start with the warp-tier queue, the other half with the cta-tier queue, so both drain
+    // from the first microsecond; every CTA then helps with whatever is left of the other queue
+#pragma unroll 1
+    for (int phase = 0; phase < 2; ++phase) {
+        const bool cta_phase = ((blockIdx.x + phase) & 1) == 0;
+        __syncthreads();                       // the two tiers lay the shared memory out differently
+        if (cta_phase) {
+            CtaSmem<PCG_GRP_NT>& s = *reinterpret_cast<CtaSmem<PCG_GRP_NT>*>(raw);
+            for (int b = threadIdx.x; b < 8 * 256; b += PCG_GRP_NT) s.hist[b] = 0u;
+            const int n = p.status[ST_NMID];
+            for (;;) {
+                __syncthreads();
+                if (threadIdx.x == 0) s_q = atomicAdd(&p.status[ST_MID_CTR], 1);
+                __syncthreads();
+                const int q = s_q;
+                if (q >= n) break;
+                cta_item<PCG_GRP_NT, 1>(p, p.q_cta[q], s, nullptr, nullptr, 0, nullptr);
+            }
+        } else {
+            WarpSmem& ws = reinterpret_cast<WarpSmem*>(raw)[wid];
+            for (int b = lane; b < 256; b += 32) ws.shist[b] = 0u;
+            __syncwarp();
+            const int n = p.status[ST_NSMALL];
+            for (;;) {
+                int q = 0;
+                if (lane == 0) q = atomicAdd(&p.status[ST_SMALL_CTR], 1);
+                q = __shfl_sync(PCG_FULL, q, 0);
+                if (q >= n) break;
+                choose_item_warp(p, p.q_warp[q], ws);
+            }
+        }
+    }
 }
 
 // 1024 < d <= 16384: one item per CLUSTER of 8 CTAs x 256 threads (<= 8 entries per thread): the longest rows are
@@ -1517,7 +1540,7 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
         if (e != cudaSuccess) { pcg_set_error("pcg_choose: prep launch: %s", cudaGetErrorString(e)); return (int)e; }
     }
     const bool have_cta = max_degree > PCG_SMALL_MAX, have_cl = max_degree > PCG_CTA_MAX, have_big = max_degree > PCG_CL_MAX;
-    if (have_cta && !g_fork) {
+    if (have_cl && !g_fork) {
         for (int q = 0; q < PCG_N_SIDE; ++q)
             if ((e = cudaStreamCreateWithFlags(&g_side[q], cudaStreamNonBlocking)) != cudaSuccess ||
                 (e = cudaEventCreateWithFlags(&g_join[q], cudaEventDisableTiming)) != cudaSuccess) {
@@ -1529,7 +1552,7 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
             return (int)e;
         }
     }
-    if (have_cta) cudaEventRecord(g_fork, stream);     // fork: the tiers run side by side, longest rows first
+    if (have_cl) cudaEventRecord(g_fork, stream);      // fork: the tiers run side by side, longest rows first
     if (have_big) {
         int64_t cap = max_degree > 49152 ? 49152 : (max_degree + 31) / 32 * 32;
         size_t dyn = (size_t)cap * 4;
@@ -1549,16 +1572,11 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
         k_choose_wide<<<n_cl * PCG_CL, PCG_GRP_NT, 0, g_side[1]>>>(p);
         cudaEventRecord(g_join[1], g_side[1]);
     }
-    if (have_cta) {
-        cudaStreamWaitEvent(g_side[0], g_fork, 0);
-        int gm = W < sms * 4 ? W : sms * 4;
-        k_choose_cta<<<gm, PCG_GRP_NT, 0, g_side[0]>>>(p);
-        cudaEventRecord(g_join[0], g_side[0]);
+    {
+        const int units = W / PCG_WARPS_PER_CTA + 1 + (have_cta ? W : 0);
+        const int gs = units < sms * 3 ? units : sms * 3;
+        k_choose_small<<<gs, PCG_GRP_NT, 0, stream>>>(p);
     }
-    int gw = (W + PCG_WARPS_PER_CTA - 1) / PCG_WARPS_PER_CTA;
-    if (gw > sms * 3) gw = sms * 3;
-    k_choose_warp<<<gw, PCG_WARPS_PER_CTA * 32, 0, stream>>>(p);
-    if (have_cta) cudaStreamWaitEvent(stream, g_join[0], 0);      // join
     if (have_cl) cudaStreamWaitEvent(stream, g_join[1], 0);
     if (have_big) cudaStreamWaitEvent(stream, g_join[2], 0);
     return pcg_check_launch("pcg_choose");
