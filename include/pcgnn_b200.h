@@ -142,13 +142,16 @@ PCG_API int pcg_select_all(const int64_t* indptr, const int32_t* indices, int64_
  * Replaces the dense-mask matmul of src/layers.py:593-624 and src/graphsage.py:80-95, 212-231.
  *   idx       the id array the items index (sel_idx from pcg_choose, or CSR indices from select_all)
  *   it_extra / it_rep  from pcg_select_all / pcg_choose, or NULL
+ *   copy_dups  != 0: rows of repeated targets (it_rep[w] != w) are filled with their representative's row by a
+ *              second kernel; 0: they are left unwritten and the consumer reads row it_rep[w] instead
+ *              (pcg_dense_fwd / pcg_dense_bwd take it_rep as `agg_rep`)
  *   partial   fp32 [cap_slots, ldf] scratch, it_done int32 [n_items] tickets zeroed by choose/select
  *   agg       fp32 [n_items, ldf]
  */
 PCG_API int pcg_aggregate(const float* feat, int64_t ldf, const int32_t* idx, const int32_t* slot_item,
                   const int32_t* it_slot0, const int32_t* it_m, const int64_t* it_base, const int32_t* it_extra,
-                  const int32_t* it_rep, int n_items, int64_t cap_slots, const int32_t* status, int norm,
-                  float* partial, int32_t* it_done, float* agg, pcg_stream_t stream);
+                  const int32_t* it_rep, int copy_dups, int n_items, int64_t cap_slots, const int32_t* status,
+                  int norm, float* partial, int32_t* it_done, float* agg, pcg_stream_t stream);
 
 /*
  * Backward of pcg_aggregate w.r.t. the feature table (only needed when `features` is trainable; the
@@ -168,10 +171,11 @@ PCG_API int pcg_aggregate_bwd(const float* d_agg, int64_t ldf, const int32_t* id
  *   w_intra_host  HOST array of R device pointers, each the reference's IntraAgg.weight [2F, E] row-major
  *   w_inter       device [F+R*E, E]
  *   cat           fp32 [B, F+R*E] (kept for backward), out fp32 [E, B]
+ *   agg_rep       int32 [R*B] or NULL: row of `agg` that holds item w's aggregate (pcg_choose's it_rep)
  */
 PCG_API int pcg_dense_fwd(const float* feat, int64_t ldf, int F, const int32_t* targets, int B, int R, int E,
-                  const float* agg, const float* const* w_intra_host, const float* w_inter, float* cat, float* out,
-                  pcg_stream_t stream);
+                  const float* agg, const int32_t* agg_rep, const float* const* w_intra_host, const float* w_inter,
+                  float* cat, float* out, pcg_stream_t stream);
 
 /*
  * Backward of pcg_dense_fwd w.r.t. the weights (the reference's features are frozen, src/model_handler.py:85-86,
@@ -180,7 +184,8 @@ PCG_API int pcg_dense_fwd(const float* feat, int64_t ldf, int F, const int32_t* 
  *   d_out    fp32 [E,B] gradient of `out`;  scratch  pcg_dense_bwd_scratch_floats(B,R,F,E) floats
  */
 PCG_API size_t pcg_dense_bwd_scratch_floats(int B, int R, int F, int E);
-PCG_API int pcg_dense_bwd(int64_t ldf, int F, int B, int R, int E, const float* agg, const float* w_inter,
+PCG_API int pcg_dense_bwd(int64_t ldf, int F, int B, int R, int E, const float* agg, const int32_t* agg_rep,
+                  const float* w_inter,
                   const float* cat, const float* out, const float* d_out, float* const* d_w_intra_host,
                   float* d_w_inter, float* scratch, pcg_stream_t stream);
 

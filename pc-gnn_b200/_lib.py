@@ -42,11 +42,11 @@ SIGNATURES = {
     "pcg_choose": (_i, [_p, _p, _l, _l, _i, _p, _p, _p, _p, _p, _i, C.POINTER(_d), _p, _d, _p, _p, _p, _p, _i, _i, _l,
                         _p, _p, _l, _p, _p, _p, _p, _p, _p, _p, _z, _p, _p]),
     "pcg_select_all": (_i, [_p, _p, _l, _i, _p, _i, _i, _l, _p, _p, _p, _p, _p, _p, _p, _p]),
-    "pcg_aggregate": (_i, [_p, _l, _p, _p, _p, _p, _p, _p, _p, _i, _l, _p, _i, _p, _p, _p, _p]),
+    "pcg_aggregate": (_i, [_p, _l, _p, _p, _p, _p, _p, _p, _p, _i, _i, _l, _p, _i, _p, _p, _p, _p]),
     "pcg_aggregate_bwd": (_i, [_p, _l, _p, _p, _p, _p, _p, _p, _i, _l, _p, _i, _p, _p]),
-    "pcg_dense_fwd": (_i, [_p, _l, _i, _p, _i, _i, _i, _p, C.POINTER(_p), _p, _p, _p, _p]),
+    "pcg_dense_fwd": (_i, [_p, _l, _i, _p, _i, _i, _i, _p, _p, C.POINTER(_p), _p, _p, _p, _p]),
     "pcg_dense_bwd_scratch_floats": (_z, [_i, _i, _i, _i]),
-    "pcg_dense_bwd": (_i, [_l, _i, _i, _i, _i, _p, _p, _p, _p, _p, C.POINTER(_p), _p, _p, _p]),
+    "pcg_dense_bwd": (_i, [_l, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, C.POINTER(_p), _p, _p, _p]),
     "pcg_head_scratch_floats": (_z, [_i, _i, _i]),
     "pcg_center_fwd": (_i, [_p, _l, _i, _p, _i, _p, _p, _p, _p]),
     "pcg_center_bwd": (_i, [_p, _l, _i, _p, _i, _p, _p, _p, _p, _p, _p]),

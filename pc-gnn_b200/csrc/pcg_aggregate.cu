@@ -33,7 +33,8 @@ __global__ void __launch_bounds__(256) k_aggregate(const float* __restrict__ fea
                                                    const int32_t* __restrict__ it_slot0,
                                                    const int32_t* __restrict__ it_m,
                                                    const int64_t* __restrict__ it_base,
-                                                   const int32_t* __restrict__ it_extra, int64_t cap_slots,
+                                                   const int32_t* __restrict__ it_extra,
+                                                   const int32_t* __restrict__ it_rep, int n_items, int64_t cap_slots,
                                                    const int32_t* __restrict__ status, int norm, float* partial,
                                                    int32_t* it_done, float* __restrict__ agg) {
     constexpr int G = 32 / LPR;          // rows per warp-wide load
@@ -44,6 +45,13 @@ __global__ void __launch_bounds__(256) k_aggregate(const float* __restrict__ fea
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int V = (int)(ldf >> 2);       // float4 per row
     const int g = lane / LPR, l = lane % LPR;
+    // items that own no slot (m == 0, no extra) never reach the slot loop below: zero their rows here
+    for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_items; w += n_warps) {
+        if (it_rep && it_rep[w] != w) continue;              // repeated targets have no row of their own
+        if (it_m[w] > 0 || (it_extra && it_extra[w] >= 0)) continue;
+        for (int c = lane; c < V; c += 32)
+            *reinterpret_cast<float4*>(agg + w * ldf + 4 * c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     // grid-stride over the handed-out slots: the launch size does not depend on the capacity
     for (int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < n_slots; s += n_warps) {
     const int w = slot_item[s];
@@ -127,16 +135,6 @@ __global__ void __launch_bounds__(256) k_aggregate(const float* __restrict__ fea
     }
 }
 
-// Items that own no slot (m == 0, no extra) never reach a warp above: zero their rows first.
-__global__ void k_zero_empty(const int32_t* __restrict__ it_m, const int32_t* __restrict__ it_extra,
-                             const int32_t* __restrict__ it_rep, int n_items, int64_t ldf, float* __restrict__ agg) {
-    const int w = blockIdx.x;
-    if (w >= n_items) return;
-    if (it_rep && it_rep[w] != w) return;                 // duplicates are copied from their representative
-    if (it_m[w] > 0 || (it_extra && it_extra[w] >= 0)) return;
-    for (int64_t c = threadIdx.x; c < ldf; c += blockDim.x) agg[(int64_t)w * ldf + c] = 0.f;
-}
-
 // agg row of a duplicate item = agg row of its representative (see k_choose_classify).
 __global__ void k_copy_dups(const int32_t* __restrict__ it_rep, int n_items, int64_t ldf, float* __restrict__ agg) {
     const int w = blockIdx.x;
@@ -208,14 +206,14 @@ __global__ void __launch_bounds__(256) k_aggregate_bwd(const float* __restrict__
 template <int LPR, int NV>
 static void launch_agg(bool bwd, const float* a0, int64_t ldf, const int32_t* idx, const int32_t* slot_item,
                        const int32_t* it_slot0, const int32_t* it_m, const int64_t* it_base, const int32_t* it_extra,
-                       int64_t cap_slots, const int32_t* status, int norm, float* partial, int32_t* it_done, float* out,
+                       const int32_t* it_rep, int n_items, int64_t cap_slots, const int32_t* status, int norm, float* partial, int32_t* it_done, float* out,
                        cudaStream_t stream) {
     int64_t blocks64 = (cap_slots * 32 + 255) / 256;
     const int64_t max_blocks = (int64_t)pcg_device_sms() * 8;      // 8 resident CTAs of 8 warps per SM
     const int blocks = (int)(blocks64 < max_blocks ? blocks64 : max_blocks);
     if (!bwd)
         k_aggregate<LPR, NV><<<blocks, 256, 0, stream>>>(a0, ldf, idx, slot_item, it_slot0, it_m, it_base, it_extra,
-                                                         cap_slots, status, norm, partial, it_done, out);
+                                                         it_rep, n_items, cap_slots, status, norm, partial, it_done, out);
     else
         k_aggregate_bwd<LPR, NV><<<blocks, 256, 0, stream>>>(a0, ldf, idx, slot_item, it_slot0, it_m, it_base, it_extra,
                                                              cap_slots, status, norm, out);
@@ -223,12 +221,12 @@ static void launch_agg(bool bwd, const float* a0, int64_t ldf, const int32_t* id
 
 static int dispatch_agg(bool bwd, const float* a0, int64_t ldf, const int32_t* idx, const int32_t* slot_item,
                         const int32_t* it_slot0, const int32_t* it_m, const int64_t* it_base, const int32_t* it_extra,
-                        int64_t cap_slots, const int32_t* status, int norm, float* partial, int32_t* it_done, float* out,
+                        const int32_t* it_rep, int n_items, int64_t cap_slots, const int32_t* status, int norm, float* partial, int32_t* it_done, float* out,
                         cudaStream_t stream) {
     const int64_t V = ldf / 4;
 #define PCG_AGG(LPR, NV)                                                                                          \
-    launch_agg<LPR, NV>(bwd, a0, ldf, idx, slot_item, it_slot0, it_m, it_base, it_extra, cap_slots, status, norm, \
-                        partial, it_done, out, stream)
+    launch_agg<LPR, NV>(bwd, a0, ldf, idx, slot_item, it_slot0, it_m, it_base, it_extra, it_rep, n_items, cap_slots, \
+                        status, norm, partial, it_done, out, stream)
     if (V <= 8) PCG_AGG(8, 1);
     else if (V <= 16) PCG_AGG(16, 1);
     else if (V <= 32) PCG_AGG(32, 1);
@@ -244,9 +242,9 @@ static int dispatch_agg(bool bwd, const float* a0, int64_t ldf, const int32_t* i
 
 extern "C" int pcg_aggregate(const float* feat, int64_t ldf, const int32_t* idx, const int32_t* slot_item,
                              const int32_t* it_slot0, const int32_t* it_m, const int64_t* it_base,
-                             const int32_t* it_extra, const int32_t* it_rep, int n_items, int64_t cap_slots,
-                             const int32_t* status, int norm, float* partial, int32_t* it_done, float* agg,
-                             pcg_stream_t stream_) {
+                             const int32_t* it_extra, const int32_t* it_rep, int copy_dups, int n_items,
+                             int64_t cap_slots, const int32_t* status, int norm, float* partial, int32_t* it_done,
+                             float* agg, pcg_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n_items == 0) return 0;
     PCG_REQUIRE(ldf > 0 && ldf % 4 == 0, "pcg_aggregate: ldf=%lld must be a positive multiple of 4", (long long)ldf);
@@ -255,11 +253,10 @@ extern "C" int pcg_aggregate(const float* feat, int64_t ldf, const int32_t* idx,
     PCG_REQUIRE(((uintptr_t)feat & 15) == 0 && ((uintptr_t)agg & 15) == 0 && ((uintptr_t)partial & 15) == 0,
                 "pcg_aggregate: feat/agg/partial must be 16-byte aligned");
     if (n_items == 0 || cap_slots == 0) return 0;
-    k_zero_empty<<<n_items, 64, 0, stream>>>(it_m, it_extra, it_rep, n_items, ldf, agg);
-    int rc = dispatch_agg(false, feat, ldf, idx, slot_item, it_slot0, it_m, it_base, it_extra, cap_slots, status, norm,
-                          partial, it_done, agg, stream);
+    int rc = dispatch_agg(false, feat, ldf, idx, slot_item, it_slot0, it_m, it_base, it_extra, it_rep, n_items, cap_slots,
+                          status, norm, partial, it_done, agg, stream);
     if (rc) return rc;
-    if (it_rep) k_copy_dups<<<n_items, 32, 0, stream>>>(it_rep, n_items, ldf, agg);
+    if (it_rep && copy_dups) k_copy_dups<<<n_items, 32, 0, stream>>>(it_rep, n_items, ldf, agg);
     return pcg_check_launch("pcg_aggregate");
 }
 
@@ -273,8 +270,8 @@ extern "C" int pcg_aggregate_bwd(const float* d_agg, int64_t ldf, const int32_t*
     PCG_REQUIRE(d_agg && idx && slot_item && it_slot0 && it_m && it_base && status && feat_grad,
                 "pcg_aggregate_bwd: null pointer");
     if (n_items == 0 || cap_slots == 0) return 0;
-    int rc = dispatch_agg(true, d_agg, ldf, idx, slot_item, it_slot0, it_m, it_base, it_extra, cap_slots, status, norm,
-                          nullptr, nullptr, feat_grad, stream);
+    int rc = dispatch_agg(true, d_agg, ldf, idx, slot_item, it_slot0, it_m, it_base, it_extra, nullptr, n_items, cap_slots,
+                          status, norm, nullptr, nullptr, feat_grad, stream);
     if (rc) return rc;
     return pcg_check_launch("pcg_aggregate_bwd");
 }

@@ -211,12 +211,14 @@ __global__ void __launch_bounds__(256) k_gemm64(int M, int N, int K, AL al, BL b
 }
 
 // ---------------------------------------------------------------------------------------- forward
-struct FwdRelA {    // A(r, i, k) = [feat[targets[i]] | agg[r*B + i]][k]
-    const float* feat; const float* agg; const int32_t* targets; int64_t ldf; int B, F;
+struct FwdRelA {    // A(r, i, k) = [feat[targets[i]] | agg[rep(r*B + i)]][k]  (rep: row of the target's first occurrence)
+    const float* feat; const float* agg; const int32_t* targets; const int32_t* rep; int64_t ldf; int B, F;
     __device__ void bind(int) {}
     __device__ const float* any() const { return feat; }
     __device__ const float* addr(int r, int i, int k) const {
-        return k < F ? feat + (int64_t)__ldg(targets + i) * ldf + k : agg + ((int64_t)r * B + i) * ldf + (k - F);
+        if (k < F) return feat + (int64_t)__ldg(targets + i) * ldf + k;
+        const int64_t w = (int64_t)r * B + i;
+        return agg + (rep ? (int64_t)__ldg(rep + w) : w) * ldf + (k - F);
     }
     __device__ float operator()(int r, int i, int k) const { return __ldg(addr(r, i, k)); }
 };
@@ -293,13 +295,15 @@ struct BwdHEp {     // dH[i][c] = v * (cat[i][F + c] > 0)
 };
 // weight gradients: z = job * S + split; job 0 -> W (rows m < K2), job 1+r -> W_r (rows m < 2F)
 struct WgA {        // A(z, m, i) = X_job[i][m]
-    const float* cat; const float* agg; int64_t ldf; int B, F, K2, S; int job;
+    const float* cat; const float* agg; const int32_t* rep; int64_t ldf; int B, F, K2, S; int job;
     __device__ void bind(int z) { job = z / S; }
     __device__ const float* any() const { return cat; }
     __device__ const float* addr(int, int m, int i) const {      // rows beyond the job's matrix are dropped by WgEp
         if (job == 0) return m < K2 ? cat + (int64_t)i * K2 + m : cat;
         if (m >= 2 * F) return cat;
-        return m < F ? cat + (int64_t)i * K2 + m : agg + ((int64_t)(job - 1) * B + i) * ldf + (m - F);
+        if (m < F) return cat + (int64_t)i * K2 + m;
+        const int64_t w = (int64_t)(job - 1) * B + i;
+        return agg + (rep ? (int64_t)__ldg(rep + w) : w) * ldf + (m - F);
     }
     __device__ float operator()(int z, int m, int i) const {
         if ((job == 0 && m >= K2) || (job > 0 && m >= 2 * F)) return 0.f;
@@ -374,7 +378,7 @@ extern "C" size_t pcg_dense_bwd_scratch_floats(int B, int R, int F, int E) {
 }
 
 extern "C" int pcg_dense_fwd(const float* feat, int64_t ldf, int F, const int32_t* targets, int B, int R, int E,
-                             const float* agg, const float* const* w_intra_host, const float* w_inter, float* cat,
+                             const float* agg, const int32_t* agg_rep, const float* const* w_intra_host, const float* w_inter, float* cat,
                              float* out, pcg_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (B == 0) return 0;
@@ -382,7 +386,7 @@ extern "C" int pcg_dense_fwd(const float* feat, int64_t ldf, int F, const int32_
     PCG_REQUIRE(R >= 1 && R <= PCG_MAX_REL && E >= 1 && E <= DENSE_MAX_E && F >= 1, "pcg_dense_fwd: bad sizes R=%d E=%d F=%d",
                 R, E, F);
     const int K2 = F + R * E;
-    FwdRelA a{feat, agg, targets, ldf, B, F};
+    FwdRelA a{feat, agg, targets, agg_rep, ldf, B, F};
     FwdRelB b;
     for (int r = 0; r < PCG_MAX_REL; ++r) b.w[r] = r < R ? w_intra_host[r] : nullptr;
     b.E = E; b.cur = nullptr;
@@ -397,7 +401,8 @@ extern "C" int pcg_dense_fwd(const float* feat, int64_t ldf, int F, const int32_
     return pcg_check_launch("pcg_dense_fwd");
 }
 
-extern "C" int pcg_dense_bwd(int64_t ldf, int F, int B, int R, int E, const float* agg, const float* w_inter,
+extern "C" int pcg_dense_bwd(int64_t ldf, int F, int B, int R, int E, const float* agg, const int32_t* agg_rep,
+                             const float* w_inter,
                              const float* cat, const float* out, const float* d_out, float* const* d_w_intra_host,
                              float* d_w_inter, float* scratch, pcg_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -415,7 +420,7 @@ extern "C" int pcg_dense_bwd(int64_t ldf, int F, int B, int R, int E, const floa
         BwdHEp ep{cat, dh, K2, F, RE};
         PCG_GEMM(true, true, false, pick_tm(B), B, (RE + 63) / 64, 1, B, RE, E, a, b, ep);
     }
-    WgA wa{cat, agg, ldf, B, F, K2, S, 0};
+    WgA wa{cat, agg, agg_rep, ldf, B, F, K2, S, 0};
     WgB wb{dz, dh, E, RE, S, 0};
     WgEp we;
     ReduceP rp;

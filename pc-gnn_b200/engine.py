@@ -330,8 +330,9 @@ class Engine:
         _lib.check(rc, "pcg_select_all")
         return s
 
-    def aggregate(self, sel: Selection, feat=None) -> torch.Tensor:
-        """agg [R*B, ldf] = normalised sum of the selected rows (``pcg_aggregate``)."""
+    def aggregate(self, sel: Selection, feat=None, copy_dups: bool = True) -> torch.Tensor:
+        """agg [R*B, ldf] = normalised sum of the selected rows (``pcg_aggregate``). copy_dups=False leaves the
+        rows of repeated targets unwritten: the consumer must read row ``sel.it_rep[w]`` (dense_fwd / dense_bwd do)."""
         feat = self.feat if feat is None else feat
         ldf = feat.shape[1]
         W = sel.B * sel.R
@@ -339,7 +340,7 @@ class Engine:
         partial = torch.empty((sel.cap_slots, ldf), dtype=torch.float32, device=self.device)
         rc = self.lib.pcg_aggregate(feat.data_ptr(), ldf, sel.idx.data_ptr(), sel.slot_item.data_ptr(),
                                     sel.it_slot0.data_ptr(), sel.it_m.data_ptr(), sel.it_base.data_ptr(),
-                                    _lib.ptr(sel.it_extra), _lib.ptr(sel.it_rep), W, sel.cap_slots,
+                                    _lib.ptr(sel.it_extra), _lib.ptr(sel.it_rep), int(copy_dups), W, sel.cap_slots,
                                     sel.status.data_ptr(), sel.norm, partial.data_ptr(), sel.it_done.data_ptr(),
                                     agg.data_ptr(), _lib.stream_ptr())
         _lib.check(rc, "pcg_aggregate")
@@ -362,7 +363,7 @@ class Engine:
         return feat_grad
 
     # ------------------------------------------------------------------ fused dense part
-    def dense_fwd(self, targets, agg, w_intra, w_inter, feat_dim):
+    def dense_fwd(self, targets, agg, w_intra, w_inter, feat_dim, agg_rep=None):
         """(combined [E,B], cat [B, F+R*E]) = relation transforms + inter-relation combine (``pcg_dense_fwd``)."""
         B = int(targets.shape[0])
         R = len(w_intra)
@@ -372,12 +373,12 @@ class Engine:
         out = torch.empty((E, B), dtype=torch.float32, device=self.device)
         ptrs = (C.c_void_p * R)(*[w.data_ptr() for w in w_intra])
         rc = self.lib.pcg_dense_fwd(self.feat.data_ptr(), self.ldf, feat_dim, targets.data_ptr(), B, R, E,
-                                    agg.data_ptr(), ptrs, w_inter.data_ptr(), cat.data_ptr(), out.data_ptr(),
+                                    agg.data_ptr(), _lib.ptr(agg_rep), ptrs, w_inter.data_ptr(), cat.data_ptr(), out.data_ptr(),
                                     _lib.stream_ptr())
         _lib.check(rc, "pcg_dense_fwd")
         return out, cat
 
-    def dense_bwd(self, agg, w_inter, cat, out, d_out, feat_dim, n_rel):
+    def dense_bwd(self, agg, w_inter, cat, out, d_out, feat_dim, n_rel, agg_rep=None):
         """Weight gradients of the fused dense part (``pcg_dense_bwd``): (list of dW_r [2F,E], dW [F+R*E,E])."""
         B = int(cat.shape[0])
         E = int(w_inter.shape[1])
@@ -391,7 +392,7 @@ class Engine:
                    for r in range(n_rel)]
         ptrs = (C.c_void_p * n_rel)(*[g.data_ptr() for g in d_intra])
         d_out = d_out.contiguous()
-        rc = self.lib.pcg_dense_bwd(agg.shape[1], feat_dim, B, n_rel, E, agg.data_ptr(), w_inter.data_ptr(),
+        rc = self.lib.pcg_dense_bwd(agg.shape[1], feat_dim, B, n_rel, E, agg.data_ptr(), _lib.ptr(agg_rep), w_inter.data_ptr(),
                                     cat.data_ptr(), out.data_ptr(), d_out.data_ptr(), ptrs, d_inter.data_ptr(),
                                     scratch.data_ptr(), _lib.stream_ptr())
         _lib.check(rc, "pcg_dense_bwd")

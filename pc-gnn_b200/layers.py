@@ -60,19 +60,19 @@ class _DenseFn(torch.autograd.Function):
     is the reference's configuration (model_handler.py:85-86); reference math: layers.py:616-629, 273-289."""
 
     @staticmethod
-    def forward(ctx, engine, targets, agg, feat_dim, w_inter, *w_intra):
+    def forward(ctx, engine, targets, agg, agg_rep, feat_dim, w_inter, *w_intra):
         w_intra = [w.contiguous() for w in w_intra]
         w_inter = w_inter.contiguous()
-        out, cat = engine.dense_fwd(targets, agg, w_intra, w_inter, feat_dim)
-        ctx.engine, ctx.feat_dim, ctx.n_rel = engine, feat_dim, len(w_intra)
+        out, cat = engine.dense_fwd(targets, agg, w_intra, w_inter, feat_dim, agg_rep)
+        ctx.engine, ctx.feat_dim, ctx.n_rel, ctx.agg_rep = engine, feat_dim, len(w_intra), agg_rep
         ctx.save_for_backward(agg, w_inter, cat, out)
         return out
 
     @staticmethod
     def backward(ctx, d_out):
         agg, w_inter, cat, out = ctx.saved_tensors
-        d_intra, d_inter = ctx.engine.dense_bwd(agg, w_inter, cat, out, d_out, ctx.feat_dim, ctx.n_rel)
-        return (None, None, None, None, d_inter, *d_intra)
+        d_intra, d_inter = ctx.engine.dense_bwd(agg, w_inter, cat, out, d_out, ctx.feat_dim, ctx.n_rel, ctx.agg_rep)
+        return (None, None, None, None, None, d_inter, *d_intra)
 
 
 class _CenterFn(torch.autograd.Function):
@@ -375,8 +375,8 @@ class InterAgg(nn.Module):
         self.last_selection = sel
         if fused:
             # frozen features (the reference's setup): aggregation + the whole dense part are two kernels
-            agg = eng.aggregate(sel)
-            combined = _DenseFn.apply(eng, targets, agg, self.feat_dim, self.weight,
+            agg = eng.aggregate(sel, copy_dups=False)     # repeated targets: the dense kernels read it_rep's row
+            combined = _DenseFn.apply(eng, targets, agg, sel.it_rep, self.feat_dim, self.weight,
                                       *[ia.weight for ia in self.intra_aggs()])
             return combined, center_scores
         agg = _AggregateFn.apply(table, eng, sel, self.feat_dim)

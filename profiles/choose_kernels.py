@@ -34,14 +34,14 @@ with torch.cuda.stream(side):
     for _ in range(2):
         eng.score_table(w, b)
         sel = eng.choose(t, lab, True, [0.5] * R, 0.5, cap)
-        eng.aggregate(sel)
+        eng.aggregate(sel, copy_dups=False)
 torch.cuda.current_stream().wait_stream(side)
 torch.cuda.synchronize()
 g = torch.cuda.CUDAGraph()
 with torch.cuda.graph(g):
     eng.score_table(w, b)
     sel = eng.choose(t, lab, True, [0.5] * R, 0.5, cap)
-    eng.aggregate(sel)
+    eng.aggregate(sel, copy_dups=False)
 for rep in range(3):
     flush.zero_()
     torch.cuda.synchronize()

@@ -30,6 +30,6 @@ for nodes, labels in batches:
     eng.score_table(w, b)
     flush.zero_()
     sel = eng.choose(t, lab, True, [0.5] * 3, 0.5, cap)
-    agg = eng.aggregate(sel)
+    agg = eng.aggregate(sel, copy_dups=False)
     torch.cuda.synchronize()
 print("ok", float(agg.sum()), int(sel.it_m[sel.it_rep.long()].sum()))
