@@ -388,7 +388,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="yelp", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=128)
+    ap.add_argument("--cpu-sample", type=int, default=1024, help="targets per CPU-baseline step (bounded sample of a batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="do not use CUDA graphs for the device-resident step")
     ap.add_argument("--torch-adam", action="store_true",
@@ -600,10 +600,10 @@ def main():
                                                "call": "model.loss(list_of_ids, cuda_labels); backward; Adam.step; loss.item()"}
         if world == 1 and not args.no_cpu_baseline and not is_big:
             sample = min(args.cpu_sample, batch)
-            rate, sec = cpu_port_rate(data, params, global_batches, sample, 6, 1, gcn=is_gcn)
+            rate, sec = cpu_port_rate(data, params, global_batches, sample, 12, 1, gcn=is_gcn)
             line["cpu_baseline"] = {
                 "value": rate, "unit": "target-nodes/s", "cores": torch.get_num_threads(), "kind": "port",
-                "sample": f"6 full train steps of oracle/port.py on the first {sample} targets of a batch "
+                "sample": f"12 full train steps of oracle/port.py on the first {sample} targets of a batch "
                           f"({sec * 1e3:.0f} ms each; host has {os.cpu_count()} cpus)",
                 }
             if not is_gcn:

@@ -37,12 +37,14 @@ for it in range(ROUNDS):
     red.flat.copy_(g)
     fa.step(do_adam=False)
     torch.cuda.synchronize()
-    assert torch.allclose(red.flat, want, rtol=1e-6, atol=1e-7), (it, float((red.flat - want).abs().max()))
+    # fp32 sums in a different order (NCCL's vs rank order): a few ulps of the largest addends
+    tol = 4e-7 * world * float(g.abs().max())
+    assert float((red.flat - want).abs().max()) <= tol, (it, float((red.flat - want).abs().max()), tol)
     every = [torch.empty_like(red.flat) for _ in range(world)]
     dist.all_gather(every, red.flat)
     assert all(torch.equal(every[0], e) for e in every), "ranks disagree on the reduced gradient"
 if rank == 0:
-    print(f"exchange ok: {ROUNDS} skewed rounds, equal to NCCL within 1e-6, bit-identical on all ranks")
+    print(f"exchange ok: {ROUNDS} skewed rounds, equal to NCCL up to fp32 summation order, bit-identical on all ranks")
 
 # ---- 2. whole train steps: fused arrangement against NCCL all-reduce + torch.optim.Adam
 d = make_graph("tiny", seed=11)
