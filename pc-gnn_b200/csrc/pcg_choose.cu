@@ -16,11 +16,11 @@
 //
 // Work decomposition (every thread holds at most a few row entries, so an item's latency is a handful of
 // dependent memory round trips plus 2-4 selection steps, whatever its length):
-//   prep     one CTA: folds repeated targets (pick_step samples with replacement), computes every item's
-//            sizes, hands out the output slots by a prefix sum (deterministic layout, no atomics on the
-//            item path) and sorts the items into four tier queues,
-//   warp     d <= 128          one warp per item,
-//   cta      128 < d <= 1024   one 256-thread CTA per item,
+//   prep     up to #SMs cooperative CTAs: folds repeated targets (pick_step samples with replacement), computes
+//            every item's sizes, hands out the output slots by a prefix sum (deterministic layout, no atomics
+//            on the item path) and sorts the items into four tier queues,
+//   warp     d <= 128          one warp per item,           } one kernel (k_choose_small) drains both queues,
+//   cta      128 < d <= 1024   one 256-thread CTA per item, } half of its CTAs starting on each
 //   wide     1024 < d <= 16384 one thread-block CLUSTER of 8 x 256 threads per item (launched first: the longest
 //            rows are the critical path); the CTAs' histograms and compaction totals are exchanged through
 //            distributed shared memory, one cluster barrier per selection step,
@@ -236,7 +236,8 @@ __device__ __forceinline__ void radix_select(Get get, int n, int kth, uint32_t* 
     need = remaining;
 }
 
-// ---- bit-serial selection (two bits per step, counts by warp reduction; no atomics, no histogram) ----
+// ---- bit-serial selection (two bits per step, counts by warp reduction): used by the big tier, whose keys
+// live in shared memory or are recomputed per pass ----
 // Decide the next digit of the k-th smallest key from the counts of the three lowest digit values.
 __device__ __forceinline__ uint32_t pick_digit(int c0, int c1, int c2, int& remaining) {
     if (remaining <= c0) return 0u;
@@ -246,106 +247,6 @@ __device__ __forceinline__ uint32_t pick_digit(int c0, int c1, int c2, int& rema
     if (remaining <= c2) return 2u;
     remaining -= c2;
     return 3u;
-}
-
-// Sum of three per-thread counters over the NT threads of the group (NT == 32: one warp reduction each;
-// else warp reductions + one exchange through wsum[3 * NT/32] with two barriers).
-template <int NT>
-__device__ __forceinline__ void grp_sum3(int& c0, int& c1, int& c2, int* wsum, int tid) {
-    c0 = __reduce_add_sync(PCG_FULL, c0);
-    c1 = __reduce_add_sync(PCG_FULL, c1);
-    c2 = __reduce_add_sync(PCG_FULL, c2);
-    if (NT > 32) {
-        constexpr int NW = NT / 32;
-        const int wid = tid >> 5, lane = tid & 31;
-        if (lane == 0) { wsum[wid * 3] = c0; wsum[wid * 3 + 1] = c1; wsum[wid * 3 + 2] = c2; }
-        __syncthreads();
-        c0 = lane < NW ? wsum[lane * 3] : 0;
-        c1 = lane < NW ? wsum[lane * 3 + 1] : 0;
-        c2 = lane < NW ? wsum[lane * 3 + 2] : 0;
-        c0 = __reduce_add_sync(PCG_FULL, c0);
-        c1 = __reduce_add_sync(PCG_FULL, c1);
-        c2 = __reduce_add_sync(PCG_FULL, c2);
-        __syncthreads();
-    }
-}
-// NT threads, NE keys per thread in REGISTERS (row position of key[e] is e*NT + tid; vmask marks the valid
-// e). Returns (T, need) like radix_select. A CTA (NT > 32) moves the keys that still match the prefix into
-// the shared list `cand` as soon as they fit, and finishes on that list.
-template <int NT, int NE>
-__device__ __forceinline__ void group_bitselect(const uint32_t (&key)[NE], uint32_t vmask, int n, int kth,
-                                                uint32_t* cand, int cand_cap, int* wsum, int* xw, int tid,
-                                                uint32_t& T, int& need) {
-    uint32_t lo = 0xffffffffu, hi = 0u;
-#pragma unroll
-    for (int e = 0; e < NE; ++e)
-        if ((vmask >> e) & 1u) { lo = min(lo, key[e]); hi = max(hi, key[e]); }
-    lo = __reduce_min_sync(PCG_FULL, lo);
-    hi = __reduce_max_sync(PCG_FULL, hi);
-    if (NT > 32) {
-        if (tid == 0) { xw[24] = (int)0xffffffffu; xw[25] = 0; }
-        __syncthreads();
-        if ((tid & 31) == 0) { atomicMin((uint32_t*)&xw[24], lo); atomicMax((uint32_t*)&xw[25], hi); }
-        __syncthreads();
-        lo = (uint32_t)xw[24];
-        hi = (uint32_t)xw[25];
-        __syncthreads();
-    }
-    if (lo == hi) { T = lo; need = kth; return; }
-    int hb = 31 - __clz(lo ^ hi);
-    uint32_t mask = hb == 31 ? 0u : ~((2u << hb) - 1u);
-    uint32_t prefix = lo & mask;
-    int remaining = kth;
-    int n_act = n, n_list = 0;
-    bool listed = false;
-    while (hb >= 0) {
-        const int shift = max(hb - 1, 0);
-        const uint32_t dmask = hb >= 1 ? 3u : 1u;
-        int c0 = 0, c1 = 0, c2 = 0;
-        if (!listed) {
-#pragma unroll
-            for (int e = 0; e < NE; ++e) {
-                const bool active = ((vmask >> e) & 1u) && ((key[e] ^ prefix) & mask) == 0u;
-                const uint32_t dg = (key[e] >> shift) & dmask;
-                c0 += active && dg == 0u;
-                c1 += active && dg == 1u;
-                c2 += active && dg == 2u;
-            }
-        } else {
-            for (int j = tid; j < n_list; j += NT) {
-                const uint32_t x = cand[j];
-                const bool active = ((x ^ prefix) & mask) == 0u;
-                const uint32_t dg = (x >> shift) & dmask;
-                c0 += active && dg == 0u;
-                c1 += active && dg == 1u;
-                c2 += active && dg == 2u;
-            }
-        }
-        grp_sum3<NT>(c0, c1, c2, wsum, tid);
-        const uint32_t dg = pick_digit(c0, c1, c2, remaining);
-        n_act = dg == 0u ? c0 : (dg == 1u ? c1 : (dg == 2u ? c2 : n_act - c0 - c1 - c2));
-        prefix |= dg << shift;
-        mask |= dmask << shift;
-        hb = shift - 1;
-        if (NT > 32 && !listed && hb >= 0 && n_act <= cand_cap) {
-            if (tid == 0) xw[26] = 0;
-            __syncthreads();
-#pragma unroll
-            for (int e = 0; e < NE; ++e) {
-                const bool active = ((vmask >> e) & 1u) && ((key[e] ^ prefix) & mask) == 0u;
-                const unsigned m = __ballot_sync(PCG_FULL, active);
-                int base = 0;
-                if ((tid & 31) == 0 && m) base = atomicAdd(&xw[26], __popc(m));
-                base = __shfl_sync(PCG_FULL, base, 0);
-                if (active) cand[base + __popc(m & lanemask_lt())] = key[e];
-            }
-            __syncthreads();
-            listed = true;
-            n_list = n_act;
-        }
-    }
-    T = prefix;
-    need = remaining;
 }
 
 // One CTA, keys behind get(0..n-1) (shared memory). Same two-bit steps; as soon as the keys still matching
