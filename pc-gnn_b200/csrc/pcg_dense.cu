@@ -229,13 +229,15 @@ struct FwdRelB {    // B(r, k, n) = W_r[k][n]
     __device__ const float* addr(int, int k, int n) const { return cur + (int64_t)k * E + n; }
     __device__ float operator()(int r, int k, int n) const { return __ldg(addr(r, k, n)); }
 };
-struct FwdRelEp {   // cat[i][F + r*E + n] = relu(v)
+struct FwdRelEp {   // cat[i][F + r*E + n] = relu(v); relation 0 also copies the self part cat[i][:F] when F <= E
     float* cat; int K2, F, E;
+    const float* self_feat; const int32_t* targets; int64_t ldf;      // self_feat == NULL: k_copy_self does it
     __device__ void bind(int) {}
     __device__ void k_range(int, int K, int& kb, int& ke) const { kb = 0; ke = K; }
     __device__ bool skip(int, int) const { return false; }
     __device__ void operator()(int r, int i, int n, float v) const {
         cat[(int64_t)i * K2 + F + r * E + n] = fmaxf(v, 0.f);
+        if (self_feat && r == 0 && n < F) cat[(int64_t)i * K2 + n] = __ldg(self_feat + (int64_t)__ldg(targets + i) * ldf + n);
     }
 };
 __global__ void k_copy_self(const float* __restrict__ feat, int64_t ldf, const int32_t* __restrict__ targets, int B,
@@ -390,8 +392,10 @@ extern "C" int pcg_dense_fwd(const float* feat, int64_t ldf, int F, const int32_
     FwdRelB b;
     for (int r = 0; r < PCG_MAX_REL; ++r) b.w[r] = r < R ? w_intra_host[r] : nullptr;
     b.E = E; b.cur = nullptr;
-    FwdRelEp ep{cat, K2, F, E};
-    k_copy_self<<<(unsigned)(((int64_t)B * F + 255) / 256), 256, 0, stream>>>(feat, ldf, targets, B, F, K2, cat);
+    const bool fold_self = F <= E;       // the relation-0 epilogue covers columns [0, E) of every target
+    FwdRelEp ep{cat, K2, F, E, fold_self ? feat : nullptr, targets, ldf};
+    if (!fold_self)
+        k_copy_self<<<(unsigned)(((int64_t)B * F + 255) / 256), 256, 0, stream>>>(feat, ldf, targets, B, F, K2, cat);
     const int tm = pick_tm(B);
     PCG_GEMM(false, false, true, tm, B, (E + 63) / 64, R, B, E, 2 * F, a, b, ep);
     CombA ca{cat, K2};

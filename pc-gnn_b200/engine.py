@@ -92,6 +92,10 @@ class Engine:
         self._ws = None
         self._ws_nodes = None
         self.score_group = None     # torch.distributed group over which the score slices are all-gathered (C5)
+        # {parameter data_ptr: gradient view}: while set (runtime.GraphedTrainStep with a flat, pre-zeroed gradient
+        # buffer), the backward kernels write a parameter's gradient straight into its view and autograd gets
+        # None for it, which removes the AccumulateGrad add kernels from the step
+        self.grad_sink = None
 
     # ------------------------------------------------------------------ resident tables
     def set_features(self, weight: torch.Tensor):
@@ -378,18 +382,26 @@ class Engine:
         _lib.check(rc, "pcg_dense_fwd")
         return out, cat
 
-    def dense_bwd(self, agg, w_inter, cat, out, d_out, feat_dim, n_rel, agg_rep=None):
-        """Weight gradients of the fused dense part (``pcg_dense_bwd``): (list of dW_r [2F,E], dW [F+R*E,E])."""
+    def sink_of(self, param):
+        """Gradient view registered for this parameter tensor, or None."""
+        return None if self.grad_sink is None else self.grad_sink.get(param.data_ptr())
+
+    def dense_bwd(self, agg, w_inter, cat, out, d_out, feat_dim, n_rel, agg_rep=None, sinks=None):
+        """Weight gradients of the fused dense part (``pcg_dense_bwd``): (list of dW_r [2F,E], dW [F+R*E,E]).
+        sinks = (d_inter_view, [d_intra_views]) writes them in place instead of into fresh buffers."""
         B = int(cat.shape[0])
         E = int(w_inter.shape[1])
         K2 = feat_dim + n_rel * E
         n = int(self.lib.pcg_dense_bwd_scratch_floats(B, n_rel, feat_dim, E))
         scratch = torch.empty(n, dtype=torch.float32, device=self.device)
         # one buffer for all gradients: [dW (K2*E) | dW_1 (2F*E) | ... ]
-        flat = torch.empty(K2 * E + n_rel * 2 * feat_dim * E, dtype=torch.float32, device=self.device)
-        d_inter = flat[:K2 * E].view(K2, E)
-        d_intra = [flat[K2 * E + r * 2 * feat_dim * E: K2 * E + (r + 1) * 2 * feat_dim * E].view(2 * feat_dim, E)
-                   for r in range(n_rel)]
+        if sinks is not None:
+            d_inter, d_intra = sinks
+        else:
+            flat = torch.empty(K2 * E + n_rel * 2 * feat_dim * E, dtype=torch.float32, device=self.device)
+            d_inter = flat[:K2 * E].view(K2, E)
+            d_intra = [flat[K2 * E + r * 2 * feat_dim * E: K2 * E + (r + 1) * 2 * feat_dim * E].view(2 * feat_dim, E)
+                       for r in range(n_rel)]
         ptrs = (C.c_void_p * n_rel)(*[g.data_ptr() for g in d_intra])
         d_out = d_out.contiguous()
         rc = self.lib.pcg_dense_bwd(agg.shape[1], feat_dim, B, n_rel, E, agg.data_ptr(), _lib.ptr(agg_rep), w_inter.data_ptr(),
@@ -413,17 +425,21 @@ class Engine:
         _lib.check(rc, "pcg_center_fwd")
         return out
 
-    def center_bwd(self, targets, d_center):
+    def center_bwd(self, targets, d_center, sinks=None):
         B = int(targets.shape[0])
-        flat = torch.empty(2 * self.F + 2, dtype=torch.float32, device=self.device)
+        if sinks is not None:
+            d_w, d_b = sinks
+        else:
+            flat = torch.empty(2 * self.F + 2, dtype=torch.float32, device=self.device)
+            d_w, d_b = flat[:2 * self.F].view(2, self.F), flat[2 * self.F:]
         scratch = torch.empty(int(self.lib.pcg_head_scratch_floats(B, self.F, 1)), dtype=torch.float32,
                               device=self.device)
         d_center = d_center.contiguous()
         rc = self.lib.pcg_center_bwd(self.feat.data_ptr(), self.ldf, self.F, targets.data_ptr(), B, d_center.data_ptr(),
-                                     flat.data_ptr(), flat[2 * self.F:].data_ptr(), scratch.data_ptr(),
+                                     d_w.data_ptr(), d_b.data_ptr(), scratch.data_ptr(),
                                      self._tickets()[0:].data_ptr(), _lib.stream_ptr())
         _lib.check(rc, "pcg_center_bwd")
-        return flat[:2 * self.F].view(2, self.F), flat[2 * self.F:]
+        return d_w, d_b
 
     def head_loss_fwd(self, emb, w, center, labels, lam):
         E, B = int(emb.shape[0]), int(emb.shape[1])
@@ -436,11 +452,11 @@ class Engine:
         _lib.check(rc, "pcg_head_loss_fwd")
         return loss.view(()), logits, p1, q1
 
-    def head_loss_bwd(self, emb, w, labels, p1, q1, lam, d_loss):
+    def head_loss_bwd(self, emb, w, labels, p1, q1, lam, d_loss, sink=None):
         E, B = int(emb.shape[0]), int(emb.shape[1])
         d_emb = torch.empty((E, B), dtype=torch.float32, device=self.device)
         d_center = torch.empty((B, 2), dtype=torch.float32, device=self.device)
-        d_w = torch.empty((2, E), dtype=torch.float32, device=self.device)
+        d_w = sink if sink is not None else torch.empty((2, E), dtype=torch.float32, device=self.device)
         scratch = torch.empty(int(self.lib.pcg_head_scratch_floats(B, 1, E)), dtype=torch.float32, device=self.device)
         d_loss = d_loss.contiguous()
         rc = self.lib.pcg_head_loss_bwd(emb.data_ptr(), E, B, w.data_ptr(), labels.data_ptr(), p1.data_ptr(),

@@ -65,13 +65,22 @@ class _DenseFn(torch.autograd.Function):
         w_inter = w_inter.contiguous()
         out, cat = engine.dense_fwd(targets, agg, w_intra, w_inter, feat_dim, agg_rep)
         ctx.engine, ctx.feat_dim, ctx.n_rel, ctx.agg_rep = engine, feat_dim, len(w_intra), agg_rep
+        ctx.w_ptrs = [w_inter.data_ptr()] + [w.data_ptr() for w in w_intra]
         ctx.save_for_backward(agg, w_inter, cat, out)
         return out
 
     @staticmethod
     def backward(ctx, d_out):
         agg, w_inter, cat, out = ctx.saved_tensors
-        d_intra, d_inter = ctx.engine.dense_bwd(agg, w_inter, cat, out, d_out, ctx.feat_dim, ctx.n_rel, ctx.agg_rep)
+        eng = ctx.engine
+        sinks = None
+        if eng.grad_sink is not None:          # gradients go straight into the flat buffer (see Engine.grad_sink)
+            views = [eng.grad_sink.get(q) for q in ctx.w_ptrs]
+            if all(v is not None for v in views):
+                sinks = (views[0], views[1:])
+        d_intra, d_inter = eng.dense_bwd(agg, w_inter, cat, out, d_out, ctx.feat_dim, ctx.n_rel, ctx.agg_rep, sinks)
+        if sinks is not None:
+            return (None,) * (6 + ctx.n_rel)
         return (None, None, None, None, None, d_inter, *d_intra)
 
 
@@ -83,11 +92,20 @@ class _CenterFn(torch.autograd.Function):
     def forward(ctx, engine, targets, weight, bias):
         weight = weight.contiguous()
         ctx.engine, ctx.targets = engine, targets
+        ctx.w_ptrs = (weight.data_ptr(), bias.data_ptr())
         return engine.center_fwd(targets, weight, bias)
 
     @staticmethod
     def backward(ctx, d_center):
-        d_w, d_b = ctx.engine.center_bwd(ctx.targets, d_center)
+        eng = ctx.engine
+        sinks = None
+        if eng.grad_sink is not None:
+            views = (eng.grad_sink.get(ctx.w_ptrs[0]), eng.grad_sink.get(ctx.w_ptrs[1]))
+            if views[0] is not None and views[1] is not None:
+                sinks = views
+        d_w, d_b = eng.center_bwd(ctx.targets, d_center, sinks)
+        if sinks is not None:
+            return None, None, None, None
         return None, None, d_w, d_b
 
 
@@ -100,6 +118,7 @@ class HeadLossFn(torch.autograd.Function):
         combined, weight, center = combined.contiguous(), weight.contiguous(), center.contiguous()
         loss, logits, p1, q1 = engine.head_loss_fwd(combined, weight, center, labels, lam)
         ctx.engine, ctx.lam = engine, lam
+        ctx.w_ptr = weight.data_ptr()
         ctx.save_for_backward(combined, weight, labels, p1, q1)
         ctx.mark_non_differentiable(logits)
         return loss, logits
@@ -107,8 +126,10 @@ class HeadLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_loss, _d_logits):
         combined, weight, labels, p1, q1 = ctx.saved_tensors
-        d_emb, d_center, d_w = ctx.engine.head_loss_bwd(combined, weight, labels, p1, q1, ctx.lam, d_loss)
-        return None, d_emb, d_w, d_center, None, None
+        eng = ctx.engine
+        sink = eng.grad_sink.get(ctx.w_ptr) if eng.grad_sink is not None else None
+        d_emb, d_center, d_w = eng.head_loss_bwd(combined, weight, labels, p1, q1, ctx.lam, d_loss, sink)
+        return None, d_emb, (None if sink is not None else d_w), d_center, None, None
 
 
 def _feature_table(features, n_nodes, device, ids=None):

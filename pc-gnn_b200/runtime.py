@@ -68,8 +68,17 @@ class GraphedTrainStep:
             self.reducer.zero()
         else:
             self.opt.zero_grad(set_to_none=False)
-        loss = self.model.loss(self.nodes, self.labels)
-        loss.backward()
+        eng = self.model.inter1.engine() if (self.fused and hasattr(self.model, "inter1")) else None
+        if eng is not None:
+            # every parameter has exactly one producer kernel and the buffer is zero: let the kernels store the
+            # gradients in place (no AccumulateGrad adds in the graph)
+            eng.grad_sink = {p.data_ptr(): v for p, v in zip(self.reducer.params, self.reducer.views)}
+        try:
+            loss = self.model.loss(self.nodes, self.labels)
+            loss.backward()
+        finally:
+            if eng is not None:
+                eng.grad_sink = None
         return loss.detach()
 
     def _capture(self):
