@@ -382,6 +382,11 @@ class Engine:
         _lib.check(rc, "pcg_dense_fwd")
         return out, cat
 
+    def side_stream(self):
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
+
     def sink_of(self, param):
         """Gradient view registered for this parameter tensor, or None."""
         return None if self.grad_sink is None else self.grad_sink.get(param.data_ptr())

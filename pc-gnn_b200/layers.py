@@ -338,6 +338,7 @@ class InterAgg(nn.Module):
         self._engine = None
         self.cap_slots_hint = None      # set to a fixed capacity to avoid sizing from host ids
         self.score_override = None      # tests: inject an [N] score table (identical score bits)
+        self.center_on_side_stream = False   # runtime.GraphedTrainStep: label_clf head as a parallel graph branch
         self.scores_external = False    # the caller refreshes eng.score itself (runtime.GraphedTrainStep on a
         #                                 partitioned graph: slice kernel -> all-gather -> this forward)
         self.last_selection = None
@@ -378,8 +379,18 @@ class InterAgg(nn.Module):
         B = targets.shape[0]
         fused = (not table.requires_grad) and self.embed_dim <= 256 and B > 0 \
             and isinstance(self.label_clf, nn.Linear) and self.label_clf.bias is not None
+        side = None
         if fused:   # [B,2] with gradient to label_clf (layers.py:236-243), one kernel
-            center_scores = _CenterFn.apply(eng, targets, self.label_clf.weight, self.label_clf.bias)
+            if self.center_on_side_stream:
+                # independent of choose / aggregate / the dense part: run it (and, since autograd replays a node on
+                # its forward stream, its backward) on a side stream, next to them; joined below
+                cur = torch.cuda.current_stream(dev)
+                side = eng.side_stream()
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    center_scores = _CenterFn.apply(eng, targets, self.label_clf.weight, self.label_clf.bias)
+            else:
+                center_scores = _CenterFn.apply(eng, targets, self.label_clf.weight, self.label_clf.bias)
         else:
             idx = targets.long()
             self_feats = self.features(idx)
@@ -399,6 +410,8 @@ class InterAgg(nn.Module):
             agg = eng.aggregate(sel, copy_dups=False)     # repeated targets: the dense kernels read it_rep's row
             combined = _DenseFn.apply(eng, targets, agg, sel.it_rep, self.feat_dim, self.weight,
                                       *[ia.weight for ia in self.intra_aggs()])
+            if side is not None:
+                torch.cuda.current_stream(dev).wait_stream(side)
             return combined, center_scores
         agg = _AggregateFn.apply(table, eng, sel, self.feat_dim)
         agg = agg.view(self._R, B, -1)[:, :, :self.feat_dim]

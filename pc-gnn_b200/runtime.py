@@ -37,6 +37,8 @@ class GraphedTrainStep:
         self.cap_slots = int(cap_slots)
         if hasattr(model, "inter1") and model.inter1.engine().score_group is not None:
             model.inter1.scores_external = True
+        if hasattr(model, "inter1"):
+            model.inter1.center_on_side_stream = True
         self.nodes = torch.zeros(self.B, dtype=torch.int32, device=dev)
         self.labels = torch.zeros(self.B, dtype=torch.int64, device=dev)
         self.pin_nodes = torch.zeros(self.B, dtype=torch.int32, pin_memory=True)
