@@ -178,6 +178,71 @@ __global__ void __launch_bounds__(256) k_gemm_v(int M, int N, int K, AL al, BL b
     }
 }
 
+// Variant of k_gemm_p for the forward GEMMs of small batches when rows are 16-byte aligned (F, E multiples of 4):
+// A rows are contiguous along k (cat / feature / aggregate rows), so the A tile is kept m-major in shared
+// memory and both operands arrive in 16-byte cp.async chunks: 16 x 64 output tiles, 3 stages over K.
+template <class AL, class BL, class EP>
+__global__ void __launch_bounds__(256) k_gemm_pv(int M, int N, int K, AL al, BL bl, EP ep) {
+    constexpr int TM = 16, KC = 32, ST = 3;
+    __shared__ __align__(16) float As[ST][TM][KC + 4];   // [m][k]
+    __shared__ __align__(16) float Bs[ST][KC][64 + 4];   // [k][n]
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int m0 = blockIdx.x * TM, n0 = blockIdx.y * 64, z = blockIdx.z;
+    al.bind(z); bl.bind(z); ep.bind(z);
+    if (ep.skip(z, m0)) return;
+    int kb, ke;
+    ep.k_range(z, K, kb, ke);
+    const int nt = (ke - kb + KC - 1) / KC;
+    auto issue = [&](int t) {
+        const int buf = t % ST, k0 = kb + t * KC;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {                    // B: 32 k-rows x 16 chunks
+            const int c = tid + 256 * j;
+            const int kk = c >> 4, q4 = (c & 15) * 4;
+            const int bb = k0 + kk < ke ? min(16, max(0, (N - (n0 + q4)) * 4)) : 0;
+            cp_async16(&Bs[buf][kk][q4], bb > 0 ? bl.addr(z, k0 + kk, n0 + q4) : bl.any(), bb);
+        }
+        if (tid < 128) {                                 // A: 16 rows x 8 chunks
+            const int mm = tid >> 3, q4 = (tid & 7) * 4;
+            const int ba = m0 + mm < M ? min(16, max(0, (ke - (k0 + q4)) * 4)) : 0;
+            cp_async16(&As[buf][mm][q4], ba > 0 ? al.addr(z, m0 + mm, k0 + q4) : al.any(), ba);
+        }
+    };
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int s = 0; s < ST - 1; ++s) {
+        if (s < nt) issue(s);
+        cp_async_commit();
+    }
+    for (int t = 0; t < nt; ++t) {
+        cp_async_wait<ST - 2>();
+        __syncthreads();
+        if (t + ST - 1 < nt) issue(t + ST - 1);
+        cp_async_commit();
+        const int cur = t % ST;
+#pragma unroll
+        for (int kk = 0; kk < KC; kk += 4) {
+            const float4 a4 = *reinterpret_cast<const float4*>(&As[cur][ty][kk]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][kk][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[cur][kk + 1][tx * 4]);
+            const float4 b2 = *reinterpret_cast<const float4*>(&Bs[cur][kk + 2][tx * 4]);
+            const float4 b3 = *reinterpret_cast<const float4*>(&Bs[cur][kk + 3][tx * 4]);
+            acc[0] = fmaf(a4.x, b0.x, acc[0]); acc[1] = fmaf(a4.x, b0.y, acc[1]); acc[2] = fmaf(a4.x, b0.z, acc[2]); acc[3] = fmaf(a4.x, b0.w, acc[3]);
+            acc[0] = fmaf(a4.y, b1.x, acc[0]); acc[1] = fmaf(a4.y, b1.y, acc[1]); acc[2] = fmaf(a4.y, b1.z, acc[2]); acc[3] = fmaf(a4.y, b1.w, acc[3]);
+            acc[0] = fmaf(a4.z, b2.x, acc[0]); acc[1] = fmaf(a4.z, b2.y, acc[1]); acc[2] = fmaf(a4.z, b2.z, acc[2]); acc[3] = fmaf(a4.z, b2.w, acc[3]);
+            acc[0] = fmaf(a4.w, b3.x, acc[0]); acc[1] = fmaf(a4.w, b3.y, acc[1]); acc[2] = fmaf(a4.w, b3.z, acc[2]); acc[3] = fmaf(a4.w, b3.w, acc[3]);
+        }
+    }
+    const int m = m0 + ty;
+    if (m < M) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int n = n0 + tx * 4 + b;
+            if (n < N) ep(z, m, n, acc[b]);
+        }
+    }
+}
+
 // rows of the batch per CTA: small batches need small tiles to fill the GPU
 static int pick_tm(int M) { return M <= 2048 ? 16 : 64; }
 #define PCG_GEMM(A_REG, A_MC, B_NC, tm, grid_m_rows, gy, gz, M, N, K, a, b, ep)                                   \
@@ -470,11 +535,25 @@ extern "C" int pcg_dense_fwd(const float* feat, int64_t ldf, int F, const int32_
     if (!fold_self)
         k_copy_self<<<(unsigned)(((int64_t)B * F + 255) / 256), 256, 0, stream>>>(feat, ldf, targets, B, F, K2, cat);
     const int tm = pick_tm(B);
-    PCG_GEMM(false, false, true, tm, B, (E + 63) / 64, R, B, E, 2 * F, a, b, ep);
+    // 16-byte cp.async operand tiles need every row start and every chunk 16-byte aligned
+    bool vec = tm == 16 && F % 4 == 0 && E % 4 == 0 && ldf % 4 == 0 && ((uintptr_t)feat & 15) == 0 &&
+               ((uintptr_t)agg & 15) == 0 && ((uintptr_t)cat & 15) == 0 && ((uintptr_t)w_inter & 15) == 0;
+    for (int r = 0; r < R; ++r) vec = vec && ((uintptr_t)w_intra_host[r] & 15) == 0;
+    if (vec) {
+        dim3 g1((unsigned)((B + 15) / 16), (unsigned)((E + 63) / 64), (unsigned)R);
+        k_gemm_pv<<<g1, 256, 0, stream>>>(B, E, 2 * F, a, b, ep);
+    } else {
+        PCG_GEMM(false, false, true, tm, B, (E + 63) / 64, R, B, E, 2 * F, a, b, ep);
+    }
     CombA ca{cat, K2};
     CombB cb{w_inter, E};
     CombEp ce{out, B};
-    PCG_GEMM(false, false, true, tm, B, (E + 63) / 64, 1, B, E, K2, ca, cb, ce);
+    if (vec) {
+        dim3 g2((unsigned)((B + 15) / 16), (unsigned)((E + 63) / 64), 1);
+        k_gemm_pv<<<g2, 256, 0, stream>>>(B, E, K2, ca, cb, ce);
+    } else {
+        PCG_GEMM(false, false, true, tm, B, (E + 63) / 64, 1, B, E, K2, ca, cb, ce);
+    }
     return pcg_check_launch("pcg_dense_fwd");
 }
 
