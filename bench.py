@@ -42,8 +42,9 @@ RHO, ALPHA, LR, WD = 0.5, 2.0, 0.01, 1e-3
 SEED = 72
 
 
-MY_KERNELS_PER_STEP = 17   # score+sort 2, choose 3 (prep, wide, small), aggregate 1, dense fwd 3, center/head fwd 2,
-#                            head/center bwd 2, dense bwd 3, gradient exchange + Adam 1 (+2 when P > 8192, +1 big tier)
+MY_KERNELS_PER_STEP = 16   # score+sort 2, choose 3 (prep, wide, small), aggregate 1, dense fwd 2, center/head fwd 2,
+#                            head/center bwd 2, dense bwd 3, gradient exchange + Adam 1 (+2 when P > 8192, +1 big tier,
+#                            +1 self copy when F > E)
 
 
 def config_dict(desc, batch, world):
