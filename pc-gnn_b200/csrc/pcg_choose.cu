@@ -19,9 +19,9 @@
 //   prep     up to #SMs cooperative CTAs: folds repeated targets (pick_step samples with replacement), computes
 //            every item's sizes, hands out the output slots by a prefix sum (deterministic layout, no atomics
 //            on the item path) and sorts the items into four tier queues,
-//   warp     d <= 128          one warp per item,           } one kernel (k_choose_small) drains both queues,
-//   cta      128 < d <= 1024   one 256-thread CTA per item, } half of its CTAs starting on each
-//   wide     1024 < d <= 16384 one thread-block CLUSTER of 8 x 256 threads per item (launched first: the longest
+//   warp     d <= 256          one warp per item,           } one kernel (k_choose_small) drains both queues,
+//   cta      256 < d <= 2048   one 256-thread CTA per item, } half of its CTAs starting on each
+//   wide     2048 < d <= 16384 one thread-block CLUSTER of 8 x 256 threads per item (launched first: the longest
 //            rows are the critical path); the CTAs' histograms and compaction totals are exchanged through
 //            distributed shared memory, one cluster barrier per selection step,
 //   big      d > 16384         one 1024-thread CTA, distances in shared memory / recomputed per pass (rare hubs).
@@ -34,10 +34,10 @@ namespace cg = cooperative_groups;
 
 
 
-#define PCG_SMALL_MAX 128      // warp tier: <= 4 entries per lane
+#define PCG_SMALL_MAX 256      // warp tier: <= 8 entries per lane
 #define PCG_WARPS_PER_CTA 8    // warp kernel: 8 items in flight per CTA
 #define PCG_GRP_NT 256         // cta tier: threads per CTA
-#define PCG_CTA_MAX 1024       // cta tier: <= 4 entries per thread
+#define PCG_CTA_MAX 2048       // cta tier: <= 8 entries per thread
 #define PCG_LARGE_NT 1024      // wide and big tiers: threads per CTA (one CTA per SM)
 #define PCG_CL 8               // wide tier: CTAs per cluster
 #define PCG_CL_MAX 16384       // wide tier: 8 x 256 threads x <= 8 entries
@@ -717,7 +717,8 @@ __device__ void choose_item_warp(const ChooseP& p, int w, WarpSmem& s) {
     const int d = it.d;
     if (d <= 32) row_in_regs<32, 1>(p, it, nbr, s.kbits, s.bits, s.shist, s.xw);
     else if (d <= 64) row_in_regs<32, 2>(p, it, nbr, s.kbits, s.bits, s.shist, s.xw);
-    else row_in_regs<32, 4>(p, it, nbr, s.kbits, s.bits, s.shist, s.xw);
+    else if (d <= 128) row_in_regs<32, 4>(p, it, nbr, s.kbits, s.bits, s.shist, s.xw);
+    else row_in_regs<32, 8>(p, it, nbr, s.kbits, s.bits, s.shist, s.xw);
     int m = it.k;
     if (it.o > 0) m += oversample<32>(p, it, lane, nbr, s.kbits, s.bits, s.hist, s.xw);
     TRACE(6);
@@ -873,7 +874,7 @@ __device__ __forceinline__ void cta_item(const ChooseP& p, int w, CtaSmem<NT>& s
         for (int q = tid; q < (p.P + 31) >> 5; q += NT) s.kbits[q] = 0u;   // ordered before the ORs by the compaction's barriers
     TRACE(1);
     const int per = (it.d + CL * NT - 1) / (CL * NT);
-    constexpr int NE_MAX = NT == PCG_GRP_NT ? (CL == 1 ? 4 : 8) : 16;
+    constexpr int NE_MAX = NT == PCG_GRP_NT ? 8 : 16;
     if (per <= 1) cta_body<NT, 1, CL>(p, it, s, sid, spp, rank, par);
     else if (per <= 2) cta_body<NT, 2, CL>(p, it, s, sid, spp, rank, par);
     else if (per <= 4 || NE_MAX == 4) cta_body<NT, 4, CL>(p, it, s, sid, spp, rank, par);
@@ -892,8 +893,8 @@ __device__ __forceinline__ void cta_item(const ChooseP& p, int w, CtaSmem<NT>& s
     TRACE(7);
 }
 
-// d <= 1024: one kernel of 256-thread CTAs serves both short tiers from two device-side queues: first the
-// rows of 128 < d <= 1024 (one per CTA), then the rows of d <= 128 (one per warp), so CTAs that get no
+// d <= 2048: one kernel of 256-thread CTAs serves both short tiers from two device-side queues: the rows of
+// 256 < d <= 2048 (one per CTA) and the rows of d <= 256 (one per warp), so CTAs that get no
 // (or short) CTA-tier rows take more of the warp-tier rows and no tier waits for the other's registers.
 __global__ void __launch_bounds__(PCG_GRP_NT, 3) k_choose_small(ChooseP p) {
     constexpr size_t SM_BYTES = sizeof(CtaSmem<PCG_GRP_NT>) > sizeof(WarpSmem) * PCG_WARPS_PER_CTA
@@ -935,7 +936,7 @@ __global__ void __launch_bounds__(PCG_GRP_NT, 3) k_choose_small(ChooseP p) {
     }
 }
 
-// 1024 < d <= 16384: one item per CLUSTER of 8 CTAs x 256 threads (<= 8 entries per thread): the longest rows are
+// 2048 < d <= 16384: one item per CLUSTER of 8 CTAs x 256 threads (<= 8 entries per thread): the longest rows are
 // the critical path of the step, so they get 8 SMs each and are launched first.
 __global__ void __cluster_dims__(PCG_CL, 1, 1) __launch_bounds__(PCG_GRP_NT, 3) k_choose_wide(ChooseP p) {
     __shared__ CtaSmem<PCG_GRP_NT> s;
@@ -1442,8 +1443,12 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
     }
     const bool have_cta = max_degree > PCG_SMALL_MAX, have_cl = max_degree > PCG_CTA_MAX, have_big = max_degree > PCG_CL_MAX;
     if (have_cl && !g_fork) {
+        // the long-row tiers are the critical path: their streams get the highest priority, so the block scheduler
+        // places their CTAs (clusters of 8 need a whole GPC slot each) before the short-row kernel fills the SMs
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
         for (int q = 0; q < PCG_N_SIDE; ++q)
-            if ((e = cudaStreamCreateWithFlags(&g_side[q], cudaStreamNonBlocking)) != cudaSuccess ||
+            if ((e = cudaStreamCreateWithPriority(&g_side[q], cudaStreamNonBlocking, prio_hi)) != cudaSuccess ||
                 (e = cudaEventCreateWithFlags(&g_join[q], cudaEventDisableTiming)) != cudaSuccess) {
                 pcg_set_error("pcg_choose: side stream: %s", cudaGetErrorString(e));
                 return (int)e;
@@ -1475,7 +1480,7 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
     }
     {
         const int units = W / PCG_WARPS_PER_CTA + 1 + (have_cta ? W : 0);
-        const int gs = units < sms * 3 ? units : sms * 3;
+        const int gs = units < sms * 3 ? units : sms * 3;     // (2 CTAs per SM, leaving room for the clusters, measured no better)
         k_choose_small<<<gs, PCG_GRP_NT, 0, stream>>>(p);
     }
     if (have_cl) cudaStreamWaitEvent(stream, g_join[1], 0);

@@ -138,14 +138,15 @@ def test_hub_rows_take_the_cta_path_and_multi_slot_aggregation():
 
 @pytest.mark.parametrize("big_pool", [False, True])
 def test_rows_in_every_tier(big_pool):
-    """Row lengths that land in the warp (<=128), cta (<=1024), cluster (<=32768) and big (>32768) tiers,
+    """Row lengths that land in the warp (<=256), cta (<=2048), cluster (<=16384) and big (>16384) tiers,
     with a small pool (per-item bitmap over pool positions) and a pool beyond 8192 positives (row-position
     bits + binary search), coarse scores so that ties cross the tier-internal chunk boundaries."""
     from pcgnn_b200.graph import RelGraph, csr_from_edges
 
     rng = np.random.default_rng(11)
     n = 60000
-    hub_deg = [40000, 33000, 20000, 9000, 5000, 3000, 1500, 1025, 1024, 600, 300, 129, 128, 100, 33, 32, 5, 4, 3]
+    hub_deg = [40000, 33000, 20000, 16400, 16300, 9000, 5000, 3000, 2049, 2048, 1500, 1025, 1024, 600, 300, 257, 256,
+               129, 128, 100, 65, 64, 33, 32, 5, 4, 3]
     rels = []
     for r in range(2):
         src, dst = [], []
