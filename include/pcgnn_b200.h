@@ -32,7 +32,7 @@ extern "C" {
 #define PCG_NORM_RSQRT 1     /* sum / sqrt(n)  (src/graphsage.py:224-226) */
 
 /* status words written by the kernels (int32 device array of PCG_STATUS_WORDS) */
-#define PCG_STATUS_WORDS 8
+#define PCG_STATUS_WORDS 12
 #define PCG_ST_SLOTS 0       /* slots handed out (aggregation consumes [0, this)) */
 #define PCG_ST_OVERFLOW 3    /* != 0: `cap_slots` was too small, results are incomplete */
 

@@ -15,7 +15,7 @@ SO_PATH = os.path.join(_HERE, "libpcgnn_b200_trace.so" if os.environ.get("PCG_LI
 
 SLOT = 64            # PCG_SLOT
 MAX_REL = 8          # PCG_MAX_REL
-STATUS_WORDS = 8     # PCG_STATUS_WORDS
+STATUS_WORDS = 12    # PCG_STATUS_WORDS
 ST_SLOTS, ST_OVERFLOW = 0, 3
 NORM_MEAN, NORM_RSQRT = 0, 1
 KB_MAX_POOL = 8192   # PCG_KB_WORDS * 32: pools up to this size use the per-item kept-pool bitmap

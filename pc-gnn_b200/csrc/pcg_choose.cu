@@ -41,6 +41,7 @@ namespace cg = cooperative_groups;
 #define PCG_LARGE_NT 1024      // wide and big tiers: threads per CTA (one CTA per SM)
 #define PCG_CL 8               // wide tier: CTAs per cluster
 #define PCG_CL_MAX 16384       // wide tier: 8 x 256 threads x <= 8 entries
+#define PCG_HUGE_MAX 131072     // huge tier: 8 x 1024 threads x <= 16 entries (ids / pool positions stashed in shared memory)
 #define PCG_KB_WORDS 256       // kept-pool bitmap words per item (pools up to 8192 positives; else row-position bits)
 #define PCG_CAND_CAP 2048      // big tier: candidate keys kept in shared memory once they fit
 #define PCG_PREP_NT 1024
@@ -77,6 +78,7 @@ struct ChooseP {
     int32_t* q_warp;
     int32_t* q_cta;
     int32_t* q_cl;
+    int32_t* q_huge;
     int32_t* q_big;
     uint32_t* bits_slab;        // [grid_big, slab_words] kept-position bitmasks of the big tier
     int64_t slab_words;
@@ -336,7 +338,7 @@ template <int NT, int NE, int CL = 1>
 __device__ __forceinline__ void hist_select(const uint32_t (&key)[NE], uint32_t vmask, int kth, uint32_t* hist, int* xw,
                                             int tid, uint32_t& T, int& need, uint32_t* chist = nullptr,
                                             int* par = nullptr) {
-    static_assert(CL == 1 || NT == 256, "cluster exchange is written for 256-thread CTAs");
+
     constexpr int NH = NT == 32 ? 1 : 8;
     const int lane = tid & 31, wid = tid >> 5;
     uint32_t* myh = hist + (NT == 32 ? 0 : (wid & (NH - 1)) * 256);
@@ -418,12 +420,14 @@ __device__ __forceinline__ void hist_select(const uint32_t (&key)[NE], uint32_t 
             }
             if (CL > 1) {
                 cg::cluster_group cl = cg::this_cluster();
-                uint32_t* mine_h = chist + *par * 256 + tid;
-                *mine_h = (uint32_t)c;
+                uint32_t* mine_h = chist + *par * 256 + (tid & 255);
+                if (tid < 256) *mine_h = (uint32_t)c;
                 cl.sync();
-                c = 0;
+                if (tid < 256) {
+                    c = 0;
 #pragma unroll
-                for (int r = 0; r < CL; ++r) c += (int)*cl.map_shared_rank(mine_h, r);
+                    for (int r = 0; r < CL; ++r) c += (int)*cl.map_shared_rank(mine_h, r);
+                }
                 *par ^= 1;
             }
             if (tid < 256) {
@@ -749,7 +753,7 @@ struct CtaSmem {
 // only what it wrote: a register spill space that keeps the tier at 64 registers); NULL: kept in registers.
 template <int NT, int NE, int CL>
 __device__ __forceinline__ void cta_body(const ChooseP& p, const Item& it, CtaSmem<NT>& s, int32_t* sid, int16_t* spp,
-                                         int rank, int* par) {
+                                         uint32_t* bits_local, int rank, int* par) {
     constexpr int NW = NT / 32;
     constexpr bool STASH = NT > PCG_GRP_NT;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -779,7 +783,7 @@ __device__ __forceinline__ void cta_body(const ChooseP& p, const Item& it, CtaSm
         uint32_t x = 0u;
         if (((vmask >> e) & 1u) && need_dist) x = dist_bits(it.sv, escore ? escore[j] : __ldg(p.score + id[e]));
         key[e] = x;
-        if (STASH) { sid[j] = id[e]; spp[j] = (int16_t)pp[e]; }
+        if (STASH) { sid[e * NT + tid] = id[e]; spp[e * NT + tid] = (int16_t)pp[e]; }   // CTA-local stash index
     }
     TRACE(2);
     uint32_t T = 0xffffffffu;
@@ -824,7 +828,7 @@ __device__ __forceinline__ void cta_body(const ChooseP& p, const Item& it, CtaSm
     }
     int base_less = 0, base_tie = 0;
     uint32_t* kbits0 = s.kbits;
-    uint32_t* bits0 = s.bits;
+    uint32_t* bits0 = bits_local;
     if (CL > 1) {
         cg::cluster_group cl = cg::this_cluster();
         cl.sync();
@@ -834,7 +838,7 @@ __device__ __forceinline__ void cta_body(const ChooseP& p, const Item& it, CtaSm
             base_tie += t >> 16;
         }
         kbits0 = cl.map_shared_rank(&s.kbits[0], 0);
-        bits0 = cl.map_shared_rank(&s.bits[0], 0);
+        bits0 = cl.map_shared_rank(bits_local, 0);
     } else {
         __syncthreads();
     }
@@ -850,9 +854,9 @@ __device__ __forceinline__ void cta_body(const ChooseP& p, const Item& it, CtaSm
         const bool sel = less || (tie && tie_before < need);
         if (sel) {
             const int64_t at = it.off + base_less + (pl & 0xffff) + __popc(ml & lt) + min(tie_before, need);
-            p.sel_idx[at] = STASH ? sid[j] : id[e];
+            p.sel_idx[at] = STASH ? sid[e * NT + tid] : id[e];
             if (p.sel_dist) p.sel_dist[at] = __uint_as_float(key[e]);
-            const int q = STASH ? (int)spp[j] : pp[e];
+            const int q = STASH ? (int)spp[e * NT + tid] : pp[e];
             if (q >= 0) atomicOr(&kbits0[q >> 5], 1u << (q & 31));
         }
         if (it.want_bits) {
@@ -864,8 +868,8 @@ __device__ __forceinline__ void cta_body(const ChooseP& p, const Item& it, CtaSm
 }
 
 template <int NT, int CL>
-__device__ __forceinline__ void cta_item(const ChooseP& p, int w, CtaSmem<NT>& s, int32_t* sid, int16_t* spp, int rank,
-                                         int* par) {
+__device__ __forceinline__ void cta_item(const ChooseP& p, int w, CtaSmem<NT>& s, int32_t* sid, int16_t* spp,
+                                         uint32_t* bits_local, int rank, int* par) {
     const int tid = threadIdx.x;
     Item it;
     item_header(p, w, it);
@@ -875,18 +879,18 @@ __device__ __forceinline__ void cta_item(const ChooseP& p, int w, CtaSmem<NT>& s
     TRACE(1);
     const int per = (it.d + CL * NT - 1) / (CL * NT);
     constexpr int NE_MAX = NT == PCG_GRP_NT ? 8 : 16;
-    if (per <= 1) cta_body<NT, 1, CL>(p, it, s, sid, spp, rank, par);
-    else if (per <= 2) cta_body<NT, 2, CL>(p, it, s, sid, spp, rank, par);
-    else if (per <= 4 || NE_MAX == 4) cta_body<NT, 4, CL>(p, it, s, sid, spp, rank, par);
-    else if (per <= 8 || NE_MAX == 8) cta_body<NT, (NE_MAX < 8 ? NE_MAX : 8), CL>(p, it, s, sid, spp, rank, par);
-    else cta_body<NT, NE_MAX, CL>(p, it, s, sid, spp, rank, par);
+    if (per <= 1) cta_body<NT, 1, CL>(p, it, s, sid, spp, bits_local, rank, par);
+    else if (per <= 2) cta_body<NT, 2, CL>(p, it, s, sid, spp, bits_local, rank, par);
+    else if (per <= 4 || NE_MAX == 4) cta_body<NT, 4, CL>(p, it, s, sid, spp, bits_local, rank, par);
+    else if (per <= 8 || NE_MAX == 8) cta_body<NT, (NE_MAX < 8 ? NE_MAX : 8), CL>(p, it, s, sid, spp, bits_local, rank, par);
+    else cta_body<NT, NE_MAX, CL>(p, it, s, sid, spp, bits_local, rank, par);
     if (CL > 1) {
         if (it.o > 0) cg::this_cluster().sync();      // kept bitmaps complete (remote ORs) before rank 0 reads them
         if (rank != 0) return;
     }
     __syncthreads();                      // kept bitmaps complete
     int m = it.k;
-    if (it.o > 0) m += oversample<NT>(p, it, tid, p.indices + it.beg, s.kbits, s.bits, s.ohist, s.xw);
+    if (it.o > 0) m += oversample<NT>(p, it, tid, p.indices + it.beg, s.kbits, bits_local, s.ohist, s.xw);
     TRACE(6);
     item_finish<NT>(p, it, tid, m);
     __syncthreads();
@@ -918,7 +922,7 @@ __global__ void __launch_bounds__(PCG_GRP_NT, 3) k_choose_small(ChooseP p) {
                 __syncthreads();
                 const int q = s_q;
                 if (q >= n) break;
-                cta_item<PCG_GRP_NT, 1>(p, p.q_cta[q], s, nullptr, nullptr, 0, nullptr);
+                cta_item<PCG_GRP_NT, 1>(p, p.q_cta[q], s, nullptr, nullptr, s.bits, 0, nullptr);
             }
         } else {
             WarpSmem& ws = reinterpret_cast<WarpSmem*>(raw)[wid];
@@ -947,8 +951,28 @@ __global__ void __cluster_dims__(PCG_CL, 1, 1) __launch_bounds__(PCG_GRP_NT, 3) 
     const int n = p.status[ST_NCL];
     const int n_cl = gridDim.x / PCG_CL, cid = blockIdx.x / PCG_CL;
     int par = 0;
-    for (int q = cid; q < n; q += n_cl) cta_item<PCG_GRP_NT, PCG_CL>(p, p.q_cl[q], s, nullptr, nullptr, rank, &par);
+    for (int q = cid; q < n; q += n_cl) cta_item<PCG_GRP_NT, PCG_CL>(p, p.q_cl[q], s, nullptr, nullptr, s.bits, rank, &par);
     cl.sync();          // nobody leaves while a peer may still address its shared memory
+}
+
+// 16384 < d <= 131072: one item per CLUSTER of 8 CTAs x 1024 threads, <= 16 keys per thread in registers, the ids and
+// pool positions stashed in shared memory (power-law hubs of config C5; one CTA alone needs ~25 us per 10^4 entries).
+#define PCG_HUGE_PER_CTA (PCG_HUGE_MAX / PCG_CL)
+__global__ void __cluster_dims__(PCG_CL, 1, 1) __launch_bounds__(PCG_LARGE_NT, 1) k_choose_huge(ChooseP p) {
+    extern __shared__ uint32_t dyn_huge[];           // ids [PER_CTA] int32 | pool positions [PER_CTA] int16 | row bits
+    int32_t* sid = reinterpret_cast<int32_t*>(dyn_huge);
+    int16_t* spp = reinterpret_cast<int16_t*>(dyn_huge + PCG_HUGE_PER_CTA);
+    uint32_t* bits = dyn_huge + PCG_HUGE_PER_CTA + PCG_HUGE_PER_CTA / 2;      // [PCG_HUGE_MAX / 32], used on rank 0
+    __shared__ CtaSmem<PCG_LARGE_NT> s;
+    cg::cluster_group cl = cg::this_cluster();
+    const int rank = (int)cl.block_rank();
+    for (int b = threadIdx.x; b < 8 * 256; b += PCG_LARGE_NT) s.hist[b] = 0u;
+    __syncthreads();
+    const int n = p.status[ST_NHUGE];
+    const int n_cl = gridDim.x / PCG_CL, cid = blockIdx.x / PCG_CL;
+    int par = 0;
+    for (int q = cid; q < n; q += n_cl) cta_item<PCG_LARGE_NT, PCG_CL>(p, p.q_huge[q], s, sid, spp, bits, rank, &par);
+    cl.sync();
 }
 
 // --------------------------------------------------------------------------------- big tier
@@ -1151,7 +1175,7 @@ __global__ void __launch_bounds__(PCG_PREP_NT, 1) k_choose_prep(ChooseP p, int c
                     int k, o;
                     item_counts(d, p.thresh[rr[u]], p.rho, pos[u], p.P, p.k_override ? p.k_override[w] : 0,
                                 p.k_override != nullptr, k, o);
-                    const int tier = d <= PCG_SMALL_MAX ? 0 : (d <= PCG_CTA_MAX ? 1 : (d <= PCG_CL_MAX ? 2 : 3));
+                    const int tier = d <= PCG_SMALL_MAX ? 0 : (d <= PCG_CTA_MAX ? 1 : (d <= PCG_CL_MAX ? 2 : (d <= PCG_HUGE_MAX ? 3 : 4)));
                     info = (((k + o + PCG_SLOT - 1) / PCG_SLOT) << 3) | (tier + 1);
                 }
                 s_info[q] = info;
@@ -1192,8 +1216,8 @@ __global__ void __launch_bounds__(PCG_PREP_NT, 1) k_choose_prep(ChooseP p, int c
     __syncthreads();
     int slot0 = s_base + __shfl_sync(PCG_FULL, wincl - ws, wid) + incl - mine;
     bool overflow = false;
-    int32_t* const queues[4] = {p.q_warp, p.q_cta, p.q_cl, p.q_big};
-    const int counters[4] = {ST_NSMALL, ST_NMID, ST_NCL, ST_NBIG};
+    int32_t* const queues[5] = {p.q_warp, p.q_cta, p.q_cl, p.q_huge, p.q_big};
+    const int counters[5] = {ST_NSMALL, ST_NMID, ST_NCL, ST_NHUGE, ST_NBIG};
     for (int c = 0; c < per; ++c) {                          // uniform trip count (ballots inside)
         const int q = c0 + c;
         int tier = -1;
@@ -1215,7 +1239,7 @@ __global__ void __launch_bounds__(PCG_PREP_NT, 1) k_choose_prep(ChooseP p, int c
             }
         }
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
+        for (int t = 0; t < 5; ++t) {
             const unsigned m = __ballot_sync(PCG_FULL, tier == t);
             if (m) {
                 int b = 0;
@@ -1296,7 +1320,7 @@ __global__ void k_entry_pool_pos(const int32_t* __restrict__ indices, int64_t nn
 }
 // ------------------------------------------------------------------------------------------- C ABI
 struct WsLayout {
-    size_t first, bar, totals, bits_slab, q_warp, q_cta, q_cl, q_big, total;
+    size_t first, bar, totals, bits_slab, q_warp, q_cta, q_cl, q_huge, q_big, total;
     int64_t slab_words;
     int grid_big;
 };
@@ -1307,7 +1331,7 @@ static WsLayout ws_layout(int B, int R, int64_t max_degree, int64_t n_nodes, int
     size_t W = (size_t)B * R;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     L.grid_big = sms;
-    L.slab_words = max_degree > PCG_CL_MAX ? (max_degree + 31) / 32 : 0;
+    L.slab_words = max_degree > PCG_HUGE_MAX ? (max_degree + 31) / 32 : 0;
     size_t o = 0;
     L.first = o; o = al(o + (size_t)n_nodes * 4);
     L.bar = o; o = al(o + 8);                    // prep grid barrier words (zero between calls)
@@ -1316,6 +1340,7 @@ static WsLayout ws_layout(int B, int R, int64_t max_degree, int64_t n_nodes, int
     L.q_warp = o; o = al(o + W * 4);
     L.q_cta = o; o = al(o + W * 4);
     L.q_cl = o; o = al(o + W * 4);
+    L.q_huge = o; o = al(o + W * 4);
     L.q_big = o; o = al(o + W * 4);
     L.total = o;
     return L;
@@ -1418,6 +1443,7 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
     p.q_warp = (int32_t*)(ws + L.q_warp);
     p.q_cta = (int32_t*)(ws + L.q_cta);
     p.q_cl = (int32_t*)(ws + L.q_cl);
+    p.q_huge = (int32_t*)(ws + L.q_huge);
     p.q_big = (int32_t*)(ws + L.q_big);
     p.bits_slab = (uint32_t*)(ws + L.bits_slab);
     p.slab_words = L.slab_words;
@@ -1441,7 +1467,8 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
         e = cudaLaunchKernelEx(&cfg, k_choose_prep, p, chunk, (int32_t*)(ws + L.bar), (int32_t*)(ws + L.totals));
         if (e != cudaSuccess) { pcg_set_error("pcg_choose: prep launch: %s", cudaGetErrorString(e)); return (int)e; }
     }
-    const bool have_cta = max_degree > PCG_SMALL_MAX, have_cl = max_degree > PCG_CTA_MAX, have_big = max_degree > PCG_CL_MAX;
+    const bool have_cta = max_degree > PCG_SMALL_MAX, have_cl = max_degree > PCG_CTA_MAX,
+               have_huge = max_degree > PCG_CL_MAX, have_big = max_degree > PCG_HUGE_MAX;
     if (have_cl && !g_fork) {
         // the long-row tiers are the critical path: their streams get the highest priority, so the block scheduler
         // places their CTAs (clusters of 8 need a whole GPC slot each) before the short-row kernel fills the SMs
@@ -1472,6 +1499,19 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
         k_choose_big<<<W < L.grid_big ? W : L.grid_big, PCG_LARGE_NT, dyn, g_side[2]>>>(p, (int)cap);
         cudaEventRecord(g_join[2], g_side[2]);
     }
+    if (have_huge) {
+        const size_t dyn = (size_t)PCG_HUGE_PER_CTA * 6 + PCG_HUGE_MAX / 8;
+        static bool configured_huge = false;
+        if (!configured_huge) {
+            e = cudaFuncSetAttribute(k_choose_huge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+            if (e != cudaSuccess) { pcg_set_error("pcg_choose: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+            configured_huge = true;
+        }
+        cudaStreamWaitEvent(g_side[0], g_fork, 0);
+        const int n_cl = W < 16 ? W : 16;
+        k_choose_huge<<<n_cl * PCG_CL, PCG_LARGE_NT, dyn, g_side[0]>>>(p);
+        cudaEventRecord(g_join[0], g_side[0]);
+    }
     if (have_cl) {
         cudaStreamWaitEvent(g_side[1], g_fork, 0);
         const int n_cl = W < 56 ? W : 56;
@@ -1483,6 +1523,7 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
         const int gs = units < sms * 3 ? units : sms * 3;     // (2 CTAs per SM, leaving room for the clusters, measured no better)
         k_choose_small<<<gs, PCG_GRP_NT, 0, stream>>>(p);
     }
+    if (have_huge) cudaStreamWaitEvent(stream, g_join[0], 0);
     if (have_cl) cudaStreamWaitEvent(stream, g_join[1], 0);
     if (have_big) cudaStreamWaitEvent(stream, g_join[2], 0);
     return pcg_check_launch("pcg_choose");

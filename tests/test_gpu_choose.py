@@ -138,14 +138,14 @@ def test_hub_rows_take_the_cta_path_and_multi_slot_aggregation():
 
 @pytest.mark.parametrize("big_pool", [False, True])
 def test_rows_in_every_tier(big_pool):
-    """Row lengths that land in the warp (<=256), cta (<=2048), cluster (<=16384) and big (>16384) tiers,
+    """Row lengths that land in the warp (<=256), cta (<=2048), wide (<=16384), huge (<=131072) and big tiers,
     with a small pool (per-item bitmap over pool positions) and a pool beyond 8192 positives (row-position
     bits + binary search), coarse scores so that ties cross the tier-internal chunk boundaries."""
     from pcgnn_b200.graph import RelGraph, csr_from_edges
 
     rng = np.random.default_rng(11)
-    n = 60000
-    hub_deg = [40000, 33000, 20000, 16400, 16300, 9000, 5000, 3000, 2049, 2048, 1500, 1025, 1024, 600, 300, 257, 256,
+    n = 150000
+    hub_deg = [140000, 131073, 131072, 70000, 40000, 33000, 20000, 16400, 16385, 16384, 16300, 9000, 5000, 3000, 2049, 2048, 1500, 1025, 1024, 600, 300, 257, 256,
                129, 128, 100, 65, 64, 33, 32, 5, 4, 3]
     rels = []
     for r in range(2):
@@ -157,7 +157,7 @@ def test_rows_in_every_tier(big_pool):
         dst.append(rng.integers(0, n, 3000))
         rels.append(csr_from_edges(n, np.concatenate(src), np.concatenate(dst)))
     graph = RelGraph(n, [a for a, _ in rels], [b for _, b in rels])
-    assert np.diff(graph.indptr).max() > 32768
+    assert np.diff(graph.indptr).max() > 131072
     feat = rng.random((n, 8), dtype=np.float32)
     score = np.round(rng.normal(size=n), 2 if not big_pool else 3).astype(np.float32)
     labels = (rng.random(n) < (0.5 if big_pool else 0.05)).astype(np.int64)
