@@ -394,6 +394,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="do not use CUDA graphs for the device-resident step")
     ap.add_argument("--torch-adam", action="store_true",
                     help="NCCL all-reduce + torch.optim.Adam instead of the fused peer-memory exchange + Adam kernel")
+    ap.add_argument("--nccl-scores", action="store_true",
+                    help="workload big: exchange the score slices with an NCCL all-gather instead of peer-memory stores")
     ap.add_argument("--nodes-per-gpu", type=int, default=1_250_000, help="workload big: rows of the CSR held per GPU")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -437,9 +439,14 @@ def main():
             e_.set_features(inter.features.weight)
             e_.score_table(inter.label_clf.weight, inter.label_clf.bias)
             whole = e_.score.clone()
-            e_.score.zero_()
-            e_.score_group = dist.group.WORLD
+            if args.nccl_scores:
+                e_.score.zero_()
+                e_.score_group = dist.group.WORLD          # slice kernel | NCCL all-gather (between two graphs)
+            else:
+                e_.enable_score_broadcast(dist.group.WORLD)  # slice kernel storing into every rank's table (one graph)
             e_.score_table(inter.label_clf.weight, inter.label_clf.bias)
+            torch.cuda.synchronize()
+            dist.barrier()
             assert torch.equal(whole, e_.score), "score exchange differs from the locally computed table"
             del whole
         drawn = part.sample_batches(n_b, batch, SEED + rank)

@@ -251,6 +251,19 @@ PCG_API int pcg_allreduce_adam(float* grad, float* param, float* m, float* v, in
                        float lr, float beta1, float beta2, float eps, float weight_decay, int do_adam,
                        pcg_stream_t stream);
 
+/*
+ * Label scores of a row partition + halo exchange in one kernel (config C5). Every rank owns a region of
+ * pcg_score_region_bytes(n_global) bytes ([n_global] fp32 score table + arrival counters; pcg_comm_alloc /
+ * _export / _import as above). pcg_score_bcast scores the n_rows feature rows at feat_rows (global ids row_lo ..)
+ * with w[0..F), b[0] (src/layers.py:236-237, column 0) and stores them into the table of EVERY rank, then waits
+ * (on the stream) until every peer's slice has arrived in the own table. Equal n_rows on all ranks. Safe to call
+ * once per training step: the gradient exchange of the step orders it against the peers' readers.
+ */
+PCG_API size_t pcg_score_region_bytes(int64_t n_global);
+PCG_API int pcg_score_bcast(const float* feat_rows, int64_t n_rows, int F, int64_t ldf, const float* w, const float* b,
+                    int64_t row_lo, int64_t n_global, void* const* regions_host, int rank, int world,
+                    uint32_t* epoch, pcg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

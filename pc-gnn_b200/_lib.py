@@ -60,6 +60,8 @@ SIGNATURES = {
     "pcg_comm_unmap": (_i, [_p]),
     "pcg_allreduce_adam": (_i, [_p, _p, _p, _p, _l, C.POINTER(_p), _i, _i, _p, _p, C.c_float, C.c_float, C.c_float,
                                 C.c_float, C.c_float, _i, _p]),
+    "pcg_score_region_bytes": (_z, [_l]),
+    "pcg_score_bcast": (_i, [_p, _l, _i, _l, _p, _p, _l, _l, C.POINTER(_p), _i, _i, _p, _p]),
     "pcg_pick_step": (_i, [_p, _l, _p, _l, _p, _p, _p]),
     "pcg_pick_step_philox": (_i, [_p, _l, _u64, _u64, _l, _p, _p, _p]),
 }

@@ -42,6 +42,7 @@ namespace cg = cooperative_groups;
 #define PCG_CL 8               // wide tier: CTAs per cluster
 #define PCG_CL_MAX 16384       // wide tier: 8 x 256 threads x <= 8 entries
 #define PCG_HUGE_MAX 131072     // huge tier: 8 x 1024 threads x <= 16 entries (ids / pool positions stashed in shared memory)
+#define PCG_HUGE16_MAX 262144   // ... on clusters of 16 CTAs (non-portable cluster size), where the device can place them
 #define PCG_KB_WORDS 256       // kept-pool bitmap words per item (pools up to 8192 positives; else row-position bits)
 #define PCG_CAND_CAP 2048      // big tier: candidate keys kept in shared memory once they fit
 #define PCG_PREP_NT 1024
@@ -79,6 +80,8 @@ struct ChooseP {
     int32_t* q_cta;
     int32_t* q_cl;
     int32_t* q_huge;
+    int32_t* q_huge16;
+    int huge16_ok;              // clusters of 16 x 1024 threads can be scheduled on this device
     int32_t* q_big;
     uint32_t* bits_slab;        // [grid_big, slab_words] kept-position bitmasks of the big tier
     int64_t slab_words;
@@ -958,21 +961,52 @@ __global__ void __cluster_dims__(PCG_CL, 1, 1) __launch_bounds__(PCG_GRP_NT, 3) 
 // 16384 < d <= 131072: one item per CLUSTER of 8 CTAs x 1024 threads, <= 16 keys per thread in registers, the ids and
 // pool positions stashed in shared memory (power-law hubs of config C5; one CTA alone needs ~25 us per 10^4 entries).
 #define PCG_HUGE_PER_CTA (PCG_HUGE_MAX / PCG_CL)
-__global__ void __cluster_dims__(PCG_CL, 1, 1) __launch_bounds__(PCG_LARGE_NT, 1) k_choose_huge(ChooseP p) {
+template <int CL>
+__global__ void __launch_bounds__(PCG_LARGE_NT, 1) k_choose_huge(ChooseP p) {
     extern __shared__ uint32_t dyn_huge[];           // ids [PER_CTA] int32 | pool positions [PER_CTA] int16 | row bits
     int32_t* sid = reinterpret_cast<int32_t*>(dyn_huge);
     int16_t* spp = reinterpret_cast<int16_t*>(dyn_huge + PCG_HUGE_PER_CTA);
-    uint32_t* bits = dyn_huge + PCG_HUGE_PER_CTA + PCG_HUGE_PER_CTA / 2;      // [PCG_HUGE_MAX / 32], used on rank 0
+    uint32_t* bits = dyn_huge + PCG_HUGE_PER_CTA + PCG_HUGE_PER_CTA / 2;      // [CL * PER_CTA / 32], used on rank 0
     __shared__ CtaSmem<PCG_LARGE_NT> s;
     cg::cluster_group cl = cg::this_cluster();
     const int rank = (int)cl.block_rank();
     for (int b = threadIdx.x; b < 8 * 256; b += PCG_LARGE_NT) s.hist[b] = 0u;
     __syncthreads();
-    const int n = p.status[ST_NHUGE];
-    const int n_cl = gridDim.x / PCG_CL, cid = blockIdx.x / PCG_CL;
+    const int n = p.status[CL == 16 ? ST_NHUGE16 : ST_NHUGE];
+    const int32_t* queue = CL == 16 ? p.q_huge16 : p.q_huge;
+    const int n_cl = gridDim.x / CL, cid = blockIdx.x / CL;
     int par = 0;
-    for (int q = cid; q < n; q += n_cl) cta_item<PCG_LARGE_NT, PCG_CL>(p, p.q_huge[q], s, sid, spp, bits, rank, &par);
+    for (int q = cid; q < n; q += n_cl) cta_item<PCG_LARGE_NT, CL>(p, queue[q], s, sid, spp, bits, rank, &par);
     cl.sync();
+}
+
+// cluster launch with a run-time cluster size (16 is a non-portable size: opt-in attribute + occupancy check)
+template <int CL>
+static cudaError_t launch_huge(const ChooseP& p, int n_clusters, cudaStream_t stream, bool probe_only, int* max_clusters) {
+    const size_t dyn = (size_t)PCG_HUGE_PER_CTA * 6 + (size_t)CL * PCG_HUGE_PER_CTA / 8;
+    static bool configured = false;
+    cudaError_t e;
+    if (!configured) {
+        e = cudaFuncSetAttribute(k_choose_huge<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess) return e;
+        if (CL > 8) {
+            e = cudaFuncSetAttribute(k_choose_huge<CL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (e != cudaSuccess) return e;
+        }
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_clusters * CL));
+    cfg.blockDim = dim3(PCG_LARGE_NT);
+    cfg.dynamicSmemBytes = dyn;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (probe_only) return cudaOccupancyMaxActiveClusters(max_clusters, k_choose_huge<CL>, &cfg);
+    return cudaLaunchKernelEx(&cfg, k_choose_huge<CL>, p);
 }
 
 // --------------------------------------------------------------------------------- big tier
@@ -1175,7 +1209,8 @@ __global__ void __launch_bounds__(PCG_PREP_NT, 1) k_choose_prep(ChooseP p, int c
                     int k, o;
                     item_counts(d, p.thresh[rr[u]], p.rho, pos[u], p.P, p.k_override ? p.k_override[w] : 0,
                                 p.k_override != nullptr, k, o);
-                    const int tier = d <= PCG_SMALL_MAX ? 0 : (d <= PCG_CTA_MAX ? 1 : (d <= PCG_CL_MAX ? 2 : (d <= PCG_HUGE_MAX ? 3 : 4)));
+                    const int tier = d <= PCG_SMALL_MAX ? 0 : (d <= PCG_CTA_MAX ? 1 : (d <= PCG_CL_MAX ? 2 : (d <= PCG_HUGE_MAX ? 3 :
+                                     ((d <= PCG_HUGE16_MAX && p.huge16_ok) ? 4 : 5))));
                     info = (((k + o + PCG_SLOT - 1) / PCG_SLOT) << 3) | (tier + 1);
                 }
                 s_info[q] = info;
@@ -1216,8 +1251,8 @@ __global__ void __launch_bounds__(PCG_PREP_NT, 1) k_choose_prep(ChooseP p, int c
     __syncthreads();
     int slot0 = s_base + __shfl_sync(PCG_FULL, wincl - ws, wid) + incl - mine;
     bool overflow = false;
-    int32_t* const queues[5] = {p.q_warp, p.q_cta, p.q_cl, p.q_huge, p.q_big};
-    const int counters[5] = {ST_NSMALL, ST_NMID, ST_NCL, ST_NHUGE, ST_NBIG};
+    int32_t* const queues[6] = {p.q_warp, p.q_cta, p.q_cl, p.q_huge, p.q_huge16, p.q_big};
+    const int counters[6] = {ST_NSMALL, ST_NMID, ST_NCL, ST_NHUGE, ST_NHUGE16, ST_NBIG};
     for (int c = 0; c < per; ++c) {                          // uniform trip count (ballots inside)
         const int q = c0 + c;
         int tier = -1;
@@ -1239,7 +1274,7 @@ __global__ void __launch_bounds__(PCG_PREP_NT, 1) k_choose_prep(ChooseP p, int c
             }
         }
 #pragma unroll
-        for (int t = 0; t < 5; ++t) {
+        for (int t = 0; t < 6; ++t) {
             const unsigned m = __ballot_sync(PCG_FULL, tier == t);
             if (m) {
                 int b = 0;
@@ -1320,7 +1355,7 @@ __global__ void k_entry_pool_pos(const int32_t* __restrict__ indices, int64_t nn
 }
 // ------------------------------------------------------------------------------------------- C ABI
 struct WsLayout {
-    size_t first, bar, totals, bits_slab, q_warp, q_cta, q_cl, q_huge, q_big, total;
+    size_t first, bar, totals, bits_slab, q_warp, q_cta, q_cl, q_huge, q_huge16, q_big, total;
     int64_t slab_words;
     int grid_big;
 };
@@ -1331,7 +1366,7 @@ static WsLayout ws_layout(int B, int R, int64_t max_degree, int64_t n_nodes, int
     size_t W = (size_t)B * R;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     L.grid_big = sms;
-    L.slab_words = max_degree > PCG_HUGE_MAX ? (max_degree + 31) / 32 : 0;
+    L.slab_words = max_degree > PCG_HUGE_MAX ? (max_degree + 31) / 32 : 0;      // (also when 16-CTA clusters take those rows)
     size_t o = 0;
     L.first = o; o = al(o + (size_t)n_nodes * 4);
     L.bar = o; o = al(o + 8);                    // prep grid barrier words (zero between calls)
@@ -1341,6 +1376,7 @@ static WsLayout ws_layout(int B, int R, int64_t max_degree, int64_t n_nodes, int
     L.q_cta = o; o = al(o + W * 4);
     L.q_cl = o; o = al(o + W * 4);
     L.q_huge = o; o = al(o + W * 4);
+    L.q_huge16 = o; o = al(o + W * 4);
     L.q_big = o; o = al(o + W * 4);
     L.total = o;
     return L;
@@ -1444,10 +1480,19 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
     p.q_cta = (int32_t*)(ws + L.q_cta);
     p.q_cl = (int32_t*)(ws + L.q_cl);
     p.q_huge = (int32_t*)(ws + L.q_huge);
+    p.q_huge16 = (int32_t*)(ws + L.q_huge16);
     p.q_big = (int32_t*)(ws + L.q_big);
     p.bits_slab = (uint32_t*)(ws + L.bits_slab);
     p.slab_words = L.slab_words;
     const int W = R * B;
+    static int huge16_state = -1;            // can this device place clusters of 16 x 1024 threads? (probed once)
+    if (huge16_state < 0) {
+        int mc = 0;
+        cudaError_t pe = launch_huge<16>(p, 1, stream, true, &mc);
+        huge16_state = (pe == cudaSuccess && mc >= 1) ? 1 : 0;
+        (void)cudaGetLastError();
+    }
+    p.huge16_ok = huge16_state;
     {
         // contiguous chunks of items over at most #SMs CTAs (they meet at grid barriers: all must be resident)
         int chunk = PCG_PREP_CHUNK;
@@ -1468,7 +1513,8 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
         if (e != cudaSuccess) { pcg_set_error("pcg_choose: prep launch: %s", cudaGetErrorString(e)); return (int)e; }
     }
     const bool have_cta = max_degree > PCG_SMALL_MAX, have_cl = max_degree > PCG_CTA_MAX,
-               have_huge = max_degree > PCG_CL_MAX, have_big = max_degree > PCG_HUGE_MAX;
+               have_huge = max_degree > PCG_CL_MAX,
+               have_big = max_degree > (p.huge16_ok ? PCG_HUGE16_MAX : PCG_HUGE_MAX);
     if (have_cl && !g_fork) {
         // the long-row tiers are the critical path: their streams get the highest priority, so the block scheduler
         // places their CTAs (clusters of 8 need a whole GPC slot each) before the short-row kernel fills the SMs
@@ -1500,16 +1546,13 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
         cudaEventRecord(g_join[2], g_side[2]);
     }
     if (have_huge) {
-        const size_t dyn = (size_t)PCG_HUGE_PER_CTA * 6 + PCG_HUGE_MAX / 8;
-        static bool configured_huge = false;
-        if (!configured_huge) {
-            e = cudaFuncSetAttribute(k_choose_huge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-            if (e != cudaSuccess) { pcg_set_error("pcg_choose: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-            configured_huge = true;
-        }
         cudaStreamWaitEvent(g_side[0], g_fork, 0);
-        const int n_cl = W < 16 ? W : 16;
-        k_choose_huge<<<n_cl * PCG_CL, PCG_LARGE_NT, dyn, g_side[0]>>>(p);
+        if (max_degree > PCG_HUGE_MAX && p.huge16_ok) {
+            e = launch_huge<16>(p, W < 4 ? W : 4, g_side[0], false, nullptr);
+            if (e != cudaSuccess) { pcg_set_error("pcg_choose: huge16 launch: %s", cudaGetErrorString(e)); return (int)e; }
+        }
+        e = launch_huge<8>(p, W < 16 ? W : 16, g_side[0], false, nullptr);
+        if (e != cudaSuccess) { pcg_set_error("pcg_choose: huge launch: %s", cudaGetErrorString(e)); return (int)e; }
         cudaEventRecord(g_join[0], g_side[0]);
     }
     if (have_cl) {

@@ -16,7 +16,8 @@
 #define ST_NCL 4         // ... the cluster tier
 #define ST_SMALL_CTR 5   // queue heads of the warp / cta tiers (device-side work distribution)
 #define ST_MID_CTR 7
-#define ST_NHUGE 8        // items queued for the huge tier
+#define ST_NHUGE 8        // items queued for the huge tier (clusters of 8)
+#define ST_NHUGE16 9      // ... for the clusters of 16
 #define ST_NBIG 6        // ... the big tier
 
 void pcg_set_error(const char* fmt, ...);

@@ -96,6 +96,7 @@ class Engine:
         # buffer), the backward kernels write a parameter's gradient straight into its view and autograd gets
         # None for it, which removes the AccumulateGrad add kernels from the step
         self.grad_sink = None
+        self._bcast = None          # (PeerRegion, epoch tensor): scores are broadcast into every rank's table (C5)
 
     # ------------------------------------------------------------------ resident tables
     def set_features(self, weight: torch.Tensor):
@@ -170,6 +171,15 @@ class Engine:
         if not w.is_contiguous():
             w = w.contiguous()
         ps, pp, pi, ws = self.sorted_pool if self.pool is not None else (None, None, None, None)
+        if self._bcast is not None:
+            region, epoch = self._bcast
+            lo = self.row_lo
+            rc = self.lib.pcg_score_bcast(self.feat.data_ptr() + lo * self.ldf * 4, self.N, self.F, self.ldf,
+                                          w.data_ptr(), b.data_ptr(), lo, self.N_global, region.regions, region.rank,
+                                          region.world, epoch.data_ptr(), _lib.stream_ptr())
+            _lib.check(rc, "pcg_score_bcast")
+            self.resort_pool()
+            return self.score
         if self.score_group is not None:
             self.score_local(w, b)
             self.score_exchange()
@@ -180,6 +190,27 @@ class Engine:
                                       _lib.ptr(pi), _lib.ptr(ws), 0 if ws is None else ws.numel(), _lib.stream_ptr())
         _lib.check(rc, "pcg_score_table")
         return self.score
+
+    def enable_score_broadcast(self, group=None):
+        """Row-partitioned graph, several ranks: keep the score table in memory that every peer has mapped, so that
+        ``score_table`` becomes slice kernel + stores into all peers' tables + arrival wait (``pcg_score_bcast``),
+        capturable in the step graph. For training steps (see the write-after-read note in csrc/pcg_comm.cu)."""
+        from .parallel import PeerRegion
+
+        region = PeerRegion(int(self.lib.pcg_score_region_bytes(self.N_global)), group)
+        if region.world == 1:
+            return
+        if region.world * self.N != self.N_global:
+            raise ValueError("score broadcast needs equal row ranges (n_global == world * rows per rank)")
+
+        class _Mem:      # __cuda_array_interface__ view of the region's table
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+        self._score_mem = _Mem(region.own, self.N_global)
+        self.score = torch.as_tensor(self._score_mem, device=self.device)
+        self._bcast = (region, torch.zeros(1, dtype=torch.int32, device=self.device))
+        self.score_group = None
 
     def score_local(self, w: torch.Tensor, b: torch.Tensor):
         """Partitioned graph: scores of the nodes whose rows live here, written into their slice of the table."""

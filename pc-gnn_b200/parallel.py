@@ -11,7 +11,7 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_range", "shard_batch", "GradAllReduce", "global_mean_loss_scale", "PeerComm", "FusedAdam"]
+__all__ = ["shard_range", "shard_batch", "GradAllReduce", "global_mean_loss_scale", "PeerRegion", "PeerComm", "FusedAdam"]
 
 
 def shard_range(n: int, rank: int, world: int):
@@ -71,11 +71,12 @@ class GradAllReduce:
         return self.flat
 
 
-class PeerComm:
-    """One region of device memory per rank that every peer of the node has mapped (CUDA IPC over NVLink /
-    NVSwitch): send buffers + flags of the fused gradient exchange (csrc/pcg_comm.cu). world == 1: no region."""
+class PeerRegion:
+    """`nbytes` of zeroed device memory on every rank of `group`, each mapped by all the other ranks of the node
+    (CUDA IPC; loads, stores and atomics on a peer's region travel over NVLink / NVSwitch).
+    ``regions`` is a ctypes array of this process's mappings (own region at [rank]); None when world == 1."""
 
-    def __init__(self, n_params: int, group=None):
+    def __init__(self, nbytes: int, group=None):
         import ctypes as C
 
         from . import _lib
@@ -86,23 +87,23 @@ class PeerComm:
         self.world = dist.get_world_size(group) if on else 1
         self.rank = dist.get_rank(group) if on else 0
         self.regions = None
-        self._own = self._mapped = None
+        self.own = None
+        self._mapped = None
         if self.world == 1:
             return
         if self.world > 8:
             raise ValueError("the peer-memory exchange is written for one node (<= 8 GPUs)")
-        nbytes = int(self.lib.pcg_comm_region_bytes(n_params))
         own = C.c_void_p()
-        _lib.check(self.lib.pcg_comm_alloc(C.byref(own), nbytes), "pcg_comm_alloc")
-        self._own = own.value
+        _lib.check(self.lib.pcg_comm_alloc(C.byref(own), int(nbytes)), "pcg_comm_alloc")
+        self.own = own.value
         buf = C.create_string_buffer(64)
-        _lib.check(self.lib.pcg_comm_export(self._own, buf), "pcg_comm_export")
+        _lib.check(self.lib.pcg_comm_export(self.own, buf), "pcg_comm_export")
         handles = [None] * self.world
         dist.all_gather_object(handles, bytes(buf.raw), group=group)
         ptrs, self._mapped = [], []
         for r in range(self.world):
             if r == self.rank:
-                ptrs.append(self._own)
+                ptrs.append(self.own)
                 continue
             q = C.c_void_p()
             _lib.check(self.lib.pcg_comm_import(handles[r], C.byref(q)), "pcg_comm_import")
@@ -116,9 +117,18 @@ class PeerComm:
             for q in self._mapped:
                 self.lib.pcg_comm_unmap(q)
             self._mapped = None
-        if self._own:
-            self.lib.pcg_comm_free(self._own)
-            self._own = None
+        if self.own:
+            self.lib.pcg_comm_free(self.own)
+            self.own = None
+
+
+class PeerComm(PeerRegion):
+    """Send buffers + flags of the fused gradient exchange (csrc/pcg_comm.cu). world == 1: no region."""
+
+    def __init__(self, n_params: int, group=None):
+        from . import _lib
+
+        super().__init__(int(_lib.lib().pcg_comm_region_bytes(n_params)), group)
 
 
 class FusedAdam:
