@@ -1,21 +1,27 @@
 #!/usr/bin/env python
 """Benchmark of the PC-GNN pick-and-choose hot path on B200 (contract: see DESIGN.md "Measurement").
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload yelp|amazon|yelp100] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload yelp|amazon|yelp100|amazon_gcn|big]
+                  [--impl reference] [--torch-adam] [--nccl-scores] [--no-graph] [--no-cpu-baseline]
 
 One "step" = one full training step of PCALayer(InterAgg3(IntraAgg x3)) on one label-balanced batch of
-B target nodes: zero_grad -> loss (score table, choose, aggregate, relation transforms, combine, head,
-both cross-entropies) -> backward -> [grad all-reduce] -> Adam step. Prints ONE JSON line.
+B target nodes per GPU: loss (score table, pool sort, choose, aggregate, relation transforms, combine, heads,
+both cross-entropies) -> backward -> gradient mean over the ranks + Adam (one kernel over NVLink peer memory;
+--torch-adam: NCCL all-reduce + torch.optim.Adam). Under torchrun every rank runs its shard; rank 0 prints ONE
+JSON line.
 
-  value      train target-nodes/s with the batch already resident in HBM (device tensors in)
-  e2e        the same through the reference-facing API with HOST inputs: model.loss(list_of_ids,
-             labels) + loss.item(), i.e. H2D of ids/labels and D2H of the loss inside the timed region
+  value      train target-nodes/s with the batch already resident in HBM (one CUDA-graph replay per step)
+  e2e        the same with HOST inputs through runtime.GraphedTrainStep.run(list_of_ids, labels): H2D of the
+             ids/labels and D2H of the loss inside the timed region (e2e_reference_api_eager: the reference's
+             own call sequence model.loss(list, labels); backward; step; loss.item(), eager)
   roofline   the slower of the two hot-path kernel groups (choose / aggregate), algorithmic bytes per
-             launch / CUDA-event time, against MEASURED_PEAKS.json
-  cpu_baseline  the oracle port (same algorithm structure as the reference, CPU) on a bounded sample
+             launch / CUDA-event time, against MEASURED_PEAKS.json; traffic = ncu DRAM bytes (profiles/)
+  cpu_baseline  the oracle port (same per-target structure as the reference, CPU) on a 1024-target batch
 
-`--impl reference` times that oracle port alone on the host cores (the reference is pure Python and is
-not present on the GPU box; oracle/port.py is its restatement, pinned by tests/golden).
+Workloads (BASELINE.json configs): yelp = C2 (default, the config the metric is quoted on), amazon = C1,
+yelp100 = C3, amazon_gcn = C4, big = C5 (row-partitioned CSR, 1.25M nodes / 1.26e8 entries per GPU).
+`--impl reference` times the oracle port alone on the host cores (the reference is pure Python and is not
+present on the GPU box; oracle/port.py is its restatement, pinned by tests/golden).
 """
 import argparse
 import json
