@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256) k_aggregate(const float* __restrict__ fea
     }
 }
 
-// agg row of a duplicate item = agg row of its representative (see k_choose_classify).
+// agg row of a duplicate item = agg row of its representative (see k_choose_prep).
 __global__ void k_copy_dups(const int32_t* __restrict__ it_rep, int n_items, int64_t ldf, float* __restrict__ agg) {
     const int w = blockIdx.x;
     if (w >= n_items) return;

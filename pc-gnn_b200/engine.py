@@ -8,7 +8,6 @@ host), which the reference's ``forward(nodes: list, labels)`` signature makes un
 from __future__ import annotations
 
 import ctypes as C
-import math
 
 import numpy as np
 import torch
