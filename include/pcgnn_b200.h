@@ -116,6 +116,10 @@ PCG_API int pcg_choose_workspace_init(void* workspace, size_t workspace_bytes, i
  *   status       int32 [PCG_STATUS_WORDS] (every word written here)
  * The slots of the items are handed out by a prefix sum in item order, so the layout of sel_idx is the same
  * on every run.
+ * Threading / devices: one host thread drives one device per process (the reference is single-threaded,
+ * src/model_handler.py:142-156; multi-GPU runs are one process per GPU). The forked side streams and the
+ * workspace's barrier words are per process, so concurrent pcg_choose calls from several threads, or calls for
+ * two devices from one process, are not supported.
  */
 PCG_API int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t n_nodes, int64_t row_lo, int R,
                const float* score,
