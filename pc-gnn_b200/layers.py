@@ -19,7 +19,6 @@ neighbour id, pool ties by position in ``train_pos``.
 """
 from __future__ import annotations
 
-import math
 from itertools import chain
 
 import numpy as np
@@ -29,7 +28,7 @@ import torch.nn.functional as F
 from torch.nn import init
 
 from . import _lib
-from .engine import Engine, padded_ld
+from .engine import Engine
 from .graph import RelGraph
 
 __all__ = ["InterAgg1", "InterAgg3", "InterAgg5", "InterAgg", "IntraAgg", "choose_step_neighs",
