@@ -147,3 +147,49 @@ def test_big_graph_generator_is_partition_independent():
         assert 0.35 < float(lab.float().mean()) < 0.65          # label-balanced like pick_step
     rows = ixf[ipf[5]:ipf[6]]
     assert 5 in rows.tolist() and bool((rows[1:] > rows[:-1]).all())   # self loop, ascending ids
+
+
+def test_pos_neg_split_keeps_order_and_matches_the_reference():
+    """utils.pos_neg_split (utils.py:256-271): ids with label 1 / the rest, both in `nodes` order."""
+    from pcgnn_b200.utils import pos_neg_split
+
+    rng = np.random.default_rng(0)
+    nodes = rng.permutation(500)[:300].tolist()
+    labels = (rng.random(300) < 0.2).astype(np.int64)
+    pos, neg = pos_neg_split(nodes, labels)
+    assert pos == [n for n, y in zip(nodes, labels) if y == 1]
+    assert neg == [n for n, y in zip(nodes, labels) if y != 1]
+    assert sorted(pos + neg) == sorted(nodes)
+    assert pos_neg_split([], []) == ([], [])
+    if H.available():
+        ref_utils = H.load(canonical=False).utils
+        rpos, rneg = ref_utils.pos_neg_split(list(nodes), labels)
+        assert list(rpos) == pos and list(rneg) == neg
+
+
+def test_from_scipy_applies_self_loops_and_symmetrisation():
+    """RelGraph.from_scipy == sparse_to_adjlist's dict of sets (utils.py:226-254): identity added, both
+    directions, rows ascending; directed input, duplicate entries and explicit zeros included."""
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(1)
+    n = 60
+    mats = []
+    for nnz in (80, 400):
+        r, c = rng.integers(0, n, nnz), rng.integers(0, n, nnz)
+        mats.append(sp.csc_matrix((np.ones(nnz), (r, c)), shape=(n, n)))      # directed, with duplicates
+    g = RelGraph.from_scipy(mats)
+    assert g.n_rel == 2 and g.n_nodes == n
+    for r, m in enumerate(mats):
+        dense = (m.toarray() != 0)
+        want = dense | dense.T | np.eye(n, dtype=bool)
+        for v in range(n):
+            row = g.row(r, v)
+            assert np.array_equal(row, np.nonzero(want[v])[0])
+    one = RelGraph.from_scipy(mats[0])
+    assert one.n_rel == 1 and np.array_equal(one.indices, g.relation(0)[1])
+    if H.available():
+        ref_utils = H.load(canonical=False).utils
+        adj = ref_utils.sparse_to_adjlist_for_train(mats[1])
+        for v in range(n):
+            assert set(int(x) for x in adj[v]) == set(g.row(1, v).tolist())
