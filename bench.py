@@ -413,7 +413,7 @@ def main():
     from pcgnn_b200 import _lib
     from pcgnn_b200.parallel import FusedAdam, GradAllReduce, PeerComm
     from pcgnn_b200.synth import make_graph
-    from tests.helpers import build_cuda_pcgnn
+    from pcgnn_b200.testing import build_cuda_pcgnn
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

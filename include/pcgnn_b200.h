@@ -194,6 +194,42 @@ PCG_API int pcg_dense_bwd(int64_t ldf, int F, int B, int R, int E, const float* 
                   float* d_w_inter, float* scratch, pcg_stream_t stream);
 
 /*
+ * Fused dense part of the step (csrc/pcg_tile.cu), one kernel per tile of targets: relation transforms
+ * (src/layers.py:616-629), inter-relation combine (src/layers.py:273-289, out is [E,B]) and the label_clf head on
+ * the batch (src/layers.py:236-243); activations stay in shared memory, weights stream in by TMA bulk copies.
+ * Supported when E is a multiple of 64 (<= 256) and the tile fits shared memory: pcg_tile_supported() != 0;
+ * other shapes use pcg_dense_fwd / pcg_center_fwd.
+ *   agg [R*B, lda] from pcg_aggregate (row of item w: agg_rep ? agg_rep[w] : w); feat / agg rows zero padded to
+ *   a multiple of 4 floats; w_clf [2,F], b_clf [2] or NULL (then no center scores)
+ *   keep_cat != 0: cat [B, F+R*E] is written for pcg_dense_bwd (autograd path), else cat may be NULL
+ */
+PCG_API int pcg_tile_supported(int B, int R, int F, int E);
+PCG_API int pcg_tile_fwd(const float* feat, int64_t ldf, int F, const int32_t* targets, int B, int R, int E,
+                 const float* agg, int64_t lda, const int32_t* agg_rep, const float* const* w_intra_host,
+                 const float* w_inter, const float* w_clf, const float* b_clf, int keep_cat, float* out,
+                 float* center, float* cat, pcg_stream_t stream);
+/*
+ * Training form: the same forward, then (dLoss == 1 is known at forward time) PCALayer's head and both
+ * cross-entropies (src/model.py:38, :54-61: loss = CE(W_head @ combined, y) + lambda * CE(center, y)), the
+ * activation backward and EVERY weight gradient of the step (what autograd derives from the calls above):
+ * d_w_head [2,E], d_w_clf [2,F], d_b_clf [2] by the tile kernel, d_w_inter [F+R*E,E] and d_w_intra_host[r] [2F,E]
+ * by a batch-split weight-gradient kernel that follows it. All gradients are OVERWRITTEN; reductions run in a
+ * fixed order (deterministic). logits [B,2] / center [B,2] may be NULL.
+ *   scratch  pcg_tile_scratch_floats(B,R,F,E) floats, 16-byte aligned; tickets  pcg_tile_ticket_ints(R,F,E)
+ *   int32, zero before the first call (the kernels re-arm them)
+ *   pdl != 0: launch with programmatic stream serialization (the kernels' prologues overlap the previous
+ *   kernel's tail; they wait for it with griddepcontrol.wait before touching its results)
+ */
+PCG_API size_t pcg_tile_scratch_floats(int B, int R, int F, int E);
+PCG_API size_t pcg_tile_ticket_ints(int R, int F, int E);
+PCG_API int pcg_tile_train(const float* feat, int64_t ldf, int F, const int32_t* targets, int B, int R, int E,
+                   const float* agg, int64_t lda, const int32_t* agg_rep, const float* const* w_intra_host,
+                   const float* w_inter, const float* w_clf, const float* b_clf, const float* w_head,
+                   const int64_t* labels, float lambda, float* out, float* center, float* logits, float* loss,
+                   float* const* d_w_intra_host, float* d_w_inter, float* d_w_clf, float* d_b_clf, float* d_w_head,
+                   float* scratch, int32_t* tickets, int pdl, pcg_stream_t stream);
+
+/*
  * label_clf similarity head on the batch's targets (src/layers.py:200, :236, :243):
  *   center[i][c] = dot(feat[targets[i], :F], w[c, :]) + b[c],  w [2,F], b [2] (nn.Linear layout)
  * and its backward: d_w [2,F], d_b [2] from d_center [B,2] (features are frozen). Deterministic.

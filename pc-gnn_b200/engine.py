@@ -95,6 +95,7 @@ class Engine:
         # buffer), the backward kernels write a parameter's gradient straight into its view and autograd gets
         # None for it, which removes the AccumulateGrad add kernels from the step
         self.grad_sink = None
+        self.grads_in_sinks = False  # set by layers.TrainStepFn when its forward stored the gradients into the sinks
         self._bcast = None          # (PeerRegion, epoch tensor): scores are broadcast into every rank's table (C5)
 
     # ------------------------------------------------------------------ resident tables
@@ -411,6 +412,54 @@ class Engine:
                                     _lib.stream_ptr())
         _lib.check(rc, "pcg_dense_fwd")
         return out, cat
+
+    # ------------------------------------------------------------------ fused dense part (csrc/pcg_tile.cu)
+    def tile_supported(self, B: int, R: int, E: int) -> bool:
+        return B > 0 and bool(self.lib.pcg_tile_supported(int(B), int(R), int(self.F), int(E)))
+
+    def tile_fwd(self, targets, agg, agg_rep, w_intra, w_inter, w_clf, b_clf, keep_cat: bool):
+        """(combined [E,B], center [B,2] or None, cat [B,F+R*E] or None): relation transforms + combine + label_clf
+        head as ONE kernel (``pcg_tile_fwd``); cat is kept only for the autograd backward (``dense_bwd``)."""
+        B, R, E = int(targets.shape[0]), len(w_intra), int(w_inter.shape[1])
+        dev = self.device
+        out = torch.empty((E, B), dtype=torch.float32, device=dev)
+        center = torch.empty((B, 2), dtype=torch.float32, device=dev) if w_clf is not None else None
+        cat = torch.empty((B, self.F + R * E), dtype=torch.float32, device=dev) if keep_cat else None
+        ptrs = (C.c_void_p * R)(*[w.data_ptr() for w in w_intra])
+        rc = self.lib.pcg_tile_fwd(self.feat.data_ptr(), self.ldf, self.F, targets.data_ptr(), B, R, E, agg.data_ptr(),
+                                   agg.shape[1], _lib.ptr(agg_rep), ptrs, w_inter.data_ptr(), _lib.ptr(w_clf),
+                                   _lib.ptr(b_clf), int(bool(keep_cat)), out.data_ptr(), _lib.ptr(center),
+                                   _lib.ptr(cat), _lib.stream_ptr())
+        _lib.check(rc, "pcg_tile_fwd")
+        return out, center, cat
+
+    def tile_train(self, targets, labels, agg, agg_rep, w_intra, w_inter, w_clf, b_clf, w_head, lam, grads,
+                   want_logits=False, pdl=False):
+        """One fused training pass behind the aggregation (``pcg_tile_train``): loss and ALL weight gradients.
+        grads = dict(inter=, intra=[...], clf_w=, clf_b=, head=) of contiguous fp32 tensors that are overwritten.
+        Returns (loss 0-d, combined [E,B], center [B,2], logits [B,2] or None)."""
+        B, R, E = int(targets.shape[0]), len(w_intra), int(w_inter.shape[1])
+        dev = self.device
+        buf = torch.empty(E * B + 2 * B + (2 * B if want_logits else 0) + 1, dtype=torch.float32, device=dev)
+        out = buf[:E * B].view(E, B)
+        center = buf[E * B:E * B + 2 * B].view(B, 2)
+        logits = buf[E * B + 2 * B:E * B + 4 * B].view(B, 2) if want_logits else None
+        loss = buf[-1:]
+        scratch = torch.empty(int(self.lib.pcg_tile_scratch_floats(B, R, self.F, E)), dtype=torch.float32, device=dev)
+        n_tk = int(self.lib.pcg_tile_ticket_ints(R, self.F, E))
+        if getattr(self, "_tile_tickets", None) is None or self._tile_tickets.numel() < n_tk:
+            self._tile_tickets = torch.zeros(n_tk, dtype=torch.int32, device=dev)
+        ptrs = (C.c_void_p * R)(*[w.data_ptr() for w in w_intra])
+        gptrs = (C.c_void_p * R)(*[g.data_ptr() for g in grads["intra"]])
+        rc = self.lib.pcg_tile_train(self.feat.data_ptr(), self.ldf, self.F, targets.data_ptr(), B, R, E, agg.data_ptr(),
+                                     agg.shape[1], _lib.ptr(agg_rep), ptrs, w_inter.data_ptr(), w_clf.data_ptr(),
+                                     b_clf.data_ptr(), w_head.data_ptr(), labels.data_ptr(), float(lam), out.data_ptr(),
+                                     center.data_ptr(), _lib.ptr(logits), loss.data_ptr(), gptrs,
+                                     grads["inter"].data_ptr(), grads["clf_w"].data_ptr(), grads["clf_b"].data_ptr(),
+                                     grads["head"].data_ptr(), scratch.data_ptr(), self._tile_tickets.data_ptr(),
+                                     int(bool(pdl)), _lib.stream_ptr())
+        _lib.check(rc, "pcg_tile_train")
+        return loss.view(()), out, center, logits
 
     def side_stream(self):
         if getattr(self, "_side", None) is None:

@@ -32,7 +32,7 @@ from .engine import Engine
 from .graph import RelGraph
 
 __all__ = ["InterAgg1", "InterAgg3", "InterAgg5", "InterAgg", "IntraAgg", "choose_step_neighs",
-           "choose_step_test", "HeadLossFn"]
+           "choose_step_test", "HeadLossFn", "TrainStepFn"]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -129,6 +129,91 @@ class HeadLossFn(torch.autograd.Function):
         sink = eng.grad_sink.get(ctx.w_ptr) if eng.grad_sink is not None else None
         d_emb, d_center, d_w = eng.head_loss_bwd(combined, weight, labels, p1, q1, ctx.lam, d_loss, sink)
         return None, d_emb, (None if sink is not None else d_w), d_center, None, None
+
+
+class _TileFn(torch.autograd.Function):
+    """(combined [E,B], center_scores [B,2]) = relation transforms + combine + label_clf head as ONE kernel
+    (``pcg_tile_fwd``: activations stay in shared memory, weights stream in by TMA bulk copies); backward =
+    the weight gradients (``pcg_dense_bwd``, ``pcg_center_bwd``). Frozen feature table (model_handler.py:85-86);
+    reference math: layers.py:616-629, 273-289, 236-243."""
+
+    @staticmethod
+    def forward(ctx, engine, targets, agg, agg_rep, feat_dim, need_grad, clf_w, clf_b, w_inter, *w_intra):
+        w_intra = [w.contiguous() for w in w_intra]
+        w_inter, clf_w = w_inter.contiguous(), clf_w.contiguous()
+        out, center, cat = engine.tile_fwd(targets, agg, agg_rep, w_intra, w_inter, clf_w, clf_b, need_grad)
+        ctx.engine, ctx.feat_dim, ctx.n_rel, ctx.agg_rep, ctx.targets = engine, feat_dim, len(w_intra), agg_rep, targets
+        ctx.w_ptrs = [w_inter.data_ptr()] + [w.data_ptr() for w in w_intra]
+        ctx.clf_ptrs = (clf_w.data_ptr(), clf_b.data_ptr())
+        if need_grad:
+            ctx.save_for_backward(agg, w_inter, cat, out)
+        return out, center
+
+    @staticmethod
+    def backward(ctx, d_out, d_center):
+        agg, w_inter, cat, out = ctx.saved_tensors
+        eng = ctx.engine
+        n_in = 9 + ctx.n_rel
+        grads = [None] * n_in
+        if d_center is not None:
+            sinks = None
+            if eng.grad_sink is not None:
+                views = (eng.grad_sink.get(ctx.clf_ptrs[0]), eng.grad_sink.get(ctx.clf_ptrs[1]))
+                sinks = views if views[0] is not None and views[1] is not None else None
+            d_w, d_b = eng.center_bwd(ctx.targets, d_center, sinks)
+            if sinks is None:
+                grads[6], grads[7] = d_w, d_b
+        if d_out is not None:
+            sinks = None
+            if eng.grad_sink is not None:
+                views = [eng.grad_sink.get(q) for q in ctx.w_ptrs]
+                sinks = (views[0], views[1:]) if all(v is not None for v in views) else None
+            d_intra, d_inter = eng.dense_bwd(agg, w_inter, cat, out, d_out, ctx.feat_dim, ctx.n_rel, ctx.agg_rep, sinks)
+            if sinks is None:
+                grads[8] = d_inter
+                grads[9:] = list(d_intra)
+        return tuple(grads)
+
+
+class TrainStepFn(torch.autograd.Function):
+    """loss = CE(W_head @ combined, y) + lambda * CE(center_scores, y) (model.py:38, :54-61) with everything
+    behind the aggregation in ONE pass (``pcg_tile_train``): in a training step dLoss == 1 is known at forward
+    time, so the forward launch also produces every weight gradient; backward() only hands them out (scaled by
+    the incoming gradient). With ``engine.grad_sink`` set the kernels store the gradients straight into the flat
+    gradient buffer and backward() returns nothing."""
+
+    @staticmethod
+    def forward(ctx, engine, targets, labels, agg, agg_rep, lam, pdl, w_head, clf_w, clf_b, w_inter, *w_intra):
+        params = [w_head, clf_w, clf_b, w_inter, *w_intra]
+        cont = [w.contiguous() for w in params]
+        sink = engine.grad_sink
+        views = [sink.get(w.data_ptr()) for w in params] if sink is not None else None
+        if views is not None and all(v is not None for v in views):
+            g = views
+            ctx.flat = None
+            engine.grads_in_sinks = True      # backward() has nothing left to do (runtime.GraphedTrainStep skips it)
+        else:
+            sizes = [w.numel() for w in params]
+            pad = [(n + 3) // 4 * 4 for n in sizes]          # 16-byte aligned starts for the float4 stores
+            flat = torch.empty(sum(pad), dtype=torch.float32, device=engine.device)
+            g, o = [], 0
+            for w, n, q in zip(params, sizes, pad):
+                g.append(flat[o:o + n].view_as(w))
+                o += q
+            ctx.flat, ctx.views = flat, g
+        grads = dict(head=g[0], clf_w=g[1], clf_b=g[2], inter=g[3], intra=g[4:])
+        loss, out, center, _ = engine.tile_train(targets, labels, agg, agg_rep, cont[4:], cont[3], cont[1], cont[2],
+                                                 cont[0], lam, grads, pdl=pdl)
+        ctx.n_in = 7 + len(params)
+        ctx.mark_non_differentiable(out, center)
+        return loss, out, center
+
+    @staticmethod
+    def backward(ctx, d_loss, _d_out, _d_center):
+        if ctx.flat is None:
+            return (None,) * ctx.n_in
+        ctx.flat.mul_(d_loss)
+        return (None,) * 7 + tuple(ctx.views)
 
 
 def _feature_table(features, n_nodes, device, ids=None):
@@ -341,6 +426,7 @@ class InterAgg(nn.Module):
         self.scores_external = False    # the caller refreshes eng.score itself (runtime.GraphedTrainStep on a
         #                                 partitioned graph: slice kernel -> all-gather -> this forward)
         self.last_selection = None
+        self.use_pdl = False            # runtime.GraphedTrainStep: programmatic dependent launch of the fused kernels
 
     # -- plumbing ---------------------------------------------------------------------------
     def intra_aggs(self):
@@ -358,7 +444,9 @@ class InterAgg(nn.Module):
         return self._engine
 
     # -- forward ----------------------------------------------------------------------------
-    def forward(self, nodes, labels, train_flag=True):
+    def _choose_and_aggregate(self, nodes, labels, train_flag):
+        """Score table -> pool sort -> choose (filter + oversample + union) -> mean aggregation for a batch
+        (layers.py:216-270, 589-624). Returns (engine, feature table, targets int32, device labels, selection)."""
         eng = self.engine()
         dev = eng.device
         table = _feature_table(self.features, eng.N_global, dev)
@@ -366,7 +454,6 @@ class InterAgg(nn.Module):
         targets, host = eng.upload_targets(nodes)
         rho = self.intra_agg1.rho
         lab = _as_device_labels(labels, dev) if train_flag else None
-
         # label-aware scores for every node (column 0 only) + the pool's: layers.py:231-237
         if self.score_override is not None:
             eng.score.copy_(self.score_override)
@@ -375,9 +462,48 @@ class InterAgg(nn.Module):
             eng.resort_pool()
         else:
             eng.score_table(self.label_clf.weight, self.label_clf.bias)
-        B = targets.shape[0]
-        fused = (not table.requires_grad) and self.embed_dim <= 256 and B > 0 \
+        if self.cap_slots_hint is not None:
+            cap = int(self.cap_slots_hint)
+        elif host is not None:
+            cap = eng.slots_bound(host, self.thresholds, rho, train_flag)
+        else:
+            cap = eng.slots_bound(targets.cpu().numpy(), self.thresholds, rho, train_flag)
+        sel = eng.choose(targets, lab, train_flag, self.thresholds, rho, cap)
+        self.last_selection = sel
+        return eng, table, targets, lab, sel
+
+    def _frozen_fast_path(self, table, B) -> bool:
+        return (not table.requires_grad) and self.embed_dim <= 256 and B > 0 \
             and isinstance(self.label_clf, nn.Linear) and self.label_clf.bias is not None
+
+    def train_loss(self, nodes, labels, head_weight, lam):
+        """PCALayer.loss for a training step (model.py:47-61) with the whole dense part, both losses and every
+        weight gradient in one pass (``TrainStepFn``); None when the shapes / a trainable feature table rule the
+        fused kernels out (the caller then composes forward() with torch ops like the reference does)."""
+        eng = self.engine()
+        table = _feature_table(self.features, eng.N_global, eng.device)
+        B = len(nodes) if not isinstance(nodes, torch.Tensor) else int(nodes.shape[0])
+        if not (self._frozen_fast_path(table, B) and eng.set_features(table) is not None
+                and eng.tile_supported(B, self._R, self.embed_dim)):
+            return None
+        eng, table, targets, lab, sel = self._choose_and_aggregate(nodes, labels, True)
+        agg = eng.aggregate(sel, copy_dups=False)     # repeated targets: the dense kernels read it_rep's row
+        loss, _, _ = TrainStepFn.apply(eng, targets, lab, agg, sel.it_rep, float(lam), bool(self.use_pdl), head_weight,
+                                       self.label_clf.weight, self.label_clf.bias, self.weight,
+                                       *[ia.weight for ia in self.intra_aggs()])
+        return loss
+
+    def forward(self, nodes, labels, train_flag=True):
+        eng, table, targets, lab, sel = self._choose_and_aggregate(nodes, labels, train_flag)
+        dev = eng.device
+        B = targets.shape[0]
+        fused = self._frozen_fast_path(table, B)
+        if fused and eng.tile_supported(B, self._R, self.embed_dim):
+            # frozen features (the reference's setup): aggregation, then ONE kernel for the dense part
+            agg = eng.aggregate(sel, copy_dups=False)
+            ws = [self.label_clf.weight, self.label_clf.bias, self.weight] + [ia.weight for ia in self.intra_aggs()]
+            need_grad = torch.is_grad_enabled() and any(w.requires_grad for w in ws)
+            return _TileFn.apply(eng, targets, agg, sel.it_rep, self.feat_dim, need_grad, *ws)
         side = None
         if fused:   # [B,2] with gradient to label_clf (layers.py:236-243), one kernel
             if self.center_on_side_stream:
@@ -394,18 +520,8 @@ class InterAgg(nn.Module):
             idx = targets.long()
             self_feats = self.features(idx)
             center_scores = self.label_clf(self_feats)
-
-        # choose (filter + oversample + union) and aggregate: layers.py:246-270, 589-624
-        if self.cap_slots_hint is not None:
-            cap = int(self.cap_slots_hint)
-        elif host is not None:
-            cap = eng.slots_bound(host, self.thresholds, rho, train_flag)
-        else:
-            cap = eng.slots_bound(targets.cpu().numpy(), self.thresholds, rho, train_flag)
-        sel = eng.choose(targets, lab, train_flag, self.thresholds, rho, cap)
-        self.last_selection = sel
         if fused:
-            # frozen features (the reference's setup): aggregation + the whole dense part are two kernels
+            # shapes the tile kernel does not cover (E not a multiple of 64): aggregation + the GEMM kernels
             agg = eng.aggregate(sel, copy_dups=False)     # repeated targets: the dense kernels read it_rep's row
             combined = _DenseFn.apply(eng, targets, agg, sel.it_rep, self.feat_dim, self.weight,
                                       *[ia.weight for ia in self.intra_aggs()])

@@ -35,9 +35,14 @@ class PCALayer(nn.Module):
         inter = self.inter1
         if self.weight.is_cuda and self.weight.shape[0] == 2 and hasattr(inter, "engine") \
                 and isinstance(self.xent, nn.CrossEntropyLoss):
-            # head + both cross-entropies fused into one kernel per direction (same math as below)
             from .layers import HeadLossFn, _as_device_labels
 
+            if train_flag and torch.is_grad_enabled() and hasattr(inter, "train_loss"):
+                # dense part + head + both cross-entropies + every weight gradient in one pass (same math as below)
+                loss = inter.train_loss(nodes, labels, self.weight, float(self.lambda_1))
+                if loss is not None:
+                    return loss
+            # head + both cross-entropies fused into one kernel per direction (same math as below)
             embeds1, label_scores = inter(nodes, labels, train_flag)
             if embeds1.shape[1] > 0:
                 lab = _as_device_labels(labels, embeds1.device)

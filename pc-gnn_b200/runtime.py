@@ -76,8 +76,11 @@ class GraphedTrainStep:
             # gradients in place (no AccumulateGrad adds in the graph)
             eng.grad_sink = {p.data_ptr(): v for p, v in zip(self.reducer.params, self.reducer.views)}
         try:
+            if eng is not None:
+                eng.grads_in_sinks = False
             loss = self.model.loss(self.nodes, self.labels)
-            loss.backward()
+            if eng is None or not eng.grads_in_sinks:    # fused pass: the forward launch stored every gradient
+                loss.backward()
         finally:
             if eng is not None:
                 eng.grad_sink = None

@@ -6,7 +6,7 @@ import bench
 from pcgnn_b200.parallel import FusedAdam, GradAllReduce
 from pcgnn_b200.runtime import GraphedTrainStep
 from pcgnn_b200.synth import make_graph
-from tests.helpers import build_cuda_pcgnn
+from pcgnn_b200.testing import build_cuda_pcgnn
 from torch.profiler import profile, ProfilerActivity
 
 spec, batch, embed, desc = bench.WORKLOADS["yelp"]
