@@ -213,21 +213,20 @@ PCG_API int pcg_tile_fwd(const float* feat, int64_t ldf, int F, const int32_t* t
  * cross-entropies (src/model.py:38, :54-61: loss = CE(W_head @ combined, y) + lambda * CE(center, y)), the
  * activation backward and EVERY weight gradient of the step (what autograd derives from the calls above):
  * d_w_head [2,E], d_w_clf [2,F], d_b_clf [2] by the tile kernel, d_w_inter [F+R*E,E] and d_w_intra_host[r] [2F,E]
- * by a batch-split weight-gradient kernel that follows it. All gradients are OVERWRITTEN; reductions run in a
+ * by a weight-gradient kernel that follows it (batch split over a thread-block cluster, partial tiles added
+ * through distributed shared memory). All gradients are OVERWRITTEN; reductions run in a
  * fixed order (deterministic). logits [B,2] / center [B,2] may be NULL.
- *   scratch  pcg_tile_scratch_floats(B,R,F,E) floats, 16-byte aligned; tickets  pcg_tile_ticket_ints(R,F,E)
- *   int32, zero before the first call (the kernels re-arm them)
+ *   scratch  pcg_tile_scratch_floats(B,R,F,E) floats, 16-byte aligned
  *   pdl != 0: launch with programmatic stream serialization (the kernels' prologues overlap the previous
  *   kernel's tail; they wait for it with griddepcontrol.wait before touching its results)
  */
 PCG_API size_t pcg_tile_scratch_floats(int B, int R, int F, int E);
-PCG_API size_t pcg_tile_ticket_ints(int R, int F, int E);
 PCG_API int pcg_tile_train(const float* feat, int64_t ldf, int F, const int32_t* targets, int B, int R, int E,
                    const float* agg, int64_t lda, const int32_t* agg_rep, const float* const* w_intra_host,
                    const float* w_inter, const float* w_clf, const float* b_clf, const float* w_head,
                    const int64_t* labels, float lambda, float* out, float* center, float* logits, float* loss,
                    float* const* d_w_intra_host, float* d_w_inter, float* d_w_clf, float* d_b_clf, float* d_w_head,
-                   float* scratch, int32_t* tickets, int pdl, pcg_stream_t stream);
+                   float* scratch, int pdl, pcg_stream_t stream);
 
 /*
  * label_clf similarity head on the batch's targets (src/layers.py:200, :236, :243):

@@ -50,9 +50,8 @@ SIGNATURES = {
     "pcg_tile_supported": (_i, [_i, _i, _i, _i]),
     "pcg_tile_fwd": (_i, [_p, _l, _i, _p, _i, _i, _i, _p, _l, _p, C.POINTER(_p), _p, _p, _p, _i, _p, _p, _p, _p]),
     "pcg_tile_scratch_floats": (_z, [_i, _i, _i, _i]),
-    "pcg_tile_ticket_ints": (_z, [_i, _i, _i]),
     "pcg_tile_train": (_i, [_p, _l, _i, _p, _i, _i, _i, _p, _l, _p, C.POINTER(_p), _p, _p, _p, _p, _p, C.c_float,
-                            _p, _p, _p, _p, C.POINTER(_p), _p, _p, _p, _p, _p, _p, _i, _p]),
+                            _p, _p, _p, _p, C.POINTER(_p), _p, _p, _p, _p, _p, _i, _p]),
     "pcg_head_scratch_floats": (_z, [_i, _i, _i]),
     "pcg_center_fwd": (_i, [_p, _l, _i, _p, _i, _p, _p, _p, _p]),
     "pcg_center_bwd": (_i, [_p, _l, _i, _p, _i, _p, _p, _p, _p, _p, _p]),

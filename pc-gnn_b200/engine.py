@@ -446,9 +446,6 @@ class Engine:
         logits = buf[E * B + 2 * B:E * B + 4 * B].view(B, 2) if want_logits else None
         loss = buf[-1:]
         scratch = torch.empty(int(self.lib.pcg_tile_scratch_floats(B, R, self.F, E)), dtype=torch.float32, device=dev)
-        n_tk = int(self.lib.pcg_tile_ticket_ints(R, self.F, E))
-        if getattr(self, "_tile_tickets", None) is None or self._tile_tickets.numel() < n_tk:
-            self._tile_tickets = torch.zeros(n_tk, dtype=torch.int32, device=dev)
         ptrs = (C.c_void_p * R)(*[w.data_ptr() for w in w_intra])
         gptrs = (C.c_void_p * R)(*[g.data_ptr() for g in grads["intra"]])
         rc = self.lib.pcg_tile_train(self.feat.data_ptr(), self.ldf, self.F, targets.data_ptr(), B, R, E, agg.data_ptr(),
@@ -456,8 +453,7 @@ class Engine:
                                      b_clf.data_ptr(), w_head.data_ptr(), labels.data_ptr(), float(lam), out.data_ptr(),
                                      center.data_ptr(), _lib.ptr(logits), loss.data_ptr(), gptrs,
                                      grads["inter"].data_ptr(), grads["clf_w"].data_ptr(), grads["clf_b"].data_ptr(),
-                                     grads["head"].data_ptr(), scratch.data_ptr(), self._tile_tickets.data_ptr(),
-                                     int(bool(pdl)), _lib.stream_ptr())
+                                     grads["head"].data_ptr(), scratch.data_ptr(), int(bool(pdl)), _lib.stream_ptr())
         _lib.check(rc, "pcg_tile_train")
         return loss.view(()), out, center, logits
 

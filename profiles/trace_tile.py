@@ -20,10 +20,10 @@ model = build_cuda_pcgnn(data.feat, data.graph, sorted(data.train_pos), params, 
 batches = bench.make_batches(data, 4, batch, 72)
 L = _lib.lib()
 L.pcg_debug_set_tile_trace.argtypes = [C.c_void_p]
-buf = torch.zeros(32, dtype=torch.int64, device="cuda")
+buf = torch.zeros(64, dtype=torch.int64, device="cuda")
 L.pcg_debug_set_tile_trace(buf.data_ptr())
 names = ["start", "dep wait", "rows loaded", "relations done", "combine done", "out/cat stored", "heads done", "dH done",
-         "partials+ticket"]
+         "dh stored"]
 for n, l in batches:
     buf.zero_()
     loss = model.loss(n.tolist(), torch.from_numpy(l).cuda())
@@ -31,4 +31,5 @@ for n, l in batches:
     t = buf.cpu().numpy()
     t0 = t[0]
     print("tile 0:", ", ".join(f"{names[i]} +{(t[i] - t0) / 1e3:.2f}" for i in range(1, 9)),
-          f"| last tile reduce {(t[17] - t[16]) / 1e3:.2f} us, kernel end +{(t[17] - t0) / 1e3:.2f}")
+          "| phase A warp 0: wait-begin +%.2f data +%.2f fma-done +%.2f scratch-written +%.2f synced +%.2f reduced +%.2f"
+          % tuple((t[i] - t0) / 1e3 for i in (20, 21, 22, 23, 24, 25)))
