@@ -116,6 +116,10 @@ PCG_API int pcg_choose_workspace_init(void* workspace, size_t workspace_bytes, i
  *   status       int32 [PCG_STATUS_WORDS] (every word written here)
  * The slots of the items are handed out by a prefix sum in item order, so the layout of sel_idx is the same
  * on every run.
+ *   phases       3: the whole step. 1: only the preparation (folding of repeated targets, item sizes, slot prefix
+ *                sum, tier queues), which reads targets / labels / indptr but NO scores, so a caller can run it on a
+ *                second stream next to pcg_score_table; 2: only the selection, after a phases == 1 call with the
+ *                same arguments has completed (stream order / event).
  * Threading / devices: one host thread drives one device per process (the reference is single-threaded,
  * src/model_handler.py:142-156; multi-GPU runs are one process per GPU). The forked side streams and the
  * workspace's barrier words are per process, so concurrent pcg_choose calls from several threads, or calls for
@@ -129,7 +133,7 @@ PCG_API int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t n_
                int train, int64_t max_degree,
                int32_t* sel_idx, float* sel_dist, int64_t cap_slots, int32_t* slot_item, int32_t* it_slot0,
                int32_t* it_m, int64_t* it_base, int32_t* it_done, int32_t* it_rep, void* workspace,
-               size_t workspace_bytes, int32_t* status, pcg_stream_t stream);
+               size_t workspace_bytes, int32_t* status, int phases, pcg_stream_t stream);
 
 /*
  * Select-all variant for the GraphSAGE / GCN baselines: the item list IS the CSR row (no copy);

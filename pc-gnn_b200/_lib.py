@@ -40,7 +40,7 @@ SIGNATURES = {
     "pcg_pool_positions": (_i, [_p, _i, _l, _p, _p]),
     "pcg_entry_pool_positions": (_i, [_p, _l, _p, _p, _p]),
     "pcg_choose": (_i, [_p, _p, _l, _l, _i, _p, _p, _p, _p, _p, _i, C.POINTER(_d), _p, _d, _p, _p, _p, _p, _i, _i, _l,
-                        _p, _p, _l, _p, _p, _p, _p, _p, _p, _p, _z, _p, _p]),
+                        _p, _p, _l, _p, _p, _p, _p, _p, _p, _p, _z, _p, _i, _p]),
     "pcg_select_all": (_i, [_p, _p, _l, _i, _p, _i, _i, _l, _p, _p, _p, _p, _p, _p, _p, _p]),
     "pcg_aggregate": (_i, [_p, _l, _p, _p, _p, _p, _p, _p, _p, _i, _i, _l, _p, _i, _p, _p, _p, _p]),
     "pcg_aggregate_bwd": (_i, [_p, _l, _p, _p, _p, _p, _p, _p, _i, _l, _p, _i, _p, _p]),

@@ -1148,6 +1148,10 @@ __device__ __forceinline__ void prep_grid_barrier(int32_t* bar, int target) {
     __syncthreads();
 }
 
+// CLUSTER: the CTAs form ONE thread-block cluster and meet at cluster barriers (hardware barrier, and the kernel
+// runs next to other kernels: the score table and the pool sort on the main stream); otherwise (more items than a
+// cluster can stage) a cooperative grid with barriers through global memory.
+template <bool CLUSTER>
 __global__ void __launch_bounds__(PCG_PREP_NT, 1) k_choose_prep(ChooseP p, int chunk, int32_t* bar, int32_t* totals) {
     __shared__ int s_info[PCG_PREP_ITEMS];   // per item of the CTA: nslots << 3 | (tier + 1), 0 for repeated targets
     __shared__ int s_wsum[32];
@@ -1163,7 +1167,11 @@ __global__ void __launch_bounds__(PCG_PREP_NT, 1) k_choose_prep(ChooseP p, int c
             if (lv >= 0 && lv < p.n_nodes) atomicMin(&first[lv], i);
         }
     if (blockIdx.x == 0 && tid < PCG_STATUS_WORDS) p.status[tid] = 0;
-    prep_grid_barrier(bar, G);               // the first-occurrence table is complete, the status words are zero
+    auto barrier = [&](int target) {
+        if (CLUSTER) { __threadfence(); cg::this_cluster().sync(); }
+        else prep_grid_barrier(bar, target);
+    };
+    barrier(G);                              // the first-occurrence table is complete, the status words are zero
     PTRACE(1);
     const int w0 = min(W, blockIdx.x * chunk), n_items = min(W, w0 + chunk) - w0;
     // ---- phase A: sizes of every item, four items per thread in flight (loads first, then the arithmetic)
@@ -1241,7 +1249,7 @@ __global__ void __launch_bounds__(PCG_PREP_NT, 1) k_choose_prep(ChooseP p, int c
     }
     const int cta_total = __shfl_sync(PCG_FULL, wincl, 31);
     if (tid == 0) totals[blockIdx.x] = cta_total;
-    prep_grid_barrier(bar, 2 * G);           // every CTA's total is published (and every read of `first` is done)
+    barrier(2 * G);                          // every CTA's total is published (and every read of `first` is done)
     if (wid == 0) {                          // slots of the CTAs before this one, added in CTA order
         int acc = 0;
         for (int c = lane; c < (int)blockIdx.x; c += 32) acc += __ldcg(totals + c);
@@ -1293,8 +1301,10 @@ __global__ void __launch_bounds__(PCG_PREP_NT, 1) k_choose_prep(ChooseP p, int c
         }
     if (tid == 0) {
         if (blockIdx.x == G - 1) p.status[ST_SLOTS] = s_base + cta_total;
-        __threadfence();
-        if (atomicAdd(&bar[1], 1) == G - 1) { bar[0] = 0; bar[1] = 0; }   // last CTA out re-arms the barrier
+        if (!CLUSTER) {
+            __threadfence();
+            if (atomicAdd(&bar[1], 1) == G - 1) { bar[0] = 0; bar[1] = 0; }   // last CTA out re-arms the barrier
+        }
     }
     PTRACE(4);
 }
@@ -1445,16 +1455,17 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
                           const int32_t* entry_pool_pos, int P, int train,
                           int64_t max_degree, int32_t* sel_idx, float* sel_dist, int64_t cap_slots,
                           int32_t* slot_item, int32_t* it_slot0, int32_t* it_m, int64_t* it_base, int32_t* it_done,
-                          int32_t* it_rep, void* workspace, size_t workspace_bytes, int32_t* status,
+                          int32_t* it_rep, void* workspace, size_t workspace_bytes, int32_t* status, int phases,
                           pcg_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     PCG_REQUIRE(R >= 1 && R <= PCG_MAX_REL, "pcg_choose: R=%d outside [1,%d]", R, PCG_MAX_REL);
+    PCG_REQUIRE(phases >= 1 && phases <= 3, "pcg_choose: phases must be 1 (prepare), 2 (select) or 3 (both)");
     PCG_REQUIRE(B >= 0, "pcg_choose: negative batch");
     if (B == 0) {   // empty batch: nothing to choose (pointers of empty buffers may be null)
         if (status) cudaMemsetAsync(status, 0, PCG_STATUS_WORDS * sizeof(int32_t), stream);
         return 0;
     }
-    PCG_REQUIRE(score || (entry_score && center_score), "pcg_choose: need a score table or explicit scores");
+    PCG_REQUIRE((phases & 2) == 0 || score || (entry_score && center_score), "pcg_choose: need a score table or explicit scores");
     PCG_REQUIRE(!(train && P > 0) || (ps_score && ps_pos && ps_id), "pcg_choose: sorted pool arrays missing");
     PCG_REQUIRE(indptr && indices && targets && sel_idx && slot_item && it_slot0 && it_m && it_base && it_done &&
                     it_rep && status,
@@ -1475,7 +1486,7 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
     p.it_slot0 = it_slot0; p.it_m = it_m; p.it_base = it_base; p.it_done = it_done; p.it_rep = it_rep; p.status = status;
     char* ws = (char*)workspace;
     // duplicate targets are folded when ids come from a score table (explicit per-target lists are all distinct)
-    p.first = (score != nullptr && entry_score == nullptr) ? (int32_t*)(ws + L.first) : nullptr;
+    p.first = entry_score == nullptr ? (int32_t*)(ws + L.first) : nullptr;
     p.q_warp = (int32_t*)(ws + L.q_warp);
     p.q_cta = (int32_t*)(ws + L.q_cta);
     p.q_cl = (int32_t*)(ws + L.q_cl);
@@ -1493,25 +1504,36 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
         (void)cudaGetLastError();
     }
     p.huge16_ok = huge16_state;
-    {
-        // contiguous chunks of items over at most #SMs CTAs (they meet at grid barriers: all must be resident)
-        int chunk = PCG_PREP_CHUNK;
-        if ((W + chunk - 1) / chunk > sms) chunk = (W + sms - 1) / sms;
-        PCG_REQUIRE(chunk <= PCG_PREP_ITEMS, "pcg_choose: batch too large (%d items; at most %d)", W, PCG_PREP_ITEMS * sms);
-        // cooperative launch: the CTAs wait on one another at the grid barriers, so all must be resident
+    if (phases & 1) {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)((W + chunk - 1) / chunk));
         cfg.blockDim = dim3(PCG_PREP_NT);
         cfg.dynamicSmemBytes = 0;
         cfg.stream = stream;
         cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeCooperative;
-        attr[0].val.cooperative = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        e = cudaLaunchKernelEx(&cfg, k_choose_prep, p, chunk, (int32_t*)(ws + L.bar), (int32_t*)(ws + L.totals));
+        if (W <= 8 * PCG_PREP_ITEMS) {
+            // one cluster of (up to) 8 CTAs, contiguous chunks of items
+            int G = 8;
+            while (G > 1 && W < G * 64) G >>= 1;
+            const int chunk = (W + G - 1) / G;
+            cfg.gridDim = dim3((unsigned)G);
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = (unsigned)G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            e = cudaLaunchKernelEx(&cfg, k_choose_prep<true>, p, chunk, (int32_t*)(ws + L.bar), (int32_t*)(ws + L.totals));
+        } else {
+            // contiguous chunks of items over at most #SMs CTAs (they meet at grid barriers: all must be resident)
+            int chunk = PCG_PREP_CHUNK;
+            if ((W + chunk - 1) / chunk > sms) chunk = (W + sms - 1) / sms;
+            PCG_REQUIRE(chunk <= PCG_PREP_ITEMS, "pcg_choose: batch too large (%d items; at most %d)", W, PCG_PREP_ITEMS * sms);
+            cfg.gridDim = dim3((unsigned)((W + chunk - 1) / chunk));
+            attr[0].id = cudaLaunchAttributeCooperative;
+            attr[0].val.cooperative = 1;
+            e = cudaLaunchKernelEx(&cfg, k_choose_prep<false>, p, chunk, (int32_t*)(ws + L.bar), (int32_t*)(ws + L.totals));
+        }
         if (e != cudaSuccess) { pcg_set_error("pcg_choose: prep launch: %s", cudaGetErrorString(e)); return (int)e; }
     }
+    if ((phases & 2) == 0) return pcg_check_launch("pcg_choose");
     const bool have_cta = max_degree > PCG_SMALL_MAX, have_cl = max_degree > PCG_CTA_MAX,
                have_huge = max_degree > PCG_CL_MAX,
                have_big = max_degree > (p.huge16_ok ? PCG_HUGE16_MAX : PCG_HUGE_MAX);

@@ -63,6 +63,15 @@ class Engine:
             raise _lib.PcgError("pcgnn_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = _lib.lib()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if self.device.type != "cuda":
+            raise _lib.PcgError(f"pcgnn_b200 runs on CUDA devices only (got {self.device})")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        if self.device.index != torch.cuda.current_device():
+            # the C ABI launches on the CURRENT device and keeps per-process side streams (one process drives one
+            # GPU, like every multi-GPU run of this package): refuse instead of launching on the wrong device
+            raise _lib.PcgError(f"engine for {self.device} but the current device is cuda:{torch.cuda.current_device()}: "
+                                "call torch.cuda.set_device() first (one process per GPU)")
         self.graph = graph
         self.row_lo = 0
         if graph is not None:
@@ -309,15 +318,17 @@ class Engine:
     def choose(self, targets, labels, train: bool, thresh, rho: float, cap_slots: int, *,
                entry_score=None, center_score=None, k_override=None, sorted_pool=None,
                indptr=None, indices=None, n_nodes=None, n_rel=None, max_degree=None,
-               want_dist: bool = False):
+               want_dist: bool = False, phases: int = 3, sel: Selection | None = None):
         """Top-k filter + oversample for every (relation, target) item (``pcg_choose``).
 
         Default: the engine's resident graph, score table and pool. The keyword overrides carry the
         explicit-list calling convention of IntraAgg.forward / choose_step_* (src/layers.py:562, 633).
-        Returns the Selection (and the distance buffer when want_dist)."""
+        Returns the Selection (and the distance buffer when want_dist).
+        phases=1 runs only the score-independent preparation (callers put it on a side stream next to
+        ``score_table``), phases=2 the selection on the Selection a phases=1 call returned."""
         B = int(targets.shape[0])
         R = self.R if n_rel is None else n_rel
-        s = self._new_selection(B, R, cap_slots, True, False)
+        s = sel if sel is not None else self._new_selection(B, R, cap_slots, True, False)
         maxdeg = self.max_degree if max_degree is None else max_degree
         nn_ = self.N if n_nodes is None else n_nodes
         ws_bytes = self.lib.pcg_choose_workspace_bytes(B, R, maxdeg, nn_)
@@ -340,13 +351,14 @@ class Engine:
             (self.indptr if indptr is None else indptr).data_ptr(),
             (self.indices if indices is None else indices).data_ptr(),
             self.N if n_nodes is None else n_nodes, self.row_lo if n_nodes is None else 0, R,
-            self.score.data_ptr() if use_table else None, _lib.ptr(entry_score), _lib.ptr(center_score),
+            (self.score.data_ptr() if self.score is not None else None) if use_table else None, _lib.ptr(entry_score),
+            _lib.ptr(center_score),
             targets.data_ptr(), _lib.ptr(labels) if train else None, B, th, _lib.ptr(k_override), float(rho),
             _lib.ptr(ps), _lib.ptr(pp), _lib.ptr(pi), _lib.ptr(self.entry_pool_pos) if use_table else None, P,
             int(bool(train)), maxdeg, s.idx.data_ptr(), _lib.ptr(dist),
             cap_slots, s.slot_item.data_ptr(), s.it_slot0.data_ptr(), s.it_m.data_ptr(), s.it_base.data_ptr(),
             s.it_done.data_ptr(), s.it_rep.data_ptr(), self._ws.data_ptr(), int(ws_bytes), s.status.data_ptr(),
-            _lib.stream_ptr())
+            int(phases), _lib.stream_ptr())
         _lib.check(rc, "pcg_choose")
         return (s, dist) if want_dist else s
 
@@ -456,6 +468,14 @@ class Engine:
                                      grads["head"].data_ptr(), scratch.data_ptr(), int(bool(pdl)), _lib.stream_ptr())
         _lib.check(rc, "pcg_tile_train")
         return loss.view(()), out, center, logits
+
+    def fork_point(self):
+        """A (4-byte memset) node in front of a stream fork. Inside a captured CUDA graph two ROOT branches start
+        several microseconds apart (measured: the second root kernel began 5 us after the first one had ended),
+        while branches that fork behind a common predecessor start together."""
+        if getattr(self, "_fork_word", None) is None:
+            self._fork_word = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._fork_word.zero_()
 
     def side_stream(self):
         if getattr(self, "_side", None) is None:

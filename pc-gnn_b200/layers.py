@@ -454,6 +454,20 @@ class InterAgg(nn.Module):
         targets, host = eng.upload_targets(nodes)
         rho = self.intra_agg1.rho
         lab = _as_device_labels(labels, dev) if train_flag else None
+        if self.cap_slots_hint is not None:
+            cap = int(self.cap_slots_hint)
+        elif host is not None:
+            cap = eng.slots_bound(host, self.thresholds, rho, train_flag)
+        else:
+            cap = eng.slots_bound(targets.cpu().numpy(), self.thresholds, rho, train_flag)
+        # the preparation of the choose step (repeated targets, item sizes, slot prefix sum, tier queues) needs no
+        # scores: it runs on a side stream next to the score table and the pool sort
+        cur = torch.cuda.current_stream(dev)
+        side = eng.side_stream()
+        eng.fork_point()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            sel = eng.choose(targets, lab, train_flag, self.thresholds, rho, cap, phases=1)
         # label-aware scores for every node (column 0 only) + the pool's: layers.py:231-237
         if self.score_override is not None:
             eng.score.copy_(self.score_override)
@@ -462,13 +476,8 @@ class InterAgg(nn.Module):
             eng.resort_pool()
         else:
             eng.score_table(self.label_clf.weight, self.label_clf.bias)
-        if self.cap_slots_hint is not None:
-            cap = int(self.cap_slots_hint)
-        elif host is not None:
-            cap = eng.slots_bound(host, self.thresholds, rho, train_flag)
-        else:
-            cap = eng.slots_bound(targets.cpu().numpy(), self.thresholds, rho, train_flag)
-        sel = eng.choose(targets, lab, train_flag, self.thresholds, rho, cap)
+        cur.wait_stream(side)
+        eng.choose(targets, lab, train_flag, self.thresholds, rho, cap, phases=2, sel=sel)
         self.last_selection = sel
         return eng, table, targets, lab, sel
 
