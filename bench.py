@@ -2,26 +2,34 @@
 """Benchmark of the PC-GNN pick-and-choose hot path on B200 (contract: see DESIGN.md "Measurement").
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload yelp|amazon|yelp100|amazon_gcn|big]
-                  [--impl reference] [--torch-adam] [--nccl-scores] [--no-graph] [--no-cpu-baseline]
+                  [--scaling weak|strong] [--impl reference] [--check-only] [--torch-adam] [--nccl-scores]
+                  [--no-graph] [--no-cpu-baseline]
 
-One "step" = one full training step of PCALayer(InterAgg3(IntraAgg x3)) on one label-balanced batch of
-B target nodes per GPU: loss (score table, pool sort, choose, aggregate, relation transforms, combine, heads,
-both cross-entropies) -> backward -> gradient mean over the ranks + Adam (one kernel over NVLink peer memory;
---torch-adam: NCCL all-reduce + torch.optim.Adam). Under torchrun every rank runs its shard; rank 0 prints ONE
-JSON line.
+One "step" = one full training step of PCALayer(InterAgg3(IntraAgg x3)) on one label-balanced batch of target
+nodes: score table + pool sort (next to the choose preparation), choose, aggregate, the fused dense / loss /
+activation-gradient kernel, the weight-gradient kernel, gradient mean over the ranks + Adam (one kernel over NVLink
+peer memory; --torch-adam: NCCL all-reduce + torch.optim.Adam). Under torchrun every rank runs its shard; rank 0
+prints ONE JSON line.
 
-  value      train target-nodes/s with the batch already resident in HBM (one CUDA-graph replay per step)
-  e2e        the same with HOST inputs through runtime.GraphedTrainStep.run(list_of_ids, labels): H2D of the
-             ids/labels and D2H of the loss inside the timed region (e2e_reference_api_eager: the reference's
-             own call sequence model.loss(list, labels); backward; step; loss.item(), eager)
-  roofline   the slower of the two hot-path kernel groups (choose / aggregate), algorithmic bytes per
-             launch / CUDA-event time, against MEASURED_PEAKS.json; traffic = ncu DRAM bytes (profiles/)
-  cpu_baseline  the oracle port (same per-target structure as the reference, CPU) on a 1024-target batch
+  value      train target-nodes/s with the batches already resident in HBM (one CUDA-graph replay per step)
+  e2e        host inputs, host<->device copies inside the timed region. 1 GPU: the REFERENCE's own loop, unchanged
+             (model_handler.py:142-156: zero_grad; model.loss(list_of_ids, cuda LongTensor labels); backward;
+             torch.optim.Adam.step; loss.item()), which the package serves from its CUDA-graph cache. N GPUs (the
+             reference has no data parallelism): runtime.GraphedTrainStep.run(ids, labels) + loss.item(); that call
+             is also reported at 1 GPU as e2e_step_graph
+  roofline   the slower of the two hot-path kernel groups (choose / aggregate): SURVEY 8(d) algorithmic bytes per
+             launch / CUDA-event time against MEASURED_PEAKS.json, next to the bytes the kernels must actually move
+             (`required_*`: without the reference's per-target pool scan, which the sorted pool makes unnecessary);
+             traffic = ncu DRAM bytes per launch (profiles/)
+  cpu_baseline  the oracle port (same per-target structure as the reference, CPU) on a bounded sample of a batch
 
 Workloads (BASELINE.json configs): yelp = C2 (default, the config the metric is quoted on), amazon = C1,
-yelp100 = C3, amazon_gcn = C4, big = C5 (row-partitioned CSR, 1.25M nodes / 1.26e8 entries per GPU).
-`--impl reference` times the oracle port alone on the host cores (the reference is pure Python and is not
-present on the GPU box; oracle/port.py is its restatement, pinned by tests/golden).
+yelp100 = C3 (BASELINE: global batch 4096 sharded over the GPUs = --scaling strong), amazon_gcn = C4, big = C5
+(row-partitioned CSR, 1.25M nodes / 1.26e8 entries per GPU). --scaling weak (default): `batch` targets per GPU;
+strong: `batch` targets in total. Shards are dealt by row length (largest first, round robin) so that every rank
+gets the same number of targets AND about the same number of neighbour entries.
+`--impl reference` times the oracle port alone on the host cores (the reference is pure Python and is not present
+on the GPU box; oracle/port.py is its restatement, pinned by tests/golden).
 """
 import argparse
 import json
@@ -48,15 +56,25 @@ RHO, ALPHA, LR, WD = 0.5, 2.0, 0.01, 1e-3
 SEED = 72
 
 
-MY_KERNELS_PER_STEP = 16   # score+sort 2, choose 3 (prep, wide, small), aggregate 1, dense fwd 2, center/head fwd 2,
-#                            head/center bwd 2, dense bwd 3, gradient exchange + Adam 1 (+2 when P > 8192, +1 big tier,
-#                            +1 self copy when F > E)
+MY_KERNELS_PER_STEP = 9    # choose prep 1 (side branch) | score table + pool sort 2, choose 2 (wide, small), aggregate 1,
+#                            fused dense/loss/activation-gradient 1, weight gradients 1, gradient exchange + Adam 1
+#                            (+2 when P > 8192, +1 per extra row tier; the graph also holds one 4-byte torch fill)
 
 
-def config_dict(desc, batch, world):
-    return {"workload": desc, "global_batch": batch * world, "rho": RHO, "thresholds": 0.5, "optimizer": "Adam",
+def config_dict(desc, global_batch, world, scaling="weak"):
+    return {"workload": desc, "global_batch": global_batch, "rho": RHO, "thresholds": 0.5, "optimizer": "Adam",
             "l2": "flushed between timed steps (256 MiB write)",
-            "parallelism": f"dp{world} (targets sharded, grads all-reduced)" if world > 1 else "single"}
+            "parallelism": (f"dp{world} (targets dealt to the ranks by row length, grads averaged; {scaling} scaling)"
+                            if world > 1 else "single")}
+
+
+def deal(nodes, labels, weight, rank, world):
+    """This rank's share of a global batch: targets sorted by `weight` (their total row length) descending and dealt
+    round robin, so every rank gets len/world targets and about the same number of neighbour entries (contiguous
+    shards differ by the hubs they happen to contain: the ranks then wait for the slowest in the exchange)."""
+    order = np.argsort(-weight[nodes], kind="stable")
+    mine = order[rank::world]
+    return nodes[mine], labels[mine]
 
 
 def measured_peaks():
@@ -232,29 +250,44 @@ def build_cuda_gcn(data, params, dev):
 
 
 def _ncu_traffic(workload, group):
-    """DRAM bytes per launch of a kernel group from the committed ncu capture (profiles/r01_traffic.json)."""
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        return t[workload][group]["bytes"]
-    except Exception:
-        return None
+    """DRAM bytes per launch of a kernel group from the committed ncu capture (profiles/r02_traffic.json)."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", name)))
+            return t[workload][group]["bytes"]
+        except Exception:
+            continue
+    return None
 
 
 def _roof(kern, dom, extra=None, workload=None):
+    """roofline object for the dominant kernel group. `achieved` follows SURVEY 8(d) (algorithmic bytes); when that
+    figure exceeds what the memory system can do (it counts a per-target scan of the whole pool that the sorted-pool
+    kernels never perform) the bytes the kernels must move are used instead, and said so."""
     peak, peak_src = measured_peaks()
-    r = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s",
-         "frac": kern[dom]["gbs"] / peak, "traffic": _ncu_traffic(workload, dom), "peak_source": peak_src,
-         "algorithmic_bytes": kern[dom]["alg_bytes"]}
+    k = kern[dom]
+    r = {"bound": "hbm", "kernel": dom, "achieved": k["gbs"], "peak": peak, "unit": "GB/s", "frac": k["gbs"] / peak,
+         "traffic": _ncu_traffic(workload, dom), "peak_source": peak_src, "algorithmic_bytes": k["alg_bytes"],
+         "bytes": "algorithmic (SURVEY 8d)"}
+    if "req_bytes" in k:
+        r.update({"required_bytes": k["req_bytes"], "required_gbs": k["req_gbs"], "required_frac": k["req_gbs"] / peak})
+        if r["frac"] > 1.2:
+            r.update({"achieved": k["req_gbs"], "frac": k["req_gbs"] / peak, "algorithmic_gbs": k["gbs"],
+                      "bytes": "required (the 8d figure counts a scan of the whole pool per positive target that the "
+                               "sorted-pool kernels do not perform; it would exceed the peak)"})
     r.update(extra or {})
     return r
 
 
 def hot_kernels_pcgnn(eng, inter, data, shards, dev_nodes, dev_labels, cap, W, K, flush, dev, batch, workload=None):
+    """choose (prep + tier kernels) and aggregate captured alone in CUDA graphs, CUDA-event time per replay, L2
+    flushed before each. Bytes per SURVEY 8(d): filter = 8 per CSR entry of the batch's rows + 16 R B + 4 B
+    + 4 P R B+ (pool scan) [+ 4 per kept id written]; aggregate = (4F + 4) per gathered row + 4 F R B."""
     import torch
 
     R, F_ = data.graph.n_rel, data.feat.shape[1]
     t_choose = t_agg = t_score = 0.0
-    alg_choose = alg_agg = 0.0
+    alg_choose = alg_agg = req_choose = 0.0
     P = eng.P
     st_nodes = dev_nodes[W].clone()
     st_labels = dev_labels[W].clone()
@@ -302,18 +335,21 @@ def hot_kernels_pcgnn(eng, inter, data, shards, dev_nodes, dev_labels, cap, W, K
         n_pos = int((labels == 1).sum())
         sum_d = sum(int(data.graph.degrees(r)[nodes - data.graph.row_lo].sum()) for r in range(R))
         m_tot = int(sel.it_m[sel.it_rep.long()].sum().item())
-        alg_choose += 8.0 * sum_d + R * batch * 16 + 4 * batch + 4.0 * P * n_pos * R + 4.0 * m_tot
+        req = 8.0 * sum_d + R * batch * 16 + 4 * batch + 4.0 * m_tot
+        req_choose += req
+        alg_choose += req + 4.0 * P * n_pos * R
         alg_agg += (4.0 * F_ + 4.0) * m_tot + 4.0 * F_ * R * batch
         assert not sel.overflowed()
     kern = {
         "choose": {"ms": t_choose / K, "alg_bytes": alg_choose / K, "gbs": alg_choose / t_choose / 1e6,
-                   "launches_per_step": 3},
+                   "req_bytes": req_choose / K, "req_gbs": req_choose / t_choose / 1e6, "launches_per_step": 3},
         "aggregate": {"ms": t_agg / K, "alg_bytes": alg_agg / K, "gbs": alg_agg / t_agg / 1e6,
-                      "launches_per_step": 1},
+                      "req_bytes": alg_agg / K, "req_gbs": alg_agg / t_agg / 1e6, "launches_per_step": 1},
         "score_table_and_pool_sort": {"ms": t_score / K, "launches_per_step": 2},
     }
     dom = "choose" if t_choose >= t_agg else "aggregate"
-    return kern, _roof(kern, dom, {"filter_plus_aggregate_gbs": (alg_choose + alg_agg) / (t_choose + t_agg) / 1e6},
+    return kern, _roof(kern, dom, {"filter_plus_aggregate_gbs": (alg_choose + alg_agg) / (t_choose + t_agg) / 1e6,
+                                   "filter_plus_aggregate_required_gbs": (req_choose + alg_agg) / (t_choose + t_agg) / 1e6},
                        workload=workload)
 
 
@@ -354,6 +390,55 @@ def hot_kernels_gcn(eng, agg_mod, data, shards, dev_nodes, cap, W, K, flush, dev
     return kern, _roof(kern, "aggregate")
 
 
+class _BatchRows:
+    """Host view of a device-resident (row-partitioned) CSR restricted to the rows of some targets — all the
+    reference ever touches (`adj_list[int(node)]` for the batch's nodes only, layers.py:219). Satisfies what
+    oracle/port.py needs from a graph: n_rel and row(r, v)."""
+
+    def __init__(self, graph, dev_graph, nodes):
+        import torch
+
+        self.n_rel = graph.n_rel
+        indptr, indices = dev_graph
+        self.rows = {}
+        ip = graph.indptr
+        for r in range(graph.n_rel):
+            for v in np.unique(nodes):
+                lv = int(v) - graph.row_lo
+                b, e = int(ip[r * graph.n_nodes + lv]), int(ip[r * graph.n_nodes + lv + 1])
+                self.rows[(r, int(v))] = indices[b:e].cpu().numpy()
+        del torch
+
+    def row(self, r, v):
+        return self.rows[(r, int(v))]
+
+
+def big_cpu_setup(args, dev):
+    """C5 for the CPU arm: the partition is generated like the GPU arm generates it (on the GPU when there is one),
+    then only the sampled batch rows, the feature table and the pool come to the host."""
+    import torch
+    from pcgnn_b200.synth_big import BigSpec, make_partition
+
+    part = make_partition(BigSpec(nodes_per_rank=args.nodes_per_gpu, seed=SEED), 0, 1, dev)
+    sample = min(args.cpu_sample, 64)           # the port (like the reference) builds a dense [B, U] mask: U ~ 3e5 here
+    drawn = part.sample_batches(4, sample, SEED)
+    batches = [(n.cpu().numpy().astype(np.int64), l.cpu().numpy()) for n, l in drawn]
+    allnodes = np.concatenate([n for n, _ in batches])
+    rows = _BatchRows(part.graph, part.graph.device(dev), allnodes)
+
+    class D:
+        pass
+
+    d = D()
+    d.feat = part.feat.cpu().numpy()
+    d.graph = rows
+    d.train_pos = part.train_pos.cpu().numpy().tolist()
+    del part
+    if torch.cuda.is_available():
+        torch.cuda.empty_cache()
+    return d, batches, sample
+
+
 def run_reference(args):
     """--impl reference: the oracle port on the host cores, same config/metric/unit."""
     rank = int(os.environ.get("RANK", "0"))
@@ -363,29 +448,106 @@ def run_reference(args):
     from pcgnn_b200.synth import make_graph
 
     spec, batch, embed, desc = WORKLOADS[args.workload]
+    world = max(args.gpus, 1)
     if args.workload == "big":
-        print(json.dumps({"impl": "reference", "unavailable": "workload big: the graph exists only as a device-side CSR "
-                          "(1e9 entries); the CPU arm is measured on the yelp / amazon workloads"}))
-        return
-    data = make_graph(spec, seed=SEED)
-    params = init_params(data.feat.shape[1], embed, data.graph.n_rel, SEED)
-    batches = make_batches(data, 4, batch, SEED)
-    sample = min(args.cpu_sample, batch)
-    rate, sec = cpu_port_rate(data, params, batches, sample, args.steps, args.warmup,
-                              gcn=args.workload.endswith("_gcn"))
+        dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+        data, batches, sample = big_cpu_setup(args, dev)
+        params = init_params(data.feat.shape[1], embed, 3, SEED)
+        note = ("oracle/port.py on %d targets per step with ONLY the batch rows of the CSR on the host (what the "
+                "reference reads, layers.py:219); its dense [B,U] mask makes larger samples infeasible" % sample)
+    else:
+        data = make_graph(spec, seed=SEED)
+        params = init_params(data.feat.shape[1], embed, data.graph.n_rel, SEED)
+        batches = make_batches(data, 4, batch, SEED)
+        sample = min(args.cpu_sample, batch)
+        note = (f"full train step of oracle/port.py on the first {sample} targets of each {batch}-target batch "
+                f"(Python loop per target like the reference)")
+    rate, sec = cpu_port_rate(data, params, batches, sample, args.steps, args.warmup, gcn=args.workload.endswith("_gcn"))
+    gb = batch if args.scaling == "strong" else batch * world
     line = {
         "impl": "reference", "metric": "train target-nodes/sec (fwd+bwd)", "value": rate, "unit": "target-nodes/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_dict(desc, batch, max(args.gpus, 1)),
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(desc, gb, world, args.scaling),
         "cpu_baseline": {"value": rate, "unit": "target-nodes/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"full train step of oracle/port.py on the first {sample} targets of each "
-                                   f"{batch}-target batch (Python loop per target like the reference; "
-                                   f"host has {os.cpu_count()} cpus)"},
+                         "sample": note + f"; host has {os.cpu_count()} cpus"},
         "e2e": {"value": rate, "unit": "target-nodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def reference_loop_arm(data, params, host_nodes, host_labels, dev, W, K, flush, is_gcn):
+    """The reference's own training loop, unchanged (model_handler.py:124, :142-156), on a fresh model:
+        optimizer = torch.optim.Adam(filter(requires_grad, params), lr, weight_decay)
+        optimizer.zero_grad(); loss = model.loss(batch_nodes: list, Variable(cuda.LongTensor(batch_label)))
+        loss.backward(); optimizer.step()            (+ loss.item(): the D2H of the step's result)
+    Returns the summed CUDA-event ms of K steps (labels are numpy on the host when a step starts)."""
+    import torch
+    from pcgnn_b200.testing import build_cuda_pcgnn
+
+    if is_gcn:
+        model = build_cuda_gcn(data, params, dev)
+    else:
+        model = build_cuda_pcgnn(data.feat, data.graph, sorted(data.train_pos), params, rho=RHO, alpha=ALPHA, device=dev)
+    opt = torch.optim.Adam(filter(lambda p: p.requires_grad, model.parameters()), lr=LR, weight_decay=WD)
+
+    def step(i):
+        opt.zero_grad()
+        lab = torch.from_numpy(host_labels[i]).to(dev)              # model_handler.py:150 (cuda LongTensor of labels)
+        loss = model.loss(host_nodes[i], lab)
+        loss.backward()
+        opt.step()
+        return loss.item()
+
+    for s_ in range(W):
+        step(s_)
+    torch.cuda.synchronize()
+    evs = []
+    for s_ in range(K):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step(W + s_)
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in evs)
+
+
+def dp_self_check(model, gstep, data, params, global_batches, shards, dev, rank, world, is_gcn):
+    """Outside the timed region, world > 1: (1) the first step's loss, averaged over the ranks (equal shards), equals
+    the loss of the whole global batch on ONE GPU (data parallel == large batch); (2) after the steps the replicas are
+    bit-identical."""
+    import torch
+    import torch.distributed as dist
+    from pcgnn_b200.testing import build_cuda_pcgnn
+
+    n, l = shards[0]
+    loss0 = gstep.run(n, l).clone()
+    torch.cuda.synchronize()
+    tot = loss0.double().clone()
+    dist.all_reduce(tot)
+    mean_loss = float(tot.item()) / world
+    gn, gl = global_batches[0]
+    if is_gcn:
+        single = build_cuda_gcn(data, params, dev)
+    else:
+        single = build_cuda_pcgnn(data.feat, data.graph, sorted(data.train_pos), params, rho=RHO, alpha=ALPHA, device=dev)
+        single.inter1.graph_cache = False
+    want = float(single.loss(gn.tolist(), torch.from_numpy(gl).to(dev)).item())
+    assert abs(mean_loss - want) <= 1e-5 * abs(want), f"data-parallel loss {mean_loss} != global-batch loss {want}"
+    for i in range(1, 4):
+        gstep.run(*shards[i])
+    torch.cuda.synchronize()
+    flat = torch.cat([p.detach().reshape(-1) for p in model.parameters() if p.requires_grad])
+    every = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(every, flat)
+    assert all(torch.equal(every[0], e) for e in every), "replicas differ after data-parallel steps"
+    if rank == 0:
+        print(f"dp self-check ok: world {world}, step-1 loss {mean_loss:.7f} == global-batch loss {want:.7f}, "
+              f"replicas bit-identical after 4 steps", file=sys.stderr)
+    return mean_loss, want
 
 
 def main():
@@ -395,6 +557,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="yelp", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the workload's batch per GPU; strong: the workload's batch in total, dealt to the GPUs")
+    ap.add_argument("--check-only", action="store_true", help="world > 1: run the data-parallel self-check and exit")
     ap.add_argument("--cpu-sample", type=int, default=1024, help="targets per CPU-baseline step (bounded sample of a batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="do not use CUDA graphs for the device-resident step")
@@ -410,7 +575,6 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from pcgnn_b200 import _lib
     from pcgnn_b200.parallel import FusedAdam, GradAllReduce, PeerComm
     from pcgnn_b200.synth import make_graph
     from pcgnn_b200.testing import build_cuda_pcgnn
@@ -423,10 +587,15 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     K, W = args.steps, max(args.warmup, 3)
-    spec, batch, embed, desc = WORKLOADS[args.workload]
+    spec, wl_batch, embed, desc = WORKLOADS[args.workload]
     is_gcn = args.workload.endswith("_gcn")
     is_big = args.workload == "big"
-    n_b = W + K
+    strong = args.scaling == "strong" and not is_big
+    global_batch = wl_batch if strong else wl_batch * world
+    if global_batch % world:
+        raise SystemExit(f"global batch {global_batch} does not divide over {world} ranks")
+    batch = global_batch // world                                  # targets per GPU
+    n_b = W + K + 4
     if is_big:
         # C5: every rank generates and holds only its own row range of the CSR; features, scores and the pool
         # are global. Each rank draws its share of the global batch from its own nodes (targets live with
@@ -480,9 +649,11 @@ def main():
         opt = FusedAdam(reducer, lr=LR, weight_decay=WD, comm=PeerComm(reducer.flat.numel()))
     fused = not args.torch_adam
     if not is_big:
-        # global batches of batch*world targets, identical on every rank; this rank's contiguous shard
-        global_batches = make_batches(data, n_b, batch * world, SEED)
-        shards = [(n[rank * batch:(rank + 1) * batch], l[rank * batch:(rank + 1) * batch]) for n, l in global_batches]
+        # global batches, identical on every rank; this rank's share dealt by total row length
+        global_batches = make_batches(data, n_b, global_batch, SEED)
+        weight = data.homo.degrees(0).astype(np.int64) if is_gcn else \
+            sum(data.graph.degrees(r).astype(np.int64) for r in range(R))
+        shards = [deal(n, l, weight, rank, world) for n, l in global_batches]
     dev_nodes = [torch.from_numpy(n.astype(np.int32)).to(dev) for n, _ in shards]
     dev_labels = [torch.from_numpy(l).to(dev) for _, l in shards]
     host_nodes = [n.tolist() for n, _ in shards]
@@ -516,13 +687,14 @@ def main():
     def step_host_eager(i):
         if not fused:
             reducer.zero()
-        lab = torch.from_numpy(host_labels[i]).to(dev)          # model_handler.py:150 (cuda LongTensor of labels)
+        lab = torch.from_numpy(host_labels[i]).to(dev)
         loss = model.loss(host_nodes[i], lab)
         loss.backward()
         finish_step()
         return loss.item()                                       # D2H of the step's result
 
     use_graph = not args.no_graph
+    gstep = None
     if use_graph:
         from pcgnn_b200.runtime import GraphedTrainStep
 
@@ -535,6 +707,16 @@ def main():
             return gstep.run(host_nodes[i], host_labels[i]).item()     # H2D ids+labels, replay, D2H loss
     else:
         step_device, step_host = step_device_eager, step_host_eager
+
+    check = None
+    if world > 1 and use_graph and not is_big:
+        check = dp_self_check(model, gstep, data, params, global_batches, shards, dev, rank, world, is_gcn)
+    if args.check_only:
+        if world == 1 and rank == 0:
+            print("dp self-check skipped: one GPU", file=sys.stderr)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     def timed(fn, first):
         evs = []
@@ -571,56 +753,70 @@ def main():
     sampler.sample()
     barrier()
     ms_dev = max_over_ranks(ms_dev)
-    # ---- host inputs through the public API (e2e) ----
+    # ---- host inputs through the step-graph API ----
     for s in range(W):
         step_host(s)
     barrier()
-    ms_e2e = timed(step_host, W)
+    ms_graph_host = timed(step_host, W)
     barrier()
-    ms_e2e = max_over_ranks(ms_e2e)
-    ms_api = None
-    if use_graph:      # the reference-facing eager call model.loss(list, labels) for comparison
-        if hasattr(inter, "scores_external"):
-            inter.scores_external = False      # the eager call computes (and exchanges) the scores itself
-        for s in range(W):
-            step_host_eager(s)
-        barrier()
-        ms_api = max_over_ranks(timed(step_host_eager, W))
-        barrier()
+    ms_graph_host = max_over_ranks(ms_graph_host)
+    if gstep is not None:
         assert not gstep.overflowed()
+    # ---- host inputs through the REFERENCE's own loop (1 GPU: the reference is single-GPU) ----
+    ms_ref_loop = None
+    if world == 1 and not is_big:
+        ms_ref_loop = reference_loop_arm(data, params, host_nodes, host_labels, dev, W, K, flush, is_gcn)
     sampler.stop_flag = True
 
     # ---- hot-path kernels alone (roofline), same batches. Each group is captured into its own CUDA graph
     # (static input buffers) so the events bracket GPU work only, not the host's launch calls. ----
+    if hasattr(inter, "scores_external"):
+        inter.scores_external = False
     kern, roof = hot_kernels_gcn(eng, inter, data, shards, dev_nodes, cap, W, K, flush, dev) if is_gcn else \
         hot_kernels_pcgnn(eng, inter, data, shards, dev_nodes, dev_labels, cap, W, K, flush, dev, batch, args.workload)
 
     if rank == 0:
-        total_nodes = batch * world * K
+        total_nodes = global_batch * K
+        io = {"h2d_bytes_per_step": batch * 4 + batch * 8, "d2h_bytes_per_step": 4}
+        e2e_graph = {"value": total_nodes / (ms_graph_host / 1e3), "unit": "target-nodes/s", "ms_per_step": ms_graph_host / K,
+                     "call": "runtime.GraphedTrainStep.run(list_of_ids, numpy_labels).item()  (pinned staging, H2D, one "
+                             "graph replay, D2H of the loss)", **io}
+        if ms_ref_loop is not None:
+            e2e = {"value": total_nodes / (ms_ref_loop / 1e3), "unit": "target-nodes/s", "ms_per_step": ms_ref_loop / K,
+                   "call": "the reference's loop unchanged (model_handler.py:142-156): opt.zero_grad(); "
+                           "model.loss(list_of_ids, cuda LongTensor(labels)); backward(); torch.optim.Adam.step(); loss.item()",
+                   **io}
+        else:
+            e2e = e2e_graph
         line = {
             "metric": "train target-nodes/sec (fwd+bwd)", "value": total_nodes / (ms_dev / 1e3),
             "unit": "target-nodes/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev / K,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(desc, batch, world),
-            "e2e": {"value": total_nodes / (ms_e2e / 1e3), "unit": "target-nodes/s", "ms_per_step": ms_e2e / K,
-                    "h2d_bytes_per_step": batch * 4 + batch * 8, "d2h_bytes_per_step": 4},
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config_dict(desc, global_batch, world, "strong" if strong else "weak"),
+            "e2e": e2e, "e2e_step_graph": e2e_graph,
             "gpu_launches": (GCN_KERNELS_PER_STEP if is_gcn else MY_KERNELS_PER_STEP) * K,
             "mode": "cuda-graph replay (runtime.GraphedTrainStep)" if use_graph else "eager",
             "roofline": roof, "kernels": kern, "clocks": sampler.result(),
         }
-        if ms_api is not None:
-            line["e2e_reference_api_eager"] = {"value": total_nodes / (ms_api / 1e3), "unit": "target-nodes/s",
-                                               "ms_per_step": ms_api / K,
-                                               "call": "model.loss(list_of_ids, cuda_labels); backward; Adam.step; loss.item()"}
-        if world == 1 and not args.no_cpu_baseline and not is_big:
-            sample = min(args.cpu_sample, batch)
-            rate, sec = cpu_port_rate(data, params, global_batches, sample, 12, 1, gcn=is_gcn)
-            line["cpu_baseline"] = {
-                "value": rate, "unit": "target-nodes/s", "cores": torch.get_num_threads(), "kind": "port",
-                "sample": f"12 full train steps of oracle/port.py on the first {sample} targets of a batch "
-                          f"({sec * 1e3:.0f} ms each; host has {os.cpu_count()} cpus)",
-                }
-            if not is_gcn:
+        if check is not None:
+            line["dp_self_check"] = {"step1_loss_mean_over_ranks": check[0], "global_batch_loss_one_gpu": check[1],
+                                     "replicas_bit_identical": True}
+        if world == 1 and not args.no_cpu_baseline:
+            if is_big:
+                del model, gstep
+                torch.cuda.empty_cache()
+                cdata, cbatches, sample = big_cpu_setup(args, dev)
+                rate, sec = cpu_port_rate(cdata, params, cbatches, sample, 3, 1)
+                note = (f"3 full train steps of oracle/port.py on {sample} targets each ({sec * 1e3:.0f} ms each) with only "
+                        f"the batch rows of the CSR on the host (what the reference reads, layers.py:219)")
+            else:
+                sample = min(args.cpu_sample, batch)
+                rate, sec = cpu_port_rate(data, params, global_batches, sample, 12, 1, gcn=is_gcn)
+                note = (f"12 full train steps of oracle/port.py on the first {sample} targets of a batch "
+                        f"({sec * 1e3:.0f} ms each)")
+            line["cpu_baseline"] = {"value": rate, "unit": "target-nodes/s", "cores": torch.get_num_threads(),
+                                    "kind": "port", "sample": note + f"; host has {os.cpu_count()} cpus"}
+            if not is_gcn and not is_big:
                 line["cpu_baseline"]["c_port_choose_aggregate_nodes_per_s"] = c_port_rate(data, global_batches)
         print(json.dumps(line))
     if world > 1:

@@ -76,7 +76,10 @@ PCG_API int pcg_entry_pool_positions(const int32_t* indices, int64_t nnz, const 
  * row has max_degree entries. The first n_nodes*4 bytes hold a per-node table that carries state between
  * calls (all bytes 0x7f between calls; pcg_choose restores it): call pcg_choose_workspace_init once after
  * allocating the buffer, and again if the same buffer is later used with another n_nodes. */
+/* pcg_choose_sticky_offset(n_nodes): byte offset in the workspace of an int32 that every pcg_choose call ORs its
+ * status[PCG_ST_OVERFLOW] into (the status block itself is rewritten by every call); the host reads and clears it. */
 PCG_API size_t pcg_choose_workspace_bytes(int B, int R, int64_t max_degree, int64_t n_nodes);
+PCG_API size_t pcg_choose_sticky_offset(int64_t n_nodes);
 PCG_API int pcg_choose_workspace_init(void* workspace, size_t workspace_bytes, int64_t n_nodes, pcg_stream_t stream);
 
 /*

@@ -36,6 +36,7 @@ SIGNATURES = {
     "pcg_sort_pool_workspace_bytes": (_z, [_i]),
     "pcg_sort_pool": (_i, [_p, _p, _i, _p, _p, _p, _p, _z, _p]),
     "pcg_choose_workspace_bytes": (_z, [_i, _i, _l, _l]),
+    "pcg_choose_sticky_offset": (_z, [_l]),
     "pcg_choose_workspace_init": (_i, [_p, _z, _l, _p]),
     "pcg_pool_positions": (_i, [_p, _i, _l, _p, _p]),
     "pcg_entry_pool_positions": (_i, [_p, _l, _p, _p, _p]),

@@ -85,6 +85,7 @@ struct ChooseP {
     int32_t* q_big;
     uint32_t* bits_slab;        // [grid_big, slab_words] kept-position bitmasks of the big tier
     int64_t slab_words;
+    int32_t* sticky;            // workspace word that keeps every call's overflow / foreign-target flag until the host clears it
 };
 
 #ifdef PCG_TRACE
@@ -1211,6 +1212,7 @@ __global__ void __launch_bounds__(PCG_PREP_NT, 1) k_choose_prep(ChooseP p, int c
                 if (rep[u] == -2) {          // not our row: empty item, error flag
                     p.it_slot0[w] = 0; p.it_m[w] = 0; p.it_base[w] = 0; p.it_done[w] = 0;
                     atomicExch(&p.status[ST_OVERFLOW], 2);
+                    atomicOr(p.sticky, 2);
                 }
                 if (rep[u] == ii[u]) {
                     const int64_t d = end[u] - beg[u];
@@ -1293,7 +1295,7 @@ __global__ void __launch_bounds__(PCG_PREP_NT, 1) k_choose_prep(ChooseP p, int c
         }
     }
     PTRACE(3);
-    if (__syncthreads_or(overflow) && tid == 0) atomicExch(&p.status[ST_OVERFLOW], 1);
+    if (__syncthreads_or(overflow) && tid == 0) { atomicExch(&p.status[ST_OVERFLOW], 1); atomicOr(p.sticky, 1); }
     if (first)                               // restore the table (all its reads are behind the second barrier)
         for (int i = blockIdx.x * NT + tid; i < B; i += G * NT) {
             const int64_t lv = (int64_t)__ldg(p.targets + i) - p.row_lo;
@@ -1379,7 +1381,7 @@ static WsLayout ws_layout(int B, int R, int64_t max_degree, int64_t n_nodes, int
     L.slab_words = max_degree > PCG_HUGE_MAX ? (max_degree + 31) / 32 : 0;      // (also when 16-CTA clusters take those rows)
     size_t o = 0;
     L.first = o; o = al(o + (size_t)n_nodes * 4);
-    L.bar = o; o = al(o + 8);                    // prep grid barrier words (zero between calls)
+    L.bar = o; o = al(o + 16);                   // prep grid barrier words (zero between calls) + the sticky overflow word
     L.totals = o; o = al(o + 1024 * 4);          // per-CTA slot totals of the prep kernel
     L.bits_slab = o; o = al(o + (size_t)L.grid_big * L.slab_words * 4);
     L.q_warp = o; o = al(o + W * 4);
@@ -1414,12 +1416,14 @@ extern "C" size_t pcg_choose_workspace_bytes(int B, int R, int64_t max_degree, i
     return ws_layout(B, R, max_degree, n_nodes, 148 * 2).total;   // sized for the largest grid we ever launch
 }
 
+extern "C" size_t pcg_choose_sticky_offset(int64_t n_nodes) { return ws_layout(1, 1, 0, n_nodes, 148).bar + 8; }
+
 extern "C" int pcg_choose_workspace_init(void* workspace, size_t workspace_bytes, int64_t n_nodes, pcg_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     WsLayout L = ws_layout(1, 1, 0, n_nodes, 148);
-    PCG_REQUIRE(workspace && workspace_bytes >= L.bar + 8, "pcg_choose_workspace_init: workspace too small");
+    PCG_REQUIRE(workspace && workspace_bytes >= L.bar + 16, "pcg_choose_workspace_init: workspace too small");
     cudaError_t e = cudaMemsetAsync(workspace, 0x7f, (size_t)n_nodes * 4, stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync((char*)workspace + L.bar, 0, 8, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync((char*)workspace + L.bar, 0, 16, stream);
     if (e != cudaSuccess) { pcg_set_error("pcg_choose_workspace_init: memset: %s", cudaGetErrorString(e)); return (int)e; }
     return 0;
 }
@@ -1493,6 +1497,7 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
     p.q_huge = (int32_t*)(ws + L.q_huge);
     p.q_huge16 = (int32_t*)(ws + L.q_huge16);
     p.q_big = (int32_t*)(ws + L.q_big);
+    p.sticky = (int32_t*)(ws + L.bar) + 2;
     p.bits_slab = (uint32_t*)(ws + L.bits_slab);
     p.slab_words = L.slab_words;
     const int W = R * B;

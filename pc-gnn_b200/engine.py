@@ -15,13 +15,39 @@ import torch
 from . import _lib
 from .graph import RelGraph
 
-__all__ = ["Engine", "Selection", "padded_ld"]
+__all__ = ["Engine", "Selection", "PinnedStaging", "padded_ld"]
 
 
 def padded_ld(feat_dim: int) -> int:
     """Row stride (floats) of the device feature table: one 128-byte line for F <= 32, else the next
     multiple of 4 (16-byte vector loads)."""
     return 32 if feat_dim <= 32 else (feat_dim + 3) // 4 * 4
+
+
+class PinnedStaging:
+    """Pinned host staging for small per-step uploads (target ids, labels): a ring of buffers, each guarded by an
+    event recorded behind its host-to-device copy, so that the host never rewrites a buffer whose copy is still
+    queued (back-to-back steps without a sync in between would otherwise train on the NEXT batch's ids)."""
+
+    def __init__(self, n: int, dtype, depth: int = 3):
+        self.n, self.dtype = int(n), dtype
+        self.bufs = [torch.empty(self.n, dtype=dtype, pin_memory=True) for _ in range(depth)]
+        self.events = [None] * depth
+        self.i = 0
+
+    def upload(self, host_array, dst: torch.Tensor):
+        """dst[:len] <- host_array (numpy) through the next free pinned buffer, asynchronously."""
+        k = len(host_array)
+        i = self.i
+        self.i = (i + 1) % len(self.bufs)
+        if self.events[i] is not None:
+            self.events[i].synchronize()          # the copy that last used this buffer has finished
+        self.bufs[i].numpy()[:k] = host_array
+        dst[:k].copy_(self.bufs[i][:k], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dst.device))
+        self.events[i] = ev
+        return dst[:k]
 
 
 class Selection:
@@ -88,6 +114,7 @@ class Engine:
             self.indptr = self.indices = None
         self.strict_rows = True     # feature table must have exactly one row per graph node
         self._feat_key = None
+        self._feat_src = None
         self.feat = None            # [N, ldf] fp32, zero padded
         self.F = self.ldf = 0
         self.score = None           # [N]
@@ -110,9 +137,12 @@ class Engine:
     # ------------------------------------------------------------------ resident tables
     def set_features(self, weight: torch.Tensor):
         """Padded device copy of the [N,F] feature table (re-made only when the source changes)."""
-        key = (weight.data_ptr(), weight._version, tuple(weight.shape), weight.device)
-        if key == self._feat_key:
+        # cache on the IDENTITY of the source tensor (kept alive here) + its version counter: a table built by a
+        # `features` callable is a fresh tensor on every call (possibly at a recycled address) and is re-padded
+        key = (weight._version, tuple(weight.shape), weight.device)
+        if self._feat_src is weight and key == self._feat_key:
             return self.feat
+        self._feat_src = weight
         w = weight.detach()
         if self.graph is not None and self.strict_rows and w.shape[0] != self.N_global:
             raise ValueError(f"feature table has {w.shape[0]} rows, graph has {self.N_global} nodes")
@@ -257,10 +287,10 @@ class Engine:
         else:
             host = np.asarray(nodes, dtype=np.int32)
         B = host.shape[0]
-        if self._pin is None or self._pin.shape[0] < B:
-            self._pin = torch.empty(max(B, 1024), dtype=torch.int32, pin_memory=True)
-        self._pin[:B].numpy()[:] = host
-        return self._pin[:B].to(self.device, non_blocking=True), host
+        if self._pin is None or self._pin.n < B:
+            self._pin = PinnedStaging(max(B, 1024), torch.int32)
+        dst = torch.empty(B, dtype=torch.int32, device=self.device)
+        return self._pin.upload(host, dst), host
 
     def slots_bound(self, host_targets, thresh, rho, train, *, k_override=None) -> int:
         """Upper bound of the slots a batch needs, from the host copy of the CSR offsets (every
@@ -361,6 +391,19 @@ class Engine:
             int(phases), _lib.stream_ptr())
         _lib.check(rc, "pcg_choose")
         return (s, dist) if want_dist else s
+
+    def overflow_since_reset(self) -> bool:
+        """True if ANY choose call since the last query ran out of slots (or met a target whose row this partition
+        does not hold): the kernels OR their flag into a workspace word that, unlike a call's status block, survives
+        later calls and CUDA-graph replays. Reads and clears it. Syncs."""
+        if self._ws is None:
+            return False
+        off = int(self.lib.pcg_choose_sticky_offset(self._ws_nodes))
+        word = self._ws[off:off + 4].view(torch.int32)
+        hit = bool(word.item())
+        if hit:
+            word.zero_()
+        return hit
 
     def select_all(self, targets, add_self: bool, cap_slots: int, norm: int) -> Selection:
         """GraphSAGE / GCN selection: whole rows (∪ self), no copy (``pcg_select_all``)."""

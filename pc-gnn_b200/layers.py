@@ -427,6 +427,8 @@ class InterAgg(nn.Module):
         #                                 partitioned graph: slice kernel -> all-gather -> this forward)
         self.last_selection = None
         self.use_pdl = False            # runtime.GraphedTrainStep: programmatic dependent launch of the fused kernels
+        self.graph_cache = True         # record the reference-facing calls into CUDA graphs (stepgraph.StepGraphCache)
+        self._graphs = None
 
     # -- plumbing ---------------------------------------------------------------------------
     def intra_aggs(self):
@@ -444,22 +446,11 @@ class InterAgg(nn.Module):
         return self._engine
 
     # -- forward ----------------------------------------------------------------------------
-    def _choose_and_aggregate(self, nodes, labels, train_flag):
-        """Score table -> pool sort -> choose (filter + oversample + union) -> mean aggregation for a batch
-        (layers.py:216-270, 589-624). Returns (engine, feature table, targets int32, device labels, selection)."""
-        eng = self.engine()
-        dev = eng.device
-        table = _feature_table(self.features, eng.N_global, dev)
-        eng.set_features(table)
-        targets, host = eng.upload_targets(nodes)
+    def _select(self, eng, targets, lab, train_flag, cap):
+        """Score table -> pool sort -> choose (filter + oversample + union) for device-resident ids / labels and a
+        given slot capacity (layers.py:216-262, 633-738). Pure kernel launches on the current stream."""
         rho = self.intra_agg1.rho
-        lab = _as_device_labels(labels, dev) if train_flag else None
-        if self.cap_slots_hint is not None:
-            cap = int(self.cap_slots_hint)
-        elif host is not None:
-            cap = eng.slots_bound(host, self.thresholds, rho, train_flag)
-        else:
-            cap = eng.slots_bound(targets.cpu().numpy(), self.thresholds, rho, train_flag)
+        dev = eng.device
         # the preparation of the choose step (repeated targets, item sizes, slot prefix sum, tier queues) needs no
         # scores: it runs on a side stream next to the score table and the pool sort
         cur = torch.cuda.current_stream(dev)
@@ -479,7 +470,33 @@ class InterAgg(nn.Module):
         cur.wait_stream(side)
         eng.choose(targets, lab, train_flag, self.thresholds, rho, cap, phases=2, sel=sel)
         self.last_selection = sel
-        return eng, table, targets, lab, sel
+        return sel
+
+    def _choose_and_aggregate(self, nodes, labels, train_flag):
+        """Upload of the batch's ids / labels, then ``_select``. Returns (engine, feature table, targets int32,
+        device labels, selection)."""
+        eng = self.engine()
+        dev = eng.device
+        table = _feature_table(self.features, eng.N_global, dev)
+        eng.set_features(table)
+        targets, host = eng.upload_targets(nodes)
+        rho = self.intra_agg1.rho
+        lab = _as_device_labels(labels, dev) if train_flag else None
+        if self.cap_slots_hint is not None:
+            cap = int(self.cap_slots_hint)
+        elif host is not None:
+            cap = eng.slots_bound(host, self.thresholds, rho, train_flag)
+        else:
+            cap = eng.slots_bound(targets.cpu().numpy(), self.thresholds, rho, train_flag)
+        return eng, table, targets, lab, self._select(eng, targets, lab, train_flag, cap)
+
+    def graphs(self):
+        """The CUDA-graph cache behind the reference-facing calls (``stepgraph.StepGraphCache``)."""
+        if self._graphs is None:
+            from .stepgraph import StepGraphCache
+
+            self._graphs = StepGraphCache(self)
+        return self._graphs
 
     def _frozen_fast_path(self, table, B) -> bool:
         return (not table.requires_grad) and self.embed_dim <= 256 and B > 0 \
@@ -495,6 +512,11 @@ class InterAgg(nn.Module):
         if not (self._frozen_fast_path(table, B) and eng.set_features(table) is not None
                 and eng.tile_supported(B, self._R, self.embed_dim)):
             return None
+        if self.graphs().usable(eng, table, B):
+            # host ids (the reference's calling convention): upload into static buffers + ONE graph replay
+            loss = self.graphs().train_loss(eng, nodes, labels, head_weight, float(lam))
+            if loss is not None:
+                return loss
         eng, table, targets, lab, sel = self._choose_and_aggregate(nodes, labels, True)
         agg = eng.aggregate(sel, copy_dups=False)     # repeated targets: the dense kernels read it_rep's row
         loss, _, _ = TrainStepFn.apply(eng, targets, lab, agg, sel.it_rep, float(lam), bool(self.use_pdl), head_weight,
@@ -503,6 +525,16 @@ class InterAgg(nn.Module):
         return loss
 
     def forward(self, nodes, labels, train_flag=True):
+        if not torch.is_grad_enabled() or not any(p.requires_grad for p in self.parameters()):
+            # no gradients wanted (utils.test -> to_prob): the whole forward is one cached graph replay
+            eng = self.engine()
+            table = _feature_table(self.features, eng.N_global, eng.device)
+            B = len(nodes) if not isinstance(nodes, torch.Tensor) else int(nodes.shape[0])
+            if self._frozen_fast_path(table, B) and eng.set_features(table) is not None \
+                    and eng.tile_supported(B, self._R, self.embed_dim) and self.graphs().usable(eng, table, B):
+                res = self.graphs().infer(eng, nodes, labels, train_flag)
+                if res is not None:
+                    return res
         eng, table, targets, lab, sel = self._choose_and_aggregate(nodes, labels, train_flag)
         dev = eng.device
         B = targets.shape[0]

@@ -24,6 +24,7 @@ class GraphedTrainStep:
                  warmup_batch=None):
         """optimizer: a capturable torch optimizer (gradient mean over ranks by NCCL between two graphs), or a
         ``parallel.FusedAdam`` (gradient exchange over peer memory + Adam inside the one step graph)."""
+        from .engine import PinnedStaging
         from .parallel import FusedAdam
 
         self.fused = isinstance(optimizer, FusedAdam)
@@ -41,9 +42,18 @@ class GraphedTrainStep:
             model.inter1.center_on_side_stream = True
         self.nodes = torch.zeros(self.B, dtype=torch.int32, device=dev)
         self.labels = torch.zeros(self.B, dtype=torch.int64, device=dev)
-        self.pin_nodes = torch.zeros(self.B, dtype=torch.int32, pin_memory=True)
-        self.pin_labels = torch.zeros(self.B, dtype=torch.int64, pin_memory=True)
+        # rings of pinned buffers guarded by events: back-to-back run() calls never rewrite a buffer whose
+        # host-to-device copy is still queued behind the previous replay
+        self.pin_nodes = PinnedStaging(self.B, torch.int32)
+        self.pin_labels = PinnedStaging(self.B, torch.int64)
         self.loss = None
+        if reducer is not None:
+            # the captured graph writes the gradients through the parameters' .grad tensors: they must BE the views
+            # of the reducer's flat buffer (otherwise the graph keeps accumulating into tensors nobody zeroes)
+            for p_, v_ in zip(reducer.params, reducer.views):
+                if p_.grad is None or p_.grad.data_ptr() != v_.data_ptr():
+                    reducer.attach()
+                    break
         # row-partitioned graph: the score slices are exchanged by an eager all-gather BETWEEN two graphs
         # (slice kernel | all-gather | everything else), so no collective is captured
         eng = model.inter1.engine() if hasattr(model, "inter1") else None
@@ -166,15 +176,16 @@ class GraphedTrainStep:
 
     def run(self, nodes, labels):
         """Batch on the host (list / numpy of ids, numpy labels): pinned staging + H2D + replay."""
-        self.pin_nodes.numpy()[:] = np.asarray(nodes, dtype=np.int32)
-        self.pin_labels.numpy()[:] = np.asarray(labels, dtype=np.int64)
-        self.nodes.copy_(self.pin_nodes, non_blocking=True)
-        self.labels.copy_(self.pin_labels, non_blocking=True)
+        self.pin_nodes.upload(np.asarray(nodes, dtype=np.int32), self.nodes)
+        self.pin_labels.upload(np.asarray(labels, dtype=np.int64), self.labels)
         return self._replay()
 
     def overflowed(self) -> bool:
-        """True if some replay needed more slots than the captured capacity (results then incomplete:
-        re-plan with a larger capacity). Syncs."""
+        """True if ANY replay since the last call needed more slots than the captured capacity (its results were
+        incomplete: re-plan with a larger capacity). PC-GNN models: a workspace word every choose call ORs its flag
+        into (``Engine.overflow_since_reset``); GCN / SAGE: the last replay's status block. Syncs."""
+        if hasattr(self.model, "inter1"):
+            return self.model.inter1.engine().overflow_since_reset()
         sel = self._sizer.last_selection
         return bool(sel is not None and sel.overflowed())
 

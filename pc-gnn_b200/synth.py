@@ -40,6 +40,7 @@ SPECS = {
     # C3: YelpChi-shaped with the old 100-d features
     "yelp100": SynthSpec("yelp100", 45954, 100, (49315, 573616, 3402743), 0.145),
     # small shapes for tests
+    "train_sig": SynthSpec("train_sig", 3000, 25, (5000, 60000, 20000), 0.12, zipf=0.7, normalize=True),
     "tiny": SynthSpec("tiny", 600, 12, (700, 5000, 2500), 0.2, zipf=0.8),
     "tiny_amz": SynthSpec("tiny_amz", 900, 25, (1500, 20000, 7000), 0.1, zipf=0.7,
                           n_unlabeled=100, normalize=True),
@@ -77,18 +78,32 @@ def row_normalize(x):
 
 
 def make_graph(spec: SynthSpec | str, seed: int = 72, *, dup_feature_frac: float = 0.0,
-               edge_scale: float = 1.0) -> SynthData:
+               edge_scale: float = 1.0, signal: float = 0.0, homophily: float = 0.0) -> SynthData:
     """Build one synthetic dataset. ``dup_feature_frac`` > 0 copies feature rows so
-    that label scores collide and the tie rule (distance, id) is exercised (F6)."""
+    that label scores collide and the tie rule (distance, id) is exercised (F6).
+    ``signal`` / ``homophily`` > 0 make the labels learnable (for training-run comparisons): positives get their
+    features shifted by ``signal`` along a fixed direction, and a fraction ``homophily`` of every relation's edges
+    is rewired to an endpoint with the same label (fraud rings). With both 0 labels are independent noise."""
     if isinstance(spec, str):
         spec = SPECS[spec]
     rng = np.random.default_rng(seed)
     n = spec.n_nodes
+    learnable = signal > 0 or homophily > 0
+    if learnable:
+        rng_l = np.random.default_rng(seed + 7919)
+        labels_sig = (rng_l.random(n) < spec.pos_rate).astype(np.int64)
+        labels_sig[:spec.n_unlabeled] = 0
+        by_label = [np.nonzero(labels_sig == c)[0] for c in (0, 1)]
     ips, ixs = [], []
     for m in spec.rel_edges:
         m = max(1, int(m * edge_scale))
         u = _zipf_endpoints(rng, n, m, spec.zipf)
         v = _zipf_endpoints(rng, n, m, spec.zipf)
+        if learnable and homophily > 0:
+            flip = rng_l.random(m) < homophily
+            for c in (0, 1):
+                sel = flip & (labels_sig[u] == c)
+                v[sel] = by_label[c][rng_l.integers(0, len(by_label[c]), int(sel.sum()))]
         ip, ix = csr_from_edges(n, u, v)
         ips.append(ip)
         ixs.append(ix)
@@ -101,11 +116,15 @@ def make_graph(spec: SynthSpec | str, seed: int = 72, *, dup_feature_frac: float
         dst = rng.choice(n, k, replace=False)
         src = rng.choice(n, k, replace=True)
         feat[dst] = feat[src]
+    if learnable and signal > 0:
+        feat[labels_sig == 1] += np.float32(signal) * rng_l.random(spec.feat_dim, dtype=np.float32)
     if spec.normalize:
         feat = row_normalize(feat)
 
     labels = (rng.random(n) < spec.pos_rate).astype(np.int64)
     labels[:spec.n_unlabeled] = 0
+    if learnable:
+        labels = labels_sig
     # stratified split without sklearn: per class shuffle + cut (model_handler.py:38-48 uses
     # train_test_split(stratify=labels); only the class proportions matter for the shape).
     index = np.arange(spec.n_unlabeled, n)

@@ -126,33 +126,29 @@ def load_data(data_name, seed: int = 72):
 def test(test_nodes, labels, model, batch_size, result=None, epoch=None, epoch_best=None, flag=None,
          print_line=True):
     """Evaluation loop with the reference's signature and return value (utils.py:280-333): batched
-    ``model.to_prob(nodes, labels, train_flag=False)`` then AUC / recall / macro-F1 / precision."""
-    from sklearn.metrics import f1_score, precision_score, recall_score, roc_auc_score
+    ``model.to_prob(nodes, labels, train_flag=False)`` then AUC / recall / macro-F1 / precision.
+
+    The batches' probabilities stay on the device (the reference copies each batch to the host, utils.py:305) and
+    the metrics are computed there (``metrics.binary_metrics``: one sort + reductions, one device->host copy)."""
+    from .metrics import binary_metrics
 
     labels = np.asarray(labels)
-    pred, anomaly = [], []
+    probs = []
     for start in range(0, len(test_nodes), batch_size):
         batch_nodes = test_nodes[start:start + batch_size]
         if len(batch_nodes) == 0:
             continue
         out = model.to_prob(batch_nodes, labels[start:start + batch_size], train_flag=False)
-        out = (out[0] if isinstance(out, tuple) else out).data.cpu().numpy()
-        pred.extend(out.argmax(axis=1).tolist())
-        anomaly.extend(out[:, 1].tolist())
-    pred = np.asarray(pred)
-    f1 = f1_score(labels, pred, zero_division=0)
-    f1_macro = f1_score(labels, pred, average="macro", zero_division=0)
-    precision = precision_score(labels, pred, zero_division=0)
-    recall = recall_score(labels, pred, zero_division=0)
-    auc = roc_auc_score(labels, anomaly)
+        probs.append((out[0] if isinstance(out, tuple) else out).detach())
+    prob = torch.cat(probs, dim=0)
+    m = binary_metrics(prob[:, 1], prob.argmax(dim=1), torch.as_tensor(labels, device=prob.device))
+    f1, f1_macro, precision, recall, auc = m["f1"], m["f1_macro"], m["precision"], m["recall"], m["auc"]
     line = f"- F1: {f1:.4f}\t- Recall: {recall:.4f}\t- Precision: {precision:.4f}\t- AUC-ROC: {auc:.4f}\t- F1-macro: {f1_macro:.4f}\n"
     if result is not None:
         writer = getattr(result, "write_val_log" if flag == "val" else "write_test_log", None)
         if writer is not None:
             try:
-                acc = float((pred == labels).mean())
-                pm = precision_score(labels, pred, zero_division=0, average="macro")
-                rm = recall_score(labels, pred, average="macro", zero_division=0)
+                acc, pm, rm = m["accuracy"], m["precision_macro"], m["recall_macro"]
                 if flag == "val":
                     writer(epoch, epoch_best, acc, f1, f1_macro, precision, pm, recall, rm, auc, line, print_line)
                 else:

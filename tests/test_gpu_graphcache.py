@@ -1,0 +1,185 @@
+"""GPU: the CUDA-graph cache behind the reference-facing calls (pcgnn_b200/stepgraph.py) and the pinned staging
+rings: model.loss(list, labels) / backward / optimizer.step in the reference's own loop shape
+(model_handler.py:142-156) must give the same trajectory as the uncached eager kernels, whatever changes between
+calls (batch size, slot demand, parameter storage), and back-to-back calls must not race their uploads."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import build_cuda_pcgnn, random_params, rel_err
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(seed=61, E=64, spec="tiny_amz"):
+    from pcgnn_b200.synth import make_graph
+
+    d = make_graph(spec, seed=seed, dup_feature_frac=0.1)
+    rng = np.random.default_rng(seed)
+    params = random_params(rng, d.feat.shape[1], E, 3)
+    return d, rng, params, sorted(d.train_pos)
+
+
+def _train(model, batches, labels_of, cached):
+    model.inter1.graph_cache = cached
+    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=0.01, weight_decay=1e-3)
+    losses = []
+    for nodes in batches:
+        opt.zero_grad()
+        loss = model.loss(nodes.tolist(), torch.from_numpy(labels_of(nodes)).cuda())   # model_handler.py:150
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    return losses
+
+
+def test_cached_training_loop_equals_eager_loop():
+    d, rng, params, tp = _setup()
+    # batch sizes change (last batch of an epoch is short, model_handler.py:134), demand for slots grows (hubs later)
+    deg = d.homo.degrees(0)
+    order = np.asarray(d.idx_train)[np.argsort(deg[d.idx_train])]
+    small, hubs = order[:200], order[-128:]
+    batches = [rng.choice(small, 128), rng.choice(small, 128), hubs, rng.choice(d.idx_train, 77),
+               rng.choice(d.idx_train, 128), rng.choice(d.idx_train, 77)]
+    out = []
+    for cached in (False, True):
+        model = build_cuda_pcgnn(d.feat, d.graph, tp, params)
+        losses = _train(model, batches, lambda n: d.labels[n], cached)
+        out.append((losses, [p.detach().cpu().numpy().copy() for p in model.parameters() if p.requires_grad], model))
+    assert np.allclose(out[0][0], out[1][0], rtol=1e-5, atol=1e-6), (out[0][0], out[1][0])
+    for a, b in zip(out[0][1], out[1][1]):
+        assert rel_err(b, a) <= 1e-4
+    cache = out[1][2].inter1.graphs()
+    assert cache.replays == len(batches)
+    assert cache.captures == 2          # two batch sizes
+    # a batch that needs more slots than the recorded capacity re-records (forced here by shrinking the record's)
+    model = out[1][2]
+    slot = next(s for k, s in cache.slots.items() if k[1] == 128)
+    slot.cap = 8
+    l_c = model.loss(hubs.tolist(), torch.from_numpy(d.labels[hubs]).cuda())
+    assert cache.captures == 3 and not model.inter1.engine().overflow_since_reset()
+    eager = out[0][2]
+    l_e = eager.loss(hubs.tolist(), torch.from_numpy(d.labels[hubs]).cuda())
+    assert abs(l_c.item() - l_e.item()) <= 1e-4 * abs(l_e.item())     # (weights of the two runs agree to 1e-4)
+    assert out[0][2].inter1.graphs().replays == 0
+    # first loss equals the oracle's (own score table: selection may differ within an ulp of a distance)
+    pm = port.PortPCGNN(d.feat, d.graph, tp, params)
+    ref = pm.step_loss_backward(batches[0].tolist(), d.labels[batches[0]])
+    assert abs(out[1][0][0] - ref) <= 1e-4 * abs(ref)
+
+
+def test_cached_graph_follows_parameter_storage_changes():
+    """FusedAdam re-points every parameter into its flat buffer: the cached graph must notice (addresses change)."""
+    from pcgnn_b200.parallel import FusedAdam, GradAllReduce
+
+    d, rng, params, tp = _setup(seed=62)
+    nodes = rng.choice(d.idx_train, 96)
+    lab = torch.from_numpy(d.labels[nodes]).cuda()
+    model = build_cuda_pcgnn(d.feat, d.graph, tp, params)
+    l0 = model.loss(nodes.tolist(), lab)
+    l0.backward()
+    g0 = [p.grad.clone() for p in model.parameters() if p.requires_grad]
+    model.zero_grad()
+    reducer = GradAllReduce(model.parameters()).attach()
+    FusedAdam(reducer, lr=0.01)                               # parameters now live in another buffer
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.requires_grad:
+                p.mul_(1.5)
+    l1 = model.loss(nodes.tolist(), lab)
+    l1.backward()
+    ref = build_cuda_pcgnn(d.feat, d.graph, tp, params)
+    ref.inter1.graph_cache = False
+    with torch.no_grad():
+        for p in ref.parameters():
+            if p.requires_grad:
+                p.mul_(1.5)
+    l2 = ref.loss(nodes.tolist(), lab)
+    l2.backward()
+    assert abs(l1.item() - l2.item()) <= 1e-6 * abs(l2.item())
+    assert abs(l1.item() - l0.item()) > 1e-3                  # and it did see the new weights
+    for p, q in zip([p for p in model.parameters() if p.requires_grad], [p for p in ref.parameters() if p.requires_grad]):
+        assert rel_err(p.grad.cpu().numpy(), q.grad.cpu().numpy()) <= 1e-5
+    assert model.inter1.graphs().captures == 2
+
+
+def test_cached_eval_forward_equals_eager():
+    d, rng, params, tp = _setup(seed=63)
+    model = build_cuda_pcgnn(d.feat, d.graph, tp, params)
+    eager = build_cuda_pcgnn(d.feat, d.graph, tp, params)
+    eager.inter1.graph_cache = False
+    for B in (100, 100, 37):
+        nodes = rng.choice(d.idx_rest, B, replace=False)
+        labels = d.labels[nodes]                              # numpy, as utils.test passes them (utils.py:303)
+        with torch.no_grad():
+            a = model.to_prob(nodes.tolist(), labels, train_flag=False)
+            b = eager.to_prob(nodes.tolist(), labels, train_flag=False)
+        assert torch.allclose(a[0], b[0], rtol=1e-6, atol=1e-7) and torch.allclose(a[1], b[1], rtol=1e-6, atol=1e-7)
+        got, want = model.inter1.last_selection.lists(), eager.inter1.last_selection.lists()
+        assert all(np.array_equal(x, y) for x, y in zip(got, want))
+    assert model.inter1.graphs().replays == 3 and model.inter1.graphs().captures == 2
+
+
+def test_back_to_back_calls_do_not_race_their_uploads():
+    """No host sync between calls: every call must train on ITS batch. Cached loss() and
+    GraphedTrainStep.run() against the same steps with a sync after each."""
+    from pcgnn_b200.parallel import FusedAdam, GradAllReduce
+    from pcgnn_b200.runtime import GraphedTrainStep
+
+    d, rng, params, tp = _setup(seed=64)
+    B = 128
+    batches = [rng.choice(d.idx_train, B) for _ in range(12)]
+    # (a) cached reference-facing call
+    res = []
+    for sync in (True, False):
+        model = build_cuda_pcgnn(d.feat, d.graph, tp, params)
+        losses = []
+        for n in batches:
+            losses.append(model.loss(n.tolist(), d.labels[n]).detach())
+            if sync:
+                torch.cuda.synchronize()
+        res.append(torch.stack(losses).cpu().numpy())
+    assert np.array_equal(res[0], res[1])
+    # (b) GraphedTrainStep.run
+    res = []
+    for sync in (True, False):
+        model = build_cuda_pcgnn(d.feat, d.graph, tp, params)
+        reducer = GradAllReduce(model.parameters()).attach()
+        opt = FusedAdam(reducer, lr=0.01, weight_decay=1e-3)
+        eng = model.inter1.engine()
+        eng.set_features(model.inter1.features.weight)
+        cap = GraphedTrainStep.plan(eng, batches, model.inter1.thresholds, 0.5)
+        step = GraphedTrainStep(model, opt, B, cap, reducer=reducer, warmup_batch=(batches[0], d.labels[batches[0]]))
+        losses = []
+        for n in batches:
+            losses.append(step.run(n, d.labels[n]).clone())
+            if sync:
+                torch.cuda.synchronize()
+        res.append(torch.stack(losses).cpu().numpy())
+        assert not step.overflowed()
+    assert np.array_equal(res[0], res[1])
+
+
+def test_overflow_flag_is_sticky_across_replays():
+    from pcgnn_b200.parallel import FusedAdam, GradAllReduce
+    from pcgnn_b200.runtime import GraphedTrainStep
+
+    d, rng, params, tp = _setup(seed=65)
+    B = 64
+    deg = d.homo.degrees(0)
+    order = np.asarray(d.idx_train)[np.argsort(deg[d.idx_train])]
+    small, big = order[:B], order[-B:]
+    model = build_cuda_pcgnn(d.feat, d.graph, tp, params)
+    reducer = GradAllReduce(model.parameters()).attach()
+    opt = FusedAdam(reducer, lr=0.01)
+    eng = model.inter1.engine()
+    eng.set_features(model.inter1.features.weight)
+    cap = GraphedTrainStep.plan(eng, [small], model.inter1.thresholds, 0.5)       # too small for the hub batch
+    step = GraphedTrainStep(model, opt, B, cap, reducer=reducer, warmup_batch=(small, d.labels[small]))
+    step.run(small, d.labels[small])
+    assert not step.overflowed()
+    step.run(big, d.labels[big])              # overflows ...
+    step.run(small, d.labels[small])          # ... and a later, fitting replay must not hide it
+    assert step.overflowed()
+    assert not step.overflowed()              # reading clears it

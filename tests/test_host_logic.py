@@ -193,3 +193,54 @@ def test_from_scipy_applies_self_loops_and_symmetrisation():
         adj = ref_utils.sparse_to_adjlist_for_train(mats[1])
         for v in range(n):
             assert set(int(x) for x in adj[v]) == set(g.row(1, v).tolist())
+
+
+def test_bench_deals_every_target_once_and_balances_row_length():
+    """bench.deal: the ranks' shards partition the global batch, have equal sizes and near-equal neighbour counts."""
+    import bench
+
+    rng = np.random.default_rng(0)
+    weight = (rng.pareto(1.2, 5000) * 20 + 1).astype(np.int64)          # power-law row lengths
+    nodes = rng.integers(0, 5000, 1024)
+    labels = rng.integers(0, 2, 1024)
+    for world in (2, 4, 8):
+        parts = [bench.deal(nodes, labels, weight, r, world) for r in range(world)]
+        assert sorted(np.concatenate([p[0] for p in parts]).tolist()) == sorted(nodes.tolist())
+        assert all(len(p[0]) == 1024 // world for p in parts)
+        loads = np.array([weight[p[0]].sum() for p in parts], dtype=np.float64)
+        contiguous = np.array([weight[nodes[r * (1024 // world):(r + 1) * (1024 // world)]].sum() for r in range(world)])
+        assert loads.max() / loads.mean() <= contiguous.max() / contiguous.mean() + 1e-9
+        assert loads.max() - loads.min() <= weight[nodes].max()           # greedy dealing: off by at most one target
+        for (n, l) in parts:                                             # labels stay attached to their nodes
+            idx = [np.nonzero(nodes == v)[0] for v in n]
+            assert all(l[j] in labels[i] for j, i in enumerate(idx))
+
+
+def test_device_metrics_equal_sklearn():
+    """metrics.binary_metrics (the device-side replacement of the sklearn calls in utils.test, utils.py:316-325)."""
+    import torch
+    from sklearn.metrics import f1_score, precision_score, recall_score, roc_auc_score
+
+    from pcgnn_b200.metrics import binary_metrics
+
+    rng = np.random.default_rng(0)
+    for n, quant in ((500, None), (2000, 20), (64, 3)):
+        y = (rng.random(n) < 0.2).astype(np.int64)
+        s = np.clip(rng.normal(0.3 + 0.25 * y, 0.2), 0, 1)
+        if quant:
+            s = np.round(s * quant) / quant                  # many tied scores
+        pred = (s > 0.5).astype(np.int64)
+        m = binary_metrics(torch.from_numpy(s), torch.from_numpy(pred), torch.from_numpy(y))
+        assert abs(m["auc"] - roc_auc_score(y, s)) < 1e-12
+        assert abs(m["f1"] - f1_score(y, pred, zero_division=0)) < 1e-12
+        assert abs(m["f1_macro"] - f1_score(y, pred, average="macro", zero_division=0)) < 1e-12
+        assert abs(m["recall"] - recall_score(y, pred, zero_division=0)) < 1e-12
+        assert abs(m["precision"] - precision_score(y, pred, zero_division=0)) < 1e-12
+        assert abs(m["recall_macro"] - recall_score(y, pred, average="macro", zero_division=0)) < 1e-12
+        assert abs(m["precision_macro"] - precision_score(y, pred, average="macro", zero_division=0)) < 1e-12
+        assert abs(m["accuracy"] - (pred == y).mean()) < 1e-12
+    # degenerate: nothing predicted positive -> zero_division=0 convention
+    y = np.array([0, 1, 0, 1]); pred = np.zeros(4, dtype=np.int64); s = np.array([.1, .2, .3, .4])
+    m = binary_metrics(torch.from_numpy(s), torch.from_numpy(pred), torch.from_numpy(y))
+    assert m["f1"] == 0.0 and m["precision"] == 0.0 and m["recall"] == 0.0
+    assert abs(m["auc"] - roc_auc_score(y, s)) < 1e-12
