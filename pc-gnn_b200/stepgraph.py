@@ -39,11 +39,7 @@ class _ReplayLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_loss):
         scaled = ctx.flat * d_loss          # fresh tensor: the static buffer is rewritten by the next replay
-        outs = []
-        for off, shape in ctx.views:
-            n = int(np.prod(shape))
-            outs.append(scaled[off:off + n].view(shape))
-        return (None, None, None, *outs)
+        return (None, None, None, *[scaled[off:off + n].view(shape) for off, n, shape in ctx.views])
 
 
 class _Slot:
@@ -164,7 +160,7 @@ class StepGraphCache:
             slot.flat = torch.zeros(sum(pad), dtype=torch.float32, device=dev)
             slot.views, g, o = [], [], 0
             for p, n, q in zip(params, sizes, pad):
-                slot.views.append((o, tuple(p.shape)))
+                slot.views.append((o, n, tuple(p.shape)))
                 g.append(slot.flat[o:o + n].view_as(p))
                 o += q
             grads = dict(head=g[0], clf_w=g[1], clf_b=g[2], inter=g[3], intra=g[4:])
