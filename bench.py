@@ -202,7 +202,7 @@ def c_port_rate(data, batches, reps=3):
     return len(batches[0][0]) / best
 
 
-GCN_KERNELS_PER_STEP = 2   # select-all + aggregate (the GCN encoder/head are torch library GEMMs, as in the reference)
+GCN_KERNELS_PER_STEP = 7   # select-all, aggregate, encoder fwd, head+CE fwd, head+CE bwd, encoder bwd, exchange + Adam
 
 
 def build_cuda_pcgnn_device(feat_dev, graph, train_pos_dev, params, dev):

@@ -6,6 +6,13 @@
  * allocates or frees, and returns 0 on success or a non-zero cudaError_t-compatible code
  * (pcg_last_error() then holds the message; thread-local). The caller owns every buffer.
  *
+ * Process-wide state (all of it): the forked side streams / events of pcg_choose (created on first use, on the
+ * device that is current then), the probe results cached per kernel (shared-memory opt-in, 16-CTA clusters), the
+ * SM count, and the pcg_set_pdl switch. The library therefore drives ONE device per process from one host thread
+ * at a time, which is how the reference runs (single-threaded, src/model_handler.py:142-156) and how every
+ * multi-GPU run of this package is laid out (one process per GPU); pc-gnn_b200/engine.py refuses an engine for a
+ * device other than the current one.
+ *
  * The reference (h22hyeon/PC-GNN) is pure Python; each function below names the reference
  * lines whose work it replaces (paths relative to /root/reference/).
  *
@@ -44,6 +51,10 @@ PCG_API const char* pcg_last_error(void);
 PCG_API int pcg_version(void);
 /* SM count of the current device (grid sizing), or a negative error. */
 PCG_API int pcg_device_sms(void);
+/* Programmatic dependent launch for the step's linear kernel chain (score table -> pool sort, aggregate -> fused
+ * dense kernel -> weight gradients -> exchange + Adam): each kernel's prologue overlaps the tail of the kernel in
+ * front; results are only touched behind griddepcontrol.wait. Process-wide; returns the previous setting. */
+PCG_API int pcg_set_pdl(int enabled);
 
 /*
  * Label-aware score table, column 0 only: score[v] = dot(feat[v, :F], w) + b[0] for all N nodes (w, b
@@ -259,6 +270,22 @@ PCG_API int pcg_head_loss_fwd(const float* emb, int E, int B, const float* w, co
 PCG_API int pcg_head_loss_bwd(const float* emb, int E, int B, const float* w, const int64_t* labels, const float* p1,
                       const float* q1, float lambda, const float* d_loss, float* d_emb, float* d_center, float* d_w,
                       float* scratch, int32_t* ticket, pcg_stream_t stream);
+
+/*
+ * Encoder of the GraphSAGE / GCN baselines (src/graphsage.py:149 Encoder, :274 GCNEncoder):
+ *   out[e][i] = relu(sum_f w[e][f] * X[i][f]),  X = agg rows (GCN; GraphSAGE with gcn=True) or [feat[targets[i]] | agg]
+ *   (GraphSAGE with gcn=False, the cat of src/graphsage.py:145; pass feat/targets, else NULL), w [E, F or 2F].
+ * Backward: d_w [E, F or 2F] from d_out [E,B] (relu mask from out); deterministic two-stage reduction.
+ *   scratch  pcg_encoder_scratch_floats(B, F_in, E) floats; ticket: one int32, zero before the first call.
+ * The head and cross-entropy behind the encoder (src/graphsage.py:169, :176-178) are pcg_head_loss_fwd/_bwd with
+ * lambda = 0.
+ */
+PCG_API size_t pcg_encoder_scratch_floats(int B, int F_in, int E);
+PCG_API int pcg_encoder_fwd(const float* agg, int64_t lda, const float* feat, int64_t ldf, const int32_t* targets, int F,
+                    const float* w, int B, int E, float* out, pcg_stream_t stream);
+PCG_API int pcg_encoder_bwd(const float* agg, int64_t lda, const float* feat, int64_t ldf, const int32_t* targets, int F,
+                    int B, int E, const float* out, const float* d_out, float* d_w, float* scratch, int32_t* ticket,
+                    pcg_stream_t stream);
 
 /*
  * Label-balanced pick step, replay form: out[t] = idx_train[bisect_right(cum, u[t]*total, 0, n-1)],

@@ -32,6 +32,7 @@ SIGNATURES = {
     "pcg_last_error": (C.c_char_p, []),
     "pcg_version": (_i, []),
     "pcg_device_sms": (_i, []),
+    "pcg_set_pdl": (_i, [_i]),
     "pcg_score_table": (_i, [_p, _l, _i, _l, _p, _p, _p, _p, _i, _p, _p, _p, _p, _z, _p]),
     "pcg_sort_pool_workspace_bytes": (_z, [_i]),
     "pcg_sort_pool": (_i, [_p, _p, _i, _p, _p, _p, _p, _z, _p]),
@@ -58,6 +59,9 @@ SIGNATURES = {
     "pcg_center_bwd": (_i, [_p, _l, _i, _p, _i, _p, _p, _p, _p, _p, _p]),
     "pcg_head_loss_fwd": (_i, [_p, _i, _i, _p, _p, _p, C.c_float, _p, _p, _p, _p, _p, _p, _p]),
     "pcg_head_loss_bwd": (_i, [_p, _i, _i, _p, _p, _p, _p, C.c_float, _p, _p, _p, _p, _p, _p, _p]),
+    "pcg_encoder_scratch_floats": (_z, [_i, _i, _i]),
+    "pcg_encoder_fwd": (_i, [_p, _l, _p, _l, _p, _i, _p, _i, _i, _p, _p]),
+    "pcg_encoder_bwd": (_i, [_p, _l, _p, _l, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "pcg_comm_region_bytes": (_z, [_l]),
     "pcg_comm_alloc": (_i, [C.POINTER(_p), _z]),
     "pcg_comm_free": (_i, [_p]),

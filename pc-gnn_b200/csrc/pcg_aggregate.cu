@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(256) k_aggregate(const float* __restrict__ fea
     constexpr int G = 32 / LPR;          // rows per warp-wide load
     constexpr int UN = (LPR == 32) ? 8 : 4;      // row loads in flight per lane group (16 in flight were measured no faster)
     const int lane = threadIdx.x & 31;
+    pcg_launch_dependents();             // the fused dense kernel behind may start streaming its weights
     int64_t n_slots = status[ST_SLOTS];
     if (n_slots > cap_slots) n_slots = cap_slots;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;

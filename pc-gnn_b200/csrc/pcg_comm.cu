@@ -45,6 +45,7 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 __global__ void __launch_bounds__(COMM_NT) k_allreduce_adam(CommP p) {
     __shared__ float s_c[2];              // step size, 1 / sqrt(bias correction 2)
     const int tid = threadIdx.x, c = blockIdx.x;
+    pcg_grid_dependency_wait();           // the weight-gradient kernel in front of this one is complete
     const uint32_t e = *(volatile uint32_t*)p.epoch + 1u;      // this step's number (1-based)
     const int i0 = c * COMM_PER_CTA + tid * 4;
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -177,7 +178,9 @@ extern "C" int pcg_allreduce_adam(float* grad, float* param, float* m, float* v,
     }
     p.epoch = epoch; p.ticket = ticket; p.rank = rank; p.world = world;
     p.lr = lr; p.b1 = beta1; p.b2 = beta2; p.eps = eps; p.wd = weight_decay; p.do_adam = do_adam;
-    k_allreduce_adam<<<(unsigned)(p.n_pad / COMM_PER_CTA), COMM_NT, 0, stream>>>(p);
+    cudaError_t le = pcg_launch(k_allreduce_adam, dim3((unsigned)(p.n_pad / COMM_PER_CTA)), dim3(COMM_NT), 0, stream,
+                                pcg_pdl_enabled() != 0, p);
+    if (le != cudaSuccess) { pcg_set_error("pcg_allreduce_adam: launch: %s", cudaGetErrorString(le)); return (int)le; }
     return pcg_check_launch("pcg_allreduce_adam");
 }
 

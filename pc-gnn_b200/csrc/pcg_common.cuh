@@ -23,6 +23,31 @@
 void pcg_set_error(const char* fmt, ...);
 int pcg_check_launch(const char* what);
 
+// Programmatic dependent launch (PDL): when enabled (pcg_set_pdl), the kernels of the step's linear chain are
+// launched with programmaticStreamSerializationAllowed, so a kernel's CTAs may become resident while the kernel in
+// front of it on the stream drains; each of them executes griddepcontrol.wait before it touches that kernel's
+// results (a no-op for launches without the attribute), and the kernels in front call
+// griddepcontrol.launch_dependents as soon as they start.
+int pcg_pdl_enabled();
+__device__ __forceinline__ void pcg_grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pcg_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+static inline cudaError_t pcg_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 #define PCG_REQUIRE(cond, ...)            \
     do {                                  \
         if (!(cond)) {                    \

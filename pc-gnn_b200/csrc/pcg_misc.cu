@@ -24,6 +24,14 @@ int pcg_check_launch(const char* what) {
 }
 
 extern "C" const char* pcg_last_error(void) { return g_err; }
+
+static int g_pdl = 0;
+int pcg_pdl_enabled() { return g_pdl; }
+extern "C" int pcg_set_pdl(int enabled) {
+    const int old = g_pdl;
+    g_pdl = enabled ? 1 : 0;
+    return old;
+}
 extern "C" int pcg_version(void) { return 100; }
 
 // ------------------------------------------------------------------------------- score table
@@ -34,6 +42,7 @@ extern "C" int pcg_version(void) { return 100; }
 __global__ void __launch_bounds__(256) k_score_table(const float* __restrict__ feat, int64_t n, int F, int64_t ldf,
                                                      const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ score) {
     extern __shared__ float sw[];
+    pcg_launch_dependents();                 // the pool sort behind this kernel may start its prologue
     for (int c = threadIdx.x; c < ldf; c += blockDim.x) sw[c] = c < F ? w[c] : 0.f;
     const float bias = b ? b[0] : 0.f;
     __syncthreads();
@@ -91,6 +100,7 @@ __global__ void __launch_bounds__(RANK_NT) k_sort_pool_rank(const float* __restr
                                                             float* __restrict__ ps_score, int32_t* __restrict__ ps_pos,
                                                             int32_t* __restrict__ ps_id) {
     extern __shared__ unsigned long long keys[];
+    pcg_grid_dependency_wait();              // the score table in front of this kernel is complete
     // stage all keys: ids first, then the dependent score gathers, 8 of each in flight per thread
     for (int base = 0; base < P; base += RANK_NT * 8) {
         int32_t id[8];
@@ -166,7 +176,9 @@ static int sort_pool_impl(const float* pool_score, int gather, const int32_t* po
             if (e != cudaSuccess) { pcg_set_error("pcg_sort_pool: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
             configured = true;
         }
-        k_sort_pool_rank<<<(P + RANK_PER - 1) / RANK_PER, RANK_NT, smem, stream>>>(pool_score, gather, pool, P, ps_score, ps_pos, ps_id);
+        cudaError_t le = pcg_launch(k_sort_pool_rank, dim3((P + RANK_PER - 1) / RANK_PER), dim3(RANK_NT), smem, stream,
+                                    gather && pcg_pdl_enabled(), pool_score, gather, pool, P, ps_score, ps_pos, ps_id);
+        if (le != cudaSuccess) { pcg_set_error("pcg_sort_pool: launch: %s", cudaGetErrorString(le)); return (int)le; }
         return 0;
     }
     const size_t a = align256((size_t)P * 4);

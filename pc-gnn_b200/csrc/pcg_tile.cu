@@ -89,8 +89,7 @@ __device__ __forceinline__ void bulk_g2s(float* dst_smem, const float* src, uint
                  ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TILE_NWC * 32) : "memory"); }
-__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void grid_dependency_wait() { pcg_grid_dependency_wait(); }
 
 __host__ __device__ __forceinline__ int ld_pad(int x) { return x + ((4 - (x & 15)) & 15); }   // multiple of 4 -> = 4 (mod 16)
 
@@ -180,6 +179,7 @@ __global__ void __launch_bounds__(TILE_NT, 1) k_tile(TileP p) {
     const int nchA = (2 * Fp + TILE_KC - 1) / TILE_KC, nchB = (K2p + TILE_KC - 1) / TILE_KC, nchD = E / TILE_KC;
 
     TTRACE(0);
+    pcg_launch_dependents();                 // the weight-gradient kernel's CTAs may queue up behind this tile
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], TILE_NWC); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -402,16 +402,24 @@ __global__ void __launch_bounds__(TILE_NT, 1) k_tile(TileP p) {
                 const int g = my_task / tpg, rem = my_task - g * tpg, rb = rem / CB, cb = rem - rb * CB;
                 float* d0 = dst + (size_t)g * dst_stride + (size_t)(rb * 8 + 2 * lr) * ld + cb * 64 + lc * 4;
                 const int per = 16 / ksplit;
-                for (int jj = 0; jj < per; ++jj) {
-                    const int j = my_ks * per + jj;
+                // slot j of a lane: row (j >> 3), columns 32 * ((j >> 2) & 1) + (j & 3) of its 2 x 8 block: slots come
+                // in groups of 4 consecutive columns (one float4 store) unless the task has 8 splits (2 slots each)
+                auto slot_sum = [&](int j) {
                     float v[8];
 #pragma unroll
                     for (int q = 0; q < 8; ++q) v[q] = q < ksplit ? sc[((size_t)(my_task + q * ntask) * 16 + j) * 32 + lane] : 0.f;
                     float a = v[0];
 #pragma unroll
                     for (int q = 1; q < 8; ++q) if (q < ksplit) a += v[q];
-                    // slot j of a lane: row (j >> 3), columns 32 * ((j >> 2) & 1) + (j & 3) of its 2 x 8 block
-                    d0[(size_t)(j >> 3) * ld + 32 * ((j >> 2) & 1) + (j & 3)] = fmaxf(a, 0.f);
+                    return fmaxf(a, 0.f);
+                };
+                if (per >= 4) {
+                    for (int j = my_ks * per; j < (my_ks + 1) * per; j += 4)
+                        *reinterpret_cast<float4*>(d0 + (size_t)(j >> 3) * ld + 32 * ((j >> 2) & 1)) =
+                            make_float4(slot_sum(j), slot_sum(j + 1), slot_sum(j + 2), slot_sum(j + 3));
+                } else {
+                    for (int j = my_ks * per; j < (my_ks + 1) * per; ++j)
+                        d0[(size_t)(j >> 3) * ld + 32 * ((j >> 2) & 1) + (j & 3)] = slot_sum(j);
                 }
             }
         }
@@ -674,6 +682,7 @@ __global__ void __launch_bounds__(256) k_wgrad(WgP p) {
     const int rows = job == 0 ? K2p : 2 * p.Fp;
     const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
     if (m0 >= rows) return;                 // the whole cluster leaves (same tile for all its CTAs)
+    pcg_launch_dependents();                // the exchange + Adam kernel may queue up
     grid_dependency_wait();
     const int per = (p.B + S - 1) / S;
     const int kb = min(p.B, split * per), ke = min(p.B, kb + per);
@@ -900,6 +909,7 @@ extern "C" int pcg_tile_train(const float* feat, int64_t ldf, int F, const int32
     p.partial = scratch + ts.partial;
     size_t smem;
     const int tm = tile_plan(B, F, R, E, 2, &p.nstage, &smem);
+    pdl = pdl || pcg_pdl_enabled();
     cudaError_t e = launch_tile_any(tm, p, smem, stream, pdl);
     if (e != cudaSuccess) { pcg_set_error("pcg_tile_train: launch: %s", cudaGetErrorString(e)); return (int)e; }
 

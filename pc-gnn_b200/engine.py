@@ -553,6 +553,29 @@ class Engine:
         _lib.check(rc, "pcg_dense_bwd")
         return d_intra, d_inter
 
+    # ------------------------------------------------------------------ GraphSAGE / GCN encoder (csrc/pcg_homo.cu)
+    def encoder_fwd(self, agg, w, targets=None):
+        """out [E,B] = relu(W @ X^T), X = agg rows or [feat[targets] | agg] (``pcg_encoder_fwd``)."""
+        B, E = int(agg.shape[0]), int(w.shape[0])
+        out = torch.empty((E, B), dtype=torch.float32, device=self.device)
+        rc = self.lib.pcg_encoder_fwd(agg.data_ptr(), agg.stride(0), self.feat.data_ptr() if targets is not None else None,
+                                      self.ldf, _lib.ptr(targets), self.F, w.data_ptr(), B, E, out.data_ptr(),
+                                      _lib.stream_ptr())
+        _lib.check(rc, "pcg_encoder_fwd")
+        return out
+
+    def encoder_bwd(self, agg, out, d_out, targets=None, sink=None):
+        """d_w [E, F or 2F] of the encoder (``pcg_encoder_bwd``)."""
+        B, E = int(agg.shape[0]), int(out.shape[0])
+        f_in = self.F * (2 if targets is not None else 1)
+        d_w = sink if sink is not None else torch.empty((E, f_in), dtype=torch.float32, device=self.device)
+        scratch = torch.empty(int(self.lib.pcg_encoder_scratch_floats(B, f_in, E)), dtype=torch.float32, device=self.device)
+        rc = self.lib.pcg_encoder_bwd(agg.data_ptr(), agg.stride(0), self.feat.data_ptr() if targets is not None else None,
+                                      self.ldf, _lib.ptr(targets), self.F, B, E, out.data_ptr(), d_out.contiguous().data_ptr(),
+                                      d_w.data_ptr(), scratch.data_ptr(), self._tickets()[3:].data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "pcg_encoder_bwd")
+        return d_w
+
     # ------------------------------------------------------------------ heads
     def _tickets(self):
         if getattr(self, "_ticket_buf", None) is None:

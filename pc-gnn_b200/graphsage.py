@@ -25,6 +25,51 @@ from .graph import RelGraph
 from .layers import _AggregateFn, _feature_table
 
 
+class _EncoderFn(torch.autograd.Function):
+    """relu(W @ X^T) -> [E,B] with X = aggregated rows (or [self | aggregate]) as one kernel per direction
+    (``pcg_encoder_fwd`` / ``_bwd``); frozen feature table (model_handler.py:85-86). Reference: graphsage.py:145-149,
+    :274."""
+
+    @staticmethod
+    def forward(ctx, engine, agg, targets, weight):
+        weight = weight.contiguous()
+        out = engine.encoder_fwd(agg, weight, targets)
+        ctx.engine, ctx.targets, ctx.w_ptr = engine, targets, weight.data_ptr()
+        ctx.save_for_backward(agg, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        agg, out = ctx.saved_tensors
+        eng = ctx.engine
+        sink = eng.grad_sink.get(ctx.w_ptr) if eng.grad_sink is not None else None
+        d_w = eng.encoder_bwd(agg, out, d_out, ctx.targets, sink)
+        return None, None, None, (None if sink is not None else d_w)
+
+
+def _encode(enc, nodes, with_self):
+    """Shared forward of Encoder / GCNEncoder: aggregate, then the encoder kernel when the feature table is frozen
+    (the reference's setup) or the torch ops when it trains."""
+    agg_mod = enc.aggregator
+    neigh_feats = agg_mod.forward(nodes, _Rows(len(nodes)))
+    eng = agg_mod._engine
+    table = getattr(enc.features, "weight", None)
+    native = (eng is not None and isinstance(table, torch.Tensor) and not table.requires_grad and neigh_feats.is_cuda
+              and agg_mod.last_targets is not None and neigh_feats.shape[0] > 0 and neigh_feats.shape[1] == eng.F
+              and (enc.weight.shape[1] * (eng.ldf + 33) + enc.weight.numel()) * 4 <= 190 * 1024)
+    if native:
+        full = agg_mod.last_agg          # [B, ldf] as the kernel wrote it (row stride ldf)
+        return _EncoderFn.apply(eng, full, agg_mod.last_targets if with_self else None, enc.weight)
+    if with_self:
+        dev = neigh_feats.device
+        index = nodes.to(dev) if isinstance(nodes, torch.Tensor) else torch.as_tensor(
+            np.asarray([int(v) for v in nodes]), device=dev, dtype=torch.long)
+        combined = torch.cat((enc.features(index.long()), neigh_feats), dim=1)
+    else:
+        combined = neigh_feats
+    return F.relu(enc.weight.mm(combined.t()))
+
+
 class _Rows:
     """Stand-in for the list of neighbour sets the reference builds per batch
     (`[self.adj_lists[int(node)] for node in nodes]`, graphsage.py:133, 267): the kernels read the
@@ -50,6 +95,7 @@ class _RowAggregator(nn.Module):
         self._engine = None
         self.cap_slots_hint = None      # fixed slot capacity (CUDA-graph use); else sized from the host ids
         self.last_selection = None
+        self.last_agg = self.last_targets = None    # the padded aggregate / device ids of the last call (encoder kernels)
 
     def bind_graph(self, adj_lists):
         """Give the aggregator the graph its rows come from (the encoders call this once)."""
@@ -78,6 +124,7 @@ class _RowAggregator(nn.Module):
         sel = eng.select_all(targets, add_self, cap, self._norm)
         self.last_selection = sel
         agg = _AggregateFn.apply(table, eng, sel, table.shape[1]) if table.requires_grad else eng.aggregate(sel)
+        self.last_agg, self.last_targets = agg, (targets if n_table is None else None)
         return agg[:, :table.shape[1]]
 
     def _aggregate(self, nodes, to_neighs, add_self):
@@ -173,15 +220,7 @@ class Encoder(nn.Module):
         init.xavier_uniform_(self.weight)
 
     def forward(self, nodes):
-        neigh_feats = self.aggregator.forward(nodes, _Rows(len(nodes)))
-        if not self.gcn:
-            dev = neigh_feats.device
-            index = nodes.to(dev) if isinstance(nodes, torch.Tensor) else torch.as_tensor(
-                np.asarray([int(v) for v in nodes]), device=dev, dtype=torch.long)
-            combined = torch.cat((self.features(index.long()), neigh_feats), dim=1)
-        else:
-            combined = neigh_feats
-        return F.relu(self.weight.mm(combined.t()))
+        return _encode(self, nodes, with_self=not self.gcn)
 
 
 class GCNEncoder(nn.Module):
@@ -204,8 +243,7 @@ class GCNEncoder(nn.Module):
         init.xavier_uniform_(self.weight)
 
     def forward(self, nodes):
-        neigh_feats = self.aggregator.forward(nodes, _Rows(len(nodes)))
-        return F.relu(self.weight.mm(neigh_feats.t()))
+        return _encode(self, nodes, with_self=False)
 
 
 class _Head(nn.Module):
@@ -221,7 +259,18 @@ class _Head(nn.Module):
         return self.weight.mm(embeds).t()
 
     def loss(self, nodes, labels):
-        return self.xent(self.forward(nodes), labels.squeeze())
+        embeds = self.enc(nodes)
+        eng = getattr(self.enc.aggregator, "_engine", None)
+        if (eng is not None and embeds.is_cuda and self.weight.shape[0] == 2 and embeds.shape[1] > 0
+                and isinstance(self.xent, nn.CrossEntropyLoss) and isinstance(embeds.grad_fn, _EncoderFn._backward_cls)):
+            # head + cross-entropy as one kernel per direction (pcg_head_loss_*, lambda = 0: no label-similarity term)
+            from .layers import HeadLossFn, _as_device_labels
+
+            lab = _as_device_labels(labels, embeds.device)
+            center = torch.zeros((embeds.shape[1], 2), dtype=torch.float32, device=embeds.device)
+            loss, _ = HeadLossFn.apply(eng, embeds, self.weight, center, lab, 0.0)
+            return loss
+        return self.xent(self.weight.mm(embeds).t(), labels.squeeze())
 
 
 class GraphSage(_Head):

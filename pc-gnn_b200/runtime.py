@@ -21,12 +21,13 @@ class GraphedTrainStep:
     (hot path: ``model.enc.aggregator``); optimizer must be capturable (e.g. Adam(capturable=True, fused=True))."""
 
     def __init__(self, model, optimizer, batch_size: int, cap_slots: int, reducer=None, world: int = 1,
-                 warmup_batch=None):
+                 warmup_batch=None, use_pdl: bool = True):
         """optimizer: a capturable torch optimizer (gradient mean over ranks by NCCL between two graphs), or a
         ``parallel.FusedAdam`` (gradient exchange over peer memory + Adam inside the one step graph)."""
         from .engine import PinnedStaging
         from .parallel import FusedAdam
 
+        self.use_pdl = bool(use_pdl)
         self.fused = isinstance(optimizer, FusedAdam)
         self.model, self.opt, self.B = model, optimizer, int(batch_size)
         self.reducer, self.world = reducer, world
@@ -97,6 +98,16 @@ class GraphedTrainStep:
         return loss.detach()
 
     def _capture(self):
+        # programmatic dependent launch for the kernels recorded below (see include/pcgnn_b200.h: pcg_set_pdl)
+        from . import _lib
+
+        prev = _lib.lib().pcg_set_pdl(1 if self.use_pdl else 0)
+        try:
+            self._capture_graphs()
+        finally:
+            _lib.lib().pcg_set_pdl(prev)
+
+    def _capture_graphs(self):
         s = torch.cuda.Stream(device=self.dev)
         s.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(s):       # warm-up on a side stream (allocator, lazy inits, cuBLAS handles)

@@ -124,15 +124,20 @@ class StepGraphCache:
     @staticmethod
     def _capture(fn, dev):
         """Two eager runs on a side stream (allocator, lazy attribute setup), then the recording."""
-        s = torch.cuda.Stream(device=dev)
-        s.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(s):
-            for _ in range(2):
-                fn()
-        torch.cuda.current_stream(dev).wait_stream(s)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            out = fn()
+        lib = _lib.lib()
+        prev = lib.pcg_set_pdl(1)             # programmatic dependent launch inside the recorded chain
+        try:
+            s = torch.cuda.Stream(device=dev)
+            s.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(s):
+                for _ in range(2):
+                    fn()
+            torch.cuda.current_stream(dev).wait_stream(s)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = fn()
+        finally:
+            lib.pcg_set_pdl(prev)
         return g, out
 
     # ------------------------------------------------------------------ training step

@@ -467,3 +467,41 @@ def test_fused_adam_train_step_follows_torch_adam():
     assert np.allclose(l0, l1, rtol=5e-5, atol=0)
     for k in p0:
         assert rel_err(p1[k], p0[k]) <= 5e-3, k
+
+
+@pytest.mark.parametrize("concat_self", [False, True])
+def test_sage_encoder_native_kernels(concat_self):
+    """GraphSAGE encoder with and without the self half (graphsage.py:145-149) through pcg_encoder_* and the
+    head + cross-entropy through pcg_head_loss_* (lambda = 0): no torch / cuBLAS op on the path."""
+    import torch.nn as nn
+    from pcgnn_b200 import graphsage as gs
+    from pcgnn_b200.synth import make_graph
+
+    d = make_graph("tiny_amz", seed=49)
+    rng = np.random.default_rng(6)
+    F_, E = d.feat.shape[1], 48
+    enc_w = port.xavier(rng, E, 2 * F_ if concat_self else F_)
+    head = port.xavier(rng, 2, E)
+    nodes = rng.choice(d.idx_train, 70).tolist()
+    labels = d.labels[nodes]
+    features = nn.Embedding(*d.feat.shape)
+    features.weight = nn.Parameter(torch.from_numpy(d.feat), requires_grad=False)
+    features = features.cuda()
+    enc = gs.Encoder(features, F_, E, d.homo, gs.MeanAggregator(features, cuda=True), gcn=not concat_self, cuda=True)
+    model = gs.GraphSage(2, enc)
+    with torch.no_grad():
+        enc.weight.copy_(torch.from_numpy(enc_w))
+        model.weight.copy_(torch.from_numpy(head))
+    model = model.cuda()
+    loss = model.loss(nodes, torch.from_numpy(labels).cuda())
+    assert type(loss.grad_fn).__name__.startswith("HeadLossFn")
+    loss.backward()
+    pm = port.PortSAGE(d.feat, d.homo, enc_w, head, concat_self=concat_self)
+    ref = pm.loss(nodes, labels)
+    ref.backward()
+    assert abs(loss.item() - float(ref)) <= TOL * abs(float(ref))
+    assert rel_err(model.weight.grad.cpu().numpy(), pm.head.grad.numpy()) <= GTOL
+    assert rel_err(enc.weight.grad.cpu().numpy(), pm.enc_w.grad.numpy()) <= GTOL
+    with torch.no_grad():
+        emb = enc(nodes)
+    assert rel_err(emb.cpu().numpy(), pm.last["combined"].detach().numpy()) <= TOL

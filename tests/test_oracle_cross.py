@@ -80,6 +80,9 @@ def test_bench_reference_arm_other_ranks_stay_silent(monkeypatch):
     assert out.returncode == 0 and out.stdout.strip() == ""
 
 
-def test_bench_reference_arm_says_unavailable_for_the_device_only_graph():
-    line = _run_bench("--impl", "reference", "--workload", "big")
-    assert line["impl"] == "reference" and "unavailable" in line
+def test_bench_reference_arm_runs_the_partitioned_graph_on_batch_rows():
+    """C5: the CPU arm materialises only the batch targets' rows (all the reference reads, layers.py:219)."""
+    line = _run_bench("--impl", "reference", "--workload", "big", "--nodes-per-gpu", "20000", "--cpu-sample", "16",
+                      "--steps", "1", "--warmup", "0")
+    assert line["impl"] == "reference" and line["value"] > 0 and "unavailable" not in line
+    assert "batch rows" in line["cpu_baseline"]["sample"]
