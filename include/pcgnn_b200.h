@@ -53,8 +53,9 @@ PCG_API int pcg_version(void);
 PCG_API int pcg_device_sms(void);
 /* Programmatic dependent launch for the step's linear kernel chain (score table -> pool sort, aggregate -> fused
  * dense kernel -> weight gradients -> exchange + Adam): each kernel's prologue overlaps the tail of the kernel in
- * front; results are only touched behind griddepcontrol.wait. Process-wide; returns the previous setting. */
-PCG_API int pcg_set_pdl(int enabled);
+ * front; results are only touched behind griddepcontrol.wait. `mask` selects the dependent launches: 1 pool sort,
+ * 2 fused dense kernel, 4 weight gradients, 8 exchange + Adam. Process-wide; returns the previous setting. */
+PCG_API int pcg_set_pdl(int mask);
 
 /*
  * Label-aware score table, column 0 only: score[v] = dot(feat[v, :F], w) + b[0] for all N nodes (w, b

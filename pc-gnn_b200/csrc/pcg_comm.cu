@@ -179,7 +179,7 @@ extern "C" int pcg_allreduce_adam(float* grad, float* param, float* m, float* v,
     p.epoch = epoch; p.ticket = ticket; p.rank = rank; p.world = world;
     p.lr = lr; p.b1 = beta1; p.b2 = beta2; p.eps = eps; p.wd = weight_decay; p.do_adam = do_adam;
     cudaError_t le = pcg_launch(k_allreduce_adam, dim3((unsigned)(p.n_pad / COMM_PER_CTA)), dim3(COMM_NT), 0, stream,
-                                pcg_pdl_enabled() != 0, p);
+                                (pcg_pdl_enabled() & 8) != 0, p);
     if (le != cudaSuccess) { pcg_set_error("pcg_allreduce_adam: launch: %s", cudaGetErrorString(le)); return (int)le; }
     return pcg_check_launch("pcg_allreduce_adam");
 }

@@ -29,7 +29,7 @@ static int g_pdl = 0;
 int pcg_pdl_enabled() { return g_pdl; }
 extern "C" int pcg_set_pdl(int enabled) {
     const int old = g_pdl;
-    g_pdl = enabled ? 1 : 0;
+    g_pdl = enabled;
     return old;
 }
 extern "C" int pcg_version(void) { return 100; }
@@ -177,7 +177,7 @@ static int sort_pool_impl(const float* pool_score, int gather, const int32_t* po
             configured = true;
         }
         cudaError_t le = pcg_launch(k_sort_pool_rank, dim3((P + RANK_PER - 1) / RANK_PER), dim3(RANK_NT), smem, stream,
-                                    gather && pcg_pdl_enabled(), pool_score, gather, pool, P, ps_score, ps_pos, ps_id);
+                                    gather && (pcg_pdl_enabled() & 1), pool_score, gather, pool, P, ps_score, ps_pos, ps_id);
         if (le != cudaSuccess) { pcg_set_error("pcg_sort_pool: launch: %s", cudaGetErrorString(le)); return (int)le; }
         return 0;
     }

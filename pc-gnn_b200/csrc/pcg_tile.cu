@@ -909,8 +909,8 @@ extern "C" int pcg_tile_train(const float* feat, int64_t ldf, int F, const int32
     p.partial = scratch + ts.partial;
     size_t smem;
     const int tm = tile_plan(B, F, R, E, 2, &p.nstage, &smem);
-    pdl = pdl || pcg_pdl_enabled();
-    cudaError_t e = launch_tile_any(tm, p, smem, stream, pdl);
+    const int mask = pcg_pdl_enabled() | (pdl ? 6 : 0);
+    cudaError_t e = launch_tile_any(tm, p, smem, stream, (mask & 2) != 0);
     if (e != cudaSuccess) { pcg_set_error("pcg_tile_train: launch: %s", cudaGetErrorString(e)); return (int)e; }
 
     WgP w = {};
@@ -934,7 +934,7 @@ extern "C" int pcg_tile_train(const float* feat, int64_t ldf, int F, const int32
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 2 : 1;
+    cfg.numAttrs = (mask & 4) ? 2 : 1;
     e = cudaLaunchKernelEx(&cfg, k_wgrad, w);
     if (e != cudaSuccess) { pcg_set_error("pcg_tile_train: wgrad launch: %s", cudaGetErrorString(e)); return (int)e; }
     return pcg_check_launch("pcg_tile_train");

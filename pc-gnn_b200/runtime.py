@@ -98,10 +98,16 @@ class GraphedTrainStep:
         return loss.detach()
 
     def _capture(self):
-        # programmatic dependent launch for the kernels recorded below (see include/pcgnn_b200.h: pcg_set_pdl)
+        # programmatic dependent launch for the kernels recorded below (see include/pcgnn_b200.h: pcg_set_pdl).
+        # Measured on C2 (profiles/README.md): the fused dense kernel and the exchange + Adam kernel gain from starting
+        # under the tail of the kernel in front (mask 2 | 8: 91.2 -> 87.8 us per replay); the cluster-launched
+        # weight-gradient kernel and the pool sort lose (mask 4: +10 us), so they keep full dependencies.
         from . import _lib
 
-        prev = _lib.lib().pcg_set_pdl(1 if self.use_pdl else 0)
+        import os
+
+        mask = int(os.environ.get("PCG_PDL_MASK", "10")) if self.use_pdl else 0
+        prev = _lib.lib().pcg_set_pdl(mask)
         try:
             self._capture_graphs()
         finally:

@@ -125,7 +125,7 @@ class StepGraphCache:
     def _capture(fn, dev):
         """Two eager runs on a side stream (allocator, lazy attribute setup), then the recording."""
         lib = _lib.lib()
-        prev = lib.pcg_set_pdl(1)             # programmatic dependent launch inside the recorded chain
+        prev = lib.pcg_set_pdl(2)             # programmatic dependent launch of the fused dense kernel (see pcg_set_pdl)
         try:
             s = torch.cuda.Stream(device=dev)
             s.wait_stream(torch.cuda.current_stream(dev))
