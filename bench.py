@@ -705,7 +705,7 @@ def main():
             return gstep.run_device(dev_nodes[i], dev_labels[i])
 
         def step_host(i):
-            return gstep.run(host_nodes[i], host_labels[i]).item()     # H2D ids+labels, replay, D2H loss
+            return gstep.run_item(shards[i][0], host_labels[i])        # host numpy ids + labels: H2D, replay, D2H loss
     else:
         step_device, step_host = step_device_eager, step_host_eager
 
@@ -780,8 +780,8 @@ def main():
         total_nodes = global_batch * K
         io = {"h2d_bytes_per_step": batch * 4 + batch * 8, "d2h_bytes_per_step": 4}
         e2e_graph = {"value": total_nodes / (ms_graph_host / 1e3), "unit": "target-nodes/s", "ms_per_step": ms_graph_host / K,
-                     "call": "runtime.GraphedTrainStep.run(list_of_ids, numpy_labels).item()  (pinned staging, H2D, one "
-                             "graph replay, D2H of the loss)", **io}
+                     "call": "runtime.GraphedTrainStep.run_item(numpy_ids, numpy_labels) -> float  (one pinned staging copy, "
+                             "one H2D, one graph replay, D2H of the loss through a pinned word)", **io}
         line = {
             "metric": "train target-nodes/sec (fwd+bwd)", "value": total_nodes / (ms_dev / 1e3),
             "unit": "target-nodes/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev / K,

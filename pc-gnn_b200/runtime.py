@@ -41,12 +41,15 @@ class GraphedTrainStep:
             model.inter1.scores_external = True
         if hasattr(model, "inter1"):
             model.inter1.center_on_side_stream = True
-        self.nodes = torch.zeros(self.B, dtype=torch.int32, device=dev)
-        self.labels = torch.zeros(self.B, dtype=torch.int64, device=dev)
-        # rings of pinned buffers guarded by events: back-to-back run() calls never rewrite a buffer whose
-        # host-to-device copy is still queued behind the previous replay
-        self.pin_nodes = PinnedStaging(self.B, torch.int32)
-        self.pin_labels = PinnedStaging(self.B, torch.int64)
+        # ids and labels of a step share ONE static device buffer ([B int64 labels | B int32 ids]) so that a host batch
+        # is one pinned staging copy + one H2D; the pinned buffers form a ring guarded by events: back-to-back run()
+        # calls never rewrite a buffer whose copy is still queued behind the previous replay
+        self._packed = torch.zeros(3 * self.B, dtype=torch.int32, device=dev)
+        self.labels = self._packed[:2 * self.B].view(torch.int64)
+        self.nodes = self._packed[2 * self.B:]
+        self._pin = PinnedStaging(3 * self.B, torch.int32)
+        self._pin_loss = torch.zeros(1, dtype=torch.float32, pin_memory=True)
+        self._loss_event = torch.cuda.Event()
         self.loss = None
         if reducer is not None:
             # the captured graph writes the gradients through the parameters' .grad tensors: they must BE the views
@@ -192,10 +195,23 @@ class GraphedTrainStep:
         return self._replay()
 
     def run(self, nodes, labels):
-        """Batch on the host (list / numpy of ids, numpy labels): pinned staging + H2D + replay."""
-        self.pin_nodes.upload(np.asarray(nodes, dtype=np.int32), self.nodes)
-        self.pin_labels.upload(np.asarray(labels, dtype=np.int64), self.labels)
+        """Batch on the host (numpy arrays, or lists, of ids and labels): one pinned staging copy + one H2D + replay.
+        Returns the (device) loss tensor."""
+        B = self.B
+        host = np.empty(3 * B, dtype=np.int32)
+        host[:2 * B].view(np.int64)[:] = labels
+        host[2 * B:] = nodes
+        self._pin.upload(host, self._packed)
         return self._replay()
+
+    def run_item(self, nodes, labels) -> float:
+        """``run`` + the loss as a Python float (device->host through a pinned word and an event; cheaper than
+        ``.item()``'s pageable copy)."""
+        loss = self.run(nodes, labels)
+        self._pin_loss.copy_(loss.reshape(1), non_blocking=True)
+        self._loss_event.record(torch.cuda.current_stream(self.dev))
+        self._loss_event.synchronize()
+        return float(self._pin_loss[0])
 
     def overflowed(self) -> bool:
         """True if ANY replay since the last call needed more slots than the captured capacity (its results were
