@@ -4,12 +4,15 @@
 // parameters (/root/reference/src/model_handler.py:124, 153). Data parallel over the batch's targets needs one
 // exchange per step: the sum of the small parameter gradient. With NCCL that is a separate, latency-bound
 // collective between two CUDA graphs plus torch's multi-tensor Adam; here every rank
-//   1. copies its flat gradient into a send buffer that all peers have mapped (CUDA IPC, NVLink / NVSwitch),
-//   2. raises a per-CTA flag in every peer's flag area (st.release.sys) and waits for the peers' flags,
-//   3. reads the peers' chunks straight over NVLink, adds them in RANK ORDER (every rank computes bit-identical
+//   1. PUSHES its flat gradient into its slot of every peer's receive area (peer memory mapped by CUDA IPC: plain
+//      16-byte stores over NVLink / NVSwitch, posted, no round trip),
+//   2. raises a per-CTA flag in every peer (st.release.sys) and waits for the peers' flags,
+//   3. adds the world's slots of its OWN receive area (local reads) in RANK ORDER (every rank computes bit-identical
 //      sums, so the replicas never drift) and divides by the world size,
 //   4. applies the Adam update (same formula as torch.optim.Adam with L2 weight decay) to its replica of the
 //      parameters and clears the gradient for the next step,
+// (Round 1 / early round 2 PULLED: flag, then a read of every peer's send buffer: one NVLink round trip per peer,
+// and those reads were issued one after the other: ~20 us at 8 GPUs against 5 us for the Adam part alone.)
 // all inside the captured step graph. world == 1 runs steps 4 only.
 #include "pcg_common.cuh"
 
@@ -23,8 +26,8 @@ struct CommP {
     float* m;
     float* v;
     int n;
-    int64_t n_pad;                        // floats per send buffer (two of them, double buffered by step parity)
-    float* peer_send[COMM_MAX_WORLD];     // every rank's send area, as mapped HERE
+    int64_t n_pad;                        // floats per slot; a receive area is [2 parities][COMM_MAX_WORLD slots][n_pad]
+    float* peer_send[COMM_MAX_WORLD];     // every rank's receive area, as mapped HERE
     uint32_t* peer_flags[COMM_MAX_WORLD]; // every rank's flag area [n_cta][COMM_MAX_WORLD]
     uint32_t* epoch;                      // steps completed so far (device counter, so graph replays advance it)
     int32_t* ticket;
@@ -52,8 +55,12 @@ __global__ void __launch_bounds__(COMM_NT) k_allreduce_adam(CommP p) {
     const bool in = i0 < p.n;             // n is padded to a multiple of 4 by the caller
     if (in) g = *reinterpret_cast<const float4*>(p.grad + i0);
     if (p.world > 1) {
-        const int64_t boff = (int64_t)(e & 1u) * p.n_pad;
-        if (in) *reinterpret_cast<float4*>(p.peer_send[p.rank] + boff + i0) = g;
+        const int64_t boff = ((int64_t)(e & 1u) * COMM_MAX_WORLD + p.rank) * p.n_pad;      // my slot, this step's parity
+        if (in) {
+#pragma unroll
+            for (int r = 0; r < COMM_MAX_WORLD; ++r)
+                if (r < p.world) *reinterpret_cast<float4*>(p.peer_send[r] + boff + i0) = g;   // own area included
+        }
         __syncthreads();
         if (tid < p.world) {
             __threadfence_system();
@@ -63,11 +70,17 @@ __global__ void __launch_bounds__(COMM_NT) k_allreduce_adam(CommP p) {
         }
         __syncthreads();
         if (in) {
+            // every rank's chunk has landed in MY receive area: local reads, added in rank order
+            const float* base = p.peer_send[p.rank] + (int64_t)(e & 1u) * COMM_MAX_WORLD * p.n_pad + i0;
+            float4 x[COMM_MAX_WORLD];
+#pragma unroll
+            for (int r = 0; r < COMM_MAX_WORLD; ++r)
+                x[r] = r < p.world ? __ldcv(reinterpret_cast<const float4*>(base + (int64_t)r * p.n_pad))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
             g = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int r = 0; r < p.world; ++r) {                 // rank order: identical sums everywhere
-                const float4 x = __ldcv(reinterpret_cast<const float4*>(p.peer_send[r] + boff + i0));
-                g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
-            }
+#pragma unroll
+            for (int r = 0; r < COMM_MAX_WORLD; ++r)
+                if (r < p.world) { g.x += x[r].x; g.y += x[r].y; g.z += x[r].z; g.w += x[r].w; }
             const float inv = 1.0f / (float)p.world;
             g.x *= inv; g.y *= inv; g.z *= inv; g.w *= inv;
         }
@@ -156,7 +169,7 @@ extern "C" int pcg_comm_unmap(void* ptr) {
 extern "C" size_t pcg_comm_region_bytes(int64_t n_params) {
     const int64_t n_pad = (n_params + COMM_PER_CTA - 1) / COMM_PER_CTA * COMM_PER_CTA;
     const int64_t n_cta = n_pad / COMM_PER_CTA;
-    return (size_t)(2 * n_pad * 4 + n_cta * COMM_MAX_WORLD * 4 + 256);
+    return (size_t)(2 * COMM_MAX_WORLD * n_pad * 4 + n_cta * COMM_MAX_WORLD * 4 + 256);
 }
 
 extern "C" int pcg_allreduce_adam(float* grad, float* param, float* m, float* v, int64_t n_params,
@@ -174,7 +187,7 @@ extern "C" int pcg_allreduce_adam(float* grad, float* param, float* m, float* v,
     for (int r = 0; r < COMM_MAX_WORLD; ++r) {
         char* base = (world > 1 && r < world) ? (char*)peer_regions_host[r] : nullptr;
         p.peer_send[r] = (float*)base;
-        p.peer_flags[r] = base ? (uint32_t*)(base + 2 * p.n_pad * 4) : nullptr;
+        p.peer_flags[r] = base ? (uint32_t*)(base + 2 * COMM_MAX_WORLD * p.n_pad * 4) : nullptr;
     }
     p.epoch = epoch; p.ticket = ticket; p.rank = rank; p.world = world;
     p.lr = lr; p.b1 = beta1; p.b2 = beta2; p.eps = eps; p.wd = weight_decay; p.do_adam = do_adam;

@@ -123,7 +123,8 @@ class PeerRegion:
 
 
 class PeerComm(PeerRegion):
-    """Send buffers + flags of the fused gradient exchange (csrc/pcg_comm.cu). world == 1: no region."""
+    """Receive areas (one slot per rank, double buffered) + flags of the fused gradient exchange (csrc/pcg_comm.cu).
+    world == 1: no region."""
 
     def __init__(self, n_params: int, group=None):
         from . import _lib
