@@ -69,6 +69,14 @@ PCG_API int pcg_score_table(const float* feat, int64_t n_nodes, int F, int64_t l
                     void* workspace, size_t workspace_bytes, pcg_stream_t stream);
 
 /*
+ * Scores of the pool members only: pool_score[i] = dot(feat[pool[i], :F], w) + b[0], bit-identical to what
+ * pcg_score_table writes for those nodes (same arithmetic). With it the pool sort (pcg_sort_pool) does not have to
+ * wait for the score table: the two run side by side (src/layers.py:232, :237: pos_scores = label_clf(features(train_pos))).
+ */
+PCG_API int pcg_pool_scores(const float* feat, int F, int64_t ldf, const float* w, const float* b, const int32_t* pool,
+                    int P, float* pool_score, pcg_stream_t stream);
+
+/*
  * Pool sorted by score: ps_score ascending with ties in pool-position order, ps_pos[i] = position in
  * `pool` of sorted entry i, ps_id[i] = pool[ps_pos[i]]. One sort per step replaces the reference's
  * torch.sort over all P pool distances for EVERY positive target (src/layers.py:683-690): with the pool

@@ -34,6 +34,7 @@ SIGNATURES = {
     "pcg_device_sms": (_i, []),
     "pcg_set_pdl": (_i, [_i]),
     "pcg_score_table": (_i, [_p, _l, _i, _l, _p, _p, _p, _p, _i, _p, _p, _p, _p, _z, _p]),
+    "pcg_pool_scores": (_i, [_p, _i, _l, _p, _p, _p, _i, _p, _p]),
     "pcg_sort_pool_workspace_bytes": (_z, [_i]),
     "pcg_sort_pool": (_i, [_p, _p, _i, _p, _p, _p, _p, _z, _p]),
     "pcg_choose_workspace_bytes": (_z, [_i, _i, _l, _l]),

@@ -70,6 +70,39 @@ __global__ void __launch_bounds__(256) k_score_table(const float* __restrict__ f
     }
 }
 
+// Scores of the pool members only, with EXACTLY the arithmetic of k_score_table (same lanes, same order, same
+// reduction tree: the values are bit-identical to score[pool[i]]). It lets the pool sort run NEXT TO the score-table
+// kernel instead of behind it (and, on a row-partitioned graph, next to the score exchange: features are replicated),
+// and it is the common predecessor from which the step's three front branches fork.
+__global__ void __launch_bounds__(256) k_pool_scores(const float* __restrict__ feat, int F, int64_t ldf,
+                                                     const float* __restrict__ w, const float* __restrict__ b,
+                                                     const int32_t* __restrict__ pool, int P, float* __restrict__ pool_score) {
+    extern __shared__ float sw[];
+    for (int c = threadIdx.x; c < ldf; c += blockDim.x) sw[c] = c < F ? w[c] : 0.f;
+    const float bias = b ? b[0] : 0.f;
+    __syncthreads();
+    const int l = threadIdx.x & 7;
+    const int V = (int)(ldf >> 2);
+    const int rows_per_block = blockDim.x >> 3;
+    for (int ib = blockIdx.x * rows_per_block + ((threadIdx.x >> 5) << 2); ib < P; ib += gridDim.x * rows_per_block) {
+        const int i = ib + ((threadIdx.x & 31) >> 3);
+        float acc = 0.f;
+        if (i < P) {
+            const float* rowp = feat + (int64_t)__ldg(pool + i) * ldf;
+            for (int c = l; c < V; c += 8) {
+                float4 x = ld_f4(rowp + 4 * c);
+                const float4 ww = *reinterpret_cast<const float4*>(sw + 4 * c);
+                acc = fmaf(x.x, ww.x, acc); acc = fmaf(x.y, ww.y, acc);
+                acc = fmaf(x.z, ww.z, acc); acc = fmaf(x.w, ww.w, acc);
+            }
+        }
+        acc += __shfl_xor_sync(PCG_FULL, acc, 4);
+        acc += __shfl_xor_sync(PCG_FULL, acc, 2);
+        acc += __shfl_xor_sync(PCG_FULL, acc, 1);
+        if (l == 0 && i < P) pool_score[i] = acc + bias;
+    }
+}
+
 __global__ void k_gather_pool(const float* __restrict__ score, const int32_t* __restrict__ pool, int P,
                               float* __restrict__ pool_score) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -207,6 +240,20 @@ extern "C" int pcg_sort_pool(const float* pool_score, const int32_t* pool, int P
                             workspace_bytes > skip ? workspace_bytes - skip : 0, stream);
     if (rc) return rc;
     return pcg_check_launch("pcg_sort_pool");
+}
+
+extern "C" int pcg_pool_scores(const float* feat, int F, int64_t ldf, const float* w, const float* b, const int32_t* pool,
+                               int P, float* pool_score, pcg_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (P <= 0) return 0;
+    PCG_REQUIRE(feat && w && pool && pool_score, "pcg_pool_scores: null pointer");
+    PCG_REQUIRE(ldf % 4 == 0 && F <= ldf && F > 0 && ldf * 4 <= 48 * 1024 && ((uintptr_t)feat & 15) == 0,
+                "pcg_pool_scores: need F <= ldf, ldf %% 4 == 0, 16-byte aligned rows (F=%d ldf=%lld)", F, (long long)ldf);
+    int blocks = (P + 31) / 32;
+    const int sms = pcg_device_sms();
+    if (blocks > sms * 16) blocks = sms * 16;
+    k_pool_scores<<<blocks, 256, (size_t)ldf * 4, stream>>>(feat, F, ldf, w, b, pool, P, pool_score);
+    return pcg_check_launch("pcg_pool_scores");
 }
 
 extern "C" int pcg_score_table(const float* feat, int64_t n_nodes, int F, int64_t ldf, const float* w, const float* b,

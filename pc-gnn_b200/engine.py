@@ -230,6 +230,50 @@ class Engine:
         _lib.check(rc, "pcg_score_table")
         return self.score
 
+    def pool_scores(self, clf_weight: torch.Tensor, clf_bias: torch.Tensor):
+        """Scores of the pool members only (``pcg_pool_scores``; bit-identical to the table's values): the pool sort
+        can then run next to the score-table kernel / the score exchange instead of behind it."""
+        if not self.P:
+            return None
+        if getattr(self, "_pool_score", None) is None or self._pool_score.shape[0] != self.P:
+            self._pool_score = torch.empty(self.P, dtype=torch.float32, device=self.device)
+        w = clf_weight.detach()
+        w = w if w.is_contiguous() else w.contiguous()
+        rc = self.lib.pcg_pool_scores(self.feat.data_ptr(), self.F, self.ldf, w.data_ptr(), clf_bias.detach().data_ptr(),
+                                      self.pool.data_ptr(), self.P, self._pool_score.data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "pcg_pool_scores")
+        return self._pool_score
+
+    def sort_pool_from(self, pool_score: torch.Tensor):
+        """Sort the resident pool by the given per-position scores into the engine's sorted-pool arrays."""
+        ps, pp, pi, ws = self.sorted_pool
+        rc = self.lib.pcg_sort_pool(pool_score.data_ptr(), self.pool.data_ptr(), self.P, ps.data_ptr(), pp.data_ptr(),
+                                    pi.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr())
+        _lib.check(rc, "pcg_sort_pool")
+
+    def score_table_only(self, clf_weight: torch.Tensor, clf_bias: torch.Tensor):
+        """The score table without the pool sort (the caller sorts the pool from ``pool_scores`` on another stream).
+        Row partitions exchange their slices as ``score_table`` does."""
+        w = clf_weight.detach()
+        w = w if w.is_contiguous() else w.contiguous()
+        b = clf_bias.detach()
+        if self._bcast is not None:
+            region, epoch = self._bcast
+            lo = self.row_lo
+            rc = self.lib.pcg_score_bcast(self.feat.data_ptr() + lo * self.ldf * 4, self.N, self.F, self.ldf,
+                                          w.data_ptr(), b.data_ptr(), lo, self.N_global, region.regions, region.rank,
+                                          region.world, epoch.data_ptr(), _lib.stream_ptr())
+            _lib.check(rc, "pcg_score_bcast")
+            return self.score
+        if self.score_group is not None:
+            self.score_local(w, b)
+            self.score_exchange()
+            return self.score
+        rc = self.lib.pcg_score_table(self.feat.data_ptr(), self.N_global, self.F, self.ldf, w.data_ptr(), b.data_ptr(),
+                                      self.score.data_ptr(), None, 0, None, None, None, None, 0, _lib.stream_ptr())
+        _lib.check(rc, "pcg_score_table")
+        return self.score
+
     def enable_score_broadcast(self, group=None):
         """Row-partitioned graph, several ranks: keep the score table in memory that every peer has mapped, so that
         ``score_table`` becomes slice kernel + stores into all peers' tables + arrival wait (``pcg_score_bcast``),
@@ -520,10 +564,12 @@ class Engine:
             self._fork_word = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._fork_word.zero_()
 
-    def side_stream(self):
-        if getattr(self, "_side", None) is None:
-            self._side = torch.cuda.Stream(device=self.device)
-        return self._side
+    def side_stream(self, which: int = 0):
+        if getattr(self, "_sides", None) is None:
+            self._sides = {}
+        if which not in self._sides:
+            self._sides[which] = torch.cuda.Stream(device=self.device)
+        return self._sides[which]
 
     def sink_of(self, param):
         """Gradient view registered for this parameter tensor, or None."""

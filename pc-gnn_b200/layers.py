@@ -452,23 +452,40 @@ class InterAgg(nn.Module):
         given slot capacity (layers.py:216-262, 633-738). Pure kernel launches on the current stream."""
         rho = self.intra_agg1.rho
         dev = eng.device
-        # the preparation of the choose step (repeated targets, item sizes, slot prefix sum, tier queues) needs no
-        # scores: it runs on a side stream next to the score table and the pool sort
         cur = torch.cuda.current_stream(dev)
-        side = eng.side_stream()
-        eng.fork_point()
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            sel = eng.choose(targets, lab, train_flag, self.thresholds, rho, cap, phases=1)
-        # label-aware scores for every node (column 0 only) + the pool's: layers.py:231-237
-        if self.score_override is not None:
-            eng.score.copy_(self.score_override)
-            eng.resort_pool()
-        elif self.scores_external:
-            eng.resort_pool()
+        side = eng.side_stream(0)
+        own_scores = self.score_override is None and not self.scores_external
+        if own_scores and eng.P and train_flag:
+            # Three branches fork behind the pool-score kernel and meet in front of the selection kernels:
+            #   side 0: preparation of the choose step (repeated targets, item sizes, slot prefix sum, tier queues): no scores
+            #   side 1: pool sort, from the pool members' scores alone (layers.py:232, :237)
+            #   main  : score table of every node, column 0 (layers.py:231, :236) [+ slice exchange on a row partition]
+            pool_score = eng.pool_scores(self.label_clf.weight, self.label_clf.bias)
+            side1 = eng.side_stream(1)
+            side.wait_stream(cur)
+            side1.wait_stream(cur)
+            with torch.cuda.stream(side):
+                sel = eng.choose(targets, lab, train_flag, self.thresholds, rho, cap, phases=1)
+            with torch.cuda.stream(side1):
+                eng.sort_pool_from(pool_score)
+            eng.score_table_only(self.label_clf.weight, self.label_clf.bias)
+            cur.wait_stream(side)
+            cur.wait_stream(side1)
         else:
-            eng.score_table(self.label_clf.weight, self.label_clf.bias)
-        cur.wait_stream(side)
+            eng.fork_point()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                sel = eng.choose(targets, lab, train_flag, self.thresholds, rho, cap, phases=1)
+            if self.score_override is not None:
+                eng.score.copy_(self.score_override)
+                eng.resort_pool()
+            elif self.scores_external:
+                eng.resort_pool()
+            elif train_flag:
+                eng.score_table(self.label_clf.weight, self.label_clf.bias)
+            else:       # eval: no oversampling, the pool is not needed (layers.py:700-738)
+                eng.score_table_only(self.label_clf.weight, self.label_clf.bias)
+            cur.wait_stream(side)
         eng.choose(targets, lab, train_flag, self.thresholds, rho, cap, phases=2, sel=sel)
         self.last_selection = sel
         return sel
