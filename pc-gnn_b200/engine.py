@@ -568,7 +568,8 @@ class Engine:
         if getattr(self, "_sides", None) is None:
             self._sides = {}
         if which not in self._sides:
-            self._sides[which] = torch.cuda.Stream(device=self.device)
+            # high priority: the side branches are short kernels that must get SM slots next to the main branch
+            self._sides[which] = torch.cuda.Stream(device=self.device, priority=-1)
         return self._sides[which]
 
     def sink_of(self, param):
