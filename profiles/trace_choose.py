@@ -56,8 +56,8 @@ for it, (nodes, labels) in enumerate(batches):
     names = ["header", "load-dist", "select", "compact", "pool-search", "pool-emit", "finish"]
     print(f"iter {it}: choose {e0.elapsed_time(e1) * 1e3:.1f} us (eager launch, events); {done.sum()} representative items; "
           f"last item ends {(ts[:, 7].max() - start) / 1e3:.1f} us after the first item starts")
-    for tier, mask in (("warp tier (d<=128)", d <= 128), ("cta tier (<=1024)", (d > 128) & (d <= 1024)),
-                       ("wide tier (<=16384)", (d > 1024) & (d <= 16384)), ("big tier", d > 16384)):
+    for tier, mask in (("warp tier (d<=256)", d <= 256), ("cta tier (<=2048)", (d > 256) & (d <= 2048)),
+                       ("wide tier (<=16384)", (d > 2048) & (d <= 16384)), ("huge / big tiers", d > 16384)):
         if not mask.any():
             continue
         idx = np.nonzero(mask)[0]
