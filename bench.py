@@ -280,35 +280,67 @@ def _roof(kern, dom, extra=None, workload=None):
 
 
 def hot_kernels_pcgnn(eng, inter, data, shards, dev_nodes, dev_labels, cap, W, K, flush, dev, batch, workload=None):
-    """choose (prep + tier kernels) and aggregate captured alone in CUDA graphs, CUDA-event time per replay, L2
-    flushed before each. Bytes per SURVEY 8(d): filter = 8 per CSR entry of the batch's rows + 16 R B + 4 B
-    + 4 P R B+ (pool scan) [+ 4 per kept id written]; aggregate = (4F + 4) per gathered row + 4 F R B."""
+    """The hot-path kernel groups captured alone in CUDA graphs, CUDA-event time per replay, L2 flushed before each:
+      front      what runs in front of the selection as in the step: pool scores -> (choose preparation || pool sort ||
+                 score table)
+      choose     the selection kernels (k_choose_small || k_choose_wide [|| huge / big tiers]): the dominant group
+      aggregate  k_aggregate
+    Bytes per SURVEY 8(d): filter = 8 per CSR entry of the batch's rows + 16 R B + 4 B + 4 P R B+ (pool scan)
+    [+ 4 per kept id written]; aggregate = (4F + 4) per gathered row + 4 F R B."""
     import torch
 
     R, F_ = data.graph.n_rel, data.feat.shape[1]
-    t_choose = t_agg = t_score = 0.0
+    t_choose = t_agg = t_front = 0.0
     alg_choose = alg_agg = req_choose = 0.0
     P = eng.P
     st_nodes = dev_nodes[W].clone()
     st_labels = dev_labels[W].clone()
+    exchange = eng.score_group is not None          # partitioned graph + NCCL scores: the all-gather stays outside the graphs
+    w_, b_ = inter.label_clf.weight, inter.label_clf.bias
+    rho = inter.intra_agg1.rho
+    holder = {}
+
+    def front():
+        cur = torch.cuda.current_stream(dev)
+        s0, s1 = eng.side_stream(0), eng.side_stream(1)
+        if exchange:
+            eng.score_local(w_, b_)
+            return
+        ps = eng.pool_scores(w_, b_)
+        s0.wait_stream(cur)
+        s1.wait_stream(cur)
+        with torch.cuda.stream(s0):
+            holder["sel"] = eng.choose(st_nodes, st_labels, True, inter.thresholds, rho, cap, phases=1)
+        with torch.cuda.stream(s1):
+            eng.sort_pool_from(ps)
+        eng.score_table_only(w_, b_)
+        cur.wait_stream(s0)
+        cur.wait_stream(s1)
+
+    def tiers():
+        if exchange:
+            holder["sel"] = eng.choose(st_nodes, st_labels, True, inter.thresholds, rho, cap)
+        else:
+            eng.choose(st_nodes, st_labels, True, inter.thresholds, rho, cap, phases=2, sel=holder["sel"])
+
     side = torch.cuda.Stream(device=dev)
     side.wait_stream(torch.cuda.current_stream(dev))
     with torch.cuda.stream(side):
         for _ in range(2):
-            eng.score_table(inter.label_clf.weight, inter.label_clf.bias)
-            sel = eng.choose(st_nodes, st_labels, True, inter.thresholds, RHO, cap)
-            eng.aggregate(sel, copy_dups=False)
+            front()
+            if exchange:
+                eng.score_exchange()
+                eng.resort_pool()
+            tiers()
+            eng.aggregate(holder["sel"], copy_dups=False)
     torch.cuda.current_stream(dev).wait_stream(side)
     torch.cuda.synchronize()
-    g_score, g_choose, g_agg = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-    exchange = eng.score_group is not None          # partitioned graph: the all-gather stays outside the graphs
-    with torch.cuda.graph(g_score):
-        if exchange:
-            eng.score_local(inter.label_clf.weight, inter.label_clf.bias)
-        else:
-            eng.score_table(inter.label_clf.weight, inter.label_clf.bias)
+    g_front, g_choose, g_agg = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g_front):
+        front()
     with torch.cuda.graph(g_choose):
-        sel = eng.choose(st_nodes, st_labels, True, inter.thresholds, RHO, cap)
+        tiers()
+    sel = holder["sel"]
     with torch.cuda.graph(g_agg):
         eng.aggregate(sel, copy_dups=False)       # as in the train step: the dense kernels read through it_rep
     for s in range(K):
@@ -318,7 +350,7 @@ def hot_kernels_pcgnn(eng, inter, data, shards, dev_nodes, dev_labels, cap, W, K
         flush.zero_()
         e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
         e0.record()
-        g_score.replay()
+        g_front.replay()
         if exchange:
             eng.score_exchange()
             eng.resort_pool()
@@ -328,7 +360,7 @@ def hot_kernels_pcgnn(eng, inter, data, shards, dev_nodes, dev_labels, cap, W, K
         g_agg.replay()
         e3.record()
         torch.cuda.synchronize()
-        t_score += e0.elapsed_time(e1)
+        t_front += e0.elapsed_time(e1)
         t_choose += e1.elapsed_time(e2)
         t_agg += e2.elapsed_time(e3)
         nodes, labels = shards[i]
@@ -342,10 +374,12 @@ def hot_kernels_pcgnn(eng, inter, data, shards, dev_nodes, dev_labels, cap, W, K
         assert not sel.overflowed()
     kern = {
         "choose": {"ms": t_choose / K, "alg_bytes": alg_choose / K, "gbs": alg_choose / t_choose / 1e6,
-                   "req_bytes": req_choose / K, "req_gbs": req_choose / t_choose / 1e6, "launches_per_step": 3},
+                   "req_bytes": req_choose / K, "req_gbs": req_choose / t_choose / 1e6,
+                   "launches_per_step": 2, "what": "the selection kernels k_choose_small || k_choose_wide (|| huge / big tiers)"},
         "aggregate": {"ms": t_agg / K, "alg_bytes": alg_agg / K, "gbs": alg_agg / t_agg / 1e6,
                       "req_bytes": alg_agg / K, "req_gbs": alg_agg / t_agg / 1e6, "launches_per_step": 1},
-        "score_table_and_pool_sort": {"ms": t_score / K, "launches_per_step": 2},
+        "front": {"ms": t_front / K, "launches_per_step": 4,
+                  "what": "k_pool_scores -> (k_choose_prep || pool sort || k_score_table) as in the step"},
     }
     dom = "choose" if t_choose >= t_agg else "aggregate"
     return kern, _roof(kern, dom, {"filter_plus_aggregate_gbs": (alg_choose + alg_agg) / (t_choose + t_agg) / 1e6,

@@ -56,8 +56,9 @@ def main(path, traffic_json=None, workload=None):
             t = json.load(open(traffic_json))
         except Exception:
             t = {}
-        t[workload] = {"choose": {"bytes": grp(["k_choose_prep", "k_choose_wide", "k_choose_small", "k_choose_huge", "k_choose_big"]),
-                                  "kernels": "k_choose_prep + k_choose_wide + k_choose_small (+ huge / big tiers)"},
+        t[workload] = {"choose": {"bytes": grp(["k_choose_wide", "k_choose_small", "k_choose_huge", "k_choose_big"]),
+                                  "kernels": "k_choose_wide + k_choose_small (+ huge / big tiers)"},
+                       "choose_prep": {"bytes": grp(["k_choose_prep"]), "kernels": "k_choose_prep"},
                        "aggregate": {"bytes": grp(["k_aggregate"]), "kernels": "k_aggregate"},
                        "source": path.split("/")[-1] + " (ncu --set full, one step replay, L2 flushed before it)"}
         json.dump(t, open(traffic_json, "w"), indent=1)

@@ -14,7 +14,7 @@ try:
     d = json.load(open("gpurun_out/r02_bench_$w.json"))
     print("$w", round(d["ms_per_step"], 4), "ms", round(d["value"] / 1e6, 2), "M/s  e2e", round(d["e2e"]["value"] / 1e6, 2),
           "ref-loop", round(d.get("e2e_reference_loop", {}).get("value", 0) / 1e6, 2), "cpu", round(d["cpu_baseline"]["value"], 1),
-          {k: round(v["ms"] * 1e3, 1) for k, v in d["kernels"].items()})
+          {k: round(v["ms"] * 1e3, 1) for k, v in d["kernels"].items()}, "roof", round(d["roofline"]["frac"], 3))
 except Exception as e:
     print("$w FAILED", e)
 PY
