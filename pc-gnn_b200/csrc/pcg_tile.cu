@@ -95,23 +95,24 @@ __host__ __device__ __forceinline__ int ld_pad(int x) { return x + ((4 - (x & 15
 
 // Shared-memory plan (floats), the same arithmetic on host and device.
 struct TileSmem {
-    int Fp, K2p, LDC, LDA, LDO, LDH, LDB;
-    size_t cat, agg, o, dzs, dhs, stage, scratch, wh, wc, rows, bars, total_bytes;
+    int Fp, K2p, LDC, LDA, LDO, LDB;
+    size_t cat, agg, o, dzs, stage, scratch, wh, wc, rows, bars, total_bytes;
 };
 __host__ __device__ inline TileSmem tile_smem(int TM, int F, int R, int E, int mode, int nstage) {
     TileSmem s;
     s.Fp = (F + 3) & ~3;
     s.K2p = s.Fp + R * E;
-    s.LDC = ld_pad(s.K2p); s.LDA = ld_pad(s.Fp); s.LDO = E + 4; s.LDH = R * E + 4;
+    s.LDC = ld_pad(s.K2p); s.LDA = ld_pad(s.Fp); s.LDO = E + 4;
     s.LDB = E;                                   // chunk rows unpadded: one bulk copy per chunk
     size_t o = 0;
     s.cat = o; o += (size_t)TM * s.LDC;
     s.agg = o; o += (size_t)R * TM * s.LDA;
     s.o = o; o += (size_t)TM * s.LDO;
     s.dzs = o; o += mode == 2 ? (size_t)TM * s.LDO : 0;
-    s.dhs = o; o += mode == 2 ? (size_t)TM * s.LDH : 0;
     s.stage = o; o += (size_t)nstage * TILE_KC * s.LDB;
-    s.scratch = o; o += 2 * (size_t)TILE_NWC * 16 * 32;      // K-split partial sums, double buffered
+    // K-split partial sums, double buffered; not needed when every GEMM phase has at least as many tasks as warps
+    const int tpg = (TM / 8) * (E / 64);
+    s.scratch = o; o += tpg >= TILE_NWC ? 0 : 2 * (size_t)TILE_NWC * 16 * 32;
     s.wh = o; o += 2 * (size_t)E;
     s.wc = o; o += 2 * (size_t)s.Fp + 4;
     s.rows = o; o += (size_t)TM * 8;
@@ -160,12 +161,11 @@ __global__ void __launch_bounds__(TILE_NT, 1) k_tile(TileP p) {
     const int NS = p.nstage;
     const TileSmem L = tile_smem(TM, p.F, p.R, p.E, p.mode, NS);
     const int F = p.F, Fp = L.Fp, E = p.E, R = p.R, K2p = L.K2p;
-    const int LDC = L.LDC, LDA = L.LDA, LDO = L.LDO, LDH = L.LDH, LDB = L.LDB;
+    const int LDC = L.LDC, LDA = L.LDA, LDO = L.LDO, LDB = L.LDB;
     float* catS = sm + L.cat;
     float* aggS = sm + L.agg;
     float* oS = sm + L.o;
     float* dzS = sm + L.dzs;
-    float* dhS = sm + L.dhs;
     float* stage = sm + L.stage;
     float* scratch = sm + L.scratch;
     float* whS = sm + L.wh;
@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(TILE_NT, 1) k_tile(TileP p) {
     // per lane. Phase A has R groups (the relations, each with its own weight chunks), phase B one. With fewer
     // tasks than warps the spare warps split K by WHOLE chunks (chunk c of a group belongs to split c % ksplit), so a
     // warp waits for few barriers and runs long independent FMA streams; the splits meet in shared memory in split
-    // order. With more tasks than warps (<= 16) a warp runs two tasks of different groups one after the other.
+    // order. With more tasks than warps (<= 32) a warp runs up to four tasks of different groups one after the other.
     // Ring protocol: every consumer warp visits every chunk in stream order (wait full / arrive empty) unless the
     // ring holds the whole stream, in which case chunks a warp does not use are not touched at all.
     constexpr int RB = TM / 8;
@@ -357,9 +357,9 @@ __global__ void __launch_bounds__(TILE_NT, 1) k_tile(TileP p) {
         const int first = it;
         float* sc = scratch + (size_t)(phase & 1) * TILE_NWC * 16 * 32;
         int my_task = -1, my_ks = 0;
-        for (int slot = 0; slot < 2; ++slot) {
+        for (int slot = 0; slot < 4; ++slot) {
             int t, ks;
-            if (ntask <= TILE_NWC) { t = wid % ntask; ks = wid / ntask; if (slot == 1 || ks >= ksplit) break; }
+            if (ntask <= TILE_NWC) { t = wid % ntask; ks = wid / ntask; if (slot >= 1 || ks >= ksplit) break; }
             else { t = wid + TILE_NWC * slot; ks = 0; if (t >= ntask) break; }
             const int g = t / tpg, rem = t - g * tpg, rb = rem / CB, cb = rem - rb * CB;
             const int row0 = rb * 8 + 2 * lr, col_lo = cb * 64 + lc * 4;
@@ -583,7 +583,8 @@ __global__ void __launch_bounds__(TILE_NT, 1) k_tile(TileP p) {
 #pragma unroll
                 for (int i = 0; i < RB; ++i) {
                     const int m = mrow + 8 * i;
-                    dhS[m * LDH + n] = catS[m * LDC + Fp + n] > 0.f ? a2[i][u] : 0.f;
+                    float* hc = catS + m * LDC + Fp + n;       // h[m][n] is read (relu mask) and replaced by dH[m][n] by this lane only
+                    *hc = *hc > 0.f ? a2[i][u] : 0.f;
                 }
             }
         }
@@ -596,7 +597,7 @@ __global__ void __launch_bounds__(TILE_NT, 1) k_tile(TileP p) {
         for (int idx = tid; idx < TM * V; idx += TILE_NWC * 32) {
             const int m = idx / V, q = idx - m * V;
             if (m0 + m < p.B)
-                *reinterpret_cast<float4*>(p.dh + (int64_t)(m0 + m) * (R * E) + 4 * q) = *reinterpret_cast<const float4*>(dhS + m * LDH + 4 * q);
+                *reinterpret_cast<float4*>(p.dh + (int64_t)(m0 + m) * (R * E) + 4 * q) = *reinterpret_cast<const float4*>(catS + m * LDC + Fp + 4 * q);
         }
     }
     TTRACE(8);
@@ -784,8 +785,8 @@ static int tile_plan(int B, int F, int R, int E, int mode, int* nstage_out, size
     const int cands[3] = {32, 16, 8};
     for (int c = 0; c < 3; ++c) {
         const int tm = cands[c];
-        if (tm > 8 && (B + tm - 1) / tm < sms - sms / 8) continue;          // would leave SMs idle
-        if ((tm / 8) * (E / 64) > TILE_NWC) continue;
+        if (tm > 8 && (B + tm - 1) / tm < sms - sms / 5) continue;          // would leave too many SMs idle
+        if ((tm / 8) * (E / 64) > TILE_NWC || R * (tm / 8) * (E / 64) > 4 * TILE_NWC) continue;
         int ns = chunks < TILE_MAX_STAGE ? chunks : TILE_MAX_STAGE;
         while (ns >= 3 && tile_smem(tm, F, R, E, mode, ns).total_bytes > TILE_SMEM_MAX) --ns;
         const TileSmem s = tile_smem(tm, F, R, E, mode, ns);
