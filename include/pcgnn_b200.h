@@ -77,6 +77,24 @@ PCG_API int pcg_pool_scores(const float* feat, int F, int64_t ldf, const float* 
                     int P, float* pool_score, pcg_stream_t stream);
 
 /*
+ * Host batches without copy nodes. The reference hands every batch over as host data (model_handler.py:142-150:
+ * Python lists of ids, a LongTensor of labels made on the spot). pcg_stage copies `bytes` (a multiple of 4, 4-byte
+ * aligned pointers) with a KERNEL, so that src or dst may be page-locked host memory (cudaHostAlloc / torch pinned
+ * memory: device-addressable under unified addressing) and a captured step graph stays a graph of kernel nodes only
+ * (graphs with memcpy nodes were measured to launch their branches several microseconds apart). Used for the loss
+ * word on its way out. pcg_pool_scores_stage is pcg_pool_scores with the same copy riding on extra CTAs of the kernel:
+ * the first kernel of the training step fetches the batch's ids and labels while it computes, which takes the host
+ * to device copy off the step's critical path altogether. The source must stay unchanged until the kernel has
+ * finished (the caller's event / synchronisation), like the source of any asynchronous copy.
+ */
+PCG_API int pcg_stage(const void* src, void* dst, size_t bytes, pcg_stream_t stream);
+/* Device address of a page-locked host buffer (cudaHostGetDevicePointer), or NULL + pcg_last_error(). */
+PCG_API void* pcg_host_device_ptr(void* host_ptr);
+PCG_API int pcg_pool_scores_stage(const float* feat, int F, int64_t ldf, const float* w, const float* b, const int32_t* pool,
+                          int P, float* pool_score, const void* stage_src, void* stage_dst, size_t stage_bytes,
+                          pcg_stream_t stream);
+
+/*
  * Pool sorted by score: ps_score ascending with ties in pool-position order, ps_pos[i] = position in
  * `pool` of sorted entry i, ps_id[i] = pool[ps_pos[i]]. One sort per step replaces the reference's
  * torch.sort over all P pool distances for EVERY positive target (src/layers.py:683-690): with the pool

@@ -35,6 +35,9 @@ SIGNATURES = {
     "pcg_set_pdl": (_i, [_i]),
     "pcg_score_table": (_i, [_p, _l, _i, _l, _p, _p, _p, _p, _i, _p, _p, _p, _p, _z, _p]),
     "pcg_pool_scores": (_i, [_p, _i, _l, _p, _p, _p, _i, _p, _p]),
+    "pcg_stage": (_i, [_p, _p, _z, _p]),
+    "pcg_host_device_ptr": (_p, [_p]),
+    "pcg_pool_scores_stage": (_i, [_p, _i, _l, _p, _p, _p, _i, _p, _p, _p, _z, _p]),
     "pcg_sort_pool_workspace_bytes": (_z, [_i]),
     "pcg_sort_pool": (_i, [_p, _p, _i, _p, _p, _p, _p, _z, _p]),
     "pcg_choose_workspace_bytes": (_z, [_i, _i, _l, _l]),
@@ -110,6 +113,14 @@ def check(rc: int, what: str = ""):
 def ptr(t):
     """Device pointer of a torch tensor (or None)."""
     return None if t is None else t.data_ptr()
+
+
+def host_device_ptr(pinned_tensor) -> int:
+    """Device address of a pinned (page-locked) host tensor; raises when the memory is not device-mapped."""
+    dev = lib().pcg_host_device_ptr(pinned_tensor.data_ptr())
+    if not dev:
+        raise PcgError(lib().pcg_last_error().decode("utf-8", "replace"))
+    return int(dev)
 
 
 def stream_ptr():

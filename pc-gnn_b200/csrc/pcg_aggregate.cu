@@ -125,14 +125,47 @@ __global__ void __launch_bounds__(256) k_aggregate(const float* __restrict__ fea
     ticket = __shfl_sync(PCG_FULL, ticket, 0);
     if (ticket != nch - 1) continue;
     __threadfence();
-    const float sc = norm_scale(m + (extra >= 0 ? 1 : 0), norm);
-    for (int col = lane; col < V; col += 32) {
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int q = 0; q < nch; ++q) f4_add(a, ld_f4_cg(partial + ((int64_t)slot0 + q) * ldf + 4 * col));
-        if (extra >= 0) f4_add(a, ld_f4(feat + (int64_t)extra * ldf + 4 * col));
-        a.x *= sc; a.y *= sc; a.z *= sc; a.w *= sc;
-        *reinterpret_cast<float4*>(agg + (int64_t)w * ldf + 4 * col) = a;
+    // Final sum of the item's nch partials by the whole warp: lane group g adds the partials g, g+G, g+2G, ... in that
+    // order, UR loads in flight per lane (a hub row of C2 owns 100-190 slots: one lane per column adding them one
+    // after the other was 10 us of dependent L2 round trips, the tail of the whole kernel), then the G group sums are
+    // added by the same shuffle tree as the slots' rows. Fixed order: deterministic.
+    constexpr int UR = NV == 1 ? 8 : (NV == 2 ? 4 : 2);
+    float4 tot[NV];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) tot[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c0 = g; c0 < nch; c0 += G * UR) {
+        float4 v[UR][NV];
+#pragma unroll
+        for (int u = 0; u < UR; ++u) {
+            const int cc = c0 + u * G;
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+                const int col = l + q * LPR;
+                v[u][q] = (cc < nch && col < V) ? ld_f4_cg(partial + ((int64_t)slot0 + cc) * ldf + 4 * col)
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UR; ++u)
+#pragma unroll
+            for (int q = 0; q < NV; ++q) f4_add(tot[q], v[u][q]);
     }
+#pragma unroll
+    for (int q = 0; q < NV; ++q) tot[q] = group_reduce<LPR>(tot[q]);
+    const float sc = norm_scale(m + (extra >= 0 ? 1 : 0), norm);
+    if (g == 0) {
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            const int col = l + q * LPR;
+            if (col < V) {
+                float4 a = tot[q];
+                if (extra >= 0) f4_add(a, ld_f4(feat + (int64_t)extra * ldf + 4 * col));
+                a.x *= sc; a.y *= sc; a.z *= sc; a.w *= sc;
+                *reinterpret_cast<float4*>(agg + (int64_t)w * ldf + 4 * col) = a;
+            }
+        }
+    }
+    if (lane == 0) it_done[w] = 0;          // every ticket of this item is taken: re-arm it for the next call on this selection
     }
 }
 

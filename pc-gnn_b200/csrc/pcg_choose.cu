@@ -89,20 +89,27 @@ struct ChooseP {
 };
 
 #ifdef PCG_TRACE
-// Debug build only (make EXTRA=-DPCG_TRACE): per-item phase timestamps, 12 int64 per item.
+// Debug build only (make EXTRA=-DPCG_TRACE): per-item phase timestamps, PCG_TRACE_SLOTS int64 per item (slots 0-7 phases,
+// 8-10 d / k / o, 11 selection steps, 12-27 selection sub-phases of the cluster tiers, 28-33 compaction / oversampling).
+#define PCG_TRACE_SLOTS 40
 __device__ long long* g_trace = nullptr;
 __device__ __forceinline__ long long trace_now() {
     long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-#define TRACE(slot) do { if (g_trace && tid == 0 && (blockIdx.x % 8 == 0 || blockDim.x != 256 || gridDim.x % 8 != 0 || true)) g_trace[(int64_t)w * 12 + (slot)] = trace_now(); } while (0)
-#define TRACE_VAL(slot, val) do { if (g_trace && tid == 0) g_trace[(int64_t)w * 12 + (slot)] = (val); } while (0)
-#define PTRACE(slot) do { if (g_trace && threadIdx.x == 0) g_trace[(int64_t)p.R * p.B * 12 + (slot)] = trace_now(); } while (0)
+#define TRACE(slot) do { if (g_trace && tid == 0) g_trace[(int64_t)w * PCG_TRACE_SLOTS + (slot)] = trace_now(); } while (0)
+#define TRACE_VAL(slot, val) do { if (g_trace && tid == 0) g_trace[(int64_t)w * PCG_TRACE_SLOTS + (slot)] = (val); } while (0)
+#define PTRACE(slot) do { if (g_trace && threadIdx.x == 0) g_trace[(int64_t)p.R * p.B * PCG_TRACE_SLOTS + (slot)] = trace_now(); } while (0)
+// cluster tiers, CTA 0 of the cluster only
+#define TRACE0(slot) do { if (g_trace && tid == 0 && cg::this_cluster().block_rank() == 0) g_trace[(int64_t)w * PCG_TRACE_SLOTS + (slot)] = trace_now(); } while (0)
+#define TRACE0_VAL(slot, val) do { if (g_trace && tid == 0 && cg::this_cluster().block_rank() == 0) g_trace[(int64_t)w * PCG_TRACE_SLOTS + (slot)] = (val); } while (0)
 #else
 #define PTRACE(slot) do {} while (0)
 #define TRACE(slot) do {} while (0)
 #define TRACE_VAL(slot, val) do {} while (0)
+#define TRACE0(slot) do {} while (0)
+#define TRACE0_VAL(slot, val) do {} while (0)
 #endif
 template <int NT>
 __device__ __forceinline__ void grp_sync() {
@@ -341,7 +348,7 @@ __device__ __forceinline__ void cta_bitselect(Get get, int n, int kth, uint32_t*
 template <int NT, int NE, int CL = 1>
 __device__ __forceinline__ void hist_select(const uint32_t (&key)[NE], uint32_t vmask, int kth, uint32_t* hist, int* xw,
                                             int tid, uint32_t& T, int& need, uint32_t* chist = nullptr,
-                                            int* par = nullptr) {
+                                            int* par = nullptr, int w = 0) {
 
     constexpr int NH = NT == 32 ? 1 : 8;
     const int lane = tid & 31, wid = tid >> 5;
@@ -390,6 +397,7 @@ __device__ __forceinline__ void hist_select(const uint32_t (&key)[NE], uint32_t 
             }
         }
         grp_sync<NT>();
+        if (CL > 1) { TRACE0(12 + 4 * step); TRACE0_VAL(11, step + 1); }
         // merge (and clear) the histograms, scan, find the bin of the k-th key
         int dg = -1, rem_in = 0, cnt_in = 0;
         if (NT == 32) {
@@ -427,12 +435,14 @@ __device__ __forceinline__ void hist_select(const uint32_t (&key)[NE], uint32_t 
                 uint32_t* mine_h = chist + *par * 256 + (tid & 255);
                 if (tid < 256) *mine_h = (uint32_t)c;
                 cl.sync();
+                TRACE0(13 + 4 * step);
                 if (tid < 256) {
                     c = 0;
 #pragma unroll
                     for (int r = 0; r < CL; ++r) c += (int)*cl.map_shared_rank(mine_h, r);
                 }
                 *par ^= 1;
+                TRACE0(14 + 4 * step);
             }
             if (tid < 256) {
                 incl = c;
@@ -453,6 +463,7 @@ __device__ __forceinline__ void hist_select(const uint32_t (&key)[NE], uint32_t 
             }
             __syncthreads();
             dg = xw[16]; rem_in = xw[17]; cnt_in = xw[18];
+            if (CL > 1) TRACE0(15 + 4 * step);
         }
         remaining = rem_in;
         prefix |= (uint32_t)dg << shift;
@@ -573,6 +584,7 @@ __device__ __forceinline__ int oversample(const ChooseP& p, const Item& it, int 
         b_less = (int)hist[67]; b_le = (int)hist[68]; Tp = hist[69];
         __syncthreads();
     }
+    if (NT > 32) { TRACE(31); }
     const int cnt_less = a_less + b_less;
     const int tie_a = a_le - a_less, ties = tie_a + (b_le - b_less);
     const int needp = o - cnt_less;            // 1 <= needp <= ties
@@ -793,7 +805,7 @@ __device__ __forceinline__ void cta_body(const ChooseP& p, const Item& it, CtaSm
     uint32_t T = 0xffffffffu;
     int need = 0x7fffffff;
     if (!all) {
-        if (k > 0) hist_select<NT, NE, CL>(key, vmask, k, s.hist, s.xw, tid, T, need, s.chist, par);
+        if (k > 0) hist_select<NT, NE, CL>(key, vmask, k, s.hist, s.xw, tid, T, need, s.chist, par, w);
         else { T = 0; need = 0; }
     }
     TRACE(3);
@@ -806,6 +818,7 @@ __device__ __forceinline__ void cta_body(const ChooseP& p, const Item& it, CtaSm
         if (lane == 0) s.cnt[e * NW + wid] = __popc(ml) | (__popc(mt) << 16);
     }
     __syncthreads();
+    if (CL > 1) TRACE0(28);
     if (wid == 0) {
         constexpr int PER = (NE * NW + 31) / 32;       // consecutive entries per lane
         int v[PER], sum = 0;
@@ -836,6 +849,7 @@ __device__ __forceinline__ void cta_body(const ChooseP& p, const Item& it, CtaSm
     if (CL > 1) {
         cg::cluster_group cl = cg::this_cluster();
         cl.sync();
+        TRACE0(29);
         for (int c = 0; c < rank; ++c) {
             const int t = *cl.map_shared_rank(&s.ctot, c);
             base_less += t & 0xffff;
@@ -890,6 +904,7 @@ __device__ __forceinline__ void cta_item(const ChooseP& p, int w, CtaSmem<NT>& s
     else cta_body<NT, NE_MAX, CL>(p, it, s, sid, spp, bits_local, rank, par);
     if (CL > 1) {
         if (it.o > 0) cg::this_cluster().sync();      // kept bitmaps complete (remote ORs) before rank 0 reads them
+        TRACE0(30);
         if (rank != 0) return;
     }
     __syncthreads();                      // kept bitmaps complete

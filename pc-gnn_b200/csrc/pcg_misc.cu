@@ -74,9 +74,45 @@ __global__ void __launch_bounds__(256) k_score_table(const float* __restrict__ f
 // reduction tree: the values are bit-identical to score[pool[i]]). It lets the pool sort run NEXT TO the score-table
 // kernel instead of behind it (and, on a row-partitioned graph, next to the score exchange: features are replicated),
 // and it is the common predecessor from which the step's three front branches fork.
+// Staging rider: the CTAs behind the first `score_blocks` copy `stage_words` 32-bit words from stage_src to stage_dst
+// (the batch's ids / labels out of mapped pinned host memory, see pcg_stage): the step's first kernel fetches the
+// batch while it computes, so a host batch needs no copy node in front of the recorded step.
+__device__ __forceinline__ uint32_t ld_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void stage_copy(const uint32_t* src, uint32_t* dst, int64_t n, int64_t first, int64_t stride) {
+    // four independent loads in flight per thread (a PCIe round trip each when src is host memory)
+    for (int64_t i = first; i < n; i += 4 * stride) {
+        uint32_t v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = i + u * stride < n ? ld_sys(src + i + u * stride) : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (i + u * stride < n) st_sys(dst + i + u * stride, v[u]);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_stage(const uint32_t* src, uint32_t* dst, int64_t n) {
+    stage_copy(src, dst, n, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
+    __threadfence_system();
+}
+
 __global__ void __launch_bounds__(256) k_pool_scores(const float* __restrict__ feat, int F, int64_t ldf,
                                                      const float* __restrict__ w, const float* __restrict__ b,
-                                                     const int32_t* __restrict__ pool, int P, float* __restrict__ pool_score) {
+                                                     const int32_t* __restrict__ pool, int P, float* __restrict__ pool_score,
+                                                     int score_blocks, const uint32_t* stage_src, uint32_t* stage_dst,
+                                                     int64_t stage_words) {
+    if ((int)blockIdx.x >= score_blocks) {
+        const int64_t nb = gridDim.x - score_blocks;
+        stage_copy(stage_src, stage_dst, stage_words, (int64_t)(blockIdx.x - score_blocks) * blockDim.x + threadIdx.x,
+                   nb * blockDim.x);
+        return;
+    }
     extern __shared__ float sw[];
     for (int c = threadIdx.x; c < ldf; c += blockDim.x) sw[c] = c < F ? w[c] : 0.f;
     const float bias = b ? b[0] : 0.f;
@@ -84,7 +120,7 @@ __global__ void __launch_bounds__(256) k_pool_scores(const float* __restrict__ f
     const int l = threadIdx.x & 7;
     const int V = (int)(ldf >> 2);
     const int rows_per_block = blockDim.x >> 3;
-    for (int ib = blockIdx.x * rows_per_block + ((threadIdx.x >> 5) << 2); ib < P; ib += gridDim.x * rows_per_block) {
+    for (int ib = blockIdx.x * rows_per_block + ((threadIdx.x >> 5) << 2); ib < P; ib += score_blocks * rows_per_block) {
         const int i = ib + ((threadIdx.x & 31) >> 3);
         float acc = 0.f;
         if (i < P) {
@@ -242,18 +278,71 @@ extern "C" int pcg_sort_pool(const float* pool_score, const int32_t* pool, int P
     return pcg_check_launch("pcg_sort_pool");
 }
 
-extern "C" int pcg_pool_scores(const float* feat, int F, int64_t ldf, const float* w, const float* b, const int32_t* pool,
-                               int P, float* pool_score, pcg_stream_t stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    if (P <= 0) return 0;
-    PCG_REQUIRE(feat && w && pool && pool_score, "pcg_pool_scores: null pointer");
+static int pool_scores_impl(const char* who, const float* feat, int F, int64_t ldf, const float* w, const float* b,
+                            const int32_t* pool, int P, float* pool_score, const void* stage_src, void* stage_dst,
+                            size_t stage_bytes, cudaStream_t stream) {
+    PCG_REQUIRE(stage_bytes == 0 || (stage_src && stage_dst), "%s: staging pointers missing", who);
+    PCG_REQUIRE(stage_bytes % 4 == 0 && ((uintptr_t)stage_src & 3) == 0 && ((uintptr_t)stage_dst & 3) == 0,
+                "%s: the staged copy works on aligned 32-bit words", who);
+    if (P <= 0) {
+        if (stage_bytes) {
+            const int64_t n = (int64_t)(stage_bytes / 4);
+            k_stage<<<(int)((n + 1023) / 1024 < 64 ? (n + 1023) / 1024 : 64), 256, 0, stream>>>((const uint32_t*)stage_src,
+                                                                                              (uint32_t*)stage_dst, n);
+            return pcg_check_launch(who);
+        }
+        return 0;
+    }
+    PCG_REQUIRE(feat && w && pool && pool_score, "%s: null pointer", who);
     PCG_REQUIRE(ldf % 4 == 0 && F <= ldf && F > 0 && ldf * 4 <= 48 * 1024 && ((uintptr_t)feat & 15) == 0,
-                "pcg_pool_scores: need F <= ldf, ldf %% 4 == 0, 16-byte aligned rows (F=%d ldf=%lld)", F, (long long)ldf);
+                "%s: need F <= ldf, ldf %% 4 == 0, 16-byte aligned rows (F=%d ldf=%lld)", who, F, (long long)ldf);
     int blocks = (P + 31) / 32;
     const int sms = pcg_device_sms();
     if (blocks > sms * 16) blocks = sms * 16;
-    k_pool_scores<<<blocks, 256, (size_t)ldf * 4, stream>>>(feat, F, ldf, w, b, pool, P, pool_score);
-    return pcg_check_launch("pcg_pool_scores");
+    const int64_t words = (int64_t)(stage_bytes / 4);
+    int64_t rider = (words + 1023) / 1024;            // four words per thread
+    if (rider > 64) rider = 64;
+    k_pool_scores<<<blocks + (int)rider, 256, (size_t)ldf * 4, stream>>>(feat, F, ldf, w, b, pool, P, pool_score, blocks,
+                                                                         (const uint32_t*)stage_src, (uint32_t*)stage_dst,
+                                                                         words);
+    return pcg_check_launch(who);
+}
+
+extern "C" int pcg_pool_scores(const float* feat, int F, int64_t ldf, const float* w, const float* b, const int32_t* pool,
+                               int P, float* pool_score, pcg_stream_t stream_) {
+    return pool_scores_impl("pcg_pool_scores", feat, F, ldf, w, b, pool, P, pool_score, nullptr, nullptr, 0,
+                            (cudaStream_t)stream_);
+}
+
+extern "C" int pcg_pool_scores_stage(const float* feat, int F, int64_t ldf, const float* w, const float* b,
+                                     const int32_t* pool, int P, float* pool_score, const void* stage_src, void* stage_dst,
+                                     size_t stage_bytes, pcg_stream_t stream_) {
+    return pool_scores_impl("pcg_pool_scores_stage", feat, F, ldf, w, b, pool, P, pool_score, stage_src, stage_dst,
+                            stage_bytes, (cudaStream_t)stream_);
+}
+
+extern "C" void* pcg_host_device_ptr(void* host_ptr) {
+    void* dev = nullptr;
+    cudaError_t e = cudaHostGetDevicePointer(&dev, host_ptr, 0);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        pcg_set_error("pcg_host_device_ptr: %s (not page-locked / not mapped)", cudaGetErrorString(e));
+        return nullptr;
+    }
+    return dev;
+}
+
+extern "C" int pcg_stage(const void* src, void* dst, size_t bytes, pcg_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (bytes == 0) return 0;
+    PCG_REQUIRE(src && dst, "pcg_stage: null pointer");
+    PCG_REQUIRE(bytes % 4 == 0 && ((uintptr_t)src & 3) == 0 && ((uintptr_t)dst & 3) == 0,
+                "pcg_stage: the copy works on aligned 32-bit words");
+    const int64_t n = (int64_t)(bytes / 4);
+    int64_t blocks = (n + 1023) / 1024;
+    if (blocks > 64) blocks = 64;
+    k_stage<<<(int)blocks, 256, 0, stream>>>((const uint32_t*)src, (uint32_t*)dst, n);
+    return pcg_check_launch("pcg_stage");
 }
 
 extern "C" int pcg_score_table(const float* feat, int64_t n_nodes, int F, int64_t ldf, const float* w, const float* b,

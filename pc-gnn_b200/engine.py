@@ -230,17 +230,32 @@ class Engine:
         _lib.check(rc, "pcg_score_table")
         return self.score
 
-    def pool_scores(self, clf_weight: torch.Tensor, clf_bias: torch.Tensor):
+    def stage(self, src_ptr: int, dst_ptr: int, nbytes: int):
+        """Copy by a kernel (``pcg_stage``): either side may be page-locked host memory (device address from
+        ``host_device_ptr``); keeps a recorded step free of memcpy nodes."""
+        _lib.check(self.lib.pcg_stage(src_ptr, dst_ptr, int(nbytes), _lib.stream_ptr()), "pcg_stage")
+
+    def pool_scores(self, clf_weight: torch.Tensor, clf_bias: torch.Tensor, stage=None):
         """Scores of the pool members only (``pcg_pool_scores``; bit-identical to the table's values): the pool sort
-        can then run next to the score-table kernel / the score exchange instead of behind it."""
+        can then run next to the score-table kernel / the score exchange instead of behind it.
+        stage = (src_ptr, dst_ptr, nbytes): that copy rides on extra CTAs of the kernel (``pcg_pool_scores_stage``)."""
         if not self.P:
+            if stage is not None:
+                self.stage(*stage)
             return None
         if getattr(self, "_pool_score", None) is None or self._pool_score.shape[0] != self.P:
             self._pool_score = torch.empty(self.P, dtype=torch.float32, device=self.device)
         w = clf_weight.detach()
         w = w if w.is_contiguous() else w.contiguous()
-        rc = self.lib.pcg_pool_scores(self.feat.data_ptr(), self.F, self.ldf, w.data_ptr(), clf_bias.detach().data_ptr(),
-                                      self.pool.data_ptr(), self.P, self._pool_score.data_ptr(), _lib.stream_ptr())
+        if stage is not None:
+            rc = self.lib.pcg_pool_scores_stage(self.feat.data_ptr(), self.F, self.ldf, w.data_ptr(),
+                                                clf_bias.detach().data_ptr(), self.pool.data_ptr(), self.P,
+                                                self._pool_score.data_ptr(), stage[0], stage[1], int(stage[2]),
+                                                _lib.stream_ptr())
+        else:
+            rc = self.lib.pcg_pool_scores(self.feat.data_ptr(), self.F, self.ldf, w.data_ptr(),
+                                          clf_bias.detach().data_ptr(), self.pool.data_ptr(), self.P,
+                                          self._pool_score.data_ptr(), _lib.stream_ptr())
         _lib.check(rc, "pcg_pool_scores")
         return self._pool_score
 

@@ -428,6 +428,8 @@ class InterAgg(nn.Module):
         self.last_selection = None
         self.use_pdl = False            # runtime.GraphedTrainStep: programmatic dependent launch of the fused kernels
         self.graph_cache = True         # record the reference-facing calls into CUDA graphs (stepgraph.StepGraphCache)
+        self.stage_in = None            # runtime.GraphedTrainStep (host batches): (src, dst, bytes) of the packed ids / labels in
+        #                                 mapped pinned memory; copied by the step's first kernel (Engine.pool_scores / stage)
         self._graphs = None
         self._fused_memo = {}
 
@@ -455,12 +457,14 @@ class InterAgg(nn.Module):
         cur = torch.cuda.current_stream(dev)
         side = eng.side_stream(0)
         own_scores = self.score_override is None and not self.scores_external
+        stage, self.stage_in = self.stage_in, None
+
         if own_scores and eng.P and train_flag:
             # Three branches fork behind the pool-score kernel and meet in front of the selection kernels:
             #   side 0: preparation of the choose step (repeated targets, item sizes, slot prefix sum, tier queues): no scores
             #   side 1: pool sort, from the pool members' scores alone (layers.py:232, :237)
             #   main  : score table of every node, column 0 (layers.py:231, :236) [+ slice exchange on a row partition]
-            pool_score = eng.pool_scores(self.label_clf.weight, self.label_clf.bias)
+            pool_score = eng.pool_scores(self.label_clf.weight, self.label_clf.bias, stage=stage)
             side1 = eng.side_stream(1)
             side.wait_stream(cur)
             side1.wait_stream(cur)
@@ -472,7 +476,10 @@ class InterAgg(nn.Module):
             cur.wait_stream(side)
             cur.wait_stream(side1)
         else:
-            eng.fork_point()
+            if stage is not None:
+                eng.stage(*stage)        # also the common node in front of the fork
+            else:
+                eng.fork_point()
             side.wait_stream(cur)
             with torch.cuda.stream(side):
                 sel = eng.choose(targets, lab, train_flag, self.thresholds, rho, cap, phases=1)

@@ -51,6 +51,16 @@ class GraphedTrainStep:
         self._pin_loss = torch.zeros(1, dtype=torch.float32, pin_memory=True)
         self._loss_event = torch.cuda.Event()
         self.loss = None
+        # host batches (fused optimizer): a second recording of the step whose FIRST kernel also fetches the packed batch
+        # out of one pinned buffer at a fixed address (mapped host memory) and which ends with a 4-byte store of the
+        # loss into a pinned word, so that a host batch costs one graph launch and one event wait (no copy calls around it)
+        self._pin_in = torch.zeros(3 * self.B, dtype=torch.int32, pin_memory=True)
+        self._pin_in_np = self._pin_in.numpy()
+        self._pin_loss_np = self._pin_loss.numpy()
+        self._host_done = torch.cuda.Event()
+        self._host_pending = False
+        self.g_host = None
+        self.loss_host = None
         if reducer is not None:
             # the captured graph writes the gradients through the parameters' .grad tensors: they must BE the views
             # of the reducer's flat buffer (otherwise the graph keeps accumulating into tensors nobody zeroes)
@@ -74,10 +84,26 @@ class GraphedTrainStep:
         self._xeng.set_features(inter.features.weight)
         self._xeng.score_local(inter.label_clf.weight, inter.label_clf.bias)
 
-    def _fwd_bwd(self):
+    def _stage_in(self):
+        """(recorded) the packed batch out of the pinned buffer, by a KERNEL reading the mapped host memory: PC-GNN
+        models hand the copy to ``InterAgg._select``, where it rides on the step's first kernel (the pool scores,
+        which need no ids); other models get a copy kernel in front. No memcpy node: the recording stays a graph of
+        kernels (with copy nodes in it the branches of the step were measured to start several microseconds apart)."""
+        from . import _lib
+
+        job = (_lib.host_device_ptr(self._pin_in), self._packed.data_ptr(), self._packed.numel() * 4)
+        inter = getattr(self.model, "inter1", None)
+        if inter is not None and hasattr(inter, "stage_in"):
+            inter.stage_in = job
+        else:
+            _lib.check(_lib.lib().pcg_stage(job[0], job[1], job[2], _lib.stream_ptr()), "pcg_stage")
+
+    def _fwd_bwd(self, host_io: bool = False):
         if self._xeng is not None and not torch.cuda.is_current_stream_capturing():
             self._score_pre()                      # eager warm-up steps: slice, exchange, then the forward
             self._xeng.score_exchange()
+        if host_io:
+            self._stage_in()
         if self.fused:
             pass                                   # the fused step leaves the gradients zeroed
         elif self.reducer is not None:
@@ -98,6 +124,10 @@ class GraphedTrainStep:
         finally:
             if eng is not None:
                 eng.grad_sink = None
+            inter = getattr(self.model, "inter1", None)
+            if host_io and getattr(inter, "stage_in", None) is not None:
+                inter.stage_in = None
+                raise RuntimeError("the staged batch copy was not consumed by the forward pass")
         return loss.detach()
 
     def _capture(self):
@@ -174,10 +204,41 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.g_opt):
             self.opt.step()
 
-    def _replay(self):
+    def _capture_host_graph(self):
+        """Fused optimizer only: the step with its host<->device copies recorded as nodes of the graph."""
+        from . import _lib
+
+        import os
+
+        torch.cuda.synchronize(self.dev)
+        mask = int(os.environ.get("PCG_PDL_MASK", "10")) if self.use_pdl else 0
+        prev = _lib.lib().pcg_set_pdl(mask)
+        try:
+            self._pin_in.copy_(self._packed)           # whatever batch is resident: replays before run() stay meaningful
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                cur = torch.cuda.current_stream(self.dev)
+                loss = self._fwd_bwd(host_io=True)
+                # the loss leaves (a 4-byte store into the mapped pinned word) next to the exchange + Adam kernel
+                side = torch.cuda.Stream(device=self.dev) if not hasattr(self.model, "inter1") \
+                    else self.model.inter1.engine().side_stream(2)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    _lib.check(_lib.lib().pcg_stage(loss.data_ptr(), _lib.host_device_ptr(self._pin_loss), 4,
+                                                    _lib.stream_ptr()), "pcg_stage")
+                self.opt.step()
+                cur.wait_stream(side)
+            self.g_host, self.loss_host = g, loss
+        finally:
+            _lib.lib().pcg_set_pdl(prev)
+
+    def _replay(self, host: bool = False):
         if self.g_pre is not None:
             self.g_pre.replay()
             self._xeng.score_exchange()
+        if host:
+            self.g_host.replay()
+            return self.loss_host
         self.g_fb.replay()
         if self.fused:
             return self.loss
@@ -190,14 +251,34 @@ class GraphedTrainStep:
     # -- public --------------------------------------------------------------------------------
     def run_device(self, nodes_dev: torch.Tensor, labels_dev: torch.Tensor):
         """Batch already in HBM (int32 ids, int64 labels). Returns the (device) loss tensor."""
-        self.nodes.copy_(nodes_dev, non_blocking=True)
-        self.labels.copy_(labels_dev, non_blocking=True)
+        if nodes_dev.dtype == torch.int32 and labels_dev.dtype == torch.int64 and labels_dev.is_contiguous():
+            # both copies in ONE multi-tensor kernel (labels seen as int32 pairs)
+            B = self.B
+            torch._foreach_copy_([self._packed[:2 * B], self._packed[2 * B:]],
+                                 [labels_dev.view(torch.int32).reshape(-1), nodes_dev.reshape(-1)], non_blocking=True)
+        else:
+            self.nodes.copy_(nodes_dev, non_blocking=True)
+            self.labels.copy_(labels_dev, non_blocking=True)
         return self._replay()
 
     def run(self, nodes, labels):
         """Batch on the host (numpy arrays, or lists, of ids and labels): one pinned staging copy + one H2D + replay.
         Returns the (device) loss tensor."""
         B = self.B
+        if self.fused:
+            # one graph launch: the step's kernels read the batch from / write the loss to pinned host memory themselves.
+            # The pinned input buffer is free again once the previous replay has finished.
+            if self.g_host is None:
+                self._capture_host_graph()
+            if self._host_pending:
+                self._host_done.synchronize()
+            pin = self._pin_in_np
+            pin[:2 * B].view(np.int64)[:] = labels
+            pin[2 * B:] = nodes
+            loss = self._replay(host=True)
+            self._host_done.record(torch.cuda.current_stream(self.dev))
+            self._host_pending = True
+            return loss
         host = np.empty(3 * B, dtype=np.int32)
         host[:2 * B].view(np.int64)[:] = labels
         host[2 * B:] = nodes
@@ -205,9 +286,14 @@ class GraphedTrainStep:
         return self._replay()
 
     def run_item(self, nodes, labels) -> float:
-        """``run`` + the loss as a Python float (device->host through a pinned word and an event; cheaper than
-        ``.item()``'s pageable copy)."""
+        """``run`` + the loss as a Python float (device->host through a pinned word; cheaper than ``.item()``'s
+        pageable copy). Fused optimizer: the D2H copy is the last node of the recorded step, so this is one graph
+        launch and one event wait."""
         loss = self.run(nodes, labels)
+        if self.fused:
+            self._host_done.synchronize()
+            self._host_pending = False
+            return float(self._pin_loss_np[0])
         self._pin_loss.copy_(loss.reshape(1), non_blocking=True)
         self._loss_event.record(torch.cuda.current_stream(self.dev))
         self._loss_event.synchronize()

@@ -44,3 +44,21 @@ for rep in range(3):
     print(f"--- replay {rep}: {len(ev)} kernels, wall {end - t0:.1f} us, sum {sum(e.device_time for e in ev):.1f} us")
     for e in ev:
         print(f"  +{e.time_range.start - t0:7.1f}  {e.device_time:6.1f} us  {e.name[:100]}")
+
+# the recording that host batches replay (runtime.GraphedTrainStep.run): H2D copy of the batch and D2H copy of the loss
+# are nodes of the graph
+n, l = batches[1]
+g.run(n, l)
+torch.cuda.synchronize()
+flush.zero_()
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    g.g_host.replay()
+    torch.cuda.synchronize()
+ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+ev.sort(key=lambda e: e.time_range.start)
+t0 = ev[0].time_range.start
+end = max(e.time_range.end for e in ev)
+print(f"--- host-batch recording: {len(ev)} nodes, wall {end - t0:.1f} us")
+for e in ev:
+    print(f"  +{e.time_range.start - t0:7.1f}  {e.device_time:6.1f} us  {e.name[:100]}")

@@ -23,7 +23,8 @@ eng.set_features(torch.from_numpy(data.feat).cuda())
 eng.set_pool(sorted(data.train_pos))
 L = _lib.lib()
 R = data.graph.n_rel
-trace = torch.zeros(batch * R * 12 + 16, dtype=torch.int64, device="cuda")
+S = 40          # PCG_TRACE_SLOTS
+trace = torch.zeros(batch * R * S + 16, dtype=torch.int64, device="cuda")
 L.pcg_debug_set_trace.argtypes = [ctypes.c_void_p]
 assert L.pcg_debug_set_trace(trace.data_ptr()) == 0
 rng = np.random.default_rng(0)
@@ -43,14 +44,15 @@ for it, (nodes, labels) in enumerate(batches):
     e1.record()
     torch.cuda.synchronize()
     raw = trace.cpu().numpy()
-    pt = raw[batch * R * 12:batch * R * 12 + 5].astype(np.float64)
+    pt = raw[batch * R * S:batch * R * S + 5].astype(np.float64)
     print("  prep kernel phases (ns): first-table=%d sizes=%d scan+queues=%d tail=%d; first item starts %+d ns after prep ends"
-          % (pt[1] - pt[0], pt[2] - pt[1], pt[3] - pt[2], pt[4] - pt[3], raw[:batch * R * 12].reshape(-1, 12)[:, 0][raw[:batch * R * 12].reshape(-1, 12)[:, 7] > 0].min() - pt[4]))
-    tr = raw[:batch * R * 12].reshape(-1, 12)
+          % (pt[1] - pt[0], pt[2] - pt[1], pt[3] - pt[2], pt[4] - pt[3], raw[:batch * R * S].reshape(-1, S)[:, 0][raw[:batch * R * S].reshape(-1, S)[:, 7] > 0].min() - pt[4]))
+    tr = raw[:batch * R * S].reshape(-1, S)
     done = tr[:, 7] > 0
     tr = tr[done]
     ts = tr[:, :8].astype(np.float64)
     d, k, o = tr[:, 8], tr[:, 9], tr[:, 10]
+    fine = tr[:, 11:].astype(np.float64)        # [:, 0] steps; [:, 1 + 4 * step + j] select sub-phases; [:, 17..] compaction / pool
     start = ts[:, 0].min()
     dur = ts[:, 7] - ts[:, 0]
     names = ["header", "load-dist", "select", "compact", "pool-search", "pool-emit", "finish"]
@@ -78,3 +80,21 @@ for it, (nodes, labels) in enumerate(batches):
                 row[c] = row[c] if row[c] > 0 else row[c - 1]
             print(f"    slow item d={d[wi]} k={k[wi]} o={o[wi]} total={dur[wi]:.0f} ns (start +{(ts[wi, 0] - start) / 1e3:.1f} us): " +
                   ", ".join(f"{n}={v:.0f}" for n, v in zip(names, np.diff(row))))
+            if tier.startswith("wide") and fine[wi, 0] > 0:
+                # CTA 0 of the cluster: per selection step (local histogram | merge + cluster barrier | remote reads |
+                # scan + broadcast), relative to the end of the load phase; then the compaction's and the pool's stamps
+                t2 = ts[wi, 2]
+                steps = int(fine[wi, 0])
+                parts, prev = [], t2
+                for st in range(steps):
+                    seg = []
+                    for j in range(4):
+                        v = fine[wi, 1 + 4 * st + j]
+                        seg.append(f"{(v - prev):.0f}" if v > 0 else "-")
+                        prev = v if v > 0 else prev
+                    parts.append("/".join(seg))
+                c28, c29, c30, c31 = fine[wi, 17], fine[wi, 18], fine[wi, 19], fine[wi, 20]
+                print(f"      select steps={steps} [hist/merge+clsync/dsmem/scan] " + "  ".join(parts) +
+                      f"; after select {ts[wi, 3] - prev:.0f}; compact: ballots+sync {c28 - ts[wi, 3]:.0f}, scan+clsync {c29 - c28:.0f}, "
+                      f"stores {ts[wi, 4] - c29:.0f}, kbits clsync {c30 - ts[wi, 4]:.0f}" +
+                      (f", pool search {c31 - c30:.0f}, ties {ts[wi, 5] - c31:.0f}" if c31 > 0 else ""))

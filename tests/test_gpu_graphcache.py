@@ -183,3 +183,55 @@ def test_overflow_flag_is_sticky_across_replays():
     step.run(small, d.labels[small])          # ... and a later, fitting replay must not hide it
     assert step.overflowed()
     assert not step.overflowed()              # reading clears it
+
+
+def test_host_batches_equal_device_batches():
+    """GraphedTrainStep.run / run_item (the recorded step fetches the batch from pinned host memory by itself and stores
+    the loss into a pinned word: pcg_pool_scores_stage / pcg_stage) against run_device on the same batches, from the
+    same initial state: identical losses, bit for bit, and identical parameters afterwards."""
+    from pcgnn_b200.parallel import FusedAdam, GradAllReduce
+    from pcgnn_b200.runtime import GraphedTrainStep
+
+    d, rng, params, tp = _setup(seed=66)
+    B = 128
+    batches = [rng.choice(d.idx_train, B) for _ in range(8)]
+    res, weights = [], []
+    for mode in ("device", "host", "host_item"):
+        model = build_cuda_pcgnn(d.feat, d.graph, tp, params)
+        reducer = GradAllReduce(model.parameters()).attach()
+        opt = FusedAdam(reducer, lr=0.01, weight_decay=1e-3)
+        eng = model.inter1.engine()
+        eng.set_features(model.inter1.features.weight)
+        cap = GraphedTrainStep.plan(eng, batches, model.inter1.thresholds, 0.5)
+        step = GraphedTrainStep(model, opt, B, cap, reducer=reducer, warmup_batch=(batches[0], d.labels[batches[0]]))
+        losses = []
+        for n in batches:
+            if mode == "device":
+                loss = step.run_device(torch.from_numpy(n.astype(np.int32)).cuda(), torch.from_numpy(d.labels[n]).cuda())
+                losses.append(float(loss.item()))
+            elif mode == "host":
+                losses.append(float(step.run(n, d.labels[n]).item()))
+            else:
+                losses.append(step.run_item(n.tolist(), d.labels[n]))
+        assert not step.overflowed()
+        res.append(np.asarray(losses, dtype=np.float32))
+        weights.append(reducer.flat_params.detach().cpu().numpy().copy() if hasattr(reducer, "flat_params")
+                       else np.concatenate([p.detach().cpu().numpy().ravel() for p in model.parameters() if p.requires_grad]))
+    assert np.array_equal(res[0], res[1]) and np.array_equal(res[0], res[2])
+    assert np.array_equal(weights[0], weights[1]) and np.array_equal(weights[0], weights[2])
+
+
+def test_stage_copies_through_pinned_host_memory():
+    from pcgnn_b200 import _lib
+
+    L = _lib.lib()
+    for n in (1, 3, 1024, 3 * 1024 + 5, 100_003):
+        src = torch.arange(n, dtype=torch.int32).pin_memory()
+        dst = torch.zeros(n, dtype=torch.int32, device="cuda")
+        _lib.check(L.pcg_stage(_lib.host_device_ptr(src), dst.data_ptr(), n * 4, _lib.stream_ptr()), "pcg_stage")
+        back = torch.zeros(n, dtype=torch.int32).pin_memory()
+        _lib.check(L.pcg_stage(dst.data_ptr(), _lib.host_device_ptr(back), n * 4, _lib.stream_ptr()), "pcg_stage")
+        torch.cuda.synchronize()
+        assert torch.equal(dst.cpu(), src) and torch.equal(back, src)
+    with pytest.raises(_lib.PcgError):
+        _lib.check(L.pcg_stage(dst.data_ptr(), dst.data_ptr() + 2, 4, _lib.stream_ptr()), "pcg_stage")
