@@ -5,20 +5,26 @@
 // exchange per step: the sum of the small parameter gradient. With NCCL that is a separate, latency-bound
 // collective between two CUDA graphs plus torch's multi-tensor Adam; here every rank
 //   1. PUSHES its flat gradient into its slot of every peer's receive area (peer memory mapped by CUDA IPC: plain
-//      16-byte stores over NVLink / NVSwitch, posted, no round trip),
-//   2. raises a per-CTA flag in every peer (st.release.sys) and waits for the peers' flags,
-//   3. adds the world's slots of its OWN receive area (local reads) in RANK ORDER (every rank computes bit-identical
-//      sums, so the replicas never drift) and divides by the world size,
-//   4. applies the Adam update (same formula as torch.optim.Adam with L2 weight decay) to its replica of the
+//      16-byte stores over NVLink / NVSwitch, posted, no round trip). Every 8-byte half of a store is
+//      {gradient word, step number}: the data carries its own arrival flag, so there is neither a system fence
+//      (a round trip: all remote stores acknowledged) nor a separate flag store behind it,
+//   2. polls the world's slots of its OWN receive area (local reads) until every word shows this step's number,
+//      adds them in RANK ORDER (every rank computes bit-identical sums, so the replicas never drift) and divides by
+//      the world size,
+//   3. applies the Adam update (same formula as torch.optim.Adam with L2 weight decay) to its replica of the
 //      parameters and clears the gradient for the next step,
-// (Round 1 / early round 2 PULLED: flag, then a read of every peer's send buffer: one NVLink round trip per peer,
-// and those reads were issued one after the other: ~20 us at 8 GPUs against 5 us for the Adam part alone.)
-// all inside the captured step graph. world == 1 runs steps 4 only.
+// all inside the captured step graph. world == 1 runs step 3 only.
+// History: round 1 PULLED (flag, then reads of every peer's send buffer, one NVLink round trip per peer): ~20 us at
+// 8 GPUs against 5 us for the Adam part alone; early round 2 pushed the data, then fence.sys + a flag per CTA and peer
+// (+15 us); flag-in-data removes the fence round trip and the flag hop.
+// Areas are double buffered by step parity: a slot is rewritten two steps later, and a rank can only be two steps
+// ahead of a peer that has not yet read if that peer had pushed twice in between, which it does after reading.
 #include "pcg_common.cuh"
 
 #define COMM_MAX_WORLD 8
 #define COMM_NT 256
 #define COMM_PER_CTA (COMM_NT * 4)
+#define COMM_SPIN_LIMIT (1u << 26)        // polls before a rank gives up on a peer (seconds): NaN gradients, never a hang
 
 struct CommP {
     float* grad;
@@ -26,9 +32,8 @@ struct CommP {
     float* m;
     float* v;
     int n;
-    int64_t n_pad;                        // floats per slot; a receive area is [2 parities][COMM_MAX_WORLD slots][n_pad]
-    float* peer_send[COMM_MAX_WORLD];     // every rank's receive area, as mapped HERE
-    uint32_t* peer_flags[COMM_MAX_WORLD]; // every rank's flag area [n_cta][COMM_MAX_WORLD]
+    int64_t n_pad;                        // floats per slot; a receive area is [2 parities][COMM_MAX_WORLD slots][2 * n_pad] words
+    uint32_t* peer_recv[COMM_MAX_WORLD];  // every rank's receive area, as mapped HERE
     uint32_t* epoch;                      // steps completed so far (device counter, so graph replays advance it)
     int32_t* ticket;
     int rank, world;
@@ -36,8 +41,13 @@ struct CommP {
     int do_adam;
 };
 
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_sys_v4(uint32_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_sys_v4(const uint32_t* p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
 }
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     uint32_t v;
@@ -54,36 +64,58 @@ __global__ void __launch_bounds__(COMM_NT) k_allreduce_adam(CommP p) {
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
     const bool in = i0 < p.n;             // n is padded to a multiple of 4 by the caller
     if (in) g = *reinterpret_cast<const float4*>(p.grad + i0);
-    if (p.world > 1) {
-        const int64_t boff = ((int64_t)(e & 1u) * COMM_MAX_WORLD + p.rank) * p.n_pad;      // my slot, this step's parity
-        if (in) {
+    if (p.world > 1 && in) {
+        // my slot of this step's parity, words {g.x, e, g.y, e} {g.z, e, g.w, e} at word offset 2 * i0
+        const int64_t area = (int64_t)(e & 1u) * COMM_MAX_WORLD * 2 * p.n_pad;
+        const int64_t mine = area + (int64_t)p.rank * 2 * p.n_pad + 2 * (int64_t)i0;
+#pragma unroll
+        for (int r = 0; r < COMM_MAX_WORLD; ++r)
+            if (r < p.world && r != p.rank) {
+                st_sys_v4(p.peer_recv[r] + mine, __float_as_uint(g.x), e, __float_as_uint(g.y), e);
+                st_sys_v4(p.peer_recv[r] + mine + 4, __float_as_uint(g.z), e, __float_as_uint(g.w), e);
+            }
+        // every peer's words for my elements land in MY area: poll them (local reads), all slots in flight per round
+        const uint32_t* base = p.peer_recv[p.rank] + area + 2 * (int64_t)i0;
+        float4 x[COMM_MAX_WORLD];
+        unsigned pending = 0;
+#pragma unroll
+        for (int r = 0; r < COMM_MAX_WORLD; ++r) {
+            x[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < p.world && r != p.rank) pending |= 1u << r;
+        }
+        x[0] = p.rank == 0 ? g : x[0];
+#pragma unroll
+        for (int r = 1; r < COMM_MAX_WORLD; ++r)
+            if (r == p.rank) x[r] = g;
+        unsigned spins = 0;
+        while (pending) {
+            uint4 lo[COMM_MAX_WORLD], hi[COMM_MAX_WORLD];
 #pragma unroll
             for (int r = 0; r < COMM_MAX_WORLD; ++r)
-                if (r < p.world) *reinterpret_cast<float4*>(p.peer_send[r] + boff + i0) = g;   // own area included
-        }
-        __syncthreads();
-        if (tid < p.world) {
-            __threadfence_system();
-            st_release_sys(p.peer_flags[tid] + (int64_t)c * COMM_MAX_WORLD + p.rank, e);
-            const uint32_t* mine = p.peer_flags[p.rank] + (int64_t)c * COMM_MAX_WORLD + tid;
-            while ((int32_t)(ld_acquire_sys(mine) - e) < 0) { }
-        }
-        __syncthreads();
-        if (in) {
-            // every rank's chunk has landed in MY receive area: local reads, added in rank order
-            const float* base = p.peer_send[p.rank] + (int64_t)(e & 1u) * COMM_MAX_WORLD * p.n_pad + i0;
-            float4 x[COMM_MAX_WORLD];
+                if ((pending >> r) & 1u) {
+                    lo[r] = ld_sys_v4(base + (int64_t)r * 2 * p.n_pad);
+                    hi[r] = ld_sys_v4(base + (int64_t)r * 2 * p.n_pad + 4);
+                }
 #pragma unroll
             for (int r = 0; r < COMM_MAX_WORLD; ++r)
-                x[r] = r < p.world ? __ldcv(reinterpret_cast<const float4*>(base + (int64_t)r * p.n_pad))
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-            g = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int r = 0; r < COMM_MAX_WORLD; ++r)
-                if (r < p.world) { g.x += x[r].x; g.y += x[r].y; g.z += x[r].z; g.w += x[r].w; }
-            const float inv = 1.0f / (float)p.world;
-            g.x *= inv; g.y *= inv; g.z *= inv; g.w *= inv;
+                if ((pending >> r) & 1u) {
+                    if (lo[r].y == e && lo[r].w == e && hi[r].y == e && hi[r].w == e) {
+                        x[r] = make_float4(__uint_as_float(lo[r].x), __uint_as_float(lo[r].z), __uint_as_float(hi[r].x),
+                                           __uint_as_float(hi[r].z));
+                        pending &= ~(1u << r);
+                    }
+                }
+            if (++spins > COMM_SPIN_LIMIT) {          // a peer never arrived: poison the step instead of hanging
+                x[0].x = __int_as_float(0x7fc00000);
+                break;
+            }
         }
+        g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < COMM_MAX_WORLD; ++r)
+            if (r < p.world) { g.x += x[r].x; g.y += x[r].y; g.z += x[r].z; g.w += x[r].w; }
+        const float inv = 1.0f / (float)p.world;
+        g.x *= inv; g.y *= inv; g.z *= inv; g.w *= inv;
     }
     if (p.do_adam) {
         if (tid == 0) {
@@ -169,7 +201,8 @@ extern "C" int pcg_comm_unmap(void* ptr) {
 extern "C" size_t pcg_comm_region_bytes(int64_t n_params) {
     const int64_t n_pad = (n_params + COMM_PER_CTA - 1) / COMM_PER_CTA * COMM_PER_CTA;
     const int64_t n_cta = n_pad / COMM_PER_CTA;
-    return (size_t)(2 * COMM_MAX_WORLD * n_pad * 4 + n_cta * COMM_MAX_WORLD * 4 + 256);
+    (void)n_cta;
+    return (size_t)(2 * COMM_MAX_WORLD * 2 * n_pad * 4 + 256);      // {word, step} pairs: two 32-bit words per gradient element
 }
 
 extern "C" int pcg_allreduce_adam(float* grad, float* param, float* m, float* v, int64_t n_params,
@@ -185,9 +218,7 @@ extern "C" int pcg_allreduce_adam(float* grad, float* param, float* m, float* v,
     p.grad = grad; p.param = param; p.m = m; p.v = v; p.n = (int)n_params;
     p.n_pad = (n_params + COMM_PER_CTA - 1) / COMM_PER_CTA * COMM_PER_CTA;
     for (int r = 0; r < COMM_MAX_WORLD; ++r) {
-        char* base = (world > 1 && r < world) ? (char*)peer_regions_host[r] : nullptr;
-        p.peer_send[r] = (float*)base;
-        p.peer_flags[r] = base ? (uint32_t*)(base + 2 * COMM_MAX_WORLD * p.n_pad * 4) : nullptr;
+        p.peer_recv[r] = (world > 1 && r < world) ? (uint32_t*)peer_regions_host[r] : nullptr;
     }
     p.epoch = epoch; p.ticket = ticket; p.rank = rank; p.world = world;
     p.lr = lr; p.b1 = beta1; p.b2 = beta2; p.eps = eps; p.wd = weight_decay; p.do_adam = do_adam;
