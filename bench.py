@@ -288,6 +288,7 @@ def hot_kernels_pcgnn(eng, inter, data, shards, dev_nodes, dev_labels, cap, W, K
     Bytes per SURVEY 8(d): filter = 8 per CSR entry of the batch's rows + 16 R B + 4 B + 4 P R B+ (pool scan)
     [+ 4 per kept id written]; aggregate = (4F + 4) per gathered row + 4 F R B."""
     import torch
+    from pcgnn_b200 import _lib
 
     R, F_ = data.graph.n_rel, data.feat.shape[1]
     t_choose = t_agg = t_front = 0.0
@@ -336,12 +337,12 @@ def hot_kernels_pcgnn(eng, inter, data, shards, dev_nodes, dev_labels, cap, W, K
     torch.cuda.current_stream(dev).wait_stream(side)
     torch.cuda.synchronize()
     g_front, g_choose, g_agg = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g_front):
+    with _lib.capture(g_front):
         front()
-    with torch.cuda.graph(g_choose):
+    with _lib.capture(g_choose):
         tiers()
     sel = holder["sel"]
-    with torch.cuda.graph(g_agg):
+    with _lib.capture(g_agg):
         eng.aggregate(sel, copy_dups=False)       # as in the train step: the dense kernels read through it_rep
     for s in range(K):
         i = W + s
@@ -402,7 +403,7 @@ def hot_kernels_gcn(eng, agg_mod, data, shards, dev_nodes, cap, W, K, flush, dev
     torch.cuda.current_stream(dev).wait_stream(side)
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
+    with _lib.capture(g):
         sel = eng.select_all(st_nodes, True, cap, _lib.NORM_RSQRT)
         eng.aggregate(sel)
     t = alg = 0.0
@@ -511,14 +512,20 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def reference_loop_arm(data, params, host_nodes, host_labels, dev, W, K, flush, is_gcn):
+def reference_loop_arm(data, params, host_nodes, host_labels, dev, W, K, flush, is_gcn, fast=False):
     """The reference's own training loop, unchanged (model_handler.py:124, :142-156), on a fresh model:
         optimizer = torch.optim.Adam(filter(requires_grad, params), lr, weight_decay)
         optimizer.zero_grad(); loss = model.loss(batch_nodes: list, Variable(cuda.LongTensor(batch_label)))
         loss.backward(); optimizer.step()            (+ loss.item(): the D2H of the step's result)
-    Returns the summed CUDA-event ms of K steps (labels are numpy on the host when a step starts)."""
+    Returns the summed CUDA-event ms of K steps (labels are numpy on the host when a step starts).
+    fast: the same loop after ``pcgnn_b200.fastloop.enable()`` (loss.backward() hands out the replay's gradients without
+    the autograd engine; optimizer.step() of the caller's torch.optim.Adam runs the package's one-kernel Adam)."""
     import torch
+    from pcgnn_b200 import fastloop
     from pcgnn_b200.testing import build_cuda_pcgnn
+
+    if fast:
+        fastloop.enable()
 
     if is_gcn:
         model = build_cuda_gcn(data, params, dev)
@@ -546,6 +553,8 @@ def reference_loop_arm(data, params, host_nodes, host_labels, dev, W, K, flush, 
         e1.record()
         evs.append((e0, e1))
     torch.cuda.synchronize()
+    if fast:
+        fastloop.disable()
     return sum(a.elapsed_time(b) for a, b in evs)
 
 
@@ -798,9 +807,11 @@ def main():
     if gstep is not None:
         assert not gstep.overflowed()
     # ---- host inputs through the REFERENCE's own loop (1 GPU: the reference is single-GPU) ----
-    ms_ref_loop = None
+    ms_ref_loop = ms_ref_loop_fast = None
     if world == 1 and not is_big:
         ms_ref_loop = reference_loop_arm(data, params, host_nodes, host_labels, dev, W, K, flush, is_gcn)
+        ms_ref_loop_fast = None if is_gcn else \
+            reference_loop_arm(data, params, host_nodes, host_labels, dev, W, K, flush, is_gcn, fast=True)
     sampler.stop_flag = True
 
     # ---- hot-path kernels alone (roofline), same batches. Each group is captured into its own CUDA graph
@@ -833,6 +844,13 @@ def main():
                         "model.loss(list_of_ids, cuda LongTensor(labels)); backward(); opt.step(); loss.item() -- served by "
                         "the package's CUDA-graph cache; host-bound: torch's Adam.step and the autograd engine are ~60% "
                         "of it (profiles/replay_cost.py)", **io}
+            if ms_ref_loop_fast is not None:
+                line["e2e_reference_loop_fast"] = {
+                    "value": total_nodes / (ms_ref_loop_fast / 1e3), "unit": "target-nodes/s",
+                    "ms_per_step": ms_ref_loop_fast / K,
+                    "call": "the same unchanged loop after pcgnn_b200.fastloop.enable(): loss.backward() stores the replay's "
+                            "gradients without the autograd engine, the caller's torch.optim.Adam.step() runs the package's "
+                            "one-kernel Adam through a pre-step hook", **io}
         if check is not None:
             line["dp_self_check"] = {"step1_loss_mean_over_ranks": check[0], "global_batch_loss_one_gpu": check[1],
                                      "replicas_bit_identical": True}

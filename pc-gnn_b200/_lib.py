@@ -123,6 +123,41 @@ def host_device_ptr(pinned_tensor) -> int:
     return int(dev)
 
 
+class capture:
+    """``with capture(graph):`` = ``with torch.cuda.graph(graph):`` with Python's garbage collector out of the way.
+    Destroying a CUDA graph while a stream is capturing invalidates the capture, and the collector may decide at any
+    moment, also in the middle of a recording, to free cyclic garbage that owns graphs (an InterAgg and its graph cache
+    reference each other). So: collect first, then keep the collector off until the recording has ended."""
+
+    def __init__(self, graph, **kw):
+        import torch
+
+        self._ctx = torch.cuda.graph(graph, **kw)
+        self._was = False
+
+    def __enter__(self):
+        import gc
+
+        gc.collect()
+        self._was = gc.isenabled()
+        gc.disable()
+        try:
+            return self._ctx.__enter__()
+        except BaseException:
+            if self._was:
+                gc.enable()
+            raise
+
+    def __exit__(self, *exc):
+        import gc
+
+        try:
+            return self._ctx.__exit__(*exc)
+        finally:
+            if self._was:
+                gc.enable()
+
+
 def stream_ptr():
     import torch
 

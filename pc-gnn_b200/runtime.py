@@ -13,6 +13,8 @@ from __future__ import annotations
 import numpy as np
 import torch
 
+from . import _lib
+
 __all__ = ["GraphedTrainStep"]
 
 
@@ -89,8 +91,6 @@ class GraphedTrainStep:
         models hand the copy to ``InterAgg._select``, where it rides on the step's first kernel (the pool scores,
         which need no ids); other models get a copy kernel in front. No memcpy node: the recording stays a graph of
         kernels (with copy nodes in it the branches of the step were measured to start several microseconds apart)."""
-        from . import _lib
-
         job = (_lib.host_device_ptr(self._pin_in), self._packed.data_ptr(), self._packed.numel() * 4)
         inter = getattr(self.model, "inter1", None)
         if inter is not None and hasattr(inter, "stage_in"):
@@ -135,8 +135,6 @@ class GraphedTrainStep:
         # Measured on C2 (profiles/README.md): the fused dense kernel and the exchange + Adam kernel gain from starting
         # under the tail of the kernel in front (mask 2 | 8: 91.2 -> 87.8 us per replay); the cluster-launched
         # weight-gradient kernel and the pool sort lose (mask 4: +10 us), so they keep full dependencies.
-        from . import _lib
-
         import os
 
         mask = int(os.environ.get("PCG_PDL_MASK", "10")) if self.use_pdl else 0
@@ -165,10 +163,10 @@ class GraphedTrainStep:
             torch.cuda.synchronize(self.dev)
             if self._xeng is not None:
                 self.g_pre = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self.g_pre):
+                with _lib.capture(self.g_pre):
                     self._score_pre()
             self.g_fb = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.g_fb):
+            with _lib.capture(self.g_fb):
                 self.loss = self._fwd_bwd()
                 self.opt.step()                    # gradient mean over the ranks + Adam, one kernel
             self.g_opt = None
@@ -195,19 +193,17 @@ class GraphedTrainStep:
         torch.cuda.synchronize(self.dev)
         if self._xeng is not None:
             self.g_pre = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.g_pre):
+            with _lib.capture(self.g_pre):
                 self._score_pre()
         self.g_fb = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g_fb):
+        with _lib.capture(self.g_fb):
             self.loss = self._fwd_bwd()
         self.g_opt = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g_opt):
+        with _lib.capture(self.g_opt):
             self.opt.step()
 
     def _capture_host_graph(self):
         """Fused optimizer only: the step with its host<->device copies recorded as nodes of the graph."""
-        from . import _lib
-
         import os
 
         torch.cuda.synchronize(self.dev)
@@ -216,7 +212,7 @@ class GraphedTrainStep:
         try:
             self._pin_in.copy_(self._packed)           # whatever batch is resident: replays before run() stay meaningful
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with _lib.capture(g):
                 cur = torch.cuda.current_stream(self.dev)
                 loss = self._fwd_bwd(host_io=True)
                 # the loss leaves (a 4-byte store into the mapped pinned word) next to the exchange + Adam kernel

@@ -20,7 +20,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, fastloop
 from .engine import PinnedStaging
 
 __all__ = ["StepGraphCache"]
@@ -134,7 +134,7 @@ class StepGraphCache:
                     fn()
             torch.cuda.current_stream(dev).wait_stream(s)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with _lib.capture(g):
                 out = fn()
         finally:
             lib.pcg_set_pdl(prev)
@@ -185,7 +185,10 @@ class StepGraphCache:
         slot.graph.replay()
         self.replays += 1
         inter.last_selection = slot.sel
-        return _ReplayLossFn.apply(slot.out, slot.flat, slot.views, *params)
+        loss = _ReplayLossFn.apply(slot.out, slot.flat, slot.views, *params)
+        if fastloop.enabled():
+            return fastloop.wrap(loss, slot.flat, slot.views, params)
+        return loss
 
     # ------------------------------------------------------------------ forward without gradients (to_prob / eval)
     def infer(self, eng, nodes, labels, train_flag):

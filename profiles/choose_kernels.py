@@ -9,6 +9,7 @@ from torch.profiler import ProfilerActivity, profile
 
 sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
 import bench  # noqa: E402
+from pcgnn_b200 import _lib  # noqa: E402
 from pcgnn_b200.engine import Engine  # noqa: E402
 from pcgnn_b200.synth import make_graph  # noqa: E402
 
@@ -38,7 +39,7 @@ with torch.cuda.stream(side):
 torch.cuda.current_stream().wait_stream(side)
 torch.cuda.synchronize()
 g = torch.cuda.CUDAGraph()
-with torch.cuda.graph(g):
+with _lib.capture(g):
     eng.score_table(w, b)
     sel = eng.choose(t, lab, True, [0.5] * R, 0.5, cap)
     eng.aggregate(sel, copy_dups=False)

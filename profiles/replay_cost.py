@@ -51,3 +51,22 @@ def seg(i):
     return out
 r=np.array([seg(i) for i in range(5,35)])
 print("zero_grad / loss / backward / step / item  (median us):", np.round(np.median(r,axis=0)*1e6,1))
+
+# the same loop after fastloop.enable() (fresh model and optimizer), then a cProfile of it
+from pcgnn_b200 import fastloop
+import cProfile, pstats, io
+model = build_cuda_pcgnn(data.feat, data.graph, sorted(data.train_pos), params, device="cuda")
+opt2 = torch.optim.Adam(filter(lambda p: p.requires_grad, model.parameters()), lr=0.01, weight_decay=1e-3)
+fastloop.enable()
+for i in range(8): full(i)
+r=np.array([seg(i) for i in range(8,38)])
+print("fastloop: zero_grad / loss / backward / step / item  (median us):", np.round(np.median(r,axis=0)*1e6,1))
+pr = cProfile.Profile()
+pr.enable()
+for rep in range(4):
+    for i in range(5, 35): full(i)
+pr.disable()
+s = io.StringIO()
+pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(45)
+print("\n".join(l[:170] for l in s.getvalue().splitlines()[:75]))
+fastloop.disable()

@@ -235,3 +235,59 @@ def test_stage_copies_through_pinned_host_memory():
         assert torch.equal(dst.cpu(), src) and torch.equal(back, src)
     with pytest.raises(_lib.PcgError):
         _lib.check(L.pcg_stage(dst.data_ptr(), dst.data_ptr() + 2, 4, _lib.stream_ptr()), "pcg_stage")
+
+
+def test_fast_reference_loop_matches_the_plain_loop():
+    """fastloop.enable(): the reference's loop unchanged (zero_grad / model.loss / backward / torch.optim.Adam.step),
+    with backward() storing the replay's gradients directly and the caller's Adam served by the one-kernel Adam.
+    Same gradients bit for bit after backward(); the same training trajectory as torch's own Adam within the rounding of
+    the two update formulas; anything unusual (explicit gradient argument, another optimizer) takes torch's own route."""
+    from pcgnn_b200 import fastloop
+
+    d, rng, params, tp = _setup(seed=67)
+    B = 128
+    batches = [rng.choice(d.idx_train, B) for _ in range(12)]
+
+    def loop(fast, optim_cls=torch.optim.Adam):
+        model = build_cuda_pcgnn(d.feat, d.graph, tp, params)
+        opt = optim_cls([p for p in model.parameters() if p.requires_grad], lr=0.01, weight_decay=1e-3)
+        if fast:
+            fastloop.enable()
+        try:
+            losses, first_grads = [], None
+            for n in batches:
+                opt.zero_grad()
+                loss = model.loss(n.tolist(), torch.from_numpy(d.labels[n]).cuda())
+                assert isinstance(loss, fastloop.StepLoss) == fast
+                loss.backward()
+                if first_grads is None:
+                    first_grads = [p.grad.detach().clone() for p in model.parameters() if p.requires_grad]
+                opt.step()
+                losses.append(loss.item())
+            weights = [p.detach().cpu().numpy().copy() for p in model.parameters() if p.requires_grad]
+            taken = "_pcg_flat" in opt.__dict__
+        finally:
+            fastloop.disable()
+        return np.asarray(losses), first_grads, weights, taken
+
+    l0, g0, w0, t0 = loop(False)
+    l1, g1, w1, t1 = loop(True)
+    assert not t0 and t1
+    assert all(torch.equal(a, b) for a, b in zip(g0, g1))
+    assert rel_err(l1, l0) <= 1e-4
+    assert max(rel_err(a, b) for a, b in zip(w1, w0)) <= 1e-3
+    # another optimizer: the hook must leave it alone, the fast backward still feeds it
+    l2, _, w2, t2 = loop(True, torch.optim.SGD)
+    l3, _, w3, _ = loop(False, torch.optim.SGD)
+    assert not t2 and np.array_equal(l2, l3) and all(np.array_equal(a, b) for a, b in zip(w2, w3))
+    # explicit gradient argument: torch's own backward
+    model = build_cuda_pcgnn(d.feat, d.graph, tp, params)
+    fastloop.enable()
+    try:
+        n = batches[0]
+        loss = model.loss(n.tolist(), torch.from_numpy(d.labels[n]).cuda())
+        loss.backward(torch.tensor(2.0, device="cuda"))
+        got = [p.grad.detach().clone() for p in model.parameters() if p.requires_grad]
+    finally:
+        fastloop.disable()
+    assert max(rel_err(a.cpu().numpy(), 2.0 * b.cpu().numpy()) for a, b in zip(got, g0)) <= 1e-6
