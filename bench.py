@@ -58,7 +58,8 @@ SEED = 72
 
 MY_KERNELS_PER_STEP = 9    # choose prep 1 (side branch) | score table + pool sort 2, choose 2 (wide, small), aggregate 1,
 #                            fused dense/loss/activation-gradient 1, weight gradients 1, gradient exchange + Adam 1
-#                            (+2 when P > 8192, +1 per extra row tier; the graph also holds one 4-byte torch fill)
+#                            (+2 when P > 8192, +1 per extra row tier, +1 loss-word copy kernel in the host-batch
+#                            recording; device batches: + one multi-tensor copy of ids / labels in front of the replay)
 
 
 def config_dict(desc, global_batch, world, scaling="weak"):
@@ -825,8 +826,10 @@ def main():
         total_nodes = global_batch * K
         io = {"h2d_bytes_per_step": batch * 4 + batch * 8, "d2h_bytes_per_step": 4}
         e2e_graph = {"value": total_nodes / (ms_graph_host / 1e3), "unit": "target-nodes/s", "ms_per_step": ms_graph_host / K,
-                     "call": "runtime.GraphedTrainStep.run_item(numpy_ids, numpy_labels) -> float  (one pinned staging copy, "
-                             "one H2D, one graph replay, D2H of the loss through a pinned word)", **io}
+                     "call": "runtime.GraphedTrainStep.run_item(numpy_ids, numpy_labels) -> float  (the host batch is packed into "
+                             "one pinned buffer; ONE graph launch: the step's first kernel reads the 12 KB of ids / labels from "
+                             "that pinned host memory over PCIe into HBM (pcg_pool_scores_stage), a copy kernel stores the loss "
+                             "into a pinned word (pcg_stage); one event wait)", **io}
         line = {
             "metric": "train target-nodes/sec (fwd+bwd)", "value": total_nodes / (ms_dev / 1e3),
             "unit": "target-nodes/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev / K,

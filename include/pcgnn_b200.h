@@ -6,12 +6,12 @@
  * allocates or frees, and returns 0 on success or a non-zero cudaError_t-compatible code
  * (pcg_last_error() then holds the message; thread-local). The caller owns every buffer.
  *
- * Process-wide state (all of it): the forked side streams / events of pcg_choose (created on first use, on the
- * device that is current then), the probe results cached per kernel (shared-memory opt-in, 16-CTA clusters), the
- * SM count, and the pcg_set_pdl switch. The library therefore drives ONE device per process from one host thread
- * at a time, which is how the reference runs (single-threaded, src/model_handler.py:142-156) and how every
- * multi-GPU run of this package is laid out (one process per GPU); pc-gnn_b200/engine.py refuses an engine for a
- * device other than the current one.
+ * Host-side state (all of it): per DEVICE ordinal, the forked side streams / events of pcg_choose (created on first
+ * use) and the probe results cached per kernel (shared-memory opt-in, 16-CTA clusters, SM count); process-wide, the
+ * pcg_set_pdl switch. Calls launch on the CURRENT device (cudaSetDevice is the caller's) and are not thread-safe per
+ * device: one host thread at a time drives a device, which is how the reference runs (single-threaded,
+ * src/model_handler.py:142-156) and how every multi-GPU run of this package is laid out (one process per GPU;
+ * pc-gnn_b200/engine.py refuses an engine for a device other than the current one).
  *
  * The reference (h22hyeon/PC-GNN) is pure Python; each function below names the reference
  * lines whose work it replaces (paths relative to /root/reference/).
@@ -161,10 +161,10 @@ PCG_API int pcg_choose_workspace_init(void* workspace, size_t workspace_bytes, i
  *                sum, tier queues), which reads targets / labels / indptr but NO scores, so a caller can run it on a
  *                second stream next to pcg_score_table; 2: only the selection, after a phases == 1 call with the
  *                same arguments has completed (stream order / event).
- * Threading / devices: one host thread drives one device per process (the reference is single-threaded,
- * src/model_handler.py:142-156; multi-GPU runs are one process per GPU). The forked side streams and the
- * workspace's barrier words are per process, so concurrent pcg_choose calls from several threads, or calls for
- * two devices from one process, are not supported.
+ * Threading / devices: the call launches on the current device; its forked side streams are kept per device, the
+ * workspace (barrier words, queues) belongs to the caller, so two devices can be driven from one process with one
+ * workspace each, but concurrent pcg_choose calls for the SAME device from several threads are not supported (the
+ * reference is single-threaded, src/model_handler.py:142-156; multi-GPU runs of this package are one process per GPU).
  */
 PCG_API int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t n_nodes, int64_t row_lo, int R,
                const float* score,

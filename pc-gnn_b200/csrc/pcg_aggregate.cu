@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(256) k_aggregate(const float* __restrict__ fea
     constexpr int G = 32 / LPR;          // rows per warp-wide load
     constexpr int UN = (LPR == 32) ? 8 : 4;      // row loads in flight per lane group (16 in flight were measured no faster)
     const int lane = threadIdx.x & 31;
+    pcg_grid_dependency_wait();          // (programmatic launch, pcg_set_pdl bit 16: resident under the selection kernels' tail)
     pcg_launch_dependents();             // the fused dense kernel behind may start streaming its weights
     int64_t n_slots = status[ST_SLOTS];
     if (n_slots > cap_slots) n_slots = cap_slots;
@@ -246,8 +247,9 @@ static void launch_agg(bool bwd, const float* a0, int64_t ldf, const int32_t* id
     const int64_t max_blocks = (int64_t)pcg_device_sms() * 8;      // 8 resident CTAs of 8 warps per SM
     const int blocks = (int)(blocks64 < max_blocks ? blocks64 : max_blocks);
     if (!bwd)
-        k_aggregate<LPR, NV><<<blocks, 256, 0, stream>>>(a0, ldf, idx, slot_item, it_slot0, it_m, it_base, it_extra,
-                                                         it_rep, n_items, cap_slots, status, norm, partial, it_done, out);
+        pcg_launch(k_aggregate<LPR, NV>, dim3(blocks), dim3(256), 0, stream, (pcg_pdl_enabled() & 16) != 0, a0, ldf, idx,
+                   slot_item, it_slot0, it_m, it_base, it_extra, it_rep, n_items, cap_slots, status, norm, partial, it_done,
+                   out);
     else
         k_aggregate_bwd<LPR, NV><<<blocks, 256, 0, stream>>>(a0, ldf, idx, slot_item, it_slot0, it_m, it_base, it_extra,
                                                              cap_slots, status, norm, out);

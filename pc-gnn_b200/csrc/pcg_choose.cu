@@ -1000,7 +1000,8 @@ __global__ void __launch_bounds__(PCG_LARGE_NT, 1) k_choose_huge(ChooseP p) {
 template <int CL>
 static cudaError_t launch_huge(const ChooseP& p, int n_clusters, cudaStream_t stream, bool probe_only, int* max_clusters) {
     const size_t dyn = (size_t)PCG_HUGE_PER_CTA * 6 + (size_t)CL * PCG_HUGE_PER_CTA / 8;
-    static bool configured = false;
+    static bool configured_dev[PCG_MAX_DEVICES];      // function attributes are per device
+    bool& configured = configured_dev[pcg_current_device()];
     cudaError_t e;
     if (!configured) {
         e = cudaFuncSetAttribute(k_choose_huge<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
@@ -1298,15 +1299,19 @@ __global__ void __launch_bounds__(PCG_PREP_NT, 1) k_choose_prep(ChooseP p, int c
                 slot0 += nsl;
             }
         }
+        // one queue reservation per (warp, tier): the up to six atomics of a round are issued together by six lanes
+        // (one L2 round trip instead of one per tier present in the warp)
+        unsigned tm[6];
+#pragma unroll
+        for (int t = 0; t < 6; ++t) tm[t] = __ballot_sync(PCG_FULL, tier == t);
+        int qb = 0;
+#pragma unroll
+        for (int t = 0; t < 6; ++t)
+            if (lane == t && tm[t]) qb = atomicAdd(&p.status[counters[t]], __popc(tm[t]));
 #pragma unroll
         for (int t = 0; t < 6; ++t) {
-            const unsigned m = __ballot_sync(PCG_FULL, tier == t);
-            if (m) {
-                int b = 0;
-                if (lane == 0) b = atomicAdd(&p.status[counters[t]], __popc(m));
-                b = __shfl_sync(PCG_FULL, b, 0);
-                if (tier == t) queues[t][b + __popc(m & lanemask_lt())] = w0 + q;
-            }
+            const int b = __shfl_sync(PCG_FULL, qb, t);
+            if (tier == t) queues[t][b + __popc(tm[t] & lanemask_lt())] = w0 + q;
         }
     }
     PTRACE(3);
@@ -1409,14 +1414,16 @@ static WsLayout ws_layout(int B, int R, int64_t max_degree, int64_t n_nodes, int
     return L;
 }
 
-static int g_sms = 0;
+// Host-side state of this file is kept PER DEVICE ordinal (side streams, fork / join events, probe results): a process
+// that drives several GPUs gets a separate set for each (the calls themselves are not thread-safe per device).
+static int g_sms[PCG_MAX_DEVICES];
 static int device_sms() {
-    if (g_sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-        if (cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_sms <= 0) g_sms = 148;
+    const int dev = pcg_current_device();
+    if (g_sms[dev] == 0) {
+        if (cudaDeviceGetAttribute(&g_sms[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_sms[dev] <= 0)
+            g_sms[dev] = 148;
     }
-    return g_sms;
+    return g_sms[dev];
 }
 
 extern "C" int pcg_device_sms(void) { return device_sms(); }
@@ -1463,8 +1470,13 @@ extern "C" int pcg_entry_pool_positions(const int32_t* indices, int64_t nnz, con
 
 // side streams + events so the tiers run side by side (fork/join; capturable)
 #define PCG_N_SIDE 3
-static cudaStream_t g_side[PCG_N_SIDE] = {nullptr, nullptr, nullptr};
-static cudaEvent_t g_fork = nullptr, g_join[PCG_N_SIDE] = {nullptr, nullptr, nullptr};
+struct SideState {
+    cudaStream_t side[PCG_N_SIDE];
+    cudaEvent_t fork, join[PCG_N_SIDE];
+    int huge16_state;            // can this device place clusters of 16 x 1024 threads? 0 = not probed, 1 = yes, 2 = no
+    size_t big_smem;             // dynamic shared memory k_choose_big is configured for
+};
+static SideState g_dev[PCG_MAX_DEVICES];
 
 extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t n_nodes, int64_t row_lo, int R,
                           const float* score,
@@ -1516,14 +1528,17 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
     p.bits_slab = (uint32_t*)(ws + L.bits_slab);
     p.slab_words = L.slab_words;
     const int W = R * B;
-    static int huge16_state = -1;            // can this device place clusters of 16 x 1024 threads? (probed once)
-    if (huge16_state < 0) {
+    SideState& S = g_dev[pcg_current_device()];
+    cudaStream_t* g_side = S.side;
+    cudaEvent_t* g_join = S.join;
+    cudaEvent_t& g_fork = S.fork;
+    if (S.huge16_state == 0) {               // probed once per device
         int mc = 0;
         cudaError_t pe = launch_huge<16>(p, 1, stream, true, &mc);
-        huge16_state = (pe == cudaSuccess && mc >= 1) ? 1 : 0;
+        S.huge16_state = (pe == cudaSuccess && mc >= 1) ? 1 : 2;
         (void)cudaGetLastError();
     }
-    p.huge16_ok = huge16_state;
+    p.huge16_ok = S.huge16_state == 1;
     if (phases & 1) {
         cudaLaunchConfig_t cfg = {};
         cfg.blockDim = dim3(PCG_PREP_NT);
@@ -1577,11 +1592,10 @@ extern "C" int pcg_choose(const int64_t* indptr, const int32_t* indices, int64_t
     if (have_big) {
         int64_t cap = max_degree > 49152 ? 49152 : (max_degree + 31) / 32 * 32;
         size_t dyn = (size_t)cap * 4;
-        static size_t configured = 0;
-        if (dyn > configured) {
+        if (dyn > S.big_smem) {
             e = cudaFuncSetAttribute(k_choose_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
             if (e != cudaSuccess) { pcg_set_error("pcg_choose: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-            configured = dyn;
+            S.big_smem = dyn;
         }
         cudaStreamWaitEvent(g_side[2], g_fork, 0);
         k_choose_big<<<W < L.grid_big ? W : L.grid_big, PCG_LARGE_NT, dyn, g_side[2]>>>(p, (int)cap);

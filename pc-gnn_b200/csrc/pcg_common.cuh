@@ -20,6 +20,14 @@
 #define ST_NHUGE16 9      // ... for the clusters of 16
 #define ST_NBIG 6        // ... the big tier
 
+// Host-side caches (function attributes already set, side streams, probe results) are kept per device ordinal.
+#define PCG_MAX_DEVICES 64
+static inline int pcg_current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= PCG_MAX_DEVICES) dev = 0;
+    return dev;
+}
+
 void pcg_set_error(const char* fmt, ...);
 int pcg_check_launch(const char* what);
 

@@ -264,7 +264,8 @@ extern "C" int pcg_center_bwd(const float* feat, int64_t ldf, int F, const int32
     if (blocks < 1) blocks = 1;
     const size_t smem = (size_t)CENTER_PER * 2 * ldf * 4;
     PCG_REQUIRE(smem <= 200 * 1024, "pcg_center_bwd: feature rows too wide (ldf=%lld)", (long long)ldf);
-    static size_t configured = 0;
+    static size_t configured_dev[PCG_MAX_DEVICES];
+    size_t& configured = configured_dev[pcg_current_device()];
     if (smem > 48 * 1024 && smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(k_center_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { pcg_set_error("pcg_center_bwd: smem attr: %s", cudaGetErrorString(e)); return (int)e; }

@@ -139,7 +139,8 @@ extern "C" int pcg_encoder_fwd(const float* agg, int64_t lda, const float* feat,
     PCG_REQUIRE(out, "pcg_encoder_fwd: null output");
     p.out = out;
     const size_t smem = ((size_t)E * p.Fin + (size_t)ENC_TI * (p.Fin + 1)) * 4;
-    static size_t configured = 0;
+    static size_t configured_dev[PCG_MAX_DEVICES];
+    size_t& configured = configured_dev[pcg_current_device()];
     rc = enc_smem([](size_t b) { return cudaFuncSetAttribute(k_encoder_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b); },
                   smem, configured, "pcg_encoder_fwd");
     if (rc) return rc;
@@ -157,7 +158,8 @@ extern "C" int pcg_encoder_bwd(const float* agg, int64_t lda, const float* feat,
     PCG_REQUIRE(out && d_out && d_w && scratch && ticket, "pcg_encoder_bwd: null pointer");
     p.out = const_cast<float*>(out); p.d_out = d_out; p.d_w = d_w; p.partial = scratch; p.ticket = ticket;
     const size_t smem = ((size_t)E * (ENC_TI + 1) + (size_t)ENC_TI * (p.Fin + 1)) * 4;
-    static size_t configured = 0;
+    static size_t configured_dev[PCG_MAX_DEVICES];
+    size_t& configured = configured_dev[pcg_current_device()];
     rc = enc_smem([](size_t b) { return cudaFuncSetAttribute(k_encoder_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b); },
                   smem, configured, "pcg_encoder_bwd");
     if (rc) return rc;

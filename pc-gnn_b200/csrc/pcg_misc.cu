@@ -238,7 +238,8 @@ static int sort_pool_impl(const float* pool_score, int gather, const int32_t* po
     if (P <= 0) return 0;
     if (P <= PCG_SORT_SMALL_MAX) {
         const size_t smem = (size_t)P * 8;
-        static bool configured = false;
+        static bool configured_dev[PCG_MAX_DEVICES];
+        bool& configured = configured_dev[pcg_current_device()];
         if (!configured) {
             cudaError_t e = cudaFuncSetAttribute(k_sort_pool_rank, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  PCG_SORT_SMALL_MAX * 8);

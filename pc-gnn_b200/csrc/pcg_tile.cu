@@ -824,7 +824,8 @@ extern "C" size_t pcg_tile_scratch_floats(int B, int R, int F, int E) { return t
 
 template <int TM>
 static cudaError_t launch_tile(const TileP& p, size_t smem, cudaStream_t stream, int pdl) {
-    static size_t configured = 0;
+    static size_t configured_dev[PCG_MAX_DEVICES];
+    size_t& configured = configured_dev[pcg_current_device()];
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(k_tile<TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
