@@ -244,3 +244,57 @@ def test_device_metrics_equal_sklearn():
     m = binary_metrics(torch.from_numpy(s), torch.from_numpy(pred), torch.from_numpy(y))
     assert m["f1"] == 0.0 and m["precision"] == 0.0 and m["recall"] == 0.0
     assert abs(m["auc"] - roc_auc_score(y, s)) < 1e-12
+
+
+def test_fastloop_routes_on_cpu():
+    """fastloop (host logic only, no kernels): the loss subclass keeps its autograd node; backward() without arguments
+    stores the recorded gradients only while enabled; every other use, and every optimizer the hook does not recognise,
+    goes through torch's own code."""
+    import torch
+
+    from pcgnn_b200 import fastloop
+
+    def make():
+        ws = [torch.nn.Parameter(torch.ones(3)), torch.nn.Parameter(torch.ones(2, 2))]
+        loss = ws[0].sum() * 2 + ws[1].sum() * 3
+        flat = torch.arange(8.0)
+        return ws, fastloop.wrap(loss, flat, [(0, 3, (3,)), (4, 4, (2, 2))], ws), flat
+
+    assert not fastloop.enabled()
+    ws, loss, _ = make()
+    assert isinstance(loss, fastloop.StepLoss) and loss.grad_fn is not None and float(loss.item()) == 18.0
+    loss.backward()                                              # not enabled: autograd
+    assert torch.equal(ws[0].grad, torch.full((3,), 2.0)) and torch.equal(ws[1].grad, torch.full((2, 2), 3.0))
+
+    fastloop.enable()
+    try:
+        fastloop.enable()                                        # idempotent
+        ws, loss, flat = make()
+        loss.backward()                                          # enabled: the recorded gradients, no engine
+        assert torch.equal(ws[0].grad, torch.tensor([0.0, 1.0, 2.0]))
+        assert torch.equal(ws[1].grad, torch.tensor([[4.0, 5.0], [6.0, 7.0]]))
+        flat.add_(100.0)                                         # the static buffer is rewritten by the next replay ...
+        assert torch.equal(ws[0].grad, torch.tensor([0.0, 1.0, 2.0]))        # ... the handed-out gradients are a copy
+        # an optimizer the hook does not take over: torch's own step consumes those gradients
+        opt = torch.optim.SGD(ws, lr=1.0)
+        opt.step()
+        assert torch.equal(ws[0].detach(), torch.tensor([1.0, 0.0, -1.0])) and "_pcg_flat" not in opt.__dict__
+        ws, loss, _ = make()
+        opt = torch.optim.Adam(ws, lr=0.1, amsgrad=True)         # Adam variant outside the kernel's formula: left alone
+        loss.backward()
+        opt.step()
+        assert "_pcg_flat" not in opt.__dict__ and len(opt.state) == 2
+        # second backward on the same loss accumulates like autograd; explicit gradient / scaled loss: torch's route
+        ws, loss, _ = make()
+        loss.backward(retain_graph=True)
+        loss.backward()
+        assert torch.equal(ws[0].grad, torch.tensor([0.0, 2.0, 4.0]))
+        ws, loss, _ = make()
+        loss.backward(torch.tensor(2.0))
+        assert torch.equal(ws[0].grad, torch.full((3,), 4.0))
+        ws, loss, _ = make()
+        (loss * 0.5).backward()
+        assert torch.equal(ws[1].grad, torch.full((2, 2), 1.5))
+    finally:
+        fastloop.disable()
+    assert not fastloop.enabled()
