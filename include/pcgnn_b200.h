@@ -86,13 +86,22 @@ PCG_API int pcg_pool_scores(const float* feat, int F, int64_t ldf, const float* 
  * the first kernel of the training step fetches the batch's ids and labels while it computes, which takes the host
  * to device copy off the step's critical path altogether. The source must stay unchanged until the kernel has
  * finished (the caller's event / synchronisation), like the source of any asynchronous copy.
+ *
+ * Epoch plans (the batch loop of src/model_handler.py:128-150 with the whole epoch's batches uploaded once): with a
+ * device-resident `cursor` word the copy takes entry (*cursor % count) of a plan: pcg_pool_scores_stage reads its
+ * source at stage_src + entry * src_stride_bytes (cursor NULL: plain); pcg_stage_indexed offsets source and destination
+ * by entry * stride each and, with bump != 0 (copies of at most 4 KB), increments the cursor behind the copy. A recorded
+ * step that fetches its batch through the cursor and ends with a bumping copy of its loss word into a per-step array
+ * replays a whole epoch without the host touching a batch.
  */
 PCG_API int pcg_stage(const void* src, void* dst, size_t bytes, pcg_stream_t stream);
 /* Device address of a page-locked host buffer (cudaHostGetDevicePointer), or NULL + pcg_last_error(). */
 PCG_API void* pcg_host_device_ptr(void* host_ptr);
 PCG_API int pcg_pool_scores_stage(const float* feat, int F, int64_t ldf, const float* w, const float* b, const int32_t* pool,
                           int P, float* pool_score, const void* stage_src, void* stage_dst, size_t stage_bytes,
-                          pcg_stream_t stream);
+                          const uint32_t* cursor, uint32_t count, int64_t src_stride_bytes, pcg_stream_t stream);
+PCG_API int pcg_stage_indexed(const void* src, void* dst, size_t bytes, uint32_t* cursor, uint32_t count,
+                      int64_t src_stride_bytes, int64_t dst_stride_bytes, int bump, pcg_stream_t stream);
 
 /*
  * Pool sorted by score: ps_score ascending with ties in pool-position order, ps_pos[i] = position in

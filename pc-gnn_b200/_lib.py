@@ -37,7 +37,8 @@ SIGNATURES = {
     "pcg_pool_scores": (_i, [_p, _i, _l, _p, _p, _p, _i, _p, _p]),
     "pcg_stage": (_i, [_p, _p, _z, _p]),
     "pcg_host_device_ptr": (_p, [_p]),
-    "pcg_pool_scores_stage": (_i, [_p, _i, _l, _p, _p, _p, _i, _p, _p, _p, _z, _p]),
+    "pcg_pool_scores_stage": (_i, [_p, _i, _l, _p, _p, _p, _i, _p, _p, _p, _z, _p, C.c_uint32, _l, _p]),
+    "pcg_stage_indexed": (_i, [_p, _p, _z, _p, C.c_uint32, _l, _l, _i, _p]),
     "pcg_sort_pool_workspace_bytes": (_z, [_i]),
     "pcg_sort_pool": (_i, [_p, _p, _i, _p, _p, _p, _p, _z, _p]),
     "pcg_choose_workspace_bytes": (_z, [_i, _i, _l, _l]),

@@ -97,19 +97,34 @@ __device__ __forceinline__ void stage_copy(const uint32_t* src, uint32_t* dst, i
     }
 }
 
-__global__ void __launch_bounds__(256) k_stage(const uint32_t* src, uint32_t* dst, int64_t n) {
+// cursor != NULL: entry (*cursor % count) of a plan: src / dst advance by that many strides (32-bit words); bump: the
+// cursor is incremented behind the copy (one CTA only: the indexed form copies a few words).
+__global__ void __launch_bounds__(256) k_stage(const uint32_t* src, uint32_t* dst, int64_t n, uint32_t* cursor,
+                                               uint32_t count, int64_t src_stride, int64_t dst_stride, int bump) {
     // no fence behind the stores: the consumer (a later kernel, or the host after an event / stream wait) is ordered
     // behind the END of this kernel, which makes them visible (a system-scope fence here cost 5 us: ncu, membar 100 %)
+    uint32_t at = 0;
+    if (cursor) {
+        at = *(volatile uint32_t*)cursor;
+        src += (int64_t)(at % count) * src_stride;
+        dst += (int64_t)(at % count) * dst_stride;
+    }
     stage_copy(src, dst, n, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
+    if (cursor && bump) {
+        __syncthreads();                     // single CTA (enforced by the launcher): every thread has read the cursor
+        if (threadIdx.x == 0) *(volatile uint32_t*)cursor = at + 1u;
+    }
 }
 
 __global__ void __launch_bounds__(256) k_pool_scores(const float* __restrict__ feat, int F, int64_t ldf,
                                                      const float* __restrict__ w, const float* __restrict__ b,
                                                      const int32_t* __restrict__ pool, int P, float* __restrict__ pool_score,
                                                      int score_blocks, const uint32_t* stage_src, uint32_t* stage_dst,
-                                                     int64_t stage_words) {
+                                                     int64_t stage_words, const uint32_t* cursor, uint32_t count,
+                                                     int64_t src_stride) {
     if ((int)blockIdx.x >= score_blocks) {
         const int64_t nb = gridDim.x - score_blocks;
+        if (cursor) stage_src += (int64_t)(*(volatile const uint32_t*)cursor % count) * src_stride;   // plan entry
         stage_copy(stage_src, stage_dst, stage_words, (int64_t)(blockIdx.x - score_blocks) * blockDim.x + threadIdx.x,
                    nb * blockDim.x);
         return;
@@ -282,15 +297,17 @@ extern "C" int pcg_sort_pool(const float* pool_score, const int32_t* pool, int P
 
 static int pool_scores_impl(const char* who, const float* feat, int F, int64_t ldf, const float* w, const float* b,
                             const int32_t* pool, int P, float* pool_score, const void* stage_src, void* stage_dst,
-                            size_t stage_bytes, cudaStream_t stream) {
+                            size_t stage_bytes, const uint32_t* cursor, uint32_t count, int64_t src_stride_bytes,
+                            cudaStream_t stream) {
     PCG_REQUIRE(stage_bytes == 0 || (stage_src && stage_dst), "%s: staging pointers missing", who);
     PCG_REQUIRE(stage_bytes % 4 == 0 && ((uintptr_t)stage_src & 3) == 0 && ((uintptr_t)stage_dst & 3) == 0,
                 "%s: the staged copy works on aligned 32-bit words", who);
+    PCG_REQUIRE(!cursor || (count > 0 && src_stride_bytes % 4 == 0), "%s: a plan cursor needs count > 0 and a stride of whole words", who);
     if (P <= 0) {
         if (stage_bytes) {
             const int64_t n = (int64_t)(stage_bytes / 4);
-            k_stage<<<(int)((n + 1023) / 1024 < 64 ? (n + 1023) / 1024 : 64), 256, 0, stream>>>((const uint32_t*)stage_src,
-                                                                                              (uint32_t*)stage_dst, n);
+            k_stage<<<(int)((n + 1023) / 1024 < 64 ? (n + 1023) / 1024 : 64), 256, 0, stream>>>(
+                (const uint32_t*)stage_src, (uint32_t*)stage_dst, n, const_cast<uint32_t*>(cursor), count, src_stride_bytes / 4, 0, 0);
             return pcg_check_launch(who);
         }
         return 0;
@@ -306,21 +323,22 @@ static int pool_scores_impl(const char* who, const float* feat, int F, int64_t l
     if (rider > 64) rider = 64;
     k_pool_scores<<<blocks + (int)rider, 256, (size_t)ldf * 4, stream>>>(feat, F, ldf, w, b, pool, P, pool_score, blocks,
                                                                          (const uint32_t*)stage_src, (uint32_t*)stage_dst,
-                                                                         words);
+                                                                         words, cursor, count, src_stride_bytes / 4);
     return pcg_check_launch(who);
 }
 
 extern "C" int pcg_pool_scores(const float* feat, int F, int64_t ldf, const float* w, const float* b, const int32_t* pool,
                                int P, float* pool_score, pcg_stream_t stream_) {
-    return pool_scores_impl("pcg_pool_scores", feat, F, ldf, w, b, pool, P, pool_score, nullptr, nullptr, 0,
+    return pool_scores_impl("pcg_pool_scores", feat, F, ldf, w, b, pool, P, pool_score, nullptr, nullptr, 0, nullptr, 0, 0,
                             (cudaStream_t)stream_);
 }
 
 extern "C" int pcg_pool_scores_stage(const float* feat, int F, int64_t ldf, const float* w, const float* b,
                                      const int32_t* pool, int P, float* pool_score, const void* stage_src, void* stage_dst,
-                                     size_t stage_bytes, pcg_stream_t stream_) {
+                                     size_t stage_bytes, const uint32_t* cursor, uint32_t count, int64_t src_stride_bytes,
+                                     pcg_stream_t stream_) {
     return pool_scores_impl("pcg_pool_scores_stage", feat, F, ldf, w, b, pool, P, pool_score, stage_src, stage_dst,
-                            stage_bytes, (cudaStream_t)stream_);
+                            stage_bytes, cursor, count, src_stride_bytes, (cudaStream_t)stream_);
 }
 
 extern "C" void* pcg_host_device_ptr(void* host_ptr) {
@@ -343,8 +361,25 @@ extern "C" int pcg_stage(const void* src, void* dst, size_t bytes, pcg_stream_t 
     const int64_t n = (int64_t)(bytes / 4);
     int64_t blocks = (n + 1023) / 1024;
     if (blocks > 64) blocks = 64;
-    k_stage<<<(int)blocks, 256, 0, stream>>>((const uint32_t*)src, (uint32_t*)dst, n);
+    k_stage<<<(int)blocks, 256, 0, stream>>>((const uint32_t*)src, (uint32_t*)dst, n, nullptr, 0, 0, 0, 0);
     return pcg_check_launch("pcg_stage");
+}
+
+extern "C" int pcg_stage_indexed(const void* src, void* dst, size_t bytes, uint32_t* cursor, uint32_t count,
+                                 int64_t src_stride_bytes, int64_t dst_stride_bytes, int bump, pcg_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (bytes == 0) return 0;
+    PCG_REQUIRE(src && dst && cursor && count > 0, "pcg_stage_indexed: null pointer or empty plan");
+    PCG_REQUIRE(bytes % 4 == 0 && ((uintptr_t)src & 3) == 0 && ((uintptr_t)dst & 3) == 0 && src_stride_bytes % 4 == 0 &&
+                    dst_stride_bytes % 4 == 0,
+                "pcg_stage_indexed: the copy works on aligned 32-bit words");
+    const int64_t n = (int64_t)(bytes / 4);
+    int64_t blocks = (n + 1023) / 1024;
+    if (blocks > 64) blocks = 64;
+    PCG_REQUIRE(!bump || blocks == 1, "pcg_stage_indexed: a copy that advances the cursor is at most 4 KB (one CTA)");
+    k_stage<<<(int)blocks, 256, 0, stream>>>((const uint32_t*)src, (uint32_t*)dst, n, cursor, count, src_stride_bytes / 4,
+                                             dst_stride_bytes / 4, bump);
+    return pcg_check_launch("pcg_stage_indexed");
 }
 
 extern "C" int pcg_score_table(const float* feat, int64_t n_nodes, int F, int64_t ldf, const float* w, const float* b,

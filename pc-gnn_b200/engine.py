@@ -230,15 +230,21 @@ class Engine:
         _lib.check(rc, "pcg_score_table")
         return self.score
 
-    def stage(self, src_ptr: int, dst_ptr: int, nbytes: int):
+    def stage(self, src_ptr: int, dst_ptr: int, nbytes: int, cursor_ptr: int = 0, count: int = 0, src_stride: int = 0):
         """Copy by a kernel (``pcg_stage``): either side may be page-locked host memory (device address from
-        ``host_device_ptr``); keeps a recorded step free of memcpy nodes."""
-        _lib.check(self.lib.pcg_stage(src_ptr, dst_ptr, int(nbytes), _lib.stream_ptr()), "pcg_stage")
+        ``host_device_ptr``); keeps a recorded step free of memcpy nodes. With a device cursor word the source is entry
+        ``*cursor % count`` of a plan (``pcg_stage_indexed``)."""
+        if cursor_ptr:
+            _lib.check(self.lib.pcg_stage_indexed(src_ptr, dst_ptr, int(nbytes), cursor_ptr, int(count), int(src_stride), 0,
+                                                  0, _lib.stream_ptr()), "pcg_stage_indexed")
+        else:
+            _lib.check(self.lib.pcg_stage(src_ptr, dst_ptr, int(nbytes), _lib.stream_ptr()), "pcg_stage")
 
     def pool_scores(self, clf_weight: torch.Tensor, clf_bias: torch.Tensor, stage=None):
         """Scores of the pool members only (``pcg_pool_scores``; bit-identical to the table's values): the pool sort
         can then run next to the score-table kernel / the score exchange instead of behind it.
-        stage = (src_ptr, dst_ptr, nbytes): that copy rides on extra CTAs of the kernel (``pcg_pool_scores_stage``)."""
+        stage = (src_ptr, dst_ptr, nbytes[, cursor_ptr, count, src_stride]): that copy rides on extra CTAs of the kernel
+        (``pcg_pool_scores_stage``); with a cursor the source is entry ``*cursor % count`` of an epoch plan."""
         if not self.P:
             if stage is not None:
                 self.stage(*stage)
@@ -251,7 +257,8 @@ class Engine:
             rc = self.lib.pcg_pool_scores_stage(self.feat.data_ptr(), self.F, self.ldf, w.data_ptr(),
                                                 clf_bias.detach().data_ptr(), self.pool.data_ptr(), self.P,
                                                 self._pool_score.data_ptr(), stage[0], stage[1], int(stage[2]),
-                                                _lib.stream_ptr())
+                                                stage[3] if len(stage) > 3 else None, int(stage[4]) if len(stage) > 3 else 0,
+                                                int(stage[5]) if len(stage) > 3 else 0, _lib.stream_ptr())
         else:
             rc = self.lib.pcg_pool_scores(self.feat.data_ptr(), self.F, self.ldf, w.data_ptr(),
                                           clf_bias.detach().data_ptr(), self.pool.data_ptr(), self.P,

@@ -63,6 +63,12 @@ class GraphedTrainStep:
         self._host_pending = False
         self.g_host = None
         self.loss_host = None
+        # epoch plan (load_plan / run_planned): every batch of an epoch in HBM, a device cursor, a third recording that
+        # fetches entry `cursor` and stores its loss into losses[cursor]
+        self._plan = None               # int32 [n_steps, 3B]
+        self._plan_losses = None        # fp32 [n_steps]
+        self._cursor = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.g_plan = None
         if reducer is not None:
             # the captured graph writes the gradients through the parameters' .grad tensors: they must BE the views
             # of the reducer's flat buffer (otherwise the graph keeps accumulating into tensors nobody zeroes)
@@ -91,10 +97,18 @@ class GraphedTrainStep:
         models hand the copy to ``InterAgg._select``, where it rides on the step's first kernel (the pool scores,
         which need no ids); other models get a copy kernel in front. No memcpy node: the recording stays a graph of
         kernels (with copy nodes in it the branches of the step were measured to start several microseconds apart)."""
-        job = (_lib.host_device_ptr(self._pin_in), self._packed.data_ptr(), self._packed.numel() * 4)
+        nbytes = self._packed.numel() * 4
+        if self._plan is not None and self._staging_plan:
+            job = (self._plan.data_ptr(), self._packed.data_ptr(), nbytes, self._cursor.data_ptr(), self._plan.shape[0],
+                   nbytes)
+        else:
+            job = (_lib.host_device_ptr(self._pin_in), self._packed.data_ptr(), nbytes)
         inter = getattr(self.model, "inter1", None)
         if inter is not None and hasattr(inter, "stage_in"):
             inter.stage_in = job
+        elif len(job) > 3:
+            _lib.check(_lib.lib().pcg_stage_indexed(job[0], job[1], job[2], job[3], job[4], job[5], 0, 0,
+                                                    _lib.stream_ptr()), "pcg_stage_indexed")
         else:
             _lib.check(_lib.lib().pcg_stage(job[0], job[1], job[2], _lib.stream_ptr()), "pcg_stage")
 
@@ -202,15 +216,21 @@ class GraphedTrainStep:
         with _lib.capture(self.g_opt):
             self.opt.step()
 
-    def _capture_host_graph(self):
-        """Fused optimizer only: the step with its host<->device copies recorded as nodes of the graph."""
+    _staging_plan = False
+
+    def _capture_host_graph(self, plan: bool = False):
+        """Fused optimizer only: the step with its batch fetch and its loss store recorded as kernels of the graph.
+        plan: the batch comes from entry `cursor` of the device-resident epoch plan, the loss goes into losses[cursor]
+        and the cursor advances."""
         import os
 
         torch.cuda.synchronize(self.dev)
         mask = int(os.environ.get("PCG_PDL_MASK", "10")) if self.use_pdl else 0
         prev = _lib.lib().pcg_set_pdl(mask)
+        self._staging_plan = plan
         try:
-            self._pin_in.copy_(self._packed)           # whatever batch is resident: replays before run() stay meaningful
+            if not plan:
+                self._pin_in.copy_(self._packed)       # whatever batch is resident: replays before run() stay meaningful
             g = torch.cuda.CUDAGraph()
             with _lib.capture(g):
                 cur = torch.cuda.current_stream(self.dev)
@@ -220,18 +240,30 @@ class GraphedTrainStep:
                     else self.model.inter1.engine().side_stream(2)
                 side.wait_stream(cur)
                 with torch.cuda.stream(side):
-                    _lib.check(_lib.lib().pcg_stage(loss.data_ptr(), _lib.host_device_ptr(self._pin_loss), 4,
-                                                    _lib.stream_ptr()), "pcg_stage")
+                    if plan:
+                        _lib.check(_lib.lib().pcg_stage_indexed(loss.data_ptr(), self._plan_losses.data_ptr(), 4,
+                                                                self._cursor.data_ptr(), self._plan.shape[0], 0, 4, 1,
+                                                                _lib.stream_ptr()), "pcg_stage_indexed")
+                    else:
+                        _lib.check(_lib.lib().pcg_stage(loss.data_ptr(), _lib.host_device_ptr(self._pin_loss), 4,
+                                                        _lib.stream_ptr()), "pcg_stage")
                 self.opt.step()
                 cur.wait_stream(side)
-            self.g_host, self.loss_host = g, loss
+            if plan:
+                self.g_plan = g
+            else:
+                self.g_host, self.loss_host = g, loss
         finally:
+            self._staging_plan = False
             _lib.lib().pcg_set_pdl(prev)
 
-    def _replay(self, host: bool = False):
+    def _replay(self, host: bool = False, plan: bool = False):
         if self.g_pre is not None:
             self.g_pre.replay()
             self._xeng.score_exchange()
+        if plan:
+            self.g_plan.replay()
+            return None
         if host:
             self.g_host.replay()
             return self.loss_host
@@ -294,6 +326,39 @@ class GraphedTrainStep:
         self._loss_event.record(torch.cuda.current_stream(self.dev))
         self._loss_event.synchronize()
         return float(self._pin_loss[0])
+
+    # -- epoch plan: the batch loop of model_handler.py:128-150 with the epoch's batches resident in HBM --------------
+    def load_plan(self, batches):
+        """Upload a whole epoch: ``batches`` = sequence of (ids, labels), each exactly ``batch_size`` long. One packed
+        host array, one H2D; afterwards ``run_planned()`` replays the step for the next entry (wrapping around) without
+        the host touching a batch: the recorded step fetches entry ``cursor`` itself, stores its loss into
+        ``plan_losses()[cursor]`` and advances the cursor on the device. Fused optimizer only."""
+        if not self.fused:
+            raise RuntimeError("epoch plans need the fused optimizer (parallel.FusedAdam)")
+        B, n = self.B, len(batches)
+        host = np.empty((n, 3 * B), dtype=np.int32)
+        for i, (ids, labels) in enumerate(batches):
+            host[i, :2 * B].view(np.int64)[:] = labels
+            host[i, 2 * B:] = ids
+        plan = torch.from_numpy(host).to(self.dev)
+        if self._plan is not None and self._plan.shape == plan.shape:
+            self._plan.copy_(plan)                     # same addresses: the recording stays valid
+        else:
+            self._plan = plan
+            self._plan_losses = torch.zeros(n, dtype=torch.float32, device=self.dev)
+            self.g_plan = None
+        self._cursor.zero_()
+        if self.g_plan is None:
+            self._capture_host_graph(plan=True)
+        return n
+
+    def run_planned(self):
+        """One step on the next entry of the plan: a graph replay, nothing else."""
+        self._replay(plan=True)
+
+    def plan_losses(self) -> torch.Tensor:
+        """Device tensor of the planned steps' losses (entry i = the most recent step on plan entry i)."""
+        return self._plan_losses
 
     def overflowed(self) -> bool:
         """True if ANY replay since the last call needed more slots than the captured capacity (its results were

@@ -291,3 +291,42 @@ def test_fast_reference_loop_matches_the_plain_loop():
     finally:
         fastloop.disable()
     assert max(rel_err(a.cpu().numpy(), 2.0 * b.cpu().numpy()) for a, b in zip(got, g0)) <= 1e-6
+
+
+def test_epoch_plan_equals_device_batches():
+    """GraphedTrainStep.load_plan / run_planned (every batch of the epoch resident in HBM, a device cursor, the recorded
+    step fetches its batch and files its loss by itself: pcg_pool_scores_stage / pcg_stage_indexed) against run_device
+    on the same sequence of batches, two epochs (the cursor wraps): identical losses and weights, bit for bit."""
+    from pcgnn_b200.parallel import FusedAdam, GradAllReduce
+    from pcgnn_b200.runtime import GraphedTrainStep
+
+    d, rng, params, tp = _setup(seed=68)
+    B, n = 128, 5
+    batches = [rng.choice(d.idx_train, B) for _ in range(n)]
+    out = []
+    for mode in ("device", "plan"):
+        model = build_cuda_pcgnn(d.feat, d.graph, tp, params)
+        reducer = GradAllReduce(model.parameters()).attach()
+        opt = FusedAdam(reducer, lr=0.01, weight_decay=1e-3)
+        eng = model.inter1.engine()
+        eng.set_features(model.inter1.features.weight)
+        cap = GraphedTrainStep.plan(eng, batches, model.inter1.thresholds, 0.5)
+        step = GraphedTrainStep(model, opt, B, cap, reducer=reducer, warmup_batch=(batches[0], d.labels[batches[0]]))
+        losses = []
+        if mode == "device":
+            for epoch in range(2):
+                for b in batches:
+                    loss = step.run_device(torch.from_numpy(b.astype(np.int32)).cuda(), torch.from_numpy(d.labels[b]).cuda())
+                    losses.append(float(loss.item()))
+        else:
+            assert step.load_plan([(b, d.labels[b]) for b in batches]) == n
+            for epoch in range(2):
+                for _ in range(n):
+                    step.run_planned()                      # no host data, no sync
+                losses += step.plan_losses().cpu().tolist()
+            assert int(step._cursor.item()) == 2 * n
+        assert not step.overflowed()
+        weights = np.concatenate([p.detach().cpu().numpy().ravel() for p in model.parameters() if p.requires_grad])
+        out.append((np.asarray(losses, dtype=np.float32), weights))
+    assert np.array_equal(out[0][0], out[1][0])
+    assert np.array_equal(out[0][1], out[1][1])
