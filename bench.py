@@ -805,16 +805,6 @@ def main():
     ms_graph_host = timed(step_host, W)
     barrier()
     ms_graph_host = max_over_ranks(ms_graph_host)
-    # ---- the same steps from a device-resident epoch plan (one upload for all batches, no host work per step) ----
-    ms_plan = None
-    if gstep is not None and fused and not is_big:
-        gstep.load_plan([(shards[s][0], host_labels[s]) for s in range(W + K)])
-        for s in range(W):
-            gstep.run_planned()
-        barrier()
-        ms_plan = timed(lambda i: gstep.run_planned(), W)
-        barrier()
-        ms_plan = max_over_ranks(ms_plan)
     if gstep is not None:
         assert not gstep.overflowed()
     # ---- host inputs through the REFERENCE's own loop (1 GPU: the reference is single-GPU) ----
@@ -831,6 +821,23 @@ def main():
         inter.scores_external = False
     kern, roof = hot_kernels_gcn(eng, inter, data, shards, dev_nodes, cap, W, K, flush, dev) if is_gcn else \
         hot_kernels_pcgnn(eng, inter, data, shards, dev_nodes, dev_labels, cap, W, K, flush, dev, batch, args.workload)
+
+    # ---- the same steps from a device-resident epoch plan (one upload for all batches, no host work per step); last, and
+    # guarded: an extra line of the report must never cost the report ----
+    ms_plan = None
+    if gstep is not None and fused and not is_big:
+        try:
+            gstep.load_plan([(shards[s][0], host_labels[s]) for s in range(W + K)])
+            for s in range(W):
+                gstep.run_planned()
+            barrier()
+            ms_plan = timed(lambda i: gstep.run_planned(), W)
+            barrier()
+            ms_plan = max_over_ranks(ms_plan)
+            assert not gstep.overflowed()
+        except Exception as exc:          # noqa: BLE001
+            print(f"epoch-plan arm skipped: {exc!r}", file=sys.stderr)
+            ms_plan = None
 
     if rank == 0:
         total_nodes = global_batch * K
