@@ -230,3 +230,36 @@ def test_full_size_yelp_shape_bit_exact():
         o = np.where(labels == 1, np.minimum((c * 0.5).astype(np.int64), len(pool)), 0)
         mm = m[r * 1024:(r + 1) * 1024]
         assert np.all(mm >= k) and np.all(mm <= k + o)
+
+
+@pytest.mark.parametrize("n,F", [(1000, 25), (45_954, 32), (600_000, 64), (524_288 + 77, 100)])
+def test_score_table_rows_and_pool_scores_are_bit_identical(n, F):
+    """pcg_score_table (two rows in flight per lane group; a capped grid above 2^19 rows) against a float64 reference,
+    and against pcg_pool_scores, whose values must be the table's, bit for bit (the pool sort runs from them while the
+    selection compares with the table)."""
+    from pcgnn_b200 import _lib
+    from pcgnn_b200.engine import padded_ld
+
+    L = _lib.lib()
+    rng = np.random.default_rng(n + F)
+    ldf = padded_ld(F)
+    feat = np.zeros((n, ldf), dtype=np.float32)
+    feat[:, :F] = rng.normal(size=(n, F)).astype(np.float32)
+    w = rng.normal(size=(2, F)).astype(np.float32) * 0.3
+    b = np.array([0.25, -0.5], dtype=np.float32)
+    pool = np.unique(rng.integers(0, n, size=min(n, 5000))).astype(np.int32)
+    rng.shuffle(pool)
+    d_feat, d_w, d_b, d_pool = (torch.from_numpy(x).cuda() for x in (feat, w, b, pool))
+    score = torch.full((n,), float("nan"), device="cuda")
+    pool_score = torch.full((len(pool),), float("nan"), device="cuda")
+    s = _lib.stream_ptr()
+    _lib.check(L.pcg_score_table(d_feat.data_ptr(), n, F, ldf, d_w.data_ptr(), d_b.data_ptr(), score.data_ptr(), None, 0,
+                                 None, None, None, None, 0, s), "pcg_score_table")
+    _lib.check(L.pcg_pool_scores(d_feat.data_ptr(), F, ldf, d_w.data_ptr(), d_b.data_ptr(), d_pool.data_ptr(), len(pool),
+                                 pool_score.data_ptr(), s), "pcg_pool_scores")
+    torch.cuda.synchronize()
+    got = score.cpu().numpy()
+    want = feat[:, :F].astype(np.float64) @ w[0].astype(np.float64) + float(b[0])
+    assert np.isfinite(got).all()
+    assert np.abs(got - want).max() <= 1e-5 * max(1.0, np.abs(want).max())
+    assert np.array_equal(got[pool].view(np.uint32), pool_score.cpu().numpy().view(np.uint32))
