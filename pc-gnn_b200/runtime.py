@@ -336,8 +336,13 @@ class GraphedTrainStep:
         if not self.fused:
             raise RuntimeError("epoch plans need the fused optimizer (parallel.FusedAdam)")
         B, n = self.B, len(batches)
+        if n == 0:
+            raise ValueError("load_plan: no batches")
         host = np.empty((n, 3 * B), dtype=np.int32)
         for i, (ids, labels) in enumerate(batches):
+            if len(ids) != B or len(labels) != B:
+                raise ValueError(f"load_plan: batch {i} has {len(ids)} ids / {len(labels)} labels, the recorded step takes "
+                                 f"exactly {B} (run a partial last batch through model.loss)")
             host[i, :2 * B].view(np.int64)[:] = labels
             host[i, 2 * B:] = ids
         plan = torch.from_numpy(host).to(self.dev)
@@ -354,6 +359,8 @@ class GraphedTrainStep:
 
     def run_planned(self):
         """One step on the next entry of the plan: a graph replay, nothing else."""
+        if self.g_plan is None:
+            raise RuntimeError("run_planned: call load_plan(batches) first")
         self._replay(plan=True)
 
     def plan_losses(self) -> torch.Tensor:
